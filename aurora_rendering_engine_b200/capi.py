@@ -1,0 +1,325 @@
+"""ctypes binding of the C ABI in ``include/are_cuda.h`` (libare_b200.so).
+
+This is plumbing only: every function here forwards to one ``are_cuda_*`` entry point.  There is no Python or
+CPU implementation of any of them — if the shared library is missing, or no CUDA device is present, the calls
+raise instead of falling back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libare_b200.so")
+
+ARE_OK = 0
+STATUS_NAMES = {0: "ARE_OK", -1: "ARE_ERR_INVALID_ARGUMENT", -2: "ARE_ERR_RUNTIME", -3: "ARE_ERR_CUDA",
+                -4: "ARE_ERR_NO_DEVICE", -5: "ARE_ERR_NOT_COMMITTED", -6: "ARE_ERR_IO"}
+
+
+class Camera(C.Structure):
+    """are_camera"""
+    _fields_ = [("pos", C.c_double * 3), ("target", C.c_double * 3), ("up", C.c_double * 3), ("vfov_deg", C.c_double),
+                ("focus_dist", C.c_double), ("defocus_angle_deg", C.c_double), ("jitter", C.c_int32), ("pad_", C.c_int32)]
+
+
+class RenderParams(C.Structure):
+    """are_render_params"""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("sample_begin", C.c_int32), ("sample_count", C.c_int32),
+                ("max_depth", C.c_int32), ("integrator", C.c_int32), ("traversal", C.c_int32), ("ao_samples", C.c_int32),
+                ("seed", C.c_uint64), ("t_min", C.c_double), ("background_bottom", C.c_double * 3),
+                ("background_top", C.c_double * 3)]
+
+
+class RenderStats(C.Structure):
+    """are_render_stats"""
+    _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("tri_tests", C.c_uint64), ("quad_tests", C.c_uint64),
+                ("sphere_tests", C.c_uint64), ("node_visits", C.c_uint64), ("kernel_ms", C.c_double), ("launches", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def make_camera(pos, target, up=(0, 1, 0), vfov_deg=40.0, focus_dist=1.0, defocus_angle_deg=0.0, jitter=1) -> Camera:
+    c = Camera()
+    c.pos[:] = [float(x) for x in pos]
+    c.target[:] = [float(x) for x in target]
+    c.up[:] = [float(x) for x in up]
+    c.vfov_deg, c.focus_dist, c.defocus_angle_deg, c.jitter = float(vfov_deg), float(focus_dist), float(defocus_angle_deg), int(jitter)
+    return c
+
+
+def make_params(width, height, sample_begin=0, sample_count=1, max_depth=50, integrator=0, traversal=0, ao_samples=32,
+                seed=1, t_min=1e-3, background_bottom=(1, 1, 1), background_top=(0.5, 0.7, 1.0)) -> RenderParams:
+    p = RenderParams()
+    p.width, p.height, p.sample_begin, p.sample_count = int(width), int(height), int(sample_begin), int(sample_count)
+    p.max_depth, p.integrator, p.traversal, p.ao_samples = int(max_depth), int(integrator), int(traversal), int(ao_samples)
+    p.seed, p.t_min = int(seed), float(t_min)
+    p.background_bottom[:] = [float(x) for x in background_bottom]
+    p.background_top[:] = [float(x) for x in background_top]
+    return p
+
+
+class AreCudaError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_fp = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes).  Every symbol include/are_cuda.h declares appears here (tests check that).
+SIGNATURES = {
+    "are_cuda_abi_version": (C.c_int, []),
+    "are_cuda_device_count": (C.c_int, []),
+    "are_cuda_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "are_cuda_destroy": (None, [_vp]),
+    "are_cuda_last_error": (C.c_char_p, [_vp]),
+    "are_cuda_set_stream": (C.c_int, [_vp, _vp]),
+    "are_cuda_add_texture": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int, C.c_int]),
+    "are_cuda_add_material": (C.c_int, [_vp, C.c_int, _dp]),
+    "are_cuda_add_triangle": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
+    "are_cuda_set_triangle_uv": (C.c_int, [_vp, C.c_int, _dp]),
+    "are_cuda_add_quad": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
+    "are_cuda_add_sphere": (C.c_int, [_vp, _dp, C.c_double, C.c_int, C.c_int]),
+    "are_cuda_add_triangles": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _ip, _ip]),
+    "are_cuda_add_spheres": (C.c_int, [_vp, C.c_int, _dp, _dp, _ip, _ip]),
+    "are_cuda_clear": (C.c_int, [_vp]),
+    "are_cuda_num_primitives": (C.c_int, [_vp]),
+    "are_cuda_commit": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "are_cuda_hit_batch": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_double, C.c_int, C.c_int, _ip, _dp, _dp, _dp, _dp]),
+    "are_cuda_scatter_batch": (C.c_int, [_vp, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _ip]),
+    "are_cuda_texture_batch": (C.c_int, [_vp, C.c_int, _ip, _dp, _dp, C.c_int, _dp]),
+    "are_cuda_camera_rays": (C.c_int, [_vp, C.POINTER(Camera), C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, C.c_int, _dp, _dp]),
+    "are_cuda_philox_batch": (C.c_int, [_vp, C.c_int, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "are_cuda_render_device": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _vp, C.POINTER(RenderStats), C.c_int]),
+    "are_cuda_render": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _fp, C.POINTER(RenderStats)]),
+    "are_cuda_tonemap": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_uint8)]),
+    "are_cuda_write_ppm": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint8)]),
+    "are_cuda_alloc_accum": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "are_cuda_zero_accum": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "are_cuda_download_accum": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _fp]),
+    "are_cuda_free_accum": (C.c_int, [_vp, _vp]),
+    "are_cuda_synchronize": (C.c_int, [_vp]),
+    "are_cuda_measure_fp32_peak": (C.c_int, [_vp, _dp, _ip, _ip]),
+}
+
+
+def load_library(path: str | None = None):
+    """dlopen libare_b200.so and declare the signatures.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(f"{p} not built — run `python -c 'import __graft_entry__ as g; g.build()'` (there is no fallback path)")
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _d(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a, t=_dp):
+    return a.ctypes.data_as(t)
+
+
+class Context:
+    """One are_cuda_ctx (one GPU).  Mirrors the header one-to-one; numpy arrays in, numpy arrays out."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = _vp()
+        st = self.lib.are_cuda_create(C.byref(h), int(device))
+        if st != ARE_OK:
+            msg = self.lib.are_cuda_last_error(None)
+            raise AreCudaError(st, (msg or b"").decode())
+        self.h = h
+        self.device = device
+
+    # -- housekeeping ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.are_cuda_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, st):
+        if st < 0:
+            raise AreCudaError(st, (self.lib.are_cuda_last_error(self.h) or b"").decode())
+        return st
+
+    def set_stream(self, cuda_stream_handle: int):
+        self._ck(self.lib.are_cuda_set_stream(self.h, _vp(cuda_stream_handle)))
+
+    # -- scene ----------------------------------------------------------------------------------------
+    def add_texture(self, kind, params, rgb=None):
+        p = _d(params, (8,))
+        if rgb is not None:
+            img = _d(rgb)
+            hh, ww = img.shape[0], img.shape[1]
+            return self._ck(self.lib.are_cuda_add_texture(self.h, int(kind), _ptr(p), _ptr(img), ww, hh))
+        return self._ck(self.lib.are_cuda_add_texture(self.h, int(kind), _ptr(p), None, 0, 0))
+
+    def add_material(self, kind, params):
+        p = _d(params, (8,))
+        return self._ck(self.lib.are_cuda_add_material(self.h, int(kind), _ptr(p)))
+
+    def add_triangle(self, Q, u, v, mat, tex):
+        Q, u, v = _d(Q, (3,)), _d(u, (3,)), _d(v, (3,))
+        return self._ck(self.lib.are_cuda_add_triangle(self.h, _ptr(Q), _ptr(u), _ptr(v), int(mat), int(tex)))
+
+    def set_triangle_uv(self, prim, uv):
+        uv = _d(uv, (6,))
+        return self._ck(self.lib.are_cuda_set_triangle_uv(self.h, int(prim), _ptr(uv)))
+
+    def add_quad(self, Q, u, v, mat, tex):
+        Q, u, v = _d(Q, (3,)), _d(u, (3,)), _d(v, (3,))
+        return self._ck(self.lib.are_cuda_add_quad(self.h, _ptr(Q), _ptr(u), _ptr(v), int(mat), int(tex)))
+
+    def add_sphere(self, c, r, mat, tex):
+        c = _d(c, (3,))
+        return self._ck(self.lib.are_cuda_add_sphere(self.h, _ptr(c), float(r), int(mat), int(tex)))
+
+    def add_triangles(self, Q, u, v, mat, tex):
+        Q, u, v = _d(Q), _d(u), _d(v)
+        mat, tex = np.ascontiguousarray(mat, np.int32), np.ascontiguousarray(tex, np.int32)
+        return self._ck(self.lib.are_cuda_add_triangles(self.h, len(Q), _ptr(Q), _ptr(u), _ptr(v), _ptr(mat, _ip), _ptr(tex, _ip)))
+
+    def add_spheres(self, c, r, mat, tex):
+        c, r = _d(c), _d(r)
+        mat, tex = np.ascontiguousarray(mat, np.int32), np.ascontiguousarray(tex, np.int32)
+        return self._ck(self.lib.are_cuda_add_spheres(self.h, len(c), _ptr(c), _ptr(r), _ptr(mat, _ip), _ptr(tex, _ip)))
+
+    def clear(self):
+        self._ck(self.lib.are_cuda_clear(self.h))
+
+    def num_primitives(self):
+        return self._ck(self.lib.are_cuda_num_primitives(self.h))
+
+    def commit(self) -> int:
+        n = C.c_uint64(0)
+        self._ck(self.lib.are_cuda_commit(self.h, C.byref(n)))
+        return n.value
+
+    # -- per-ray harness ------------------------------------------------------------------------------
+    def hit_batch(self, Q, D, t_min=0.0, precision=64, traversal=0):
+        Q, D = _d(Q), _d(D)
+        n = len(Q)
+        prim = np.empty(n, np.int32)
+        t, P, N, uv = np.empty(n), np.empty((n, 3)), np.empty((n, 3)), np.empty((n, 2))
+        self._ck(self.lib.are_cuda_hit_batch(self.h, n, _ptr(Q), _ptr(D), float(t_min), int(precision), int(traversal),
+                                             _ptr(prim, _ip), _ptr(t), _ptr(P), _ptr(N), _ptr(uv)))
+        return prim, t, P, N, uv
+
+    def scatter_batch(self, mat, tex, wi, N, P, uv, rnd, precision=64):
+        mat, tex = np.ascontiguousarray(mat, np.int32), np.ascontiguousarray(tex, np.int32)
+        wi, N, P, uv, rnd = _d(wi), _d(N), _d(P), _d(uv), _d(rnd)
+        n = len(mat)
+        wo, att, emit, alive = np.empty((n, 3)), np.empty((n, 3)), np.empty((n, 3)), np.empty(n, np.int32)
+        self._ck(self.lib.are_cuda_scatter_batch(self.h, n, _ptr(mat, _ip), _ptr(tex, _ip), _ptr(wi), _ptr(N), _ptr(P), _ptr(uv),
+                                                 _ptr(rnd), int(precision), _ptr(wo), _ptr(att), _ptr(emit), _ptr(alive, _ip)))
+        return wo, att, emit, alive
+
+    def texture_batch(self, tex, uv, P, precision=64):
+        tex = np.ascontiguousarray(tex, np.int32)
+        uv, P = _d(uv), _d(P)
+        n = len(tex)
+        rgb = np.empty((n, 3))
+        self._ck(self.lib.are_cuda_texture_batch(self.h, n, _ptr(tex, _ip), _ptr(uv), _ptr(P), int(precision), _ptr(rgb)))
+        return rgb
+
+    def camera_rays(self, cam: Camera, width, height, px, py, rnd, precision=64):
+        px, py = np.ascontiguousarray(px, np.int32), np.ascontiguousarray(py, np.int32)
+        rnd = _d(rnd)
+        n = len(px)
+        Q, D = np.empty((n, 3)), np.empty((n, 3))
+        self._ck(self.lib.are_cuda_camera_rays(self.h, C.byref(cam), int(width), int(height), n, _ptr(px, _ip), _ptr(py, _ip),
+                                               _ptr(rnd), int(precision), _ptr(Q), _ptr(D)))
+        return Q, D
+
+    def philox_batch(self, seed, counters):
+        c = np.ascontiguousarray(counters, np.uint32)
+        out = np.empty_like(c)
+        self._ck(self.lib.are_cuda_philox_batch(self.h, len(c), int(seed), _ptr(c, C.POINTER(C.c_uint32)), _ptr(out, C.POINTER(C.c_uint32))))
+        return out
+
+    # -- rendering ------------------------------------------------------------------------------------
+    def render_device(self, cam: Camera, params: RenderParams, accum_ptr: int, want_stats=False, count_tests=False):
+        st = RenderStats() if want_stats else None
+        self._ck(self.lib.are_cuda_render_device(self.h, C.byref(cam), C.byref(params), _vp(accum_ptr),
+                                                 C.byref(st) if st is not None else None, int(bool(count_tests))))
+        return st
+
+    def render(self, cam: Camera, params: RenderParams, out: np.ndarray | None = None):
+        """Host-buffer call: returns (accum float32 (H,W,3) of sample SUMS, RenderStats)."""
+        if out is None:
+            out = np.empty((params.height, params.width, 3), np.float32)
+        st = RenderStats()
+        self._ck(self.lib.are_cuda_render(self.h, C.byref(cam), C.byref(params), _ptr(out, _fp), C.byref(st)))
+        return out, st
+
+    def tonemap(self, accum_ptr: int, width, height, inv_spp, encoder=0):
+        out = np.empty((height, width, 3), np.uint8)
+        self._ck(self.lib.are_cuda_tonemap(self.h, _vp(accum_ptr), int(width), int(height), float(inv_spp), int(encoder),
+                                           _ptr(out, C.POINTER(C.c_uint8))))
+        return out
+
+    def write_ppm(self, path, rgb8: np.ndarray):
+        rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+        h, w = rgb8.shape[:2]
+        st = self.lib.are_cuda_write_ppm(os.fsencode(path), w, h, _ptr(rgb8, C.POINTER(C.c_uint8)))
+        if st < 0:
+            raise AreCudaError(st, f"cannot write {path}")
+
+    def alloc_accum(self, width, height) -> int:
+        p = _vp()
+        self._ck(self.lib.are_cuda_alloc_accum(self.h, int(width), int(height), C.byref(p)))
+        return p.value
+
+    def zero_accum(self, ptr, width, height):
+        self._ck(self.lib.are_cuda_zero_accum(self.h, _vp(ptr), int(width), int(height)))
+
+    def download_accum(self, ptr, width, height):
+        out = np.empty((height, width, 3), np.float32)
+        self._ck(self.lib.are_cuda_download_accum(self.h, _vp(ptr), int(width), int(height), _ptr(out, _fp)))
+        return out
+
+    def free_accum(self, ptr):
+        self._ck(self.lib.are_cuda_free_accum(self.h, _vp(ptr)))
+
+    def synchronize(self):
+        self._ck(self.lib.are_cuda_synchronize(self.h))
+
+    def measure_fp32_peak(self):
+        t, sm, clk = C.c_double(0), C.c_int(0), C.c_int(0)
+        self._ck(self.lib.are_cuda_measure_fp32_peak(self.h, C.byref(t), C.byref(sm), C.byref(clk)))
+        return dict(tflops=t.value, sm_count=sm.value, sm_clock_khz=clk.value)

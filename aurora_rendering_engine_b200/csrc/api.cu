@@ -1,0 +1,604 @@
+// api.cu — implementation of the C ABI declared in include/are_cuda.h.
+//
+// Error model: nothing throws across the boundary; every entry point returns an are_status and leaves a message
+// retrievable with are_cuda_last_error (the C++ shim turns ARE_ERR_INVALID_ARGUMENT / ARE_ERR_RUNTIME back into
+// std::invalid_argument / std::runtime_error, matching /root/reference/src/object/triangle.cpp:13-36 and
+// src/texture.cpp:13-79).  There is no CPU implementation behind any of these calls.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/are_cuda.h"
+#include "dev_types.h"
+#include "kernels.h"
+#include "scene.h"
+
+using namespace areb;
+
+struct are_cuda_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	std::string err;
+	HostScene scene;
+	CompiledScene cs;
+	DevScene dev;
+	bool committed = false;
+	std::vector<void *> scene_allocs;
+	unsigned long long *d_counters = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	float *own_accum = nullptr;
+	size_t own_accum_elems = 0;
+	int sm_count = 0;
+	CompileOptions opt;
+};
+
+static std::string g_create_error;
+
+namespace {
+
+int fail(are_cuda_ctx *c, int status, const std::string &msg) {
+	if (c) c->err = msg;
+	else g_create_error = msg;
+	return status;
+}
+#define CK(call)                                                                                              \
+	do {                                                                                                      \
+		cudaError_t e_ = (call);                                                                              \
+		if (e_ != cudaSuccess) return fail(ctx, ARE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+	} while (0)
+
+struct Bind {  // make the context's device current for the duration of a call
+	int prev = -1;
+	explicit Bind(are_cuda_ctx *c) {
+		cudaGetDevice(&prev);
+		if (prev != c->device) cudaSetDevice(c->device);
+		else prev = -1;
+	}
+	~Bind() {
+		if (prev >= 0) cudaSetDevice(prev);
+	}
+};
+
+void free_scene_allocs(are_cuda_ctx *ctx) {
+	for (void *p : ctx->scene_allocs) cudaFree(p);
+	ctx->scene_allocs.clear();
+	std::memset(&ctx->dev, 0, sizeof ctx->dev);
+	ctx->committed = false;
+}
+
+template <typename T>
+int upload(are_cuda_ctx *ctx, const std::vector<T> &v, const T **out, uint64_t &bytes) {
+	*out = nullptr;
+	if (v.empty()) return ARE_OK;
+	void *d = nullptr;
+	CK(cudaMalloc(&d, v.size() * sizeof(T)));
+	ctx->scene_allocs.push_back(d);
+	CK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+	bytes += v.size() * sizeof(T);
+	*out = static_cast<const T *>(d);
+	return ARE_OK;
+}
+
+inline size_t nz(size_t b) { return b ? b : 1; }
+// scoped temporary device buffer
+struct Tmp {
+	void *p = nullptr;
+	~Tmp() {
+		if (p) cudaFree(p);
+	}
+	template <typename T>
+	T *as() { return static_cast<T *>(p); }
+};
+#define TMP_IN(tmp, host, bytes)                                                              \
+	do {                                                                                      \
+		CK(cudaMalloc(&(tmp).p, nz(bytes)));                                      \
+		CK(cudaMemcpyAsync((tmp).p, (host), (bytes), cudaMemcpyHostToDevice, ctx->stream));   \
+	} while (0)
+#define TMP_OUT(tmp, bytes) CK(cudaMalloc(&(tmp).p, nz(bytes)))
+#define GET_OUT(host, tmp, bytes)                                                                          \
+	do {                                                                                                   \
+		if (host) CK(cudaMemcpyAsync((host), (tmp).p, (bytes), cudaMemcpyDeviceToHost, ctx->stream));      \
+	} while (0)
+
+bool resolve_traversal(are_cuda_ctx *ctx, int traversal, bool &use_bvh) {
+	const bool brute_ok = ctx->dev.brute != nullptr;
+	if (traversal == ARE_TRAVERSAL_BRUTE) {
+		if (!brute_ok) return false;
+		use_bvh = false;
+	} else if (traversal == ARE_TRAVERSAL_BVH) use_bvh = true;
+	else use_bvh = !(brute_ok && ctx->cs.n_hot <= 32);
+	return true;
+}
+
+int need_commit(are_cuda_ctx *ctx) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	if (!ctx->committed) return fail(ctx, ARE_ERR_NOT_COMMITTED, "scene not committed: call are_cuda_commit first");
+	return ARE_OK;
+}
+
+int add_prim(are_cuda_ctx *ctx, int type, const double Q[3], const double u[3], const double v[3], int mat, int tex) {
+	if (!ctx || !Q || !u || !v) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	// are::Triangle's ctor rejects null Material* / Texture* (triangle.cpp:13-20); ids play that role here
+	if (mat < 0 || mat >= (int)ctx->scene.materials.size()) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "Material pointer cannot be null");
+	if (tex < 0 || tex >= (int)ctx->scene.textures.size()) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "Texture pointer cannot be null");
+	if (const char *m = validate_edges(u, v)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, m);
+	HostPrim p;
+	p.type = type; p.mat = mat; p.tex = tex;
+	std::memcpy(p.Q, Q, sizeof p.Q);
+	std::memcpy(p.u, u, sizeof p.u);
+	std::memcpy(p.v, v, sizeof p.v);
+	ctx->scene.prims.push_back(p);
+	ctx->committed = false;
+	return (int)ctx->scene.prims.size() - 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int are_cuda_abi_version(void) { return ARE_CUDA_ABI_VERSION; }
+
+int are_cuda_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int are_cuda_create(are_cuda_ctx **out, int device) {
+	are_cuda_ctx *ctx = nullptr;
+	if (!out) return fail(nullptr, ARE_ERR_INVALID_ARGUMENT, "out is null");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		cudaGetLastError();
+		return fail(nullptr, ARE_ERR_NO_DEVICE, "no CUDA device available: this library has no CPU path");
+	}
+	if (device < 0 || device >= n) return fail(nullptr, ARE_ERR_INVALID_ARGUMENT, "device index out of range");
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) return fail(nullptr, ARE_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + "; kernels are built for sm_100a only");
+	ctx = new are_cuda_ctx();
+	ctx->device = device;
+	ctx->sm_count = prop.multiProcessorCount;
+	std::memset(&ctx->dev, 0, sizeof ctx->dev);
+	Bind b(ctx);
+	cudaError_t e1 = cudaMalloc((void **)&ctx->d_counters, CNT_N * sizeof(unsigned long long));
+	cudaError_t e2 = cudaEventCreate(&ctx->ev0), e3 = cudaEventCreate(&ctx->ev1);
+	if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+		std::string m = std::string("context set-up failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
+		delete ctx;
+		return fail(nullptr, ARE_ERR_CUDA, m);
+	}
+	*out = ctx;
+	return ARE_OK;
+}
+
+void are_cuda_destroy(are_cuda_ctx *ctx) {
+	if (!ctx) return;
+	Bind b(ctx);
+	cudaStreamSynchronize(ctx->stream);
+	free_scene_allocs(ctx);
+	if (ctx->own_accum) cudaFree(ctx->own_accum);
+	if (ctx->d_counters) cudaFree(ctx->d_counters);
+	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	delete ctx;
+}
+
+const char *are_cuda_last_error(are_cuda_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int are_cuda_set_stream(are_cuda_ctx *ctx, void *cuda_stream) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+	return ARE_OK;
+}
+
+int are_cuda_add_texture(are_cuda_ctx *ctx, int kind, const double params[8], const double *rgb, int w, int h) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	if (kind < ARE_TEX_SOLID || kind > ARE_TEX_IMAGE) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown texture kind");
+	HostTexture t;
+	t.kind = kind;
+	if (params) std::memcpy(t.p, params, sizeof t.p);
+	if (kind == ARE_TEX_IMAGE) {
+		// are::Texture(w,h,fill) throws std::runtime_error on non-positive sizes (src/texture.cpp:53-55)
+		if (w <= 0 || h <= 0) return fail(ctx, ARE_ERR_RUNTIME, "Texture width and height must be positive.");
+		if (!rgb) return fail(ctx, ARE_ERR_RUNTIME, "Texture is not initialized.");
+		t.w = w; t.h = h;
+		t.rgb.assign(rgb, rgb + (size_t)w * h * 3);
+	} else if ((kind == ARE_TEX_CHECKER_UV || kind == ARE_TEX_CHECKER_3D) && !(t.p[0] != 0.0)) {
+		return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "checker scale must be non-zero");
+	}
+	ctx->scene.textures.push_back(std::move(t));
+	ctx->committed = false;
+	return (int)ctx->scene.textures.size() - 1;
+}
+
+int are_cuda_add_material(are_cuda_ctx *ctx, int kind, const double params[8]) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	if (kind < ARE_MAT_DIFFUSE || kind > ARE_MAT_DIFFUSE_LIGHT) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown material kind");
+	HostMaterial m;
+	m.kind = kind;
+	if (params) std::memcpy(m.p, params, sizeof m.p);
+	if (kind == ARE_MAT_DIELECTRIC && !(m.p[0] > 0.0)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "index of refraction must be positive");
+	if (kind == ARE_MAT_REFLECTIVE && !params) { m.p[1] = m.p[2] = m.p[3] = 1.0; }
+	ctx->scene.materials.push_back(m);
+	ctx->committed = false;
+	return (int)ctx->scene.materials.size() - 1;
+}
+
+int are_cuda_add_triangle(are_cuda_ctx *ctx, const double Q[3], const double u[3], const double v[3], int material_id, int texture_id) {
+	return add_prim(ctx, PT_TRIANGLE, Q, u, v, material_id, texture_id);
+}
+
+int are_cuda_set_triangle_uv(are_cuda_ctx *ctx, int prim_id, const double uv[6]) {
+	if (!ctx || !uv) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	if (prim_id < 0 || prim_id >= (int)ctx->scene.prims.size() || ctx->scene.prims[prim_id].type != PT_TRIANGLE)
+		return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "prim_id is not a triangle");
+	std::memcpy(ctx->scene.prims[prim_id].uv, uv, 6 * sizeof(double));
+	ctx->committed = false;
+	return ARE_OK;
+}
+
+int are_cuda_add_quad(are_cuda_ctx *ctx, const double Q[3], const double u[3], const double v[3], int material_id, int texture_id) {
+	return add_prim(ctx, PT_QUAD, Q, u, v, material_id, texture_id);
+}
+
+int are_cuda_add_sphere(are_cuda_ctx *ctx, const double center[3], double radius, int material_id, int texture_id) {
+	if (!ctx || !center) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	if (!(radius > 0.0) || !std::isfinite(radius)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "sphere radius must be positive");
+	if (material_id < 0 || material_id >= (int)ctx->scene.materials.size()) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "Material pointer cannot be null");
+	if (texture_id < 0 || texture_id >= (int)ctx->scene.textures.size()) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "Texture pointer cannot be null");
+	HostPrim p;
+	p.type = PT_SPHERE; p.mat = material_id; p.tex = texture_id;
+	std::memcpy(p.Q, center, sizeof p.Q);
+	p.u[0] = radius; p.u[1] = p.u[2] = 0.0;
+	p.v[0] = p.v[1] = p.v[2] = 0.0;
+	ctx->scene.prims.push_back(p);
+	ctx->committed = false;
+	return (int)ctx->scene.prims.size() - 1;
+}
+
+int are_cuda_add_triangles(are_cuda_ctx *ctx, int n, const double *Q, const double *u, const double *v, const int *material_id, const int *texture_id) {
+	if (!ctx || n < 0 || (n && (!Q || !u || !v || !material_id || !texture_id))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	const size_t before = ctx->scene.prims.size();
+	ctx->scene.prims.reserve(before + n);
+	for (int i = 0; i < n; ++i) {
+		int r = add_prim(ctx, PT_TRIANGLE, Q + 3 * (size_t)i, u + 3 * (size_t)i, v + 3 * (size_t)i, material_id[i], texture_id[i]);
+		if (r < 0) { ctx->scene.prims.resize(before); return r; }
+	}
+	return (int)before;
+}
+
+int are_cuda_add_spheres(are_cuda_ctx *ctx, int n, const double *center, const double *radius, const int *material_id, const int *texture_id) {
+	if (!ctx || n < 0 || (n && (!center || !radius || !material_id || !texture_id))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	const size_t before = ctx->scene.prims.size();
+	ctx->scene.prims.reserve(before + n);
+	for (int i = 0; i < n; ++i) {
+		int r = are_cuda_add_sphere(ctx, center + 3 * (size_t)i, radius[i], material_id[i], texture_id[i]);
+		if (r < 0) { ctx->scene.prims.resize(before); return r; }
+	}
+	return (int)before;
+}
+
+int are_cuda_clear(are_cuda_ctx *ctx) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	Bind b(ctx);
+	cudaStreamSynchronize(ctx->stream);
+	ctx->scene = HostScene();
+	free_scene_allocs(ctx);
+	return ARE_OK;
+}
+
+int are_cuda_num_primitives(are_cuda_ctx *ctx) { return ctx ? (int)ctx->scene.prims.size() : ARE_ERR_INVALID_ARGUMENT; }
+
+int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	Bind b(ctx);
+	CK(cudaStreamSynchronize(ctx->stream));
+	free_scene_allocs(ctx);
+	std::string err;
+	ctx->opt.brute_max = (int)brute_smem_limit_prims();
+	if (const char *e = getenv("ARE_CUDA_NO_FUSE")) ctx->opt.fuse_parallelograms = !(e[0] == '1');
+	if (const char *e = getenv("ARE_CUDA_LEAF_SIZE")) ctx->opt.leaf_size = atoi(e);
+	if (!compile_scene(ctx->scene, ctx->opt, ctx->cs, err)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, err);
+	const CompiledScene &cs = ctx->cs;
+	DevScene d;
+	std::memset(&d, 0, sizeof d);
+	uint64_t bytes = 0;
+	int st;
+#define UP(vec, field)                                                     \
+	if ((st = upload(ctx, cs.vec, &d.field, bytes)) != ARE_OK) return st;
+	UP(brute, brute) UP(brute_ids, brute_ids) UP(bvh_prims, bvh_prims) UP(bvh_ids, bvh_ids) UP(nodes, nodes)
+	UP(info, info) UP(prim_plane, prim_plane) UP(tri_uv, tri_uv) UP(tri64, tri64) UP(quad64, quad64) UP(sph64, sph64)
+	UP(tri_uv64, tri_uv64) UP(mats, mats) UP(texs, texs) UP(tex_data, tex_data)
+#undef UP
+	d.brute_range = cs.brute_range;
+	d.n_nodes = (int)cs.nodes.size();
+	d.root_leaf_meta = cs.root_leaf_meta;
+	d.n_hot = cs.n_hot;
+	d.n_tri = cs.n_tri; d.n_quad = cs.n_quad; d.n_sph = cs.n_sph;
+	d.n_mat = (int)cs.mats.size(); d.n_tex = (int)cs.texs.size();
+	CK(cudaStreamSynchronize(ctx->stream));
+	ctx->dev = d;
+	ctx->committed = true;
+	if (h2d_bytes) *h2d_bytes = bytes;
+	return ARE_OK;
+}
+
+// ---- per-ray harness -------------------------------------------------------------------------------------
+int are_cuda_hit_batch(are_cuda_ctx *ctx, int n, const double *ray_Q, const double *ray_D, double t_min, int precision, int traversal,
+	int *prim, double *t, double *P, double *N, double *uv) {
+	int st = need_commit(ctx);
+	if (st) return st;
+	if (n < 0 || (n && (!ray_Q || !ray_D))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null ray arrays");
+	if (precision != 32 && precision != 64) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "precision must be 32 or 64");
+	if (n == 0) return ARE_OK;
+	Bind b(ctx);
+	const size_t n3 = (size_t)n * 3 * sizeof(double);
+	Tmp dQ, dD, dprim, dt, dP, dN, duv;
+	TMP_IN(dQ, ray_Q, n3);
+	TMP_IN(dD, ray_D, n3);
+	TMP_OUT(dprim, n * sizeof(int)); TMP_OUT(dt, n * sizeof(double)); TMP_OUT(dP, n3); TMP_OUT(dN, n3); TMP_OUT(duv, (size_t)n * 2 * sizeof(double));
+	if (precision == 64) launch_hit64(ctx->dev, n, dQ.as<double>(), dD.as<double>(), t_min, dprim.as<int>(), dt.as<double>(), dP.as<double>(), dN.as<double>(), duv.as<double>(), ctx->stream);
+	else {
+		bool use_bvh;
+		if (!resolve_traversal(ctx, traversal, use_bvh)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "scene too large for brute-force traversal");
+		launch_hit32(ctx->dev, n, dQ.as<double>(), dD.as<double>(), t_min, use_bvh, dprim.as<int>(), dt.as<double>(), dP.as<double>(), dN.as<double>(), duv.as<double>(), ctx->stream);
+	}
+	CK(cudaGetLastError());
+	GET_OUT(prim, dprim, n * sizeof(int)); GET_OUT(t, dt, n * sizeof(double)); GET_OUT(P, dP, n3); GET_OUT(N, dN, n3); GET_OUT(uv, duv, (size_t)n * 2 * sizeof(double));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
+int are_cuda_scatter_batch(are_cuda_ctx *ctx, int n, const int *material_id, const int *texture_id, const double *wi, const double *N, const double *P,
+	const double *uv, const double *rnd, int precision, double *wo, double *attenuation, double *emitted, int *alive) {
+	int st = need_commit(ctx);
+	if (st) return st;
+	if (n < 0 || (n && (!material_id || !texture_id || !wi || !N || !P || !uv || !rnd))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null input arrays");
+	if (precision != 32 && precision != 64) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "precision must be 32 or 64");
+	for (int i = 0; i < n; ++i)
+		if (material_id[i] < 0 || material_id[i] >= ctx->dev.n_mat || texture_id[i] < 0 || texture_id[i] >= ctx->dev.n_tex)
+			return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "material / texture id out of range");
+	if (n == 0) return ARE_OK;
+	Bind b(ctx);
+	const size_t n3 = (size_t)n * 3 * sizeof(double);
+	Tmp dm, dx, dwi, dN, dP, duv, drnd, dwo, datt, dem, dal;
+	TMP_IN(dm, material_id, n * sizeof(int)); TMP_IN(dx, texture_id, n * sizeof(int));
+	TMP_IN(dwi, wi, n3); TMP_IN(dN, N, n3); TMP_IN(dP, P, n3);
+	TMP_IN(duv, uv, (size_t)n * 2 * sizeof(double)); TMP_IN(drnd, rnd, (size_t)n * 4 * sizeof(double));
+	TMP_OUT(dwo, n3); TMP_OUT(datt, n3); TMP_OUT(dem, n3); TMP_OUT(dal, n * sizeof(int));
+	if (precision == 64) launch_scatter64(ctx->dev, n, dm.as<int>(), dx.as<int>(), dwi.as<double>(), dN.as<double>(), dP.as<double>(), duv.as<double>(), drnd.as<double>(), dwo.as<double>(), datt.as<double>(), dem.as<double>(), dal.as<int>(), ctx->stream);
+	else launch_scatter32(ctx->dev, n, dm.as<int>(), dx.as<int>(), dwi.as<double>(), dN.as<double>(), dP.as<double>(), duv.as<double>(), drnd.as<double>(), dwo.as<double>(), datt.as<double>(), dem.as<double>(), dal.as<int>(), ctx->stream);
+	CK(cudaGetLastError());
+	GET_OUT(wo, dwo, n3); GET_OUT(attenuation, datt, n3); GET_OUT(emitted, dem, n3); GET_OUT(alive, dal, n * sizeof(int));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
+int are_cuda_texture_batch(are_cuda_ctx *ctx, int n, const int *texture_id, const double *uv, const double *P, int precision, double *rgb) {
+	int st = need_commit(ctx);
+	if (st) return st;
+	if (n < 0 || (n && (!texture_id || !uv || !P || !rgb))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null arrays");
+	if (precision != 32 && precision != 64) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "precision must be 32 or 64");
+	for (int i = 0; i < n; ++i)
+		if (texture_id[i] < 0 || texture_id[i] >= ctx->dev.n_tex) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "texture id out of range");
+	if (n == 0) return ARE_OK;
+	Bind b(ctx);
+	Tmp dx, duv, dP, drgb;
+	TMP_IN(dx, texture_id, n * sizeof(int)); TMP_IN(duv, uv, (size_t)n * 2 * sizeof(double)); TMP_IN(dP, P, (size_t)n * 3 * sizeof(double));
+	TMP_OUT(drgb, (size_t)n * 3 * sizeof(double));
+	if (precision == 64) launch_texture64(ctx->dev, n, dx.as<int>(), duv.as<double>(), dP.as<double>(), drgb.as<double>(), ctx->stream);
+	else launch_texture32(ctx->dev, n, dx.as<int>(), duv.as<double>(), dP.as<double>(), drgb.as<double>(), ctx->stream);
+	CK(cudaGetLastError());
+	GET_OUT(rgb, drgb, (size_t)n * 3 * sizeof(double));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
+int are_cuda_camera_rays(are_cuda_ctx *ctx, const are_camera *cam, int width, int height, int n, const int *px, const int *py, const double *rnd,
+	int precision, double *ray_Q, double *ray_D) {
+	if (!ctx || !cam || n < 0 || (n && (!px || !py || !rnd))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	if (width <= 0 || height <= 0 || !(cam->focus_dist > 0.0)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "bad camera / image size");
+	if (precision != 32 && precision != 64) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "precision must be 32 or 64");
+	if (n == 0) return ARE_OK;
+	Bind b(ctx);
+	CamBasis cb;
+	make_cam_basis(cam->pos, cam->target, cam->up, cam->vfov_deg, cam->focus_dist, cam->defocus_angle_deg, cam->jitter, width, height, cb);
+	Tmp dpx, dpy, drnd, dQ, dD;
+	TMP_IN(dpx, px, n * sizeof(int)); TMP_IN(dpy, py, n * sizeof(int)); TMP_IN(drnd, rnd, (size_t)n * 4 * sizeof(double));
+	TMP_OUT(dQ, (size_t)n * 3 * sizeof(double)); TMP_OUT(dD, (size_t)n * 3 * sizeof(double));
+	if (precision == 64) launch_camera64(cb, width, height, n, dpx.as<int>(), dpy.as<int>(), drnd.as<double>(), dQ.as<double>(), dD.as<double>(), ctx->stream);
+	else launch_camera32(cb, width, height, n, dpx.as<int>(), dpy.as<int>(), drnd.as<double>(), dQ.as<double>(), dD.as<double>(), ctx->stream);
+	CK(cudaGetLastError());
+	GET_OUT(ray_Q, dQ, (size_t)n * 3 * sizeof(double)); GET_OUT(ray_D, dD, (size_t)n * 3 * sizeof(double));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
+int are_cuda_philox_batch(are_cuda_ctx *ctx, int n, uint64_t seed, const uint32_t *counter, uint32_t *out) {
+	if (!ctx || n < 0 || (n && (!counter || !out))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	if (n == 0) return ARE_OK;
+	Bind b(ctx);
+	Tmp dc, dout;
+	TMP_IN(dc, counter, (size_t)n * 16);
+	TMP_OUT(dout, (size_t)n * 16);
+	launch_philox(n, seed, dc.as<uint32_t>(), dout.as<uint32_t>(), ctx->stream);
+	CK(cudaGetLastError());
+	GET_OUT(out, dout, (size_t)n * 16);
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
+// ---- rendering -------------------------------------------------------------------------------------------
+int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_render_params *p, float *accum, are_render_stats *stats, int count_tests) {
+	int st = need_commit(ctx);
+	if (st) return st;
+	if (!cam || !p || !accum) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	if (p->width <= 0 || p->height <= 0 || p->sample_count < 0 || p->sample_begin < 0 || p->max_depth < 1 || !(cam->focus_dist > 0.0))
+		return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "bad render parameters");
+	if ((long long)p->width * p->height > 0x7fffffffLL) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "image too large");
+	Bind b(ctx);
+	RenderArgs a;
+	std::memset(&a, 0, sizeof a);
+	a.sc = ctx->dev;
+	make_cam_basis(cam->pos, cam->target, cam->up, cam->vfov_deg, cam->focus_dist, cam->defocus_angle_deg, cam->jitter, p->width, p->height, a.cam);
+	a.key = philox_key(p->seed);
+	a.W = p->width; a.H = p->height;
+	a.s_begin = p->sample_begin; a.s_count = p->sample_count;
+	a.max_depth = p->max_depth;
+	a.ao_samples = p->ao_samples > 0 ? p->ao_samples : 32;
+	a.tmin = (float)p->t_min;
+	for (int k = 0; k < 3; ++k) { a.bg_bottom[k] = (float)p->background_bottom[k]; a.bg_top[k] = (float)p->background_top[k]; }
+	a.accum = accum;
+	a.counters = ctx->d_counters;
+	bool use_bvh = false;
+	if (p->integrator == ARE_INTEGRATOR_RT_AO) {
+		if (!ctx->dev.brute) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "RT_AO integrator needs a scene that fits the brute-force list");
+	} else if (p->integrator != ARE_INTEGRATOR_PATH) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown integrator");
+	else if (!resolve_traversal(ctx, p->traversal, use_bvh)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "scene too large for brute-force traversal");
+	CK(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * sizeof(unsigned long long), ctx->stream));
+	if (stats) CK(cudaEventRecord(ctx->ev0, ctx->stream));
+	int launched = 0;
+	if (p->sample_count > 0) {
+		launched = p->integrator == ARE_INTEGRATOR_RT_AO ? launch_render_rtao(a, ctx->stream) : launch_render_path(a, use_bvh, count_tests != 0, ctx->stream);
+		if (launched < 0) return fail(ctx, ARE_ERR_CUDA, "render launch configuration rejected");
+		CK(cudaGetLastError());
+	}
+	if (stats) {
+		CK(cudaEventRecord(ctx->ev1, ctx->stream));
+		unsigned long long c[CNT_N];
+		CK(cudaMemcpyAsync(c, ctx->d_counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		float ms = 0.f;
+		CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		std::memset(stats, 0, sizeof *stats);
+		stats->samples = (uint64_t)p->width * p->height * p->sample_count;
+		stats->rays = c[CNT_RAYS];
+		if (use_bvh) {
+			stats->node_visits = c[CNT_NODES]; stats->quad_tests = c[CNT_QUADS]; stats->tri_tests = c[CNT_TRIS]; stats->sphere_tests = c[CNT_SPHERES];
+		} else {  // brute force: every ray tests every hot primitive — exact by construction
+			stats->quad_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.brute_range.nq;
+			stats->tri_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.brute_range.nt;
+			stats->sphere_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.brute_range.ns;
+		}
+		stats->kernel_ms = ms;
+		stats->launches = (uint64_t)launched;
+	}
+	return ARE_OK;
+}
+
+int are_cuda_alloc_accum(are_cuda_ctx *ctx, int width, int height, float **out) {
+	if (!ctx || !out || width <= 0 || height <= 0) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "bad argument");
+	Bind b(ctx);
+	void *d = nullptr;
+	CK(cudaMalloc(&d, (size_t)width * height * 3 * sizeof(float)));
+	CK(cudaMemsetAsync(d, 0, (size_t)width * height * 3 * sizeof(float), ctx->stream));
+	*out = static_cast<float *>(d);
+	return ARE_OK;
+}
+int are_cuda_zero_accum(are_cuda_ctx *ctx, float *accum, int width, int height) {
+	if (!ctx || !accum) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "bad argument");
+	Bind b(ctx);
+	CK(cudaMemsetAsync(accum, 0, (size_t)width * height * 3 * sizeof(float), ctx->stream));
+	return ARE_OK;
+}
+int are_cuda_download_accum(are_cuda_ctx *ctx, const float *accum, int width, int height, float *host) {
+	if (!ctx || !accum || !host) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "bad argument");
+	Bind b(ctx);
+	CK(cudaMemcpyAsync(host, accum, (size_t)width * height * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+int are_cuda_free_accum(are_cuda_ctx *ctx, float *accum) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	Bind b(ctx);
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaFree(accum));
+	return ARE_OK;
+}
+int are_cuda_synchronize(are_cuda_ctx *ctx) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	Bind b(ctx);
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
+int are_cuda_render(are_cuda_ctx *ctx, const are_camera *cam, const are_render_params *p, float *accum_host, are_render_stats *stats) {
+	int st = need_commit(ctx);
+	if (st) return st;
+	if (!p || !accum_host) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	if (p->width <= 0 || p->height <= 0) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "bad render parameters");
+	Bind b(ctx);
+	const size_t elems = (size_t)p->width * p->height * 3;
+	if (ctx->own_accum_elems < elems) {
+		if (ctx->own_accum) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(ctx->own_accum)); ctx->own_accum = nullptr; ctx->own_accum_elems = 0; }
+		CK(cudaMalloc((void **)&ctx->own_accum, elems * sizeof(float)));
+		ctx->own_accum_elems = elems;
+	}
+	CK(cudaMemsetAsync(ctx->own_accum, 0, elems * sizeof(float), ctx->stream));
+	are_render_stats local;
+	st = are_cuda_render_device(ctx, cam, p, ctx->own_accum, stats ? stats : &local, 0);
+	if (st) return st;
+	CK(cudaMemcpyAsync(accum_host, ctx->own_accum, elems * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
+int are_cuda_tonemap(are_cuda_ctx *ctx, const float *accum, int width, int height, double inv_spp, int encoder, uint8_t *out_host) {
+	if (!ctx || !accum || !out_host || width <= 0 || height <= 0) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "bad argument");
+	if (encoder < ARE_ENCODE_GAMMA22_TRUNC || encoder > ARE_ENCODE_SQRT_TRUNC) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown encoder");
+	Bind b(ctx);
+	const size_t n = (size_t)width * height * 3;
+	Tmp d;
+	TMP_OUT(d, n);
+	launch_tonemap(accum, width, height, inv_spp, encoder, d.as<uint8_t>(), ctx->stream);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(out_host, d.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
+int are_cuda_write_ppm(const char *path, int width, int height, const uint8_t *rgb8) {
+	if (!path || !rgb8 || width <= 0 || height <= 0) return ARE_ERR_INVALID_ARGUMENT;
+	FILE *f = fopen(path, "wb");
+	if (!f) return ARE_ERR_IO;
+	fprintf(f, "P6\n%d %d\n255\n", width, height);  // src/texture.cpp:378, rt.cpp:379
+	size_t n = (size_t)width * height * 3;
+	bool ok = fwrite(rgb8, 1, n, f) == n;
+	fclose(f);
+	return ok ? ARE_OK : ARE_ERR_IO;
+}
+
+int are_cuda_measure_fp32_peak(are_cuda_ctx *ctx, double *tflops, int *sm_count, int *sm_clock_khz) {
+	if (!ctx || !tflops) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	Bind b(ctx);
+	Tmp sink;
+	TMP_OUT(sink, 16);
+	double best = 0.0;
+	for (int rep = 0; rep < 6; ++rep) {
+		CK(cudaEventRecord(ctx->ev0, ctx->stream));
+		double flops = launch_fp32_peak(sink.as<float>(), ctx->sm_count, 4096, ctx->stream);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(ctx->ev1, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		float ms = 0.f;
+		CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		if (rep >= 2 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+	}
+	*tflops = best;
+	if (sm_count) *sm_count = ctx->sm_count;
+	if (sm_clock_khz) {
+		int khz = 0;
+		cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+		*sm_clock_khz = khz;
+	}
+	return ARE_OK;
+}
+
+}  // extern "C"

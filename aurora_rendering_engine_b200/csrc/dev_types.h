@@ -1,0 +1,102 @@
+// dev_types.h — plain records shared by the host scene compiler (g++) and the sm_100a kernels (nvcc).
+//
+// HBM layout.  Everything the fp32 render kernels touch per ray is packed in 16-byte lanes so
+// one LDS.128 / LDG.128 moves a quarter of a primitive:
+//
+//   "plane form" primitive, 3 x float4 (48 B) — used for triangles, parallelograms (quads) and fused
+//   triangle pairs alike:
+//       r0 = (n.x, n.y, n.z, d0)     unit plane normal, d0 = n·Q           t = (d0 - n·o) / (n·d)
+//       r1 = (A.x, A.y, A.z, aQ)     alpha = A·p - aQ   with A = (v x N)/(N·N), N = u x v
+//       r2 = (B.x, B.y, B.z, bQ)     beta  = B·p - bQ   with B = (N x u)/(N·N)
+//   sphere, same 48 B slot:  r0 = (c.x, c.y, c.z, r), r1.x = r*r
+//
+// The fp64 copies (Q,u,v as the host gave them) feed only the decision-exact harness kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ARE_HD __host__ __device__
+#else
+#define ARE_HD
+#endif
+
+namespace areb {
+
+enum PrimType : int { PT_TRIANGLE = 0, PT_QUAD = 1, PT_SPHERE = 2 };
+enum MatKind : int { MK_DIFFUSE = 0, MK_REFLECTIVE = 1, MK_LAMBERTIAN = 2, MK_METAL = 3, MK_DIELECTRIC = 4, MK_LIGHT = 5 };
+enum TexKind : int { TK_SOLID = 0, TK_CHECKER_UV = 1, TK_CHECKER_3D = 2, TK_NOISE = 3, TK_IMAGE = 4 };
+
+struct f4 { float x, y, z, w; };  // layout-compatible with CUDA's float4 (16-byte aligned by the allocator)
+
+struct HotPrim { f4 r0, r1, r2; };  // 48 B
+
+// ids of the user primitives behind one hot primitive: b >= 0 only for a fused triangle pair
+// (a = the triangle on the alpha >= beta side of the diagonal and the lower user id).
+struct HotIds { int a, b; };
+
+struct PrimInfo { int user_id, mat, tex, type; };  // per device primitive (device order: triangles, quads, spheres)
+
+struct MaterialRec {
+	int kind, pad_;
+	double p[8];
+	float pf[8];
+};
+
+struct TextureRec {
+	int kind, w, h, pad_;
+	long long data_off;  // IMAGE: float offset into tex_data (rgb per texel). NOISE: float offset of 256x3 gradients, followed by 768 ints
+	double p[8];
+	float pf[8];
+};
+
+// BVH2 node, 64 B, both children's boxes inline (one node fetch = 4 x LDG.128):
+//   b0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   b1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
+//   b2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
+//   child[i] >= 0: inner node index.  child[i] < 0: leaf, first hot primitive = ~child[i],
+//   meta[i] = nq | nt << 8 | ns << 16  (quads+fused pairs, triangles, spheres; stored in that order)
+struct BvhNode {
+	f4 b0, b1, b2;
+	int child[2];
+	int meta[2];
+};
+
+// A contiguous run of hot primitives sorted by test kind: [first, first+nq) quad test, then nt triangle tests,
+// then ns sphere tests.  The brute-force list is one big range; every BVH leaf is a small one.
+struct HotRange { int first, nq, nt, ns; };
+
+struct DevScene {
+	// --- fp32 render data ---
+	const HotPrim *brute;      // type-sorted hot primitives (nullptr when the scene is too big for the brute path)
+	const HotIds *brute_ids;
+	HotRange brute_range;
+	const HotPrim *bvh_prims;  // leaf-ordered hot primitives
+	const HotIds *bvh_ids;
+	const BvhNode *nodes;
+	int n_nodes;
+	int root_leaf_meta;        // when the whole scene is one leaf (n_nodes == 0)
+	int n_hot;
+	// --- per device primitive ---
+	const PrimInfo *info;
+	const HotPrim *prim_plane; // plane form (or sphere record) of every user primitive, device order
+	const float *tri_uv;       // 6 floats per triangle
+	int n_tri, n_quad, n_sph;
+	// --- fp64 harness data (host values, untouched) ---
+	const double *tri64;       // 9 doubles per triangle: Q, u, v
+	const double *quad64;      // 9 doubles per quad
+	const double *sph64;       // 4 doubles per sphere: c, r
+	const double *tri_uv64;    // 6 doubles per triangle
+	// --- materials / textures ---
+	const MaterialRec *mats;
+	const TextureRec *texs;
+	const float *tex_data;
+	int n_mat, n_tex;
+};
+
+// camera basis precomputed on the host in fp64 (mirrors oracle cam_setup; experiments/rt.cpp:339-343)
+struct CamBasis {
+	double pos[3], fwd[3], right[3], up[3];
+	double sx, sy, lens_r, focus;
+	int jitter, pad_;
+};
+
+}  // namespace areb

@@ -1,0 +1,51 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (implemented in harness64.cu / render.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dev_types.h"
+#include "philox.cuh"
+
+namespace areb {
+
+struct RenderArgs {
+	DevScene sc;
+	CamBasis cam;
+	PhiloxKey key;   // the ten round keys of the render seed (constant-bank operands in the kernel)
+	int W, H;
+	int s_begin, s_count;
+	int max_depth;
+	int ao_samples;
+	float tmin;
+	float bg_bottom[3], bg_top[3];
+	float *accum;                    // W*H*3 floats, sample SUMS are added
+	unsigned long long *counters;    // [0] rays [1] node visits [2] quad tests [3] tri tests [4] sphere tests
+};
+
+enum { CNT_RAYS = 0, CNT_NODES = 1, CNT_QUADS = 2, CNT_TRIS = 3, CNT_SPHERES = 4, CNT_N = 8 };
+
+// fp64 harness (harness64.cu, -fmad=false)
+void launch_hit64(const DevScene &sc, int n, const double *Q, const double *D, double tmin, int *prim, double *t, double *P, double *N, double *uv, cudaStream_t s);
+void launch_scatter64(const DevScene &sc, int n, const int *mat, const int *tex, const double *wi, const double *N, const double *P, const double *uv,
+	const double *rnd, double *wo, double *att, double *emit, int *alive, cudaStream_t s);
+void launch_texture64(const DevScene &sc, int n, const int *tex, const double *uv, const double *P, double *rgb, cudaStream_t s);
+void launch_camera64(const CamBasis &cb, int W, int H, int n, const int *px, const int *py, const double *rnd, double *Q, double *D, cudaStream_t s);
+void launch_philox(int n, uint64_t seed, const uint32_t *ctr, uint32_t *out, cudaStream_t s);
+
+// fp32 harness: the render kernels' own device routines (render.cu)
+void launch_hit32(const DevScene &sc, int n, const double *Q, const double *D, double tmin, bool use_bvh, int *prim, double *t, double *P, double *N, double *uv, cudaStream_t s);
+void launch_scatter32(const DevScene &sc, int n, const int *mat, const int *tex, const double *wi, const double *N, const double *P, const double *uv,
+	const double *rnd, double *wo, double *att, double *emit, int *alive, cudaStream_t s);
+void launch_texture32(const DevScene &sc, int n, const int *tex, const double *uv, const double *P, double *rgb, cudaStream_t s);
+void launch_camera32(const CamBasis &cb, int W, int H, int n, const int *px, const int *py, const double *rnd, double *Q, double *D, cudaStream_t s);
+
+// render kernels. Returns the number of kernels launched, <0 on a launch-configuration error.
+int launch_render_path(const RenderArgs &a, bool use_bvh, bool count_tests, cudaStream_t s);
+int launch_render_rtao(const RenderArgs &a, cudaStream_t s);
+void launch_tonemap(const float *accum, int W, int H, double inv_spp, int encoder, uint8_t *out, cudaStream_t s);
+// register-resident FFMA loop; returns FLOPs executed per launch
+double launch_fp32_peak(float *sink, int sm_count, int iters, cudaStream_t s);
+
+size_t brute_smem_limit_prims();
+
+}  // namespace areb

@@ -1,0 +1,444 @@
+// scene.cpp — scene compiler: validation, plane-form records, parallelogram fusion, brute list, binned-SAH BVH2.
+#include "scene.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <unordered_map>
+
+#include "philox.cuh"
+
+namespace areb {
+
+namespace {
+
+struct D3 {
+	double x, y, z;
+};
+inline D3 d3(const double *p) { return { p[0], p[1], p[2] }; }
+inline D3 operator+(D3 a, D3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
+inline D3 operator-(D3 a, D3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+inline D3 operator*(double s, D3 a) { return { s * a.x, s * a.y, s * a.z }; }
+inline double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline D3 cross(D3 a, D3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+inline double len(D3 a) { return std::sqrt(dot(a, a)); }
+inline bool near_zero(D3 a) {  // are::Vec3::near_zero, src/basic/vec3.cpp:143-146
+	const double s = 1e-8;
+	return std::fabs(a.x) < s && std::fabs(a.y) < s && std::fabs(a.z) < s;
+}
+
+struct Box {
+	double lo[3], hi[3];
+	void reset() {
+		for (int k = 0; k < 3; ++k) { lo[k] = std::numeric_limits<double>::infinity(); hi[k] = -lo[k]; }
+	}
+	void grow(D3 p) {
+		const double v[3] = { p.x, p.y, p.z };
+		for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], v[k]); hi[k] = std::max(hi[k], v[k]); }
+	}
+	void grow(const Box &b) {
+		for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); }
+	}
+	double area() const {
+		double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+		if (dx < 0 || dy < 0 || dz < 0) return 0.0;
+		return 2.0 * (dx * dy + dy * dz + dz * dx);
+	}
+};
+
+// plane form of the parallelogram / triangle (Q,u,v)
+HotPrim plane_form(D3 Q, D3 u, D3 v) {
+	D3 N = cross(u, v);
+	double nn = dot(N, N);
+	D3 n = (1.0 / std::sqrt(nn)) * N;
+	D3 A = (1.0 / nn) * cross(v, N), B = (1.0 / nn) * cross(N, u);
+	HotPrim h;
+	h.r0 = { (float)n.x, (float)n.y, (float)n.z, (float)dot(n, Q) };
+	h.r1 = { (float)A.x, (float)A.y, (float)A.z, (float)dot(A, Q) };
+	h.r2 = { (float)B.x, (float)B.y, (float)B.z, (float)dot(B, Q) };
+	return h;
+}
+HotPrim sphere_form(D3 c, double r) {
+	HotPrim h;
+	h.r0 = { (float)c.x, (float)c.y, (float)c.z, (float)r };
+	h.r1 = { (float)(r * r), 0.f, 0.f, 0.f };
+	h.r2 = { 0.f, 0.f, 0.f, 0.f };
+	return h;
+}
+
+enum HotKind { HK_QUAD = 0, HK_TRI = 1, HK_SPHERE = 2 };
+struct HotItem {
+	int kind;
+	HotPrim rec;
+	HotIds ids;
+	Box box;
+	double c[3];  // centroid
+};
+
+struct VKey {
+	uint64_t a[3];
+	bool operator==(const VKey &o) const { return a[0] == o.a[0] && a[1] == o.a[1] && a[2] == o.a[2]; }
+};
+inline VKey vkey(D3 p) {
+	VKey k;
+	double v[3] = { p.x == 0.0 ? 0.0 : p.x, p.y == 0.0 ? 0.0 : p.y, p.z == 0.0 ? 0.0 : p.z };  // -0 -> +0
+	std::memcpy(k.a, v, sizeof v);
+	return k;
+}
+struct EKey {
+	VKey p, q;
+	bool operator==(const EKey &o) const { return p == o.p && q == o.q; }
+};
+struct EHash {
+	size_t operator()(const EKey &e) const {
+		uint64_t h = 0x9E3779B97F4A7C15ull;
+		const uint64_t *w = e.p.a;
+		for (int i = 0; i < 3; ++i) h = (h ^ w[i]) * 0xD6E8FEB86659FD93ull;
+		w = e.q.a;
+		for (int i = 0; i < 3; ++i) h = (h ^ w[i]) * 0xD6E8FEB86659FD93ull;
+		return (size_t)(h ^ (h >> 32));
+	}
+};
+inline bool vless(const VKey &x, const VKey &y) { return std::lexicographical_compare(x.a, x.a + 3, y.a, y.a + 3); }
+inline EKey ekey(D3 p, D3 q) {
+	VKey a = vkey(p), b = vkey(q);
+	if (vless(b, a)) std::swap(a, b);
+	return { a, b };
+}
+
+// ---- BVH builder ------------------------------------------------------------------------------------
+struct ChildRef {
+	int ref, meta;
+	Box box;
+};
+
+struct Builder {
+	std::vector<HotItem> &items;
+	std::vector<int> idx;
+	CompiledScene &out;
+	int leaf_size;
+	int max_depth = 0;
+	Builder(std::vector<HotItem> &it, CompiledScene &o, int ls) : items(it), out(o), leaf_size(ls) {
+		idx.resize(items.size());
+		for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+	}
+	static void put_box(f4 &bxy, float &zlo, float &zhi, const Box &b) {
+		// pad outwards: fp32 rounding of the bounds and of the slab arithmetic must never cut a primitive off
+		float lo[3], hi[3];
+		for (int k = 0; k < 3; ++k) {
+			double m = std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
+			double pad = 1e-5 * (m + (b.hi[k] - b.lo[k])) + 1e-7;
+			lo[k] = (float)(b.lo[k] - pad);
+			hi[k] = (float)(b.hi[k] + pad);
+		}
+		bxy = { lo[0], hi[0], lo[1], hi[1] };
+		zlo = lo[2];
+		zhi = hi[2];
+	}
+	ChildRef make_leaf(int lo, int hi) {
+		ChildRef c;
+		c.box.reset();
+		int first = (int)out.bvh_prims.size(), cnt[3] = { 0, 0, 0 };
+		for (int kind = 0; kind < 3; ++kind)
+			for (int i = lo; i < hi; ++i) {
+				const HotItem &it = items[idx[i]];
+				if (it.kind != kind) continue;
+				out.bvh_prims.push_back(it.rec);
+				out.bvh_ids.push_back(it.ids);
+				c.box.grow(it.box);
+				cnt[kind]++;
+			}
+		c.ref = ~first;
+		c.meta = cnt[0] | (cnt[1] << 8) | (cnt[2] << 16);
+		return c;
+	}
+	ChildRef build(int lo, int hi, int depth) {
+		max_depth = std::max(max_depth, depth);
+		const int n = hi - lo;
+		if (n <= leaf_size) return make_leaf(lo, hi);
+		Box bounds, cb;
+		bounds.reset();
+		cb.reset();
+		for (int i = lo; i < hi; ++i) {
+			const HotItem &it = items[idx[i]];
+			bounds.grow(it.box);
+			cb.grow(D3{ it.c[0], it.c[1], it.c[2] });
+		}
+		int mid = -1;
+		if (depth < 40) {
+			const int NB = 16;
+			double best_cost = std::numeric_limits<double>::infinity();
+			int best_axis = -1, best_split = -1;
+			for (int ax = 0; ax < 3; ++ax) {
+				double ext = cb.hi[ax] - cb.lo[ax];
+				if (!(ext > 0.0)) continue;
+				Box bb[NB];
+				int bc[NB] = { 0 };
+				for (int b = 0; b < NB; ++b) bb[b].reset();
+				const double scale = NB / ext;
+				for (int i = lo; i < hi; ++i) {
+					const HotItem &it = items[idx[i]];
+					int b = std::min(NB - 1, (int)((it.c[ax] - cb.lo[ax]) * scale));
+					bb[b].grow(it.box);
+					bc[b]++;
+				}
+				double right_area[NB];
+				int right_cnt[NB];
+				Box acc;
+				acc.reset();
+				int c = 0;
+				for (int b = NB - 1; b > 0; --b) {
+					acc.grow(bb[b]);
+					c += bc[b];
+					right_area[b] = acc.area();
+					right_cnt[b] = c;
+				}
+				acc.reset();
+				c = 0;
+				for (int b = 0; b < NB - 1; ++b) {
+					acc.grow(bb[b]);
+					c += bc[b];
+					if (c == 0 || right_cnt[b + 1] == 0) continue;
+					double cost = acc.area() * c + right_area[b + 1] * right_cnt[b + 1];
+					if (cost < best_cost) { best_cost = cost; best_axis = ax; best_split = b; }
+				}
+			}
+			if (best_axis >= 0) {
+				const double ext = cb.hi[best_axis] - cb.lo[best_axis], scale = NB / ext, clo = cb.lo[best_axis];
+				auto it = std::partition(idx.begin() + lo, idx.begin() + hi, [&](int id) {
+					int b = std::min(NB - 1, (int)((items[id].c[best_axis] - clo) * scale));
+					return b <= best_split;
+				});
+				mid = (int)(it - idx.begin());
+				if (mid == lo || mid == hi) mid = -1;
+			}
+		}
+		if (mid < 0) {  // coincident centroids or depth guard: median split on the widest axis
+			int ax = 0;
+			for (int k = 1; k < 3; ++k)
+				if (cb.hi[k] - cb.lo[k] > cb.hi[ax] - cb.lo[ax]) ax = k;
+			mid = lo + n / 2;
+			std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) { return items[a].c[ax] < items[b].c[ax]; });
+		}
+		const int me = (int)out.nodes.size();
+		out.nodes.push_back(BvhNode());
+		ChildRef l = build(lo, mid, depth + 1), r = build(mid, hi, depth + 1);
+		BvhNode nd;
+		put_box(nd.b0, nd.b2.x, nd.b2.y, l.box);
+		put_box(nd.b1, nd.b2.z, nd.b2.w, r.box);
+		nd.child[0] = l.ref; nd.child[1] = r.ref;
+		nd.meta[0] = l.meta; nd.meta[1] = r.meta;
+		out.nodes[me] = nd;
+		ChildRef c;
+		c.ref = me;
+		c.meta = 0;
+		c.box = l.box;
+		c.box.grow(r.box);
+		return c;
+	}
+};
+
+}  // namespace
+
+const char *validate_edges(const double u[3], const double v[3]) {
+	if (near_zero(d3(u))) return "Edge vector u cannot be zero vector";
+	if (near_zero(d3(v))) return "Edge vector v cannot be zero vector";
+	if (near_zero(cross(d3(u), d3(v)))) return "Edge vectors u and v cannot be collinear";
+	return nullptr;
+}
+
+void make_noise_tables(uint64_t seed, double *grad768, int *perm768) {
+	PhiloxKey key = philox_key(seed);
+	for (int i = 0; i < 256; ++i) {
+		Rnd4<double> r = rnd4<double>(key, (uint32_t)i, 0u, 0u, 0x5045524Cu);
+		double z = 1.0 - 2.0 * r.x, rxy = std::sqrt(std::max(0.0, 1.0 - z * z)), phi = 2.0 * 3.14159265358979323846 * r.y;
+		grad768[3 * i] = rxy * std::cos(phi);
+		grad768[3 * i + 1] = rxy * std::sin(phi);
+		grad768[3 * i + 2] = z;
+	}
+	for (int a = 0; a < 3; ++a) {
+		int *p = perm768 + 256 * a;
+		for (int i = 0; i < 256; ++i) p[i] = i;
+		for (int i = 255; i > 0; --i) {
+			U4 o = philox4x32_10(key, (uint32_t)i, (uint32_t)(a + 1), 0u, 0x5045524Cu);
+			int target = (int)(o.x % (uint32_t)(i + 1));
+			std::swap(p[i], p[target]);
+		}
+	}
+}
+
+void make_cam_basis(const double pos[3], const double target[3], const double up[3], double vfov_deg, double focus_dist,
+	double defocus_angle_deg, int jitter, int W, int H, CamBasis &out) {
+	D3 p = d3(pos);
+	D3 f = d3(target) - p;
+	f = (1.0 / len(f)) * f;
+	D3 r = cross(f, d3(up));
+	r = (1.0 / len(r)) * r;
+	D3 u = cross(r, f);
+	const double scale = std::tan(vfov_deg * 0.5 * 3.14159265358979323846 / 180.0);
+	const double P[3] = { p.x, p.y, p.z }, F[3] = { f.x, f.y, f.z }, R[3] = { r.x, r.y, r.z }, U[3] = { u.x, u.y, u.z };
+	std::memcpy(out.pos, P, sizeof P);
+	std::memcpy(out.fwd, F, sizeof F);
+	std::memcpy(out.right, R, sizeof R);
+	std::memcpy(out.up, U, sizeof U);
+	out.sx = ((double)W / (double)H) * scale;
+	out.sy = scale;
+	out.focus = focus_dist;
+	out.lens_r = defocus_angle_deg > 0.0 ? focus_dist * std::tan(defocus_angle_deg * 0.5 * 3.14159265358979323846 / 180.0) : 0.0;
+	out.jitter = jitter;
+	out.pad_ = 0;
+}
+
+bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene &out, std::string &err) {
+	out = CompiledScene();
+	const int nmat = (int)hs.materials.size(), ntex = (int)hs.textures.size();
+	// ---- materials / textures ----
+	for (const HostMaterial &m : hs.materials) {
+		MaterialRec r;
+		std::memset(&r, 0, sizeof r);
+		r.kind = m.kind;
+		for (int i = 0; i < 8; ++i) { r.p[i] = m.p[i]; r.pf[i] = (float)m.p[i]; }
+		int over = -1;
+		if (m.kind == MK_LAMBERTIAN || m.kind == MK_LIGHT) over = (int)m.p[0];
+		else if (m.kind == MK_METAL) over = (int)m.p[1];
+		if (over >= ntex) { err = "material references a texture id that does not exist"; return false; }
+		out.mats.push_back(r);
+	}
+	for (const HostTexture &t : hs.textures) {
+		TextureRec r;
+		std::memset(&r, 0, sizeof r);
+		r.kind = t.kind;
+		r.w = t.w;
+		r.h = t.h;
+		for (int i = 0; i < 8; ++i) { r.p[i] = t.p[i]; r.pf[i] = (float)t.p[i]; }
+		while (out.tex_data.size() % 4) out.tex_data.push_back(0.f);
+		r.data_off = (long long)out.tex_data.size();
+		if (t.kind == TK_IMAGE) {
+			if (t.w <= 0 || t.h <= 0 || t.rgb.size() != (size_t)t.w * t.h * 3) { err = "image texture without pixel data"; return false; }
+			for (double c : t.rgb) out.tex_data.push_back((float)c);
+		} else if (t.kind == TK_NOISE) {
+			double grad[768];
+			int perm[768];
+			make_noise_tables((uint64_t)t.p[1], grad, perm);
+			size_t base = out.tex_data.size();
+			out.tex_data.resize(base + 768 + 768 + 1536);
+			for (int i = 0; i < 768; ++i) out.tex_data[base + i] = (float)grad[i];
+			std::memcpy(&out.tex_data[base + 768], perm, sizeof perm);
+			std::memcpy(&out.tex_data[base + 1536], grad, sizeof grad);
+		}
+		out.texs.push_back(r);
+	}
+	// ---- device primitive order: triangles, quads, spheres ----
+	std::vector<int> order;
+	for (int type = 0; type < 3; ++type)
+		for (size_t i = 0; i < hs.prims.size(); ++i)
+			if (hs.prims[i].type == type) order.push_back((int)i);
+	std::vector<Box> pbox(order.size());
+	for (size_t dp = 0; dp < order.size(); ++dp) {
+		const HostPrim &p = hs.prims[order[dp]];
+		if (p.mat < 0 || p.mat >= nmat) { err = "primitive references a material id that does not exist"; return false; }
+		if (p.tex < 0 || p.tex >= ntex) { err = "primitive references a texture id that does not exist"; return false; }
+		out.info.push_back({ order[dp], p.mat, p.tex, p.type });
+		Box b;
+		b.reset();
+		D3 Q = d3(p.Q), u = d3(p.u), v = d3(p.v);
+		if (p.type == PT_SPHERE) {
+			double r = p.u[0];
+			out.prim_plane.push_back(sphere_form(Q, r));
+			out.sph64.insert(out.sph64.end(), { p.Q[0], p.Q[1], p.Q[2], r });
+			b.grow(Q - D3{ r, r, r });
+			b.grow(Q + D3{ r, r, r });
+			out.n_sph++;
+		} else {
+			out.prim_plane.push_back(plane_form(Q, u, v));
+			std::vector<double> &dst = p.type == PT_TRIANGLE ? out.tri64 : out.quad64;
+			dst.insert(dst.end(), p.Q, p.Q + 3);
+			dst.insert(dst.end(), p.u, p.u + 3);
+			dst.insert(dst.end(), p.v, p.v + 3);
+			b.grow(Q); b.grow(Q + u); b.grow(Q + v);
+			if (p.type == PT_QUAD) { b.grow(Q + u + v); out.n_quad++; }
+			else {
+				out.n_tri++;
+				for (int k = 0; k < 6; ++k) { out.tri_uv.push_back((float)p.uv[k]); out.tri_uv64.push_back(p.uv[k]); }
+			}
+		}
+		pbox[dp] = b;
+	}
+	// ---- hot list with parallelogram fusion ----
+	std::vector<HotItem> hot;
+	hot.reserve(order.size());
+	const int nt = out.n_tri;
+	std::vector<char> fused(nt, 0);
+	auto push_item = [&](int kind, const HotPrim &rec, HotIds ids, const Box &b) {
+		HotItem it;
+		it.kind = kind; it.rec = rec; it.ids = ids; it.box = b;
+		for (int k = 0; k < 3; ++k) it.c[k] = 0.5 * (b.lo[k] + b.hi[k]);
+		hot.push_back(it);
+	};
+	if (opt.fuse_parallelograms && nt >= 2) {
+		struct EdgeUse { int tri, opp; };
+		std::unordered_multimap<EKey, EdgeUse, EHash> edges;
+		edges.reserve((size_t)nt * 3);
+		auto vert = [&](int t, int k) {
+			const double *q = &out.tri64[9 * (size_t)t];
+			D3 Q = d3(q);
+			return k == 0 ? Q : (k == 1 ? Q + d3(q + 3) : Q + d3(q + 6));
+		};
+		for (int t = 0; t < nt; ++t)
+			for (int k = 0; k < 3; ++k) edges.insert({ ekey(vert(t, (k + 1) % 3), vert(t, (k + 2) % 3)), { t, k } });
+		for (int t = 0; t < nt; ++t) {
+			if (fused[t]) continue;
+			for (int k = 0; k < 3 && !fused[t]; ++k) {
+				D3 d0 = vert(t, (k + 1) % 3), d1 = vert(t, (k + 2) % 3), a = vert(t, k);
+				auto range = edges.equal_range(ekey(d0, d1));
+				for (auto it = range.first; it != range.second; ++it) {
+					int j = it->second.tri;
+					if (j == t || fused[j]) continue;
+					D3 b = vert(j, it->second.opp);
+					D3 e = (a + b) - (d0 + d1);
+					double scale = len(a - d0) + len(b - d0) + len(d1 - d0);
+					if (len(e) > 1e-9 * scale) continue;
+					// lower user id takes the alpha >= beta side (ties on the diagonal go to it, like a linear scan)
+					int ta = t, tb = j;
+					D3 va = a, vb = b;
+					if (out.info[tb].user_id < out.info[ta].user_id) { std::swap(ta, tb); std::swap(va, vb); }
+					HotPrim rec = plane_form(d0, va - d0, vb - d0);
+					Box bx = pbox[t];
+					bx.grow(pbox[j]);
+					push_item(HK_QUAD, rec, { ta, tb }, bx);
+					fused[t] = fused[j] = 1;
+					out.n_fused_pairs++;
+					break;
+				}
+			}
+		}
+	}
+	for (size_t dp = 0; dp < order.size(); ++dp) {
+		int type = out.info[dp].type;
+		if (type == PT_TRIANGLE && fused[dp]) continue;
+		int kind = type == PT_TRIANGLE ? HK_TRI : (type == PT_QUAD ? HK_QUAD : HK_SPHERE);
+		push_item(kind, out.prim_plane[dp], { (int)dp, -1 }, pbox[dp]);
+	}
+	out.n_hot = (int)hot.size();
+	// ---- brute list (type-sorted) ----
+	if (out.n_hot <= opt.brute_max) {
+		int cnt[3] = { 0, 0, 0 };
+		for (int kind = 0; kind < 3; ++kind)
+			for (const HotItem &it : hot)
+				if (it.kind == kind) { out.brute.push_back(it.rec); out.brute_ids.push_back(it.ids); cnt[kind]++; }
+		out.brute_range = { 0, cnt[0], cnt[1], cnt[2] };
+	}
+	// ---- BVH ----
+	if (out.n_hot > 0) {
+		Builder b(hot, out, std::max(1, std::min(opt.leaf_size, 16)));
+		out.bvh_prims.reserve(hot.size());
+		out.bvh_ids.reserve(hot.size());
+		ChildRef root = b.build(0, out.n_hot, 0);
+		if (root.ref < 0) out.root_leaf_meta = root.meta;
+		out.bvh_depth = b.max_depth;
+	}
+	return true;
+}
+
+}  // namespace areb

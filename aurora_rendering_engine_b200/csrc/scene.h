@@ -1,0 +1,83 @@
+// scene.h — host-side scene container and scene compiler (flattening to the device layout of dev_types.h).
+//
+// The container holds exactly what a reference-style host program hands over: the (Q,u,v) of every
+// are::Triangle in its are::ObjectSet (include/object/triangle.h:19, object_set.h:10-12) plus the material and
+// texture each one points at, extended with the quad / sphere / material / texture kinds the north_star adds.
+// compile() turns it into structure-of-arrays blocks ready for one cudaMemcpy each:
+//   * device primitive order = triangles, quads, spheres (user ids kept in PrimInfo)
+//   * plane-form fp32 record per primitive (dev_types.h)
+//   * "hot" primitive list = what the render loop tests: coplanar triangle pairs forming a parallelogram are
+//     fused into ONE quad test (halves the work on box-like scenes; the owning triangle is recovered after the
+//     loop), everything else is passed through
+//   * type-sorted brute-force list (small scenes) and a binned-SAH BVH2 with leaf-ordered primitives
+#pragma once
+#include <string>
+#include <vector>
+
+#include "dev_types.h"
+
+namespace areb {
+
+struct HostTexture {
+	int kind = 0;
+	double p[8] = { 0 };
+	int w = 0, h = 0;
+	std::vector<double> rgb;
+};
+struct HostMaterial {
+	int kind = 0;
+	double p[8] = { 0 };
+};
+struct HostPrim {
+	int type = 0, mat = 0, tex = 0;
+	double Q[3], u[3], v[3];  // sphere: Q = centre, u[0] = radius
+	double uv[6] = { 0, 0, 1, 0, 0, 1 };
+};
+
+struct HostScene {
+	std::vector<HostTexture> textures;
+	std::vector<HostMaterial> materials;
+	std::vector<HostPrim> prims;  // user order; index = user primitive id
+};
+
+struct CompiledScene {
+	std::vector<HotPrim> brute;
+	std::vector<HotIds> brute_ids;
+	HotRange brute_range = { 0, 0, 0, 0 };
+	std::vector<HotPrim> bvh_prims;
+	std::vector<HotIds> bvh_ids;
+	std::vector<BvhNode> nodes;
+	int root_leaf_meta = 0;
+	int n_hot = 0, n_fused_pairs = 0;
+	std::vector<PrimInfo> info;
+	std::vector<HotPrim> prim_plane;
+	std::vector<float> tri_uv;
+	std::vector<double> tri64, quad64, sph64, tri_uv64;
+	int n_tri = 0, n_quad = 0, n_sph = 0;
+	std::vector<MaterialRec> mats;
+	std::vector<TextureRec> texs;
+	std::vector<float> tex_data;
+	int bvh_depth = 0;
+};
+
+struct CompileOptions {
+	bool fuse_parallelograms = true;
+	int leaf_size = 4;
+	int brute_max = 1024;
+};
+
+// Validation mirroring are::Triangle's ctor (src/object/triangle.cpp:22-36): returns nullptr when fine, else the
+// reference's exception message.
+const char *validate_edges(const double u[3], const double v[3]);
+
+// Returns false and fills err on inconsistent ids etc.
+bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene &out, std::string &err);
+
+// Perlin tables: 256 unit gradients (xyz doubles) + 3x256 permutations from Philox(seed); spec shared with the oracle.
+void make_noise_tables(uint64_t seed, double *grad768, int *perm768);
+
+// camera basis exactly as experiments/rt.cpp:339-343 computes it, in fp64
+void make_cam_basis(const double pos[3], const double target[3], const double up[3], double vfov_deg, double focus_dist,
+	double defocus_angle_deg, int jitter, int W, int H, CamBasis &out);
+
+}  // namespace areb

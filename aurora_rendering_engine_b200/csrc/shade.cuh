@@ -1,0 +1,245 @@
+// shade.cuh — surface resolution, texture evaluation, sampling and material scatter on the device.
+// One templated source: T = double for the per-ray harness (checked against the reference / oracle to ~1e-12),
+// T = float inside the render kernels.  Reference arithmetic used (paths under /root/reference):
+//   metal       are::reflect                          src/basic/vec3.cpp:182-184
+//   dielectric  are::refract (fabs quirk kept)        src/basic/vec3.cpp:188-199
+//   lambertian  cosine gather + rotateToHemisphere    experiments/rt.cpp:285-289, 50-55
+//   fuzz / AO   uniform sphere, z = 1-2v              experiments/rt.cpp:226-231
+//   uv checker  CheckerTexture::at                    experiments/rt.cpp:98-101
+//   bary -> uv  Tri::bary2uv                          experiments/rt.cpp:139-142
+//   camera      render() ray set-up                   experiments/rt.cpp:339-343,364-366
+#pragma once
+#include "dev_types.h"
+#include "philox.cuh"
+#include "vec.cuh"
+
+namespace areb {
+
+template <typename T> __device__ __forceinline__ T mparam(const MaterialRec &m, int i);
+template <> __device__ __forceinline__ double mparam<double>(const MaterialRec &m, int i) { return m.p[i]; }
+template <> __device__ __forceinline__ float mparam<float>(const MaterialRec &m, int i) { return m.pf[i]; }
+template <typename T> __device__ __forceinline__ T tparam(const TextureRec &t, int i);
+template <> __device__ __forceinline__ double tparam<double>(const TextureRec &t, int i) { return t.p[i]; }
+template <> __device__ __forceinline__ float tparam<float>(const TextureRec &t, int i) { return t.pf[i]; }
+
+// fp32 normalisation = one MUFU.RSQ (rsqrt(0)=inf -> NaN vector, same convention as the reference)
+__device__ __forceinline__ V3<double> nrm(V3<double> a) { return normalized(a); }
+__device__ __forceinline__ V3<float> nrm(V3<float> a) { return rsqrtf(len2(a)) * a; }
+
+template <typename T> struct Pi { static constexpr T value = T(3.14159265358979323846); };
+
+// ---- textures -----------------------------------------------------------------------------------------
+template <typename T>
+__device__ T perlin_noise(const float *tab, V3<T> p) {
+	const int *perm = reinterpret_cast<const int *>(tab + 768);
+	T fx = floor_t(p.x), fy = floor_t(p.y), fz = floor_t(p.z);
+	T u = p.x - fx, v = p.y - fy, w = p.z - fz;
+	int i = (int)fx, j = (int)fy, k = (int)fz;
+	T uu = u * u * (T(3) - T(2) * u), vv = v * v * (T(3) - T(2) * v), ww = w * w * (T(3) - T(2) * w), acc = T(0);
+#pragma unroll
+	for (int di = 0; di < 2; ++di)
+#pragma unroll
+		for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+			for (int dk = 0; dk < 2; ++dk) {
+				int g = perm[(i + di) & 255] ^ perm[256 + ((j + dj) & 255)] ^ perm[512 + ((k + dk) & 255)];
+				V3<T> gv = mk<T>(T(tab[3 * g]), T(tab[3 * g + 1]), T(tab[3 * g + 2]));
+				V3<T> wv = mk<T>(u - T(di), v - T(dj), w - T(dk));
+				acc += (di ? uu : T(1) - uu) * (dj ? vv : T(1) - vv) * (dk ? ww : T(1) - ww) * dot(gv, wv);
+			}
+	return acc;
+}
+// NOISE tables are kept in double precision for the fp64 harness (second half of the block)
+template <typename T>
+__device__ T perlin_noise_tab(const DevScene &sc, const TextureRec &t, V3<T> p);
+template <>
+__device__ __forceinline__ float perlin_noise_tab<float>(const DevScene &sc, const TextureRec &t, V3<float> p) {
+	return perlin_noise<float>(sc.tex_data + t.data_off, p);
+}
+template <>
+__device__ inline double perlin_noise_tab<double>(const DevScene &sc, const TextureRec &t, V3<double> p) {
+	// layout: [768 float gradients][768 int perm][768 double gradients]
+	const float *tab = sc.tex_data + t.data_off;
+	const int *perm = reinterpret_cast<const int *>(tab + 768);
+	const double *gd = reinterpret_cast<const double *>(tab + 1536);
+	double fx = floor(p.x), fy = floor(p.y), fz = floor(p.z);
+	double u = p.x - fx, v = p.y - fy, w = p.z - fz;
+	int i = (int)fx, j = (int)fy, k = (int)fz;
+	double uu = u * u * (3 - 2 * u), vv = v * v * (3 - 2 * v), ww = w * w * (3 - 2 * w), acc = 0.0;
+	for (int di = 0; di < 2; ++di)
+		for (int dj = 0; dj < 2; ++dj)
+			for (int dk = 0; dk < 2; ++dk) {
+				int g = perm[(i + di) & 255] ^ perm[256 + ((j + dj) & 255)] ^ perm[512 + ((k + dk) & 255)];
+				V3<double> gv = mk<double>(gd[3 * g], gd[3 * g + 1], gd[3 * g + 2]);
+				V3<double> wv = mk<double>(u - di, v - dj, w - dk);
+				acc += (di * uu + (1 - di) * (1 - uu)) * (dj * vv + (1 - dj) * (1 - vv)) * (dk * ww + (1 - dk) * (1 - ww)) * dot(gv, wv);
+			}
+	return acc;
+}
+
+template <typename T>
+__device__ V3<T> tex_eval(const DevScene &sc, int id, T u, T v, V3<T> P) {
+	const TextureRec &t = sc.texs[id];
+	switch (t.kind) {
+	case TK_SOLID:
+		return mk<T>(tparam<T>(t, 0), tparam<T>(t, 1), tparam<T>(t, 2));
+	case TK_CHECKER_UV: {
+		int xx = (int)floor_t(u * tparam<T>(t, 0)), yy = (int)floor_t(v * tparam<T>(t, 0));
+		return ((xx + yy) % 2 == 0) ? mk<T>(tparam<T>(t, 1), tparam<T>(t, 2), tparam<T>(t, 3)) : mk<T>(tparam<T>(t, 4), tparam<T>(t, 5), tparam<T>(t, 6));
+	}
+	case TK_CHECKER_3D: {
+		T inv = T(1) / tparam<T>(t, 0);
+		int xi = (int)floor_t(inv * P.x), yi = (int)floor_t(inv * P.y), zi = (int)floor_t(inv * P.z);
+		return ((xi + yi + zi) % 2 == 0) ? mk<T>(tparam<T>(t, 1), tparam<T>(t, 2), tparam<T>(t, 3)) : mk<T>(tparam<T>(t, 4), tparam<T>(t, 5), tparam<T>(t, 6));
+	}
+	case TK_NOISE: {
+		T acc = T(0), weight = T(1);
+		V3<T> q = P;
+		for (int i = 0; i < 7; ++i) {
+			acc += weight * perlin_noise_tab<T>(sc, t, q);
+			weight *= T(0.5);
+			q = T(2) * q;
+		}
+		T g = T(0.5) * (T(1) + sin_t(tparam<T>(t, 0) * P.z + T(10) * abs_t(acc)));
+		return mk<T>(g, g, g);
+	}
+	default: {
+		T uc = min_t(T(1), max_t(T(0), u)), vc = T(1) - min_t(T(1), max_t(T(0), v));
+		int i = (int)(uc * T(t.w)), j = (int)(vc * T(t.h));
+		i = i > t.w - 1 ? t.w - 1 : i;
+		j = j > t.h - 1 ? t.h - 1 : j;
+		const float *c = sc.tex_data + t.data_off + ((long long)j * t.w + i) * 3;
+		return mk<T>(T(c[0]), T(c[1]), T(c[2]));
+	}
+	}
+}
+
+// ---- sampling -----------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ V3<T> cosine_dir(V3<T> n, T r1, T r2) {
+	T sn, cs;
+	sincos2pi_t(r1, &sn, &cs);
+	T r2s = sqrt_t(r2);
+	T lx = r2s * cs, ly = r2s * sn;
+	V3<T> up = abs_t(n.z) < T(0.999) ? mk<T>(T(0), T(0), T(1)) : mk<T>(T(1), T(0), T(0));
+	V3<T> tangent = nrm(cross(n, up));
+	V3<T> bitangent = cross(n, tangent);
+	T lz = sqrt_t(max_t(T(0), T(1) - lx * lx - ly * ly));
+	return lx * tangent + ly * bitangent + lz * n;
+}
+template <typename T>
+__device__ __forceinline__ V3<T> sphere_dir(T r0, T r1) {
+	T z = T(1) - T(2) * r0, rxy = sqrt_t(max_t(T(0), T(1) - z * z)), sn, cs;
+	sincos2pi_t(r1, &sn, &cs);
+	return mk<T>(rxy * cs, rxy * sn, z);
+}
+
+__device__ __forceinline__ int mat_texture(const MaterialRec &m, int prim_tex) {
+	int o = -1;
+	if (m.kind == MK_LAMBERTIAN || m.kind == MK_LIGHT) o = (int)m.pf[0];
+	else if (m.kind == MK_METAL) o = (int)m.pf[1];
+	return o >= 0 ? o : prim_tex;
+}
+
+// Material response. wi unit incoming, Ng geometric unit normal (either side). Returns alive.
+template <typename T>
+__device__ bool scatter(const DevScene &sc, int mat, int tex, V3<T> wi, V3<T> Ng, V3<T> P, T u, T v, Rnd4<T> r,
+	V3<T> &wo, V3<T> &att, V3<T> &emit) {
+	const MaterialRec &m = sc.mats[mat];
+	const bool front = dot(wi, Ng) < T(0);
+	const V3<T> nf = front ? Ng : -Ng;
+	emit = mk<T>(T(0), T(0), T(0));
+	att = emit;
+	wo = mk<T>(nan_t<T>(), nan_t<T>(), nan_t<T>());
+	const int kind = m.kind;
+	if (kind == MK_LIGHT) {
+		emit = mparam<T>(m, 1) * tex_eval<T>(sc, mat_texture(m, tex), u, v, P);
+		return false;
+	}
+	if (kind == MK_DIELECTRIC) {
+		T ior = mparam<T>(m, 0), ri = front ? T(1) / ior : ior;
+		T cos_t = min_t(dot(-wi, nf), T(1)), sin_t = sqrt_t(max_t(T(0), T(1) - cos_t * cos_t));
+		T r0 = (T(1) - ri) / (T(1) + ri);
+		r0 = r0 * r0;
+		T x = T(1) - cos_t, x2 = x * x;
+		T schlick = r0 + (T(1) - r0) * (x2 * x2 * x);
+		V3<T> d = (ri * sin_t > T(1) || schlick > r.x) ? reflect(wi, nf) : refract(wi, nf, ri);
+		wo = nrm(d);
+		att = mk<T>(T(1), T(1), T(1));
+		return true;
+	}
+	if (kind == MK_METAL) {
+		att = tex_eval<T>(sc, mat_texture(m, tex), u, v, P);
+		V3<T> d = nrm(reflect(wi, nf)) + mparam<T>(m, 0) * sphere_dir<T>(r.x, r.y);
+		if (!(dot(d, nf) > T(0))) return false;
+		wo = nrm(d);
+		return true;
+	}
+	if (kind == MK_REFLECTIVE && r.z < mparam<T>(m, 0)) {
+		wo = nrm(reflect(wi, nf));
+		att = mk<T>(mparam<T>(m, 1), mparam<T>(m, 2), mparam<T>(m, 3));
+		return true;
+	}
+	att = tex_eval<T>(sc, mat_texture(m, tex), u, v, P);
+	wo = nrm(cosine_dir<T>(nf, r.x, r.y));
+	return true;
+}
+
+// ---- surface resolution -------------------------------------------------------------------------------
+// Geometric unit normal (not flipped) and (u,v) of device primitive `dp` at point P, fp32 render data.
+// (a,b) = planar coordinates of P in the primitive's own (u,v) frame (ignored for spheres).
+__device__ __forceinline__ void surface_at(const DevScene &sc, int dp, V3<float> P, float a, float b, V3<float> &N, float &u, float &v) {
+	const HotPrim &h = sc.prim_plane[dp];
+	if (dp >= sc.n_tri + sc.n_quad) {
+		float inv_r = 1.0f / h.r0.w;
+		N = inv_r * (P - mk<float>(h.r0.x, h.r0.y, h.r0.z));
+		float theta = acosf(fmaxf(-1.0f, fminf(1.0f, -N.y))), phi = atan2f(-N.z, N.x) + Pi<float>::value;
+		u = phi * (0.5f / Pi<float>::value);
+		v = theta * (1.0f / Pi<float>::value);
+	} else {
+		N = mk<float>(h.r0.x, h.r0.y, h.r0.z);
+		if (dp < sc.n_tri) {
+			const float *t = sc.tri_uv + 6 * dp;
+			float b0 = 1.0f - a - b;
+			u = t[0] * b0 + t[2] * a + t[4] * b;
+			v = t[1] * b0 + t[3] * a + t[5] * b;
+		} else {
+			u = a;
+			v = b;
+		}
+	}
+}
+
+// ---- camera -------------------------------------------------------------------------------------------
+template <typename T>
+struct CamT {
+	V3<T> pos, fwd, right, up;
+	T sx, sy, lens_r, focus;
+	int jitter;
+};
+template <typename T>
+__host__ __device__ __forceinline__ CamT<T> cam_from_basis(const CamBasis &b) {
+	CamT<T> c;
+	c.pos = ld3<T>(b.pos); c.fwd = ld3<T>(b.fwd); c.right = ld3<T>(b.right); c.up = ld3<T>(b.up);
+	c.sx = T(b.sx); c.sy = T(b.sy); c.lens_r = T(b.lens_r); c.focus = T(b.focus);
+	c.jitter = b.jitter;
+	return c;
+}
+// r = (sx, sy, lens r0, lens r1); the caller substitutes sx = sy = 0.5 when jitter is off
+template <typename T>
+__device__ __forceinline__ void cam_ray(const CamT<T> &c, T inv_w, T inv_h, int x, int y, Rnd4<T> r, V3<T> &o, V3<T> &d) {
+	T fx = (T(2) * (T(x) + r.x) * inv_w - T(1)) * c.sx, fy = (T(1) - T(2) * (T(y) + r.y) * inv_h) * c.sy;
+	V3<T> dir = c.fwd + (fx * c.right + fy * c.up);
+	if (c.lens_r > T(0)) {
+		T rr = c.lens_r * sqrt_t(r.z), sn, cs;
+		sincos2pi_t(r.w, &sn, &cs);
+		V3<T> off = (rr * cs) * c.right + (rr * sn) * c.up;
+		o = c.pos + off;
+		d = nrm(c.focus * dir - off);
+	} else {
+		o = c.pos;
+		d = nrm(dir);
+	}
+}
+
+}  // namespace areb

@@ -1,0 +1,211 @@
+/* are_cuda.h — C ABI of the B200-native path-tracing core behind the Aurora Rendering Engine API.
+ *
+ * The reference (NanoEra/aurora-rendering-engine) has no FFI or plugin interface: its boundary is the C++
+ * class API under include/basic, include/material, include/object and texture.h.  This header
+ * is the thin extern "C" layer a host program calls after it has built its are::ObjectSet; every entry point
+ * names the reference interface it stands in for.  Plain pointers and sizes only — no C++ or torch types.
+ *
+ *   scene description      replaces walking  are::ObjectSet::triangles         include/object/object_set.h:10-12
+ *     are_cuda_add_triangle          <-      are::Triangle(Q,u,v,Material*,Texture*) include/object/triangle.h:19
+ *     are_cuda_add_material          <-      are::Diffuse / are::Reflective    include/material/diffuse.h:11, reflective.h:11
+ *     are_cuda_add_texture           <-      are::Texture (fill / PPM image)   include/texture.h:13-15
+ *   per-ray harness
+ *     are_cuda_hit_batch             <-      are::Object::intersect_ray        include/object/object.h:35 (src/object/triangle.cpp:82-121)
+ *     are_cuda_scatter_batch         <-      are::reflect / are::refract       include/basic/vec3.h:79-80 (src/basic/vec3.cpp:182-199)
+ *     are_cuda_camera_rays           <-      pinhole ray set-up                experiments/rt.cpp:339-343,364-366
+ *   rendering
+ *     are_cuda_render[_device]       <-      render()+trace()                  experiments/rt.cpp:251-374 (the reference's only sampling loop)
+ *     are_cuda_tonemap               <-      writePPM / Texture::save_texture  experiments/rt.cpp:377-392, src/texture.cpp:362-395
+ *
+ * Conventions: all functions return ARE_OK (0) or a negative are_status; no exception crosses this boundary
+ * (the C++ shim in include/are_cuda.hpp re-throws std::runtime_error / std::invalid_argument to match the
+ * reference's error behaviour).  Vectors are 3 consecutive doubles, exactly the layout of are::Vec3
+ * (double e_[3], include/basic/vec3.h:11).  One context drives one GPU; contexts are not thread-safe (the
+ * reference is single-threaded).  There is no CPU fallback: without a CUDA device are_cuda_create fails.
+ */
+#ifndef ARE_CUDA_H
+#define ARE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARE_CUDA_ABI_VERSION 1
+
+typedef struct are_cuda_ctx are_cuda_ctx;
+
+typedef enum are_status {
+	ARE_OK = 0,
+	ARE_ERR_INVALID_ARGUMENT = -1, /* what the reference reports as std::invalid_argument */
+	ARE_ERR_RUNTIME = -2, /* what the reference reports as std::runtime_error */
+	ARE_ERR_CUDA = -3, /* CUDA runtime / launch failure; see are_cuda_last_error */
+	ARE_ERR_NO_DEVICE = -4, /* no usable sm_100 device: there is deliberately no CPU path */
+	ARE_ERR_NOT_COMMITTED = -5, /* scene changed since the last are_cuda_commit */
+	ARE_ERR_IO = -6
+} are_status;
+
+typedef enum are_material_kind {
+	ARE_MAT_DIFFUSE = 0, /* are::Diffuse — rendered as a Lambertian surface coloured by the primitive's texture */
+	ARE_MAT_REFLECTIVE = 1, /* are::Reflective(reflectivity): mirror with probability r, Lambertian otherwise. p: [0]=reflectivity [1..3]=mirror tint */
+	ARE_MAT_LAMBERTIAN = 2, /* p: [0]=texture override (-1: use the primitive's texture) */
+	ARE_MAT_METAL = 3, /* p: [0]=fuzz [1]=texture override (-1: primitive's) */
+	ARE_MAT_DIELECTRIC = 4, /* p: [0]=index of refraction */
+	ARE_MAT_DIFFUSE_LIGHT = 5 /* p: [0]=texture override (-1: primitive's) [1]=radiance scale */
+} are_material_kind;
+
+typedef enum are_texture_kind {
+	ARE_TEX_SOLID = 0, /* p: [0..2]=rgb                      (are::Texture(w,h,fill), rt.cpp SolidTexture :85-92) */
+	ARE_TEX_CHECKER_UV = 1, /* p: [0]=scale [1..3]=even rgb [4..6]=odd rgb, on surface (u,v) (rt.cpp CheckerTexture :93-102) */
+	ARE_TEX_CHECKER_3D = 2, /* p: [0]=scale [1..3]=even rgb [4..6]=odd rgb, on floor(p/scale) */
+	ARE_TEX_NOISE = 3, /* p: [0]=scale [1]=table seed; 0.5*(1+sin(scale*p.z+10*turb(p,7))) */
+	ARE_TEX_IMAGE = 4 /* rgb = w*h*3 doubles in [0,1], row-major image_[y][x] as are::Texture holds them (src/texture.cpp:31-47) */
+} are_texture_kind;
+
+typedef enum are_integrator {
+	ARE_INTEGRATOR_PATH = 0, /* unbiased path tracer: camera jitter, spp loop, max_depth bounces */
+	ARE_INTEGRATOR_RT_AO = 1 /* the reference's experiments/rt.cpp shading: primary + 32 AO rays + one mirror bounce (+cosine gather) */
+} are_integrator;
+
+typedef enum are_traversal {
+	ARE_TRAVERSAL_AUTO = 0, /* brute force from shared memory for small scenes, BVH otherwise */
+	ARE_TRAVERSAL_BRUTE = 1,
+	ARE_TRAVERSAL_BVH = 2
+} are_traversal;
+
+typedef enum are_encoder {
+	ARE_ENCODE_GAMMA22_TRUNC = 0, /* clamp, pow(c,1/2.2)*255, truncate      experiments/rt.cpp:383-386 */
+	ARE_ENCODE_LINEAR_TRUNC = 1, /* clamp(c*255,0,255), truncate, no gamma  src/texture.cpp:384-386    */
+	ARE_ENCODE_SQRT_TRUNC = 2 /* gamma 2: int(256*clamp(sqrt(c),0,0.999)) */
+} are_encoder;
+
+/* Pinhole / thin-lens camera.  Pixel (x,y), sub-pixel offset (sx,sy) in [0,1):
+ *   fwd=normalize(target-pos); right=normalize(fwd x up); up'=right x fwd; s=tan(vfov/2); aspect=W/H
+ *   fx=(2(x+sx)/W-1)*aspect*s; fy=(1-2(y+sy)/H)*s; dir=normalize(fwd+right*fx+up'*fy)
+ * which with sx=sy=0.5 is the reference's ray set-up (experiments/rt.cpp:339-343,364-366).  With
+ * defocus_angle>0 the origin is moved on a lens disk of radius focus_dist*tan(defocus_angle/2) and the ray
+ * aims at pos+focus_dist*(fwd+right*fx+up'*fy). */
+typedef struct are_camera {
+	double pos[3];
+	double target[3];
+	double up[3];
+	double vfov_deg;
+	double focus_dist; /* > 0; 1.0 for a pinhole */
+	double defocus_angle_deg; /* 0 = pinhole */
+	int32_t jitter; /* 0: pixel centres (sx=sy=0.5); 1: sx,sy uniform in [0,1) */
+	int32_t pad_;
+} are_camera;
+
+typedef struct are_render_params {
+	int32_t width, height;
+	int32_t sample_begin; /* first GLOBAL sample index rendered by this call */
+	int32_t sample_count; /* number of samples per pixel rendered by this call */
+	int32_t max_depth; /* max ray segments per path (path integrator) */
+	int32_t integrator; /* are_integrator */
+	int32_t traversal; /* are_traversal */
+	int32_t ao_samples; /* RT_AO integrator: AO / gather rays per shaded point (reference: 32) */
+	uint64_t seed; /* Philox4x32-10 key; counter = (pixel, global sample, bounce, stream) */
+	double t_min; /* self-intersection guard: hits with t <= t_min are ignored */
+	double background_bottom[3]; /* radiance of a missed ray: lerp(bottom, top, 0.5*(dir.y+1)) */
+	double background_top[3];
+} are_render_params;
+
+/* Counters filled by the render kernels (exact, counted on the device). */
+typedef struct are_render_stats {
+	uint64_t samples; /* W*H*sample_count */
+	uint64_t rays; /* every ray segment cast, incl. bounces / AO rays */
+	uint64_t tri_tests, quad_tests, sphere_tests; /* ray-primitive tests executed */
+	uint64_t node_visits; /* BVH node (AABB pair) visits */
+	double kernel_ms; /* device time of the render kernel(s), CUDA events on the launch stream */
+	uint64_t launches; /* kernels launched by this call */
+} are_render_stats;
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int are_cuda_abi_version(void);
+int are_cuda_device_count(void); /* number of visible CUDA devices, 0 if none / no driver */
+int are_cuda_create(are_cuda_ctx **out, int device);
+void are_cuda_destroy(are_cuda_ctx *ctx);
+const char *are_cuda_last_error(are_cuda_ctx *ctx); /* ctx may be NULL: last error of a failed create */
+/* Use an existing CUDA stream (cudaStream_t passed as void*; NULL = the legacy default stream) for all work. */
+int are_cuda_set_stream(are_cuda_ctx *ctx, void *cuda_stream);
+
+/* ---- scene description (host side, cheap; nothing touches the GPU until commit) ---------------------- */
+/* Each add_* returns the new non-negative id, or a negative are_status. */
+int are_cuda_add_texture(are_cuda_ctx *ctx, int kind, const double params[8], const double *rgb, int w, int h);
+int are_cuda_add_material(are_cuda_ctx *ctx, int kind, const double params[8]);
+/* Same validation as are::Triangle's ctor (src/object/triangle.cpp:9-46): u, v and u x v must not be near_zero. */
+int are_cuda_add_triangle(are_cuda_ctx *ctx, const double Q[3], const double u[3], const double v[3], int material_id, int texture_id);
+/* Optional texture coordinates of the three vertices Q, Q+u, Q+v (default (0,0),(1,0),(0,1)). */
+int are_cuda_set_triangle_uv(are_cuda_ctx *ctx, int prim_id, const double uv[6]);
+int are_cuda_add_quad(are_cuda_ctx *ctx, const double Q[3], const double u[3], const double v[3], int material_id, int texture_id);
+int are_cuda_add_sphere(are_cuda_ctx *ctx, const double center[3], double radius, int material_id, int texture_id);
+/* Bulk forms for large scenes (arrays of n items, 3 doubles per vector); return the id of the first item added. */
+int are_cuda_add_triangles(are_cuda_ctx *ctx, int n, const double *Q, const double *u, const double *v, const int *material_id, const int *texture_id);
+int are_cuda_add_spheres(are_cuda_ctx *ctx, int n, const double *center, const double *radius, const int *material_id, const int *texture_id);
+int are_cuda_clear(are_cuda_ctx *ctx);
+int are_cuda_num_primitives(are_cuda_ctx *ctx);
+/* Flatten to SoA, build the BVH (host, binned SAH) and upload. Returns bytes uploaded via *h2d_bytes (may be NULL). */
+int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes);
+
+/* ---- per-ray harness ----------------------------------------------------------------------------------- */
+/* Closest hit of n rays against the committed scene.  D is normalised first, as are::Ray's ctor does
+ * (src/basic/ray.cpp:5).  precision: 64 = fp64 kernels with the reference's GEOMETRY_EPSILON decisions,
+ * 32 = the fp32 device routines the renderer itself uses.  traversal: are_traversal.
+ * Outputs (host pointers, any may be NULL): prim[n] (-1 = miss), t[n], P[3n] hit point, N[3n] geometric unit
+ * normal (not flipped), uv[2n] surface coordinates.  Miss => t, P, N, uv are NaN. */
+int are_cuda_hit_batch(are_cuda_ctx *ctx, int n, const double *ray_Q, const double *ray_D, double t_min,
+	int precision, int traversal, int *prim, double *t, double *P, double *N, double *uv);
+
+/* Material response for n surface interactions with explicit random numbers rnd[4n] in [0,1).
+ * wi = unit incoming direction, N = geometric unit normal (either side), P = hit point, uv = surface coords.
+ * Outputs: wo[3n] unit scattered direction (NaN when !alive), attenuation[3n], emitted[3n], alive[n]. */
+int are_cuda_scatter_batch(are_cuda_ctx *ctx, int n, const int *material_id, const int *texture_id,
+	const double *wi, const double *N, const double *P, const double *uv, const double *rnd, int precision,
+	double *wo, double *attenuation, double *emitted, int *alive);
+
+/* Texture evaluation at n points (texture_id[n], uv[2n], P[3n]) -> rgb[3n]. */
+int are_cuda_texture_batch(are_cuda_ctx *ctx, int n, const int *texture_id, const double *uv, const double *P,
+	int precision, double *rgb);
+
+/* Camera rays for n (pixel x, pixel y, sx, sy, lens r0, lens r1) tuples: px[n], py[n], rnd[4n]. */
+int are_cuda_camera_rays(are_cuda_ctx *ctx, const are_camera *cam, int width, int height, int n,
+	const int *px, const int *py, const double *rnd, int precision, double *ray_Q, double *ray_D);
+
+/* The counter-based generator itself: out[4n] = Philox4x32-10(key = seed, counter[4n]). */
+int are_cuda_philox_batch(are_cuda_ctx *ctx, int n, uint64_t seed, const uint32_t *counter, uint32_t *out);
+
+/* ---- rendering ----------------------------------------------------------------------------------------- */
+/* Adds the radiance SUM of samples [sample_begin, sample_begin+sample_count) of every pixel into
+ * accum_rgb_device (W*H*3 floats, row-major, device pointer on this context's GPU; the caller zeroes it before
+ * the first call and divides by the total spp at the end).  Asynchronous on the context's stream unless
+ * stats != NULL, in which case the call synchronises and fills *stats (count_tests != 0 additionally runs the
+ * counting variant of the kernel so tri/quad/sphere/node counters are exact; rays and samples are always counted). */
+int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_render_params *params,
+	float *accum_rgb_device, are_render_stats *stats, int count_tests);
+
+/* Whole call with HOST buffers: zero a device accumulator, render, copy W*H*3 floats (sample sums) back. */
+int are_cuda_render(are_cuda_ctx *ctx, const are_camera *cam, const are_render_params *params,
+	float *accum_rgb_host, are_render_stats *stats);
+
+/* 8-bit encode of accum/spp on the device; out_rgb8_host = W*H*3 bytes, P6 payload order. */
+int are_cuda_tonemap(are_cuda_ctx *ctx, const float *accum_rgb_device, int width, int height, double inv_spp,
+	int encoder, uint8_t *out_rgb8_host);
+/* Write a binary P6 file exactly as the reference does ("P6\n%d %d\n255\n" + payload). */
+int are_cuda_write_ppm(const char *path, int width, int height, const uint8_t *rgb8);
+
+/* Device scratch owned by the context (so hosts without a CUDA allocator can still drive render_device). */
+int are_cuda_alloc_accum(are_cuda_ctx *ctx, int width, int height, float **accum_rgb_device);
+int are_cuda_zero_accum(are_cuda_ctx *ctx, float *accum_rgb_device, int width, int height);
+int are_cuda_download_accum(are_cuda_ctx *ctx, const float *accum_rgb_device, int width, int height, float *host);
+int are_cuda_free_accum(are_cuda_ctx *ctx, float *accum_rgb_device);
+int are_cuda_synchronize(are_cuda_ctx *ctx);
+
+/* Measured FP32 FMA issue peak of this device (TFLOP/s): a register-resident FFMA micro-kernel, used as the
+ * roofline denominator next to the nominal SMs x 128 lanes x 2 x clock figure. */
+int are_cuda_measure_fp32_peak(are_cuda_ctx *ctx, double *tflops, int *sm_count, int *sm_clock_khz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARE_CUDA_H */
