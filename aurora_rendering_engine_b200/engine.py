@@ -1,0 +1,125 @@
+"""Render-job driver: one process per GPU, samples sharded across ranks, one sum-reduce of the accumulators.
+
+Partition: rank r of N renders ALL pixels for the global sample indices
+``[r*spp/N, (r+1)*spp/N)``.  Philox counters carry the global sample index, so the union over ranks is exactly
+the sample set a single GPU would draw; the only exchange is a float32 sum of the W*H*3 accumulators
+(``torch.distributed.reduce`` — NCCL over NVLink on GPUs, gloo in the CPU tests of this host logic).
+
+PyTorch is used here for device memory, streams and the process group only; every pixel is computed by
+``libare_b200.so`` through :mod:`aurora_rendering_engine_b200.capi`.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+
+
+def shard_samples(spp: int, world: int, rank: int) -> tuple[int, int]:
+    """(first global sample, count) of ``rank``; remainders go to the low ranks; disjoint and covering."""
+    if world < 1 or not (0 <= rank < world) or spp < 0:
+        raise ValueError("bad shard request")
+    base, rem = divmod(spp, world)
+    count = base + (1 if rank < rem else 0)
+    begin = rank * base + min(rank, rem)
+    return begin, count
+
+
+def chunk_ranges(begin: int, count: int, chunk: int):
+    """Split [begin, begin+count) into launches of at most ``chunk`` samples per pixel."""
+    if chunk < 1:
+        raise ValueError("chunk must be >= 1")
+    out = []
+    s = begin
+    while s < begin + count:
+        c = min(chunk, begin + count - s)
+        out.append((s, c))
+        s += c
+    return out
+
+
+def dist_env():
+    """(rank, local_rank, world) from the torchrun environment (1-process defaults)."""
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def reduce_sum_to_root(tensor, world: int, root: int = 0):
+    """In-place sum-reduce of the accumulator onto ``root`` (no-op for one rank)."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.reduce(tensor, dst=root, op=dist.ReduceOp.SUM)
+    return tensor
+
+
+@dataclass
+class JobResult:
+    accum: object          # torch tensor (H,W,3) float32 of sample sums (valid on root after finish())
+    samples: int = 0       # this rank
+    rays: int = 0          # this rank (only counted when stats are requested)
+    kernel_ms: float = 0.0
+    launches: int = 0
+
+
+class RenderJob:
+    """A scene committed on this rank's GPU plus a device accumulator; ``render_range`` adds samples into it."""
+
+    def __init__(self, scene_desc, device_index: int = 0, traversal: int = 0):
+        import torch
+        self.torch = torch
+        self.sc = scene_desc
+        self.device_index = device_index
+        torch.cuda.set_device(device_index)
+        self.ctx = capi.Context(device_index)
+        self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        scene_desc.feed(self.ctx)
+        self.h2d_bytes = self.ctx.commit()
+        self.cam = capi.make_camera(**scene_desc.camera_args())
+        self.traversal = traversal
+        self.accum = torch.zeros((scene_desc.height, scene_desc.width, 3), dtype=torch.float32, device=f"cuda:{device_index}")
+        self.result = JobResult(self.accum)
+
+    def params(self, begin, count, **over):
+        return capi.make_params(**self.sc.params_args(sample_begin=begin, sample_count=count, traversal=self.traversal, **over))
+
+    def render_range(self, begin: int, count: int, want_stats: bool = False, **over):
+        st = self.ctx.render_device(self.cam, self.params(begin, count, **over), self.accum.data_ptr(), want_stats=want_stats)
+        self.result.launches += 1
+        self.result.samples += self.sc.width * self.sc.height * count
+        if st is not None:
+            self.result.rays += st.rays
+            self.result.kernel_ms += st.kernel_ms
+        return st
+
+    def finish(self, world: int):
+        reduce_sum_to_root(self.accum, world)
+        return self.result
+
+    def image(self, total_spp: int) -> np.ndarray:
+        return (self.accum / float(total_spp)).cpu().numpy()
+
+    def save_ppm(self, path: str, total_spp: int, encoder: int = 0):
+        rgb8 = self.ctx.tonemap(self.accum.data_ptr(), self.sc.width, self.sc.height, 1.0 / total_spp, encoder)
+        self.ctx.write_ppm(path, rgb8)
+        return rgb8
+
+    def close(self):
+        self.ctx.close()
+
+
+def render_job(scene_desc, spp: int, chunk: int = 64, traversal: int = 0, want_stats: bool = False):
+    """Whole job on this rank (call under torchrun for N GPUs): shard, render in chunks, reduce. Returns RenderJob."""
+    import torch
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    job = RenderJob(scene_desc, local_rank, traversal)
+    begin, count = shard_samples(spp, world, rank)
+    for b, c in chunk_ranges(begin, count, chunk):
+        job.render_range(b, c, want_stats=want_stats)
+    job.finish(world)
+    return job

@@ -289,10 +289,12 @@ def textured(width=1920, height=1080, spp=1024, image_rgb=None):
     noise = s.tex(TEX_NOISE, 4.0, 2)
     image = s.tex(TEX_IMAGE, rgb=np.ascontiguousarray(image_rgb))
     light = s.solid(4, 4, 4)
-    s.quad((-30, 0, -30), (60, 0, 0), (0, 0, 60), lam, checker)
-    s.sphere((0, 2, 0), 2.0, lam, noise)
-    s.sphere((4.5, 2, 1.5), 2.0, lam, image)
-    s.sphere((-4.5, 1.5, 2.0), 1.5, s.mat(MAT_METAL, 0.05, -1), s.solid(0.8, 0.8, 0.9))
+    # the ground sits at y = -0.1, inside a checker cell: a surface lying exactly ON a cell boundary (y = 0) would make
+    # floor(y / scale) flip with the sign of the last rounding error, in fp64 and fp32 alike
+    s.quad((-30, -0.1, -30), (60, 0, 0), (0, 0, 60), lam, checker)
+    s.sphere((0, 1.9, 0), 2.0, lam, noise)
+    s.sphere((4.5, 1.9, 1.5), 2.0, lam, image)
+    s.sphere((-4.5, 1.4, 2.0), 1.5, s.mat(MAT_METAL, 0.05, -1), s.solid(0.8, 0.8, 0.9))
     s.quad((3, 1, -2), (2, 0, 0), (0, 2, 0), emit, light)
     s.quad((-3, 6, -3), (6, 0, 0), (0, 0, 6), emit, light)
     s.camera = dict(pos=(0, 4, 14), target=(0, 2, 0), up=(0, 1, 0), vfov_deg=35.0, focus_dist=10.0, jitter=1)

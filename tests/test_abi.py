@@ -1,0 +1,80 @@
+"""The C-ABI shared library loads on a CPU-only box and exports exactly what include/are_cuda.h declares.
+No compute call is made here (no GPU); on a box without a device are_cuda_create must fail loudly, not fall back."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from aurora_rendering_engine_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "are_cuda.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(are_cuda_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_compiles_as_c_and_cxx(tmp_path):
+    for comp, std, ext in (("gcc", "-std=c99", "c"), ("g++", "-std=c++17", "cpp")):
+        f = tmp_path / f"t.{ext}"
+        f.write_text('#include "are_cuda.h"\nint main(void){ are_camera c; are_render_params p; are_render_stats s; (void)c; (void)p; (void)s; return ARE_CUDA_ABI_VERSION - 1; }\n')
+        subprocess.run([comp, std, "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(f), "-o", str(tmp_path / "t.o")], check=True)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/are_cuda.h but not exported by libare_b200.so"
+    assert sorted(capi.SIGNATURES) == names, "capi.SIGNATURES and the header disagree"
+    assert lib.are_cuda_abi_version() == 1
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof/offsetof of the three ABI structs, as the C compiler sees them, equal the ctypes mirrors."""
+    f = tmp_path / "s.c"
+    f.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "are_cuda.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(are_camera), '
+                 'offsetof(are_camera, vfov_deg), offsetof(are_camera, jitter), sizeof(are_render_params), offsetof(are_render_params, seed), '
+                 'offsetof(are_render_params, background_top), sizeof(are_render_stats), offsetof(are_render_stats, kernel_ms));return 0;}\n')
+    exe = tmp_path / "s"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(f), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    exp = [C.sizeof(capi.Camera), capi.Camera.vfov_deg.offset, capi.Camera.jitter.offset, C.sizeof(capi.RenderParams), capi.RenderParams.seed.offset,
+           capi.RenderParams.background_top.offset, C.sizeof(capi.RenderStats), capi.RenderStats.kernel_ms.offset]
+    assert got == exp
+
+
+def test_no_cpu_fallback(lib):
+    if lib.are_cuda_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(capi.AreCudaError) as e:
+        capi.Context(0)
+    assert e.value.status == -4 and "no CPU path" in str(e.value)
+
+
+def test_product_never_touches_the_oracle():
+    """Nothing under the package or include/ may reference oracle/ (it is test infrastructure)."""
+    bad = []
+    for base in (os.path.join(ROOT, "aurora_rendering_engine_b200"), os.path.join(ROOT, "include")):
+        for dp, _, files in os.walk(base):
+            if os.sep + "lib" in dp:
+                continue
+            for fn in files:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp", "Makefile")):
+                    txt = open(os.path.join(dp, fn), errors="ignore").read()
+                    if re.search(r"liboracle|are_oracle|oracle_binding|libare_ref|from oracle|import oracle", txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad
+
+
+def test_kernels_are_built_for_sm100a_only(lib):
+    out = subprocess.run(["cuobjdump", "-lelf", capi.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
+    assert archs == {"100a"}, archs

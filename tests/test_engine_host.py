@@ -1,0 +1,87 @@
+"""Host logic of the multi-GPU job driver: sample sharding, chunking, and the N>1 reduce path on gloo (CPU)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from aurora_rendering_engine_b200 import engine, scenes
+
+
+@pytest.mark.parametrize("spp,world", [(16384, 1), (16384, 8), (1000, 3), (7, 8), (0, 4), (500, 4)])
+def test_shard_samples_cover_disjoint(spp, world):
+    seen = []
+    for r in range(world):
+        b, c = engine.shard_samples(spp, world, r)
+        assert c >= 0 and abs(c - spp / world) < 1
+        seen += list(range(b, b + c))
+    assert seen == list(range(spp))
+
+
+def test_shard_samples_rejects_bad_input():
+    for args in [(10, 0, 0), (10, 2, 2), (10, 2, -1), (-1, 2, 0)]:
+        with pytest.raises(ValueError):
+            engine.shard_samples(*args)
+
+
+def test_chunk_ranges():
+    assert engine.chunk_ranges(5, 10, 4) == [(5, 4), (9, 4), (13, 2)]
+    assert engine.chunk_ranges(0, 0, 4) == []
+    with pytest.raises(ValueError):
+        engine.chunk_ranges(0, 4, 0)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    assert engine.dist_env() == (rank, rank, world)
+    # each rank "renders" its own sample shard: here a deterministic stand-in per global sample index
+    spp, H, W = 10, 4, 5
+    b, c = engine.shard_samples(spp, world, rank)
+    acc = torch.zeros((H, W, 3), dtype=torch.float32)
+    for s in range(b, b + c):
+        acc += torch.full((H, W, 3), float(s + 1))
+    engine.reduce_sum_to_root(acc, world)
+    q.put((rank, acc.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_reduce_on_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.all(res[0] == sum(range(1, 11)))  # root holds the sum over ALL samples 1..10
+
+
+def test_scene_generators_shapes():
+    s = scenes.rt_cornell()
+    assert s.num_prims == 34 and len(s.tris) == 34  # experiments/rt.cpp:153-185: 5 quads + 2 boxes = 17 quads
+    s = scenes.cornell_box()
+    assert s.num_prims == 36 and (s.width, s.height, s.spp, s.max_depth) == (2048, 2048, 16384, 50)
+    assert scenes.cornell_box(as_quads=True).num_prims == 6 + 24
+    s = scenes.rtiow_final()
+    assert 470 <= s.num_prims <= 490 and (s.width, s.height, s.spp) == (1200, 675, 500)
+    s = scenes.textured()
+    assert (s.width, s.height, s.spp) == (1920, 1080, 1024) and s.textures[2][2].shape == (512, 1024, 3)
+    s = scenes.stress(n_prims=2000)
+    assert s.num_prims == 2000 and len(s.spheres) == 1000 and len(s.tris) == 1000
+    img = scenes.synthetic_image(8, 4)
+    assert img[3, 5].tolist() == [5, 3, 5 ^ 3]
+
+
+def test_scene_feeds_the_cpu_twin(oracle):
+    for sc in (scenes.rt_cornell(), scenes.cornell_box(), scenes.textured(width=8, height=8), scenes.stress(n_prims=100)):
+        osc = sc.feed(oracle.scene())
+        assert osc.num_primitives() == sc.num_prims

@@ -1,0 +1,300 @@
+"""Per-ray parity (north_star check (a)): identical precomputed rays and random numbers go to the CPU oracle and,
+through the C ABI, to the CUDA kernels.
+
+precision=64 kernels reproduce the reference's decisions: the winning primitive, t and the hit point must be
+BIT-IDENTICAL (the oracle itself is pinned bit-for-bit to the real reference in test_oracle_vs_reference.py).
+precision=32 kernels are the render loop's own routines: t / normal / scattered direction within 1e-5 relative
+on rays that are not within 1e-4 of an accept/reject threshold (SURVEY.md §7 "hard parts").
+"""
+import numpy as np
+import pytest
+
+from aurora_rendering_engine_b200 import capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+REL32 = 1e-5  # the north_star's per-ray tolerance
+
+
+def _rays(n, seed, scale=0.3):
+    rng = np.random.RandomState(seed)
+    return scale * rng.uniform(-1, 1, (n, 3)), rng.uniform(-1, 1, (n, 3))
+
+
+def _mixed_scene():
+    s = scenes.SceneDesc("mixed")
+    lam = s.mat(scenes.MAT_LAMBERTIAN, -1)
+    met = s.mat(scenes.MAT_METAL, 0.3, -1)
+    gl = s.mat(scenes.MAT_DIELECTRIC, 1.5)
+    refl = s.mat(scenes.MAT_REFLECTIVE, 0.6, 0.9, 0.8, 0.7)
+    dif = s.mat(scenes.MAT_DIFFUSE)
+    lit = s.mat(scenes.MAT_DIFFUSE_LIGHT, -1, 2.0)
+    grey = s.solid(0.5, 0.6, 0.7)
+    chk = s.tex(scenes.TEX_CHECKER_UV, 8, 0.9, 0.9, 0.9, 0.1, 0.1, 0.1)
+    chk3 = s.tex(scenes.TEX_CHECKER_3D, 0.32, .2, .3, .1, .9, .9, .9)
+    noise = s.tex(scenes.TEX_NOISE, 4.0, 2)
+    img = s.tex(scenes.TEX_IMAGE, rgb=scenes.synthetic_image(64, 32).astype(np.float64) / 255.0)
+    rng = np.random.RandomState(7)
+    mats = [lam, met, gl, refl, dif, lit]
+    texs = [grey, chk, chk3, noise, img]
+    for i in range(40):
+        c = rng.uniform(-2, 2, 3)
+        kind = i % 3
+        m, t = mats[i % len(mats)], texs[i % len(texs)]
+        if kind == 0:
+            s.sphere(c, rng.uniform(0.1, 0.5), m, t)
+        elif kind == 1:
+            s.quad(c, rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 3), m, t)
+        else:
+            s.tri(c, rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 3), m, t, uv=rng.uniform(0, 1, 6))
+    # a parallelogram split into two triangles (exercises the fused-pair path)
+    s.quad_as_tris((-3, -3, -3), (3, -3, -3), (3, -3, 3), (-3, -3, 3), lam, chk)
+    s.camera = dict(pos=(0, 0, 8), target=(0, 0, 0), vfov_deg=40.0, focus_dist=8.0, defocus_angle_deg=1.0, jitter=1)
+    return s
+
+
+def _feed_both(sc, ctx, oracle):
+    sc.feed(ctx)
+    ctx.commit()
+    return sc.feed(oracle.scene())
+
+
+def test_hit64_bit_exact_triangles(ctx, oracle):
+    """34-triangle rt.cpp Cornell set, the survey's ray distribution (Q in 0.3*U(-1,1)^3, D in U(-1,1)^3)."""
+    sc = scenes.rt_cornell()
+    osc = _feed_both(sc, ctx, oracle)
+    Q, D = _rays(200_000, 12345)
+    prim, t, P, N, uv = ctx.hit_batch(Q, D, t_min=0.0, precision=64)
+    oprim, ot, oP, oN, ouv = osc.hit_batch(Q, D, 0.0)
+    assert np.array_equal(prim, oprim)
+    hit = oprim >= 0
+    assert hit.sum() > 100_000
+    assert np.array_equal(t[hit], ot[hit]), "t not bit-identical"
+    assert np.array_equal(P[hit], oP[hit]), "hit point not bit-identical"
+    assert np.array_equal(N[hit], oN[hit])
+    assert np.allclose(uv[hit], ouv[hit], rtol=0, atol=1e-15)
+    assert np.isnan(t[~hit]).all() and np.isnan(P[~hit]).all()
+
+
+def test_hit64_bit_exact_mixed_primitives(ctx, oracle):
+    sc = _mixed_scene()
+    osc = _feed_both(sc, ctx, oracle)
+    Q, D = _rays(100_000, 5, scale=3.0)
+    for tmin in (0.0, 1e-3):
+        prim, t, P, N, uv = ctx.hit_batch(Q, D, t_min=tmin, precision=64)
+        oprim, ot, oP, oN, ouv = osc.hit_batch(Q, D, tmin)
+        assert np.array_equal(prim, oprim)
+        hit = oprim >= 0
+        assert np.array_equal(t[hit], ot[hit])
+        assert np.array_equal(P[hit], oP[hit])
+        assert np.allclose(N[hit], oN[hit], rtol=0, atol=1e-15)
+        assert np.allclose(uv[hit], ouv[hit], rtol=0, atol=1e-12)  # acos/atan2 last-ulp differences only
+
+
+@pytest.mark.parametrize("traversal", [1, 2])
+@pytest.mark.parametrize("scene_name", ["rt_cornell", "cornell_box", "mixed"])
+def test_hit32_within_tolerance(ctx, oracle, scene_name, traversal):
+    sc = _mixed_scene() if scene_name == "mixed" else scenes.by_name(scene_name)
+    osc = _feed_both(sc, ctx, oracle)
+    if scene_name == "cornell_box":
+        rng = np.random.RandomState(3)
+        Q = rng.uniform(100, 450, (100_000, 3))
+        D = rng.uniform(-1, 1, (100_000, 3))
+    else:
+        Q, D = _rays(100_000, 11, scale=0.3 if scene_name == "rt_cornell" else 3.0)
+    prim, t, P, N, uv = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=traversal)
+    oprim, ot, oP, oN, ouv = osc.hit_batch(Q, D, 1e-3)
+    # Coincident surfaces (the Cornell boxes stand ON the floor: their bottom faces lie in the floor plane) tie in t;
+    # which of the two is reported is decided by rounding noise in fp64 and fp32 alike, so an id difference at equal t
+    # is not a decision mismatch.
+    both = (prim >= 0) & (oprim >= 0)
+    tie = both & (np.abs(t - ot) <= 1e-5 * np.maximum(1.0, np.abs(ot)))
+    real_mism = (prim != oprim) & ~tie
+    ok = (prim == oprim) & (oprim >= 0)
+    Dn = D / np.linalg.norm(D, axis=1, keepdims=True)
+    # fp32 carries ~6e-8 of the LARGEST magnitude entering the computation (ray origin / hit point coordinates), so
+    # the 1e-5 bound is relative to max(t, |origin|, |hit point|); grazing rays (|N.D| < 0.05) amplify it and are excluded.
+    mag = np.maximum.reduce([np.abs(ot[ok]), np.abs(Q[ok]).max(axis=1), np.abs(oP[ok]).max(axis=1)])
+    rel_t = np.abs(t[ok] - ot[ok]) / mag
+    cond = np.abs(np.sum(oN[ok] * Dn[ok], axis=1)) > 0.05
+    nerr = np.linalg.norm(N[ok] - oN[ok], axis=1)
+    perr = np.linalg.norm(P[ok] - oP[ok], axis=1) / mag
+    rep = dict(mismatch=real_mism.mean(), ties=(tie & (prim != oprim)).mean(), cond_frac=cond.mean(), max_rel_t=rel_t[cond].max(),
+               max_n=nerr[cond].max(), max_p=perr[cond].max(), p999_rel_t_all=np.percentile(rel_t, 99.9), hit_frac=(oprim >= 0).mean())
+    msg = ", ".join(f"{k}={v:.3g}" for k, v in rep.items())
+    print(f"[hit32 {scene_name} trav={traversal}] {msg}")
+    # real decision flips happen only for rays grazing an edge / tangent: must be rare
+    assert rep["mismatch"] < 5e-4, msg
+    assert rep["cond_frac"] > 0.8, msg
+    assert rep["max_rel_t"] < REL32, msg
+    assert rep["max_n"] < REL32, msg
+    assert rep["max_p"] < REL32, msg
+    assert rep["p999_rel_t_all"] < 1e-4, msg
+
+
+def test_bvh_and_brute_agree(ctx, oracle):
+    sc = scenes.rtiow_final(width=64, height=36, spp=1)
+    sc.feed(ctx)
+    ctx.commit()
+    rng = np.random.RandomState(2)
+    Q = np.tile(np.array([13.0, 2.0, 3.0]), (200_000, 1)) + rng.uniform(-0.05, 0.05, (200_000, 3))
+    D = -Q + rng.uniform(-6, 6, (200_000, 3)) * np.array([1.0, 0.3, 1.0])
+    pb, tb, *_ = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=1)
+    pv, tv, *_ = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=2)
+    assert (pb >= 0).mean() > 0.5
+    assert np.array_equal(pb, pv)
+    assert np.array_equal(tb[pb >= 0], tv[pv >= 0])  # same arithmetic, different visiting order
+
+
+def _scatter_inputs(sc, n, seed):
+    rng = np.random.RandomState(seed)
+    nm, nt = len(sc.materials), len(sc.textures)
+    mat = rng.randint(0, nm, n).astype(np.int32)
+    tex = rng.randint(0, nt, n).astype(np.int32)
+    wi = rng.normal(size=(n, 3))
+    wi /= np.linalg.norm(wi, axis=1, keepdims=True)
+    N = rng.normal(size=(n, 3))
+    N /= np.linalg.norm(N, axis=1, keepdims=True)
+    P = rng.uniform(-3, 3, (n, 3))
+    uv = rng.uniform(0, 1, (n, 2))
+    rnd = rng.randint(0, 1 << 24, (n, 4)).astype(np.float64) / float(1 << 24)
+    return mat, tex, wi, N, P, uv, rnd
+
+
+def test_scatter64_matches_oracle(ctx, oracle):
+    sc = _mixed_scene()
+    osc = _feed_both(sc, ctx, oracle)
+    args = _scatter_inputs(sc, 100_000, 21)
+    wo, att, emit, alive = ctx.scatter_batch(*args, precision=64)
+    owo, oatt, oemit, oalive = osc.scatter_batch(*args)
+    assert np.array_equal(alive, oalive)
+    a = oalive == 1
+    assert np.allclose(wo[a], owo[a], rtol=0, atol=1e-12)
+    assert np.isnan(wo[~a]).all()
+    # image texels are stored as fp32 on the device (1e-8 quantisation); everything else is fp64 end to end
+    kinds = np.array([t_[0] for t_ in sc.textures])
+    mats = np.array([m_[0] for m_ in sc.materials])
+    eff_tex = np.array([(int(sc.materials[m][1][0]) if mats[m] in (scenes.MAT_LAMBERTIAN, scenes.MAT_DIFFUSE_LIGHT) else
+                         int(sc.materials[m][1][1]) if mats[m] == scenes.MAT_METAL else -1) for m in args[0]])
+    eff_tex = np.where(eff_tex >= 0, eff_tex, args[1])
+    img = kinds[eff_tex] == scenes.TEX_IMAGE
+    assert np.abs(att - oatt)[~img].max() < 1e-12 and np.abs(att - oatt)[img].max() < 1e-7
+    assert np.abs(emit - oemit)[~img].max() < 1e-12 and np.abs(emit - oemit)[img].max() < 1e-6
+
+
+def test_scatter32_within_tolerance(ctx, oracle):
+    sc = _mixed_scene()
+    osc = _feed_both(sc, ctx, oracle)
+    args = _scatter_inputs(sc, 100_000, 22)
+    wo, att, emit, alive = ctx.scatter_batch(*args, precision=32)
+    owo, oatt, oemit, oalive = osc.scatter_batch(*args)
+    flips = alive != oalive
+    assert flips.mean() < 1e-4
+    a = (oalive == 1) & ~flips
+    err = np.linalg.norm(wo[a] - owo[a], axis=1)
+    # dielectric reflect-vs-refract and Reflective lobe choice flip only when a random number sits within fp32 eps of a threshold
+    big = err > REL32
+    assert big.mean() < 1e-4, f"{big.mean():.2e} of scattered directions differ by more than 1e-5"
+    # colours: checker / image lookups may flip at a cell boundary, noise is smooth
+    cerr = np.abs(att - oatt).max(axis=1)
+    assert (cerr > 1e-4).mean() < 2e-3
+    assert np.allclose(emit[~flips], oemit[~flips], rtol=1e-4, atol=1e-4) or (np.abs(emit - oemit).max(axis=1) > 1e-4).mean() < 2e-3
+
+
+def test_reflect_refract_against_library_values(ctx, oracle):
+    """Metal fuzz 0 == are::reflect, dielectric refraction == are::refract (the SURVEY §8c known answers included)."""
+    s = scenes.SceneDesc("m")
+    white = s.solid(1, 1, 1)
+    mirror = s.mat(scenes.MAT_METAL, 0.0, -1)
+    glass = s.mat(scenes.MAT_DIELECTRIC, 1.5)
+    s.tri((0, 0, 0), (1, 0, 0), (0, 1, 0), mirror, white)
+    s.feed(ctx)
+    ctx.commit()
+    wi = np.array([[1, -1, 0]], float) / np.sqrt(2)
+    N = np.array([[0, 1, 0]], float)
+    z3, z2 = np.zeros((1, 3)), np.zeros((1, 2))
+    wo, *_ = ctx.scatter_batch([mirror], [white], wi, N, z3, z2, np.zeros((1, 4)), precision=64)
+    assert np.allclose(wo[0], oracle.reflect(wi, N)[0] / np.linalg.norm(oracle.reflect(wi, N)[0]), atol=1e-15)
+    assert np.allclose(wo[0], np.array([1, 1, 0]) / np.sqrt(2), atol=1e-15)
+    # rnd.x = 0.999 > schlick -> refraction, front face: eta = 1/1.5
+    wo, *_ = ctx.scatter_batch([glass], [white], wi, N, z3, z2, np.array([[0.999, 0, 0, 0]]), precision=64)
+    lib = oracle.refract(wi, N, [1 / 1.5])[0]
+    assert np.allclose(lib, [0.47140452079103162, -0.88191710368819698, 0.0], atol=1e-15)
+    assert np.allclose(wo[0], lib / np.linalg.norm(lib), atol=1e-14)
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-12), (32, 2e-5)])
+def test_texture_batch(ctx, oracle, precision, tol):
+    sc = _mixed_scene()
+    osc = _feed_both(sc, ctx, oracle)
+    rng = np.random.RandomState(4)
+    n = 50_000
+    tex = rng.randint(0, len(sc.textures), n).astype(np.int32)
+    uv = rng.uniform(-0.2, 1.2, (n, 2))
+    P = rng.uniform(-3, 3, (n, 3))
+    rgb = ctx.texture_batch(tex, uv, P, precision=precision)
+    orgb = osc.texture_batch(tex, uv, P)
+    err = np.abs(rgb - orgb).max(axis=1)
+    if precision == 64:
+        img = np.array([sc.textures[t][0] == scenes.TEX_IMAGE for t in tex])
+        assert err[~img].max() < tol
+        assert err[img].max() < 1e-7   # texels are held as fp32 on the device
+    else:
+        assert (err > tol * 50).mean() < 2e-3  # cell-boundary flips of the checker / nearest-texel lookups only
+        assert np.median(err) < tol
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-13), (32, 1e-5)])
+def test_camera_rays(ctx, oracle, precision, tol):
+    rng = np.random.RandomState(9)
+    n = 50_000
+    for cam_args, W, H in [
+        (dict(pos=(0, 0, 4), target=(0, 0, 0), up=(0, 1, 0), vfov_deg=50.0, jitter=0), 512, 512),  # rt.cpp:399
+        (dict(pos=(13, 2, 3), target=(0, 0, 0), up=(0, 1, 0), vfov_deg=20.0, focus_dist=10.0, defocus_angle_deg=0.6, jitter=1), 1200, 675),
+    ]:
+        cam = capi.make_camera(**cam_args)
+        px, py = rng.randint(0, W, n).astype(np.int32), rng.randint(0, H, n).astype(np.int32)
+        rnd = rng.randint(0, 1 << 24, (n, 4)).astype(np.float64) / float(1 << 24)
+        if not cam.jitter:
+            rnd[:, :2] = 0.5
+        Q, D = ctx.camera_rays(cam, W, H, px, py, rnd, precision=precision)
+        oQ, oD = oracle.camera_rays(cam, W, H, px, py, rnd)
+        assert np.abs(Q - oQ).max() < tol * 20
+        assert np.abs(D - oD).max() < tol
+
+
+def test_philox_matches_oracle_and_kat(ctx, oracle):
+    rng = np.random.RandomState(0)
+    ctr = rng.randint(0, 1 << 32, (10_000, 4), dtype=np.uint64).astype(np.uint32)
+    for seed in (0, 1, 0x299F31D0A4093822):
+        assert np.array_equal(ctx.philox_batch(seed, ctr), oracle.philox(seed, ctr))
+    # Random123 known answers (philox4x32-10)
+    kat = ctx.philox_batch(0, np.zeros((1, 4), np.uint32))[0]
+    assert [hex(x) for x in kat] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    kat = ctx.philox_batch(0xFFFFFFFFFFFFFFFF, np.full((1, 4), 0xFFFFFFFF, np.uint32))[0]
+    assert [hex(x) for x in kat] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+
+
+def test_error_behaviour(ctx):
+    """Reference conventions carried across the ABI: invalid triangles are refused like are::Triangle's ctor does."""
+    with pytest.raises(capi.AreCudaError) as e:
+        ctx.hit_batch(np.zeros((1, 3)), np.ones((1, 3)))
+    assert e.value.status == -5  # not committed
+    tex = ctx.add_texture(scenes.TEX_SOLID, [1, 1, 1, 0, 0, 0, 0, 0])
+    mat = ctx.add_material(scenes.MAT_DIFFUSE, np.zeros(8))
+    for Q, u, v, msg in [((0, 0, 0), (0, 0, 0), (0, 1, 0), "u cannot be zero"), ((0, 0, 0), (1, 0, 0), (0, 0, 0), "v cannot be zero"),
+                         ((0, 0, 0), (1, 0, 0), (2, 0, 0), "collinear")]:
+        with pytest.raises(capi.AreCudaError) as e:
+            ctx.add_triangle(Q, u, v, mat, tex)
+        assert e.value.status == -1 and msg in str(e.value)
+    with pytest.raises(capi.AreCudaError, match="Material pointer cannot be null"):
+        ctx.add_triangle((0, 0, 0), (1, 0, 0), (0, 1, 0), 99, tex)
+    with pytest.raises(capi.AreCudaError, match="Texture pointer cannot be null"):
+        ctx.add_triangle((0, 0, 0), (1, 0, 0), (0, 1, 0), mat, -1)
+    with pytest.raises(capi.AreCudaError, match="must be positive"):
+        ctx.add_texture(scenes.TEX_IMAGE, np.zeros(8), np.zeros((0, 0, 3)))
+    assert ctx.num_primitives() == 0
+    # empty scene renders the background only
+    ctx.commit()
+    prim, t, *_ = ctx.hit_batch(np.zeros((4, 3)), np.ones((4, 3)))
+    assert (prim == -1).all() and np.isnan(t).all()
