@@ -315,7 +315,7 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	if ((st = upload(ctx, cs.vec, &d.field, bytes)) != ARE_OK) return st;
 	UP(brute, brute) UP(brute_ids, brute_ids) UP(bvh_prims, bvh_prims) UP(bvh_ids, bvh_ids) UP(nodes, nodes)
 	UP(info, info) UP(prim_plane, prim_plane) UP(tri_uv, tri_uv) UP(tri64, tri64) UP(quad64, quad64) UP(sph64, sph64)
-	UP(tri_uv64, tri_uv64) UP(mats, mats) UP(texs, texs) UP(tex_data, tex_data)
+	UP(tri_uv64, tri_uv64) UP(mats, mats) UP(texs, texs) UP(tex_data, tex_data) UP(rt_tris, rt_tris)
 #undef UP
 	d.brute_range = cs.brute_range;
 	d.n_nodes = (int)cs.nodes.size();
@@ -459,7 +459,10 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 	a.counters = ctx->d_counters;
 	bool use_bvh = false;
 	if (p->integrator == ARE_INTEGRATOR_RT_AO) {
-		if (!ctx->dev.brute) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "RT_AO integrator needs a scene that fits the brute-force list");
+		// experiments/rt.cpp knows triangles only, tested by linear scan from shared memory
+		if (ctx->cs.n_tri == 0 || ctx->cs.n_quad != 0 || ctx->cs.n_sph != 0 || ctx->cs.n_tri > 1000)
+			return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "RT_AO integrator renders triangle-only scenes of at most 1000 triangles");
+		make_rt_cam(cam->pos, cam->target, cam->up, cam->vfov_deg, p->width, p->height, a.rtcam);
 	} else if (p->integrator != ARE_INTEGRATOR_PATH) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown integrator");
 	else if (!resolve_traversal(ctx, p->traversal, use_bvh)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "scene too large for brute-force traversal");
 	CK(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * sizeof(unsigned long long), ctx->stream));

@@ -79,6 +79,9 @@ struct DevScene {
 	const PrimInfo *info;
 	const HotPrim *prim_plane; // plane form (or sphere record) of every user primitive, device order
 	const float *tri_uv;       // 6 floats per triangle
+	// rt.cpp-style fp32 triangle records for the RT_AO integrator, 3 x float4 per triangle:
+	//   (v0.xyz, e1.x) (e1.yz, e2.xy) (e2.z, n.xyz)   with n = normalize(e1 x e2) computed in fp32 as rt.cpp:121 does
+	const f4 *rt_tris;
 	int n_tri, n_quad, n_sph;
 	// --- fp64 harness data (host values, untouched) ---
 	const double *tri64;       // 9 doubles per triangle: Q, u, v
@@ -97,6 +100,12 @@ struct CamBasis {
 	double pos[3], fwd[3], right[3], up[3];
 	double sx, sy, lens_r, focus;
 	int jitter, pad_;
+};
+
+// camera of the RT_AO integrator: the basis computed in fp32 with the very operations of experiments/rt.cpp:339-343
+struct RtCam {
+	float pos[3], fwd[3], right[3], up[3];
+	float aspect, scale;
 };
 
 }  // namespace areb

@@ -4,9 +4,11 @@
 // Ray directions are unit length (are::Ray's convention, /root/reference/src/basic/ray.cpp:5), so t is the
 // geometric distance.  Triangles and parallelograms are held in the 48-byte plane form of dev_types.h: the
 // same hit the reference's Möller–Trumbore routine finds (src/object/triangle.cpp:82-121 — two-sided, no
-// culling), evaluated as plane distance + two planar coordinates, 16 FP32 instructions + one MUFU.RCP instead
-// of ~27 + RCP.  A hot quad may stand for a fused pair of coplanar triangles forming a parallelogram; the
-// owning triangle is recovered after the loop from alpha >= beta.
+// culling), evaluated as plane distance + two planar coordinates: 15 FFMA/FMUL + one MUFU.RCP + 4 compares +
+// 2 selects per test (the reference's formulation needs ~27 + RCP + 7 + 4).  A hot quad may stand for a fused
+// pair of coplanar triangles forming a parallelogram; the owning triangle is recovered after the loop.
+//
+// The loop keeps only (t, index) of the best candidate; planar coordinates are recomputed once for the winner.
 #pragma once
 #include "dev_types.h"
 #include "vec.cuh"
@@ -16,38 +18,63 @@ namespace areb {
 struct Hit {
 	float t;   // closest distance so far (INFINITY = none)
 	int idx;   // index into the hot array traversed (-1 = miss)
-	float a, b;  // planar coordinates in the hot primitive's frame
 };
 
 __device__ __forceinline__ float4 ldg4(const f4 *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ float4 lds4(const f4 *p) { return *reinterpret_cast<const float4 *>(p); }
 
-// One plane-form test. QUAD: accept alpha,beta in [0,1]; else triangle: alpha,beta >= 0, alpha+beta <= 1.
-template <bool QUAD>
-__device__ __forceinline__ void test_plane(float4 r0, float4 r1, float4 r2, V3<float> o, V3<float> d, float tmin, int idx, Hit &h) {
-	float denom = r0.x * d.x + r0.y * d.y + r0.z * d.z;
-	float num = r0.w - (r0.x * o.x + r0.y * o.y + r0.z * o.z);
-	float t = __fdividef(num, denom);  // denom == 0 -> inf/NaN, rejected by the window test below
-	float px = fmaf(t, d.x, o.x), py = fmaf(t, d.y, o.y), pz = fmaf(t, d.z, o.z);
-	float a = r1.x * px + r1.y * py + r1.z * pz - r1.w;
-	float b = r2.x * px + r2.y * py + r2.z * pz - r2.w;
-	bool ok = (t > tmin) & (t < h.t) & (a >= 0.0f) & (b >= 0.0f);
-	if (QUAD) ok = ok & (a <= 1.0f) & (b <= 1.0f);
-	else ok = ok & (a + b <= 1.0f);
-	if (ok) { h.t = t; h.idx = idx; h.a = a; h.b = b; }
+// single MUFU.RCP; rcp(0) = inf, so a ray parallel to the plane gives t = +-inf / NaN and fails the window test
+__device__ __forceinline__ float rcp_fast(float x) {
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+__device__ __forceinline__ float sqrt_fast(float x) {
+	float r;
+	asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
 }
 
-// Sphere: r0 = (c, r), r1.x = r*r. oc = c - o; h = d·oc; c = |oc|^2 - r^2; disc = h^2 - c (|d| = 1)
+// planar coordinates of point p in a plane-form record
+__device__ __forceinline__ void plane_coords(float4 r1, float4 r2, V3<float> p, float &a, float &b) {
+	a = fmaf(r1.x, p.x, fmaf(r1.y, p.y, fmaf(r1.z, p.z, -r1.w)));
+	b = fmaf(r2.x, p.x, fmaf(r2.y, p.y, fmaf(r2.z, p.z, -r2.w)));
+}
+
+// One plane-form test. QUAD: accept alpha,beta in [0,1]; else triangle: alpha,beta >= 0, alpha+beta <= 1.
+// Range checks run on the float bit patterns: x in [0,1]  <=>  bits(x) <= 0x3f800000 as unsigned (negative
+// values have the sign bit set, NaN is above 0x7f800000), so two coordinates cost one UMAX + one ISETP.
+template <bool QUAD>
+__device__ __forceinline__ void test_plane(float4 r0, float4 r1, float4 r2, V3<float> o, V3<float> d, float tmin, int idx, Hit &h) {
+	float denom = fmaf(r0.x, d.x, fmaf(r0.y, d.y, r0.z * d.z));
+	float num = fmaf(-r0.x, o.x, fmaf(-r0.y, o.y, fmaf(-r0.z, o.z, r0.w)));
+	float t = num * rcp_fast(denom);
+	V3<float> p = mk<float>(fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z));
+	float a, b;
+	plane_coords(r1, r2, p, a, b);
+	bool ok = (t > tmin) & (t < h.t);
+	if (QUAD) {
+		ok = ok & (max(__float_as_uint(a), __float_as_uint(b)) <= 0x3f800000u);
+	} else {
+		float c = 1.0f - (a + b);
+		ok = ok & ((int)(__float_as_uint(a) | __float_as_uint(b) | __float_as_uint(c)) >= 0);
+	}
+	if (ok) { h.t = t; h.idx = idx; }
+}
+
+// Sphere: r0 = (c, r), r1.x = r*r.  Discriminant from the perpendicular offset l = oc - (oc·d)d, i.e.
+// disc = r^2 - |l|^2 (Haines et al., "Precision improvements for ray/sphere intersection"): no h^2 - |oc|^2
+// cancellation, so small spheres far from the origin and huge spheres under the origin both keep fp32 accuracy.
 __device__ __forceinline__ void test_sphere(float4 r0, float4 r1, V3<float> o, V3<float> d, float tmin, int idx, Hit &h) {
 	float ox = r0.x - o.x, oy = r0.y - o.y, oz = r0.z - o.z;
-	float hh = d.x * ox + d.y * oy + d.z * oz;
-	float c = ox * ox + oy * oy + oz * oz - r1.x;
-	float disc = hh * hh - c;
-	float sq = sqrtf(fmaxf(disc, 0.0f));
+	float hh = fmaf(d.x, ox, fmaf(d.y, oy, d.z * oz));
+	float lx = fmaf(-hh, d.x, ox), ly = fmaf(-hh, d.y, oy), lz = fmaf(-hh, d.z, oz);
+	float disc = r1.x - fmaf(lx, lx, fmaf(ly, ly, lz * lz));
+	float sq = sqrt_fast(fmaxf(disc, 0.0f));
 	float t0 = hh - sq, t1 = hh + sq;
-	float t = (t0 > tmin) ? t0 : t1;  // nearest root inside the window (t0 < t1 always)
+	float t = (t0 > tmin) ? t0 : t1;  // nearest root inside the window (t0 <= t1)
 	bool ok = (disc >= 0.0f) & (t > tmin) & (t < h.t);
-	if (ok) { h.t = t; h.idx = idx; h.a = 0.0f; h.b = 0.0f; }
+	if (ok) { h.t = t; h.idx = idx; }
 }
 
 // Test a type-sorted run of hot primitives. LD = ldg4 (global / L2) or lds4 (shared-memory copy).
@@ -136,19 +163,34 @@ __device__ __forceinline__ void intersect_bvh(const DevScene &sc, V3<float> o, V
 // ---- map a hot hit back to the user primitive ---------------------------------------------------------
 struct Resolved {
 	int dev_prim;   // device primitive index (device order: triangles, quads, spheres)
-	float a, b;     // planar coordinates in that primitive's own frame
+	float a, b;     // planar coordinates in that primitive's own frame (0 for spheres)
 };
-__device__ __forceinline__ Resolved resolve_hit(const DevScene &sc, const HotIds *ids, const Hit &h, V3<float> P) {
+// hot = the array (shared or global) the winning index refers to; spheres carry no planar coordinates
+__device__ __forceinline__ Resolved resolve_hit(const DevScene &sc, const HotIds *ids, int idx, V3<float> P) {
 	Resolved r;
-	HotIds id = ids[h.idx];
-	r.a = h.a;
-	r.b = h.b;
+	const HotIds id = ids[idx];
 	r.dev_prim = id.a;
-	if (id.b >= 0) {  // fused pair: pick the triangle, recompute its own barycentrics from its plane form
-		r.dev_prim = (h.a >= h.b) ? id.a : id.b;
-		const HotPrim &tp = sc.prim_plane[r.dev_prim];
-		r.a = tp.r1.x * P.x + tp.r1.y * P.y + tp.r1.z * P.z - tp.r1.w;
-		r.b = tp.r2.x * P.x + tp.r2.y * P.y + tp.r2.z * P.z - tp.r2.w;
+	r.a = 0.0f;
+	r.b = 0.0f;
+	if (id.a < sc.n_tri + sc.n_quad) {
+		if (id.b >= 0) {
+			// fused pair: the hot parallelogram is (d0; a - d0; b - d0) with triangle id.a on the alpha >= beta side.
+			// Both triangles are coplanar with it, so deciding on the pair's own coordinates = deciding on which side
+			// of the shared diagonal P lies; use triangle id.a's barycentrics: inside it <=> all three >= 0.
+			const HotPrim &ta = sc.prim_plane[id.a];
+			float a0, b0;
+			plane_coords(*reinterpret_cast<const float4 *>(&ta.r1), *reinterpret_cast<const float4 *>(&ta.r2), P, a0, b0);
+			const bool in_a = (a0 >= 0.0f) & (b0 >= 0.0f) & (a0 + b0 <= 1.0f);
+			if (in_a) { r.a = a0; r.b = b0; }
+			else {
+				r.dev_prim = id.b;
+				const HotPrim &tb = sc.prim_plane[id.b];
+				plane_coords(*reinterpret_cast<const float4 *>(&tb.r1), *reinterpret_cast<const float4 *>(&tb.r2), P, r.a, r.b);
+			}
+		} else {
+			const HotPrim &tp = sc.prim_plane[id.a];
+			plane_coords(*reinterpret_cast<const float4 *>(&tp.r1), *reinterpret_cast<const float4 *>(&tp.r2), P, r.a, r.b);
+		}
 	}
 	return r;
 }

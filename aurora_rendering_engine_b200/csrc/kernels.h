@@ -11,6 +11,7 @@ namespace areb {
 struct RenderArgs {
 	DevScene sc;
 	CamBasis cam;
+	RtCam rtcam;     // RT_AO integrator only
 	PhiloxKey key;   // the ten round keys of the render seed (constant-bank operands in the kernel)
 	int W, H;
 	int s_begin, s_count;

@@ -6,8 +6,7 @@
 //                   shared-memory copy of the hot primitives, or BVH2 from L2), material scatter, texture
 //                   evaluation, accumulation.  Replaces render()+trace() of the reference's only sampling
 //                   renderer (/root/reference/experiments/rt.cpp:251-374) as a general path tracer.
-//   k_render_rtao   the reference's own shading (rt.cpp:221-334: primary + AO rays + one mirror bounce + cosine
-//                   gather with Russian roulette), same arithmetic, Philox instead of mt19937.
+//   (k_render_rtao, the reference's own rt.cpp shading loop, lives in rtao.cu.)
 //   k_hit32 / k_scatter32 / k_texture32 / k_camera32   per-ray harness over the SAME device routines.
 //   k_tonemap       reference encoders (rt.cpp:383-386 gamma 2.2 truncate; src/texture.cpp:384-386 linear truncate).
 //   k_fp32_peak     FFMA issue-rate micro-kernel (roofline denominator).
@@ -25,7 +24,7 @@ namespace areb {
 typedef V3<float> F3;
 
 #define RENDER_THREADS 128
-#define BRUTE_MAX_PRIMS 1024  // 48 KB of shared memory
+#define BRUTE_MAX_PRIMS 512  // 24 KB of shared memory; larger scenes traverse the BVH
 
 size_t brute_smem_limit_prims() { return BRUTE_MAX_PRIMS; }
 
@@ -36,95 +35,155 @@ __device__ __forceinline__ F3 background(const RenderArgs &A, F3 d) {
 }
 __device__ __forceinline__ bool finite3(F3 v) { return isfinite(v.x) && isfinite(v.y) && isfinite(v.z); }
 
-// pixel owned by this thread: a warp covers an 8x4 tile, a block a 16x8 tile (coherent primary rays and texture reads)
-__device__ __forceinline__ void thread_pixel(int W, int &x, int &y) {
+// A warp owns an 8x4 pixel tile, a block (4 warps) a 16x8 tile: coherent primary rays and texture reads.
+__device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 	const int tiles_x = (W + 15) >> 4;
 	const int bx = blockIdx.x % tiles_x, by = blockIdx.x / tiles_x;
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	x = bx * 16 + (warp & 1) * 8 + (lane & 7);
-	y = by * 8 + (warp >> 1) * 4 + (lane >> 3);
+	const int warp = threadIdx.x >> 5;
+	x0 = bx * 16 + (warp & 1) * 8;
+	y0 = by * 8 + (warp >> 1) * 4;
 }
 
+// Path-tracing megakernel.
+//
+// Work distribution: the warp's tile x sample range is a pool of 32*s_count (pixel, sample) tasks, task k = pixel
+// (k & 31) of the tile, sample (k >> 5).  A lane whose path ends pulls the next task with a ballot/popc ticket in
+// the same loop trip (path regeneration), so all 32 lanes stay busy until the pool is empty; finished samples are
+// added to the tile's accumulators in shared memory (one RED.ADD.F32 x3 per sample).  Each trip = trace one ray
+// segment for every lane, classify, then ONE Philox call per lane that feeds either the camera (new path) or the
+// material scatter (continuing path).
 template <bool BVH, bool COUNT>
 __global__ void __launch_bounds__(RENDER_THREADS) k_render_path(const __grid_constant__ RenderArgs A) {
 	extern __shared__ float4 s_raw[];
+	__shared__ float s_acc[RENDER_THREADS / 32][96];
 	const HotPrim *s_prims = reinterpret_cast<const HotPrim *>(s_raw);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int i = lane; i < 96; i += 32) s_acc[warp][i] = 0.0f;
 	if (!BVH) {
 		const float4 *src = reinterpret_cast<const float4 *>(A.sc.brute);
 		const int n4 = A.sc.n_hot * 3;
 		for (int i = threadIdx.x; i < n4; i += RENDER_THREADS) s_raw[i] = __ldg(src + i);
-		__syncthreads();
 	}
-	int x, y;
-	thread_pixel(A.W, x, y);
-	const bool inside = x < A.W && y < A.H;
-	const uint32_t pixel = (uint32_t)(y * A.W + x);
+	__syncthreads();
+	int x0, y0;
+	warp_tile_origin(A.W, x0, y0);
 	const CamT<float> cam = cam_from_basis<float>(A.cam);
 	const float inv_w = 1.0f / (float)A.W, inv_h = 1.0f / (float)A.H;
 	const HotRange br = A.sc.brute_range;
 	const HotIds *ids = BVH ? A.sc.bvh_ids : A.sc.brute_ids;
+	const unsigned full = 0xffffffffu;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const int total = (x0 < A.W && y0 < A.H) ? 32 * A.s_count : 0;
 
-	F3 sum = mk<float>(0.f, 0.f, 0.f), o = sum, d = sum, thr = sum;
-	int s = 0, bounce = 0;
+	int next = 0;          // next unissued task (warp-uniform)
+	int task = -1;         // this lane's task, -1 = needs one
+	bool exhausted = false;
+	bool ray_ok = false;
+	int pl = lane, px = 0, py = 0, bounce = 0;
+	uint32_t pixel = 0, sample = 0;
+	F3 o = mk<float>(0.f, 0.f, 0.f), d = mk<float>(0.f, 0.f, 1.f), thr = o;
+	// surface interaction carried from the classify stage to the scatter stage
+	F3 sP = o, sN = o;
+	float su = 0.f, sv = 0.f;
+	int smat = 0, stex = 0;
 	unsigned int rays = 0;
 	TravCounters tc = { 0, 0, 0, 0 };
-	const int s_count = inside ? A.s_count : 0;
 
 	while (true) {
-		if (bounce == 0) {
-			if (s >= s_count) break;
-			Rnd4<float> r = rnd4<float>(A.key, pixel, (uint32_t)(A.s_begin + s), 0u, 0u);
-			if (!cam.jitter) { r.x = 0.5f; r.y = 0.5f; }
-			cam_ray<float>(cam, inv_w, inv_h, x, y, r, o, d);
-			thr = mk<float>(1.f, 1.f, 1.f);
-			bounce = 1;
+		// ---- A. trace + classify ----------------------------------------------------------------------
+		if (ray_ok) {
+			Hit h;
+			h.t = INFINITY; h.idx = -1;
+			if (BVH) intersect_bvh<COUNT>(A.sc, o, d, A.tmin, h, &tc);
+			else intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, o, d, A.tmin, h);
+			++rays;
+			F3 contrib = mk<float>(0.f, 0.f, 0.f);
+			bool done;
+			if (h.idx < 0) {
+				contrib = thr * background(A, d);
+				done = true;
+			} else {
+				sP = o + h.t * d;
+				const Resolved rs = resolve_hit(A.sc, ids, h.idx, sP);
+				const PrimInfo pi = A.sc.info[rs.dev_prim];
+				surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, su, sv);
+				smat = pi.mat; stex = pi.tex;
+				const MaterialRec &m = A.sc.mats[smat];
+				if (m.kind == MK_LIGHT) {
+					contrib = thr * (m.pf[1] * tex_eval<float>(A.sc, mat_texture(m, stex), su, sv, sP));
+					done = true;
+				} else done = bounce >= A.max_depth;  // truncated path contributes nothing (RTIOW depth cut-off)
+			}
+			if (done) {
+				if (finite3(contrib)) {
+					float *acc = &s_acc[warp][pl * 3];
+					atomicAdd(acc, contrib.x); atomicAdd(acc + 1, contrib.y); atomicAdd(acc + 2, contrib.z);
+				}
+				task = -1;
+			}
 		}
-		Hit h;
-		h.t = INFINITY; h.idx = -1; h.a = 0.f; h.b = 0.f;
-		if (BVH) intersect_bvh<COUNT>(A.sc, o, d, A.tmin, h, &tc);
-		else intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, o, d, A.tmin, h);
-		++rays;
-		if (h.idx < 0) {
-			F3 c = thr * background(A, d);
-			if (finite3(c)) sum = sum + c;
-			++s; bounce = 0;
-			continue;
+		// ---- B. lanes without a task take tickets -----------------------------------------------------
+		{
+			const bool need = task < 0 && !exhausted;
+			const unsigned m = __ballot_sync(full, need);
+			if (m == 0u && __all_sync(full, exhausted)) break;
+			if (need) {
+				const int k = next + __popc(m & lt_mask);
+				if (k < total) {
+					pl = k & 31;
+					px = x0 + (pl & 7); py = y0 + (pl >> 3);
+					if (px < A.W && py < A.H) {
+						task = k;
+						sample = (uint32_t)(A.s_begin + (k >> 5));
+						pixel = (uint32_t)(py * A.W + px);
+						bounce = 0;
+					}
+				} else exhausted = true;
+			}
+			next += __popc(m);
 		}
-		const F3 P = o + h.t * d;
-		const Resolved rs = resolve_hit(A.sc, ids, h, P);
-		const PrimInfo pi = A.sc.info[rs.dev_prim];
-		F3 N, wo, att, emit;
-		float u, v;
-		surface_at(A.sc, rs.dev_prim, P, rs.a, rs.b, N, u, v);
-		const Rnd4<float> r = rnd4<float>(A.key, pixel, (uint32_t)(A.s_begin + s), (uint32_t)bounce, 0u);
-		const bool alive = scatter<float>(A.sc, pi.mat, pi.tex, d, N, P, u, v, r, wo, att, emit);
-		if (!alive) {
-			F3 c = thr * emit;
-			if (finite3(c)) sum = sum + c;
-			++s; bounce = 0;
-			continue;
+		// ---- C. one Philox draw per lane: camera ray for a new path, scatter for a continuing one -------
+		ray_ok = false;
+		if (task >= 0) {
+			Rnd4<float> r = rnd4<float>(A.key, pixel, sample, (uint32_t)bounce, 0u);
+			if (bounce == 0) {
+				if (!cam.jitter) { r.x = 0.5f; r.y = 0.5f; }
+				cam_ray<float>(cam, inv_w, inv_h, px, py, r, o, d);
+				thr = mk<float>(1.f, 1.f, 1.f);
+				bounce = 1;
+				ray_ok = true;
+			} else {
+				F3 wo, att, emit;
+				if (scatter<float>(A.sc, smat, stex, d, sN, sP, su, sv, r, wo, att, emit)) {
+					thr = thr * att;
+					o = sP;
+					d = wo;
+					++bounce;
+					ray_ok = true;
+				} else task = -1;  // absorbed (e.g. fuzzed metal reflection below the surface): sample contributes 0
+			}
 		}
-		thr = thr * att;
-		o = P;
-		d = wo;
-		if (++bounce > A.max_depth) { ++s; bounce = 0; }  // truncated path contributes nothing (RTIOW depth cut-off)
 	}
-	if (inside) {
-		float *acc = A.accum + (size_t)pixel * 3;
-		acc[0] += sum.x; acc[1] += sum.y; acc[2] += sum.z;
+	__syncwarp();
+	{
+		const int hx = x0 + (lane & 7), hy = y0 + (lane >> 3);
+		if (hx < A.W && hy < A.H && A.s_count > 0) {
+			float *acc = A.accum + ((size_t)hy * A.W + hx) * 3;
+			acc[0] += s_acc[warp][lane * 3]; acc[1] += s_acc[warp][lane * 3 + 1]; acc[2] += s_acc[warp][lane * 3 + 2];
+		}
 	}
 	// counters: one atomic per warp
 	unsigned long long r64 = rays;
 #pragma unroll
 	for (int off = 16; off > 0; off >>= 1) r64 += __shfl_down_sync(0xffffffffu, r64, off);
-	if ((threadIdx.x & 31) == 0 && r64) atomicAdd(A.counters + CNT_RAYS, r64);
+	if (lane == 0 && r64) atomicAdd(A.counters + CNT_RAYS, r64);
 	if (BVH && COUNT) {
 		unsigned long long c[4] = { tc.nodes, tc.quads, tc.tris, tc.spheres };
 #pragma unroll
 		for (int k = 0; k < 4; ++k) {
 #pragma unroll
 			for (int off = 16; off > 0; off >>= 1) c[k] += __shfl_down_sync(0xffffffffu, c[k], off);
-			if ((threadIdx.x & 31) == 0 && c[k]) atomicAdd(A.counters + CNT_NODES + k, c[k]);
+			if (lane == 0 && c[k]) atomicAdd(A.counters + CNT_NODES + k, c[k]);
 		}
 	}
 }
@@ -144,182 +203,6 @@ int launch_render_path(const RenderArgs &a, bool use_bvh, bool count_tests, cuda
 }
 
 // =========================================================================================================
-// rt.cpp shading (config 0)
-// =========================================================================================================
-#define RT_EPS 1e-5f  // rt.cpp:15
-
-struct RtSurf {
-	F3 p, n, albedo;
-	int mat_kind;
-	float refl;
-	F3 tint;
-};
-
-__device__ __forceinline__ bool rt_closest(const RenderArgs &A, const HotPrim *s_prims, F3 o, F3 d, RtSurf &sf, unsigned int &rays) {
-	Hit h;
-	h.t = INFINITY; h.idx = -1; h.a = 0.f; h.b = 0.f;
-	const HotRange br = A.sc.brute_range;
-	intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, o, d, RT_EPS, h);
-	++rays;
-	if (h.idx < 0) return false;
-	const F3 P = o + h.t * d;
-	const Resolved rs = resolve_hit(A.sc, A.sc.brute_ids, h, P);
-	const PrimInfo pi = A.sc.info[rs.dev_prim];
-	float u, v;
-	surface_at(A.sc, rs.dev_prim, P, rs.a, rs.b, sf.n, u, v);
-	sf.p = P;
-	sf.albedo = tex_eval<float>(A.sc, pi.tex, u, v, P);
-	const MaterialRec &m = A.sc.mats[pi.mat];
-	sf.mat_kind = m.kind;
-	sf.refl = m.pf[0];
-	sf.tint = mk<float>(m.pf[1], m.pf[2], m.pf[3]);
-	return true;
-}
-__device__ __forceinline__ bool rt_occluded(const RenderArgs &A, const HotPrim *s_prims, F3 o, F3 d, unsigned int &rays) {
-	Hit h;
-	h.t = INFINITY; h.idx = -1; h.a = 0.f; h.b = 0.f;
-	const HotRange br = A.sc.brute_range;
-	intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, o, d, RT_EPS, h);
-	++rays;
-	return h.idx >= 0;
-}
-// rt.cpp:221-248
-__device__ float rt_ao(const RenderArgs &A, const HotPrim *s_prims, F3 p, F3 n, uint32_t pixel, uint32_t sample, uint32_t slot_base, unsigned int &rays) {
-	const int N = A.ao_samples;
-	int unocc = 0;
-	F3 axis = cross(mk<float>(0.f, 0.f, 1.f), n);
-	const float sa = length(axis), ca = n.z;
-	const bool rot = sa > RT_EPS;
-	float sang = 0.f, cang = 1.f;
-	if (rot) {
-		axis = (1.0f / sa) * axis;
-		float ang = acosf(ca);
-		sincosf(ang, &sang, &cang);
-	}
-	const F3 org = p + RT_EPS * n;
-	for (int i = 0; i < N; ++i) {
-		Rnd4<float> r = rnd4<float>(A.key, pixel, sample, slot_base + (uint32_t)i, 1u);
-		F3 hd = sphere_dir<float>(r.y, r.x);  // theta = 2*pi*u, z = cos(acos(1-2v)) = 1-2v
-		if (hd.z < 0.f) hd.z = -hd.z;
-		F3 dd = hd;
-		if (rot) dd = cang * hd + sang * cross(axis, hd) + (dot(axis, hd) * (1.0f - cang)) * axis;
-		dd = nrm(dd);
-		if (!rt_occluded(A, s_prims, org, dd, rays)) ++unocc;
-	}
-	return 0.25f + 0.75f * ((float)unocc / (float)N);
-}
-__device__ __forceinline__ F3 clamp01(F3 c) {
-	return mk<float>(fmaxf(0.f, fminf(1.f, c.x)), fmaxf(0.f, fminf(1.f, c.y)), fmaxf(0.f, fminf(1.f, c.z)));
-}
-// rt.cpp:50-55
-__device__ __forceinline__ F3 rt_rotate(F3 n, float u, float v) {
-	F3 up = fabsf(n.z) < 0.999f ? mk<float>(0.f, 0.f, 1.f) : mk<float>(1.f, 0.f, 0.f);
-	F3 tangent = nrm(cross(n, up));
-	F3 bitangent = cross(n, tangent);
-	return u * tangent + v * bitangent + sqrtf(fmaxf(0.f, 1.f - u * u - v * v)) * n;
-}
-// rt.cpp:278-329 — cosine gather with Russian roulette, only for non-mirror surfaces
-__device__ F3 rt_gather(const RenderArgs &A, const HotPrim *s_prims, const RtSurf &sf, uint32_t pixel, uint32_t sample, int depth, unsigned int &rays) {
-	const uint32_t N = (uint32_t)A.ao_samples;
-	F3 accum = mk<float>(0.f, 0.f, 0.f);
-	for (uint32_t k = 0; k < N; ++k) {
-		const uint32_t slot = ((uint32_t)depth * N + k) * 4u;
-		Rnd4<float> r = rnd4<float>(A.key, pixel, sample, slot, 2u);
-		float sn, cs, r2s = sqrtf(r.y);
-		sincospif(2.0f * r.x, &sn, &cs);
-		F3 dir = rt_rotate(sf.n, r2s * cs, r2s * sn);
-		F3 org = sf.p + RT_EPS * sf.n, thr = sf.albedo;
-		for (int b = 0; b < 3; ++b) {
-			RtSurf bs;
-			if (!rt_closest(A, s_prims, org, dir, bs, rays)) break;
-			thr = thr * bs.albedo;
-			r = rnd4<float>(A.key, pixel, sample, slot + 1u + (uint32_t)b, 2u);
-			float pr = fmaxf(thr.x, fmaxf(thr.y, thr.z));
-			if (r.x > pr) break;
-			thr = (1.0f / pr) * thr;
-			F3 nd;
-			if (bs.mat_kind == MK_REFLECTIVE) {
-				F3 view = nrm(-dir);
-				nd = view - (2.0f * dot(view, bs.n)) * bs.n;
-			} else {
-				float nsn, ncs, nr2s = sqrtf(r.z);
-				sincospif(2.0f * r.y, &nsn, &ncs);
-				nd = rt_rotate(bs.n, nr2s * ncs, nr2s * nsn);
-			}
-			org = bs.p + RT_EPS * bs.n;
-			dir = nd;
-		}
-		accum = accum + thr;
-	}
-	return (1.0f / (float)N) * accum;
-}
-
-__global__ void __launch_bounds__(RENDER_THREADS) k_render_rtao(const __grid_constant__ RenderArgs A) {
-	extern __shared__ float4 s_raw[];
-	const HotPrim *s_prims = reinterpret_cast<const HotPrim *>(s_raw);
-	{
-		const float4 *src = reinterpret_cast<const float4 *>(A.sc.brute);
-		const int n4 = A.sc.n_hot * 3;
-		for (int i = threadIdx.x; i < n4; i += RENDER_THREADS) s_raw[i] = __ldg(src + i);
-		__syncthreads();
-	}
-	int x, y;
-	thread_pixel(A.W, x, y);
-	const bool inside = x < A.W && y < A.H;
-	const uint32_t pixel = (uint32_t)(y * A.W + x);
-	const CamT<float> cam = cam_from_basis<float>(A.cam);
-	const float inv_w = 1.0f / (float)A.W, inv_h = 1.0f / (float)A.H;
-	const F3 bg = mk<float>(A.bg_bottom[0], A.bg_bottom[1], A.bg_bottom[2]);
-	F3 sum = mk<float>(0.f, 0.f, 0.f);
-	unsigned int rays = 0;
-	const int s_count = inside ? A.s_count : 0;
-	for (int s = 0; s < s_count; ++s) {
-		const uint32_t sample = (uint32_t)(A.s_begin + s);
-		Rnd4<float> c; c.x = 0.5f; c.y = 0.5f; c.z = 0.f; c.w = 0.f;  // rt.cpp:364-366 pixel centres
-		F3 o, d;
-		cam_ray<float>(cam, inv_w, inv_h, x, y, c, o, d);
-		F3 col = bg;
-		RtSurf s0;
-		if (rt_closest(A, s_prims, o, d, s0, rays)) {
-			const float ao0 = rt_ao(A, s_prims, s0.p, s0.n, pixel, sample, 0u, rays);
-			if (s0.mat_kind == MK_REFLECTIVE) {  // rt.cpp:267-275
-				F3 view = nrm(o - s0.p);
-				F3 refl = view - (2.0f * dot(view, s0.n)) * s0.n;
-				F3 reflected = bg;
-				RtSurf s1;
-				if (rt_closest(A, s_prims, s0.p + RT_EPS * s0.n, refl, s1, rays)) {
-					const float ao1 = rt_ao(A, s_prims, s1.p, s1.n, pixel, sample, (uint32_t)A.ao_samples, rays);
-					F3 a1 = s1.albedo;
-					if (s1.mat_kind != MK_REFLECTIVE) a1 = a1 + rt_gather(A, s_prims, s1, pixel, sample, 1, rays);
-					reflected = clamp01(ao1 * a1);
-				}
-				col = clamp01(ao0 * ((1.0f - s0.refl) * s0.albedo + (s0.refl * reflected) * s0.tint));
-			} else {
-				F3 a0 = s0.albedo + rt_gather(A, s_prims, s0, pixel, sample, 0, rays);
-				col = clamp01(ao0 * a0);
-			}
-		}
-		sum = sum + col;
-	}
-	if (inside) {
-		float *acc = A.accum + (size_t)pixel * 3;
-		acc[0] += sum.x; acc[1] += sum.y; acc[2] += sum.z;
-	}
-	unsigned long long r64 = rays;
-#pragma unroll
-	for (int off = 16; off > 0; off >>= 1) r64 += __shfl_down_sync(0xffffffffu, r64, off);
-	if ((threadIdx.x & 31) == 0 && r64) atomicAdd(A.counters + CNT_RAYS, r64);
-}
-
-int launch_render_rtao(const RenderArgs &a, cudaStream_t s) {
-	const int tiles = ((a.W + 15) / 16) * ((a.H + 7) / 8);
-	if (tiles <= 0 || !a.sc.brute || a.sc.n_hot > BRUTE_MAX_PRIMS) return -1;
-	size_t smem = (size_t)a.sc.n_hot * sizeof(HotPrim);
-	k_render_rtao<<<tiles, RENDER_THREADS, smem, s>>>(a);
-	return 1;
-}
-
-// =========================================================================================================
 // fp32 per-ray harness
 // =========================================================================================================
 __global__ void k_hit32(DevScene sc, int n, const double *__restrict__ Q, const double *__restrict__ D, float tmin, int use_bvh,
@@ -328,7 +211,7 @@ __global__ void k_hit32(DevScene sc, int n, const double *__restrict__ Q, const 
 	if (i >= n) return;
 	F3 o = ld3<float>(Q + 3 * i), d = nrm(ld3<float>(D + 3 * i));
 	Hit h;
-	h.t = INFINITY; h.idx = -1; h.a = 0.f; h.b = 0.f;
+	h.t = INFINITY; h.idx = -1;
 	TravCounters tc;
 	if (use_bvh) intersect_bvh<false>(sc, o, d, tmin, h, &tc);
 	else intersect_range<ldg4>(sc.brute, sc.brute_range.first, sc.brute_range.nq, sc.brute_range.nt, sc.brute_range.ns, o, d, tmin, h);
@@ -338,7 +221,7 @@ __global__ void k_hit32(DevScene sc, int n, const double *__restrict__ Q, const 
 	int uid = -1;
 	if (h.idx >= 0) {
 		x = o + h.t * d;
-		Resolved rs = resolve_hit(sc, use_bvh ? sc.bvh_ids : sc.brute_ids, h, x);
+		Resolved rs = resolve_hit(sc, use_bvh ? sc.bvh_ids : sc.brute_ids, h.idx, x);
 		uid = sc.info[rs.dev_prim].user_id;
 		surface_at(sc, rs.dev_prim, x, rs.a, rs.b, nn, cu, cv);
 	}

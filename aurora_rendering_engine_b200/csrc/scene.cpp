@@ -290,6 +290,25 @@ void make_cam_basis(const double pos[3], const double target[3], const double up
 	out.pad_ = 0;
 }
 
+void make_rt_cam(const double pos[3], const double target[3], const double up[3], double vfov_deg, int W, int H, RtCam &out) {
+	// every operation in fp32 and in rt.cpp's order: forward = (target - pos).normalized(); right = forward.cross(up).normalized();
+	// up' = right.cross(forward); aspect = float(w) / h; scale = tan(fov * 0.5f * M_PI / 180.f)
+	volatile float px = (float)pos[0], py = (float)pos[1], pz = (float)pos[2];
+	volatile float fx = (float)target[0] - px, fy = (float)target[1] - py, fz = (float)target[2] - pz;
+	volatile float il = 1.0f / std::sqrt((float)(fx * fx + fy * fy + fz * fz));
+	fx = fx * il; fy = fy * il; fz = fz * il;
+	const float ux = (float)up[0], uy = (float)up[1], uz = (float)up[2];
+	volatile float rx = fy * uz - fz * uy, ry = fz * ux - fx * uz, rz = fx * uy - fy * ux;
+	il = 1.0f / std::sqrt((float)(rx * rx + ry * ry + rz * rz));
+	rx = rx * il; ry = ry * il; rz = rz * il;
+	out.pos[0] = px; out.pos[1] = py; out.pos[2] = pz;
+	out.fwd[0] = fx; out.fwd[1] = fy; out.fwd[2] = fz;
+	out.right[0] = rx; out.right[1] = ry; out.right[2] = rz;
+	out.up[0] = ry * fz - rz * fy; out.up[1] = rz * fx - rx * fz; out.up[2] = rx * fy - ry * fx;
+	out.aspect = (float)W / (float)H;
+	out.scale = (float)std::tan((float)vfov_deg * 0.5f * 3.14159265358979323846 / 180.f);
+}
+
 bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene &out, std::string &err) {
 	out = CompiledScene();
 	const int nmat = (int)hs.materials.size(), ntex = (int)hs.textures.size();
@@ -361,6 +380,16 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 			else {
 				out.n_tri++;
 				for (int k = 0; k < 6; ++k) { out.tri_uv.push_back((float)p.uv[k]); out.tri_uv64.push_back(p.uv[k]); }
+				{  // rt.cpp:118-122 in fp32: n = (v1 - v0).cross(v2 - v0).normalized(), normalized() = v * (1.0f / length)
+					const float v0[3] = { (float)p.Q[0], (float)p.Q[1], (float)p.Q[2] };
+					const float e1[3] = { (float)p.u[0], (float)p.u[1], (float)p.u[2] }, e2[3] = { (float)p.v[0], (float)p.v[1], (float)p.v[2] };
+					volatile float cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+					volatile float l2 = cx * cx + cy * cy + cz * cz;
+					const float il = 1.0f / std::sqrt((float)l2);
+					out.rt_tris.push_back({ v0[0], v0[1], v0[2], e1[0] });
+					out.rt_tris.push_back({ e1[1], e1[2], e2[0], e2[1] });
+					out.rt_tris.push_back({ e2[2], cx * il, cy * il, cz * il });
+				}
 			}
 		}
 		pbox[dp] = b;

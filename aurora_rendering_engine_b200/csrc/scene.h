@@ -52,6 +52,7 @@ struct CompiledScene {
 	std::vector<PrimInfo> info;
 	std::vector<HotPrim> prim_plane;
 	std::vector<float> tri_uv;
+	std::vector<f4> rt_tris;  // 3 per triangle: rt.cpp-style fp32 record (v0, e1, e2, n)
 	std::vector<double> tri64, quad64, sph64, tri_uv64;
 	int n_tri = 0, n_quad = 0, n_sph = 0;
 	std::vector<MaterialRec> mats;
@@ -79,5 +80,8 @@ void make_noise_tables(uint64_t seed, double *grad768, int *perm768);
 // camera basis exactly as experiments/rt.cpp:339-343 computes it, in fp64
 void make_cam_basis(const double pos[3], const double target[3], const double up[3], double vfov_deg, double focus_dist,
 	double defocus_angle_deg, int jitter, int W, int H, CamBasis &out);
+
+// the same camera with rt.cpp's own fp32 operations (experiments/rt.cpp:339-343), for the RT_AO integrator
+void make_rt_cam(const double pos[3], const double target[3], const double up[3], double vfov_deg, int W, int H, RtCam &out);
 
 }  // namespace areb

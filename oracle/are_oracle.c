@@ -679,7 +679,11 @@ void orc_scatter_batch(const orc_scene *s, int n, const int *mat, const int *tex
 }
 
 /* ---- camera (experiments/rt.cpp:339-343,364-366 + jitter + thin lens) -------------------------------- */
-typedef struct { v3 pos, fwd, right, up; double sx, sy, lens_r, focus; int jitter; } cam_basis;
+typedef struct {
+	v3 pos, fwd, right, up; double sx, sy, lens_r, focus; int jitter;
+	/* the same camera with rt.cpp's own fp32 operations (rt.cpp:339-343): pos, forward, right, up, aspect, scale */
+	float rt_pos[3], rt_fwd[3], rt_right[3], rt_up[3], rt_aspect, rt_scale;
+} cam_basis;
 static cam_basis cam_setup(const orc_camera *c, int W, int H) {
 	cam_basis b;
 	b.pos = vld(c->pos);
@@ -691,6 +695,22 @@ static cam_basis cam_setup(const orc_camera *c, int W, int H) {
 	b.sy = scale;
 	b.focus = c->focus_dist;
 	b.jitter = c->jitter;
+	{ /* rt.cpp:339-343 in fp32: forward = (target - pos).normalized(); right = forward.cross(up).normalized(); up' = right.cross(forward) */
+		float px = (float)c->pos[0], py = (float)c->pos[1], pz = (float)c->pos[2];
+		float fx = (float)c->target[0] - px, fy = (float)c->target[1] - py, fz = (float)c->target[2] - pz;
+		float il = 1.0f / sqrtf(fx * fx + fy * fy + fz * fz);
+		fx = fx * il; fy = fy * il; fz = fz * il;
+		float ux = (float)c->up[0], uy = (float)c->up[1], uz = (float)c->up[2];
+		float rx = fy * uz - fz * uy, ry = fz * ux - fx * uz, rz = fx * uy - fy * ux;
+		il = 1.0f / sqrtf(rx * rx + ry * ry + rz * rz);
+		rx = rx * il; ry = ry * il; rz = rz * il;
+		b.rt_pos[0] = px; b.rt_pos[1] = py; b.rt_pos[2] = pz;
+		b.rt_fwd[0] = fx; b.rt_fwd[1] = fy; b.rt_fwd[2] = fz;
+		b.rt_right[0] = rx; b.rt_right[1] = ry; b.rt_right[2] = rz;
+		b.rt_up[0] = ry * fz - rz * fy; b.rt_up[1] = rz * fx - rx * fz; b.rt_up[2] = rx * fy - ry * fx;
+		b.rt_aspect = (float)W / H;                                         /* rt.cpp:342 */
+		b.rt_scale = (float)tan((float)c->vfov_deg * 0.5f * M_PI / 180.f); /* rt.cpp:343 */
+	}
 	b.lens_r = c->defocus_angle_deg > 0.0 ? c->focus_dist * tan(c->defocus_angle_deg * 0.5 * M_PI / 180.0) : 0.0;
 	return b;
 }
@@ -818,7 +838,7 @@ static float rt_ao(const orc_scene *s, f3 p, f3 n, const orc_params *pp, uint32_
 	for (int i = 0; i < N; ++i) {
 		float r[4];
 		rnd4f(pp->seed, pixel, sample, slot_base + (uint32_t)i, 1, r);
-		float theta = 2 * (float)M_PI * r[0];
+		float theta = (float)(2 * M_PI * r[0]); /* rt.cpp:227: the product is formed in double, then narrowed */
 		float phi = acosf(1 - 2 * r[1]);
 		float x = sinf(phi) * cosf(theta), y = sinf(phi) * sinf(theta), z = cosf(phi);
 		if (z < 0) z = -z;
@@ -868,7 +888,7 @@ static f3 rt_trace(const orc_scene *s, f3 o, f3 d, const orc_params *pp, uint32_
 			float r[4];
 			uint32_t slot = ((uint32_t)depth * N + k) * 4u;
 			rnd4f(pp->seed, pixel, sample, slot, 2, r);
-			float phi = 2 * (float)M_PI * r[0], r2s = sqrtf(r[1]);
+			float phi = (float)(2 * M_PI * r[0]), r2s = sqrtf(r[1]); /* rt.cpp:286: double product, narrowed */
 			f3 dir = rt_rotate(n, r2s * cosf(phi), r2s * sinf(phi));
 			f3 org = f_add(p, fsc(n, RT_EPS)), thr = albedo;
 			int b = 0;
@@ -887,7 +907,7 @@ static f3 rt_trace(const orc_scene *s, f3 o, f3 d, const orc_params *pp, uint32_
 					f3 view = fnorm(f_sub(F(0, 0, 0), dir));
 					nd = f_sub(view, fsc(bn, 2 * fdot(view, bn)));
 				} else {
-					float nphi = 2 * (float)M_PI * r[1], nr2s = sqrtf(r[2]);
+					float nphi = (float)(2 * M_PI * r[1]), nr2s = sqrtf(r[2]);
 					nd = rt_rotate(bn, nr2s * cosf(nphi), nr2s * sinf(nphi));
 				}
 				org = f_add(bp, fsc(bn, RT_EPS));
@@ -901,11 +921,13 @@ static f3 rt_trace(const orc_scene *s, f3 o, f3 d, const orc_params *pp, uint32_
 	return fclamp01(fsc(albedo, ao));
 }
 static v3 rtao_sample(const orc_scene *s, const cam_basis *cb, const orc_params *p, int x, int y, uint32_t sample, orc_stats *st) {
-	/* rt.cpp:339-343,364-366 in fp32, pixel centres */
-	f3 fwd = tof(cb->fwd), right = tof(cb->right), up = tof(cb->up);
-	float fx = (2 * (x + 0.5f) / p->width - 1) * (float)cb->sx, fy = (1 - 2 * (y + 0.5f) / p->height) * (float)cb->sy;
-	f3 dir = fnorm(f_add(fwd, f_add(fsc(right, fx), fsc(up, fy))));
-	f3 c = fclamp01(rt_trace(s, tof(cb->pos), dir, p, (uint32_t)(y * p->width + x), sample, 0, st));
+	/* rt.cpp:364-366, pixel centres, fp32 */
+	f3 fwd = F(cb->rt_fwd[0], cb->rt_fwd[1], cb->rt_fwd[2]), right = F(cb->rt_right[0], cb->rt_right[1], cb->rt_right[2]);
+	f3 up = F(cb->rt_up[0], cb->rt_up[1], cb->rt_up[2]), pos = F(cb->rt_pos[0], cb->rt_pos[1], cb->rt_pos[2]);
+	float fx = (2 * (x + 0.5f) / p->width - 1) * cb->rt_aspect * cb->rt_scale;
+	float fy = (1 - 2 * (y + 0.5f) / p->height) * cb->rt_scale;
+	f3 dir = fnorm(f_add(f_add(fwd, fsc(right, fx)), fsc(up, fy)));
+	f3 c = fclamp01(rt_trace(s, pos, dir, p, (uint32_t)(y * p->width + x), sample, 0, st));
 	return V(c.x, c.y, c.z);
 }
 

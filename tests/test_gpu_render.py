@@ -73,9 +73,9 @@ def test_scene_matches_cpu_twin(ctx, oracle, name, kw, spp, traversal):
 
 
 def test_stress_scene_bvh_equals_brute_and_matches_cpu_twin(ctx, oracle):
-    """Config-4 style scene scaled to 1000 primitives so the brute-force list still fits: BVH and brute force run the
+    """Config-4 style scene scaled to 500 primitives so the brute-force list still fits: BVH and brute force run the
     same per-primitive arithmetic, so their images must be IDENTICAL; both must match the CPU twin."""
-    sc = scenes.stress(n_prims=1000, width=96, height=54)
+    sc = scenes.stress(n_prims=500, width=96, height=54)
     cam = capi.make_camera(**sc.camera_args())
     sc.feed(ctx)
     ctx.commit()
