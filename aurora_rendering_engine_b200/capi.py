@@ -36,7 +36,7 @@ class RenderParams(C.Structure):
 class RenderStats(C.Structure):
     """are_render_stats"""
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("tri_tests", C.c_uint64), ("quad_tests", C.c_uint64),
-                ("sphere_tests", C.c_uint64), ("node_visits", C.c_uint64), ("kernel_ms", C.c_double), ("launches", C.c_uint64)]
+                ("sphere_tests", C.c_uint64), ("node_visits", C.c_uint64), ("box_tests", C.c_uint64), ("kernel_ms", C.c_double), ("launches", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -94,6 +94,7 @@ SIGNATURES = {
     "are_cuda_clear": (C.c_int, [_vp]),
     "are_cuda_num_primitives": (C.c_int, [_vp]),
     "are_cuda_commit": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "are_cuda_compile_probe": (C.c_int, [C.c_int, _dp, _dp, _dp, _ip]),
     "are_cuda_hit_batch": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_double, C.c_int, C.c_int, _ip, _dp, _dp, _dp, _dp]),
     "are_cuda_scatter_batch": (C.c_int, [_vp, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _ip]),
     "are_cuda_texture_batch": (C.c_int, [_vp, C.c_int, _ip, _dp, _dp, C.c_int, _dp]),
@@ -128,6 +129,18 @@ def load_library(path: str | None = None):
     if path is None:
         _lib = lib
     return lib
+
+
+def compile_probe(Q, u, v) -> dict:
+    """Host-only scene-compiler probe (are_cuda_compile_probe): no GPU involved."""
+    lib = load_library()
+    Q, u, v = (np.ascontiguousarray(x, dtype=np.float64) for x in (Q, u, v))
+    out = np.zeros(8, np.int32)
+    st = lib.are_cuda_compile_probe(len(Q), Q.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp), out.ctypes.data_as(_ip))
+    if st != ARE_OK:
+        raise AreCudaError(st, "compile probe rejected the triangles")
+    keys = ("hot_slots", "fused_pairs", "boxes", "bvh_nodes", "bvh_depth", "brute_quads", "brute_tris", "brute_boxes")
+    return dict(zip(keys, (int(x) for x in out)))
 
 
 def _d(a, shape=None):

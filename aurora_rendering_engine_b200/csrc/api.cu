@@ -304,6 +304,7 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	std::string err;
 	ctx->opt.brute_max = (int)brute_smem_limit_prims();
 	if (const char *e = getenv("ARE_CUDA_NO_FUSE")) ctx->opt.fuse_parallelograms = !(e[0] == '1');
+	if (const char *e = getenv("ARE_CUDA_NO_BOXES")) ctx->opt.fuse_boxes = !(e[0] == '1');
 	if (const char *e = getenv("ARE_CUDA_LEAF_SIZE")) ctx->opt.leaf_size = atoi(e);
 	if (!compile_scene(ctx->scene, ctx->opt, ctx->cs, err)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, err);
 	const CompiledScene &cs = ctx->cs;
@@ -315,7 +316,7 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	if ((st = upload(ctx, cs.vec, &d.field, bytes)) != ARE_OK) return st;
 	UP(brute, brute) UP(brute_ids, brute_ids) UP(bvh_prims, bvh_prims) UP(bvh_ids, bvh_ids) UP(nodes, nodes)
 	UP(info, info) UP(prim_plane, prim_plane) UP(tri_uv, tri_uv) UP(tri64, tri64) UP(quad64, quad64) UP(sph64, sph64)
-	UP(tri_uv64, tri_uv64) UP(mats, mats) UP(texs, texs) UP(tex_data, tex_data) UP(rt_tris, rt_tris)
+	UP(tri_uv64, tri_uv64) UP(mats, mats) UP(texs, texs) UP(tex_data, tex_data) UP(rt_tris, rt_tris) UP(box_faces, box_faces)
 #undef UP
 	d.brute_range = cs.brute_range;
 	d.n_nodes = (int)cs.nodes.size();
@@ -327,6 +328,30 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	ctx->dev = d;
 	ctx->committed = true;
 	if (h2d_bytes) *h2d_bytes = bytes;
+	return ARE_OK;
+}
+
+int are_cuda_compile_probe(int n_tri, const double *Q, const double *u, const double *v, int out[8]) {
+	if (n_tri < 0 || !out || (n_tri && (!Q || !u || !v))) return ARE_ERR_INVALID_ARGUMENT;
+	HostScene hs;
+	hs.textures.emplace_back();
+	hs.materials.emplace_back();
+	for (int i = 0; i < n_tri; ++i) {
+		if (validate_edges(u + 3 * (size_t)i, v + 3 * (size_t)i)) return ARE_ERR_INVALID_ARGUMENT;
+		HostPrim p;
+		p.type = PT_TRIANGLE;
+		std::memcpy(p.Q, Q + 3 * (size_t)i, sizeof p.Q);
+		std::memcpy(p.u, u + 3 * (size_t)i, sizeof p.u);
+		std::memcpy(p.v, v + 3 * (size_t)i, sizeof p.v);
+		hs.prims.push_back(p);
+	}
+	CompileOptions opt;
+	opt.brute_max = (int)brute_smem_limit_prims();
+	CompiledScene cs;
+	std::string err;
+	if (!compile_scene(hs, opt, cs, err)) return ARE_ERR_INVALID_ARGUMENT;
+	const int r[8] = { cs.n_hot, cs.n_fused_pairs, cs.n_boxes, (int)cs.nodes.size(), cs.bvh_depth, cs.brute_range.nq, cs.brute_range.nt, cs.brute_range.nb };
+	std::memcpy(out, r, sizeof r);
 	return ARE_OK;
 }
 
@@ -448,6 +473,12 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 	std::memset(&a, 0, sizeof a);
 	a.sc = ctx->dev;
 	make_cam_basis(cam->pos, cam->target, cam->up, cam->vfov_deg, cam->focus_dist, cam->defocus_angle_deg, cam->jitter, p->width, p->height, a.cam);
+	for (int k = 0; k < 3; ++k) {
+		a.camf.pos[k] = (float)a.cam.pos[k]; a.camf.fwd[k] = (float)a.cam.fwd[k];
+		a.camf.right[k] = (float)a.cam.right[k]; a.camf.up[k] = (float)a.cam.up[k];
+	}
+	a.camf.sx = (float)a.cam.sx; a.camf.sy = (float)a.cam.sy; a.camf.lens_r = (float)a.cam.lens_r; a.camf.focus = (float)a.cam.focus;
+	a.camf.jitter = a.cam.jitter;
 	a.key = philox_key(p->seed);
 	a.W = p->width; a.H = p->height;
 	a.s_begin = p->sample_begin; a.s_count = p->sample_count;
@@ -485,10 +516,12 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 		stats->rays = c[CNT_RAYS];
 		if (use_bvh) {
 			stats->node_visits = c[CNT_NODES]; stats->quad_tests = c[CNT_QUADS]; stats->tri_tests = c[CNT_TRIS]; stats->sphere_tests = c[CNT_SPHERES];
+			stats->box_tests = c[CNT_BOXES];
 		} else {  // brute force: every ray tests every hot primitive — exact by construction
 			stats->quad_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.brute_range.nq;
 			stats->tri_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.brute_range.nt;
 			stats->sphere_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.brute_range.ns;
+			stats->box_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.brute_range.nb;
 		}
 		stats->kernel_ms = ms;
 		stats->launches = (uint64_t)launched;

@@ -9,6 +9,11 @@
 //       r1 = (A.x, A.y, A.z, aQ)     alpha = A·p - aQ   with A = (v x N)/(N·N), N = u x v
 //       r2 = (B.x, B.y, B.z, bQ)     beta  = B·p - bQ   with B = (N x u)/(N·N)
 //   sphere, same 48 B slot:  r0 = (c.x, c.y, c.z, r), r1.x = r*r
+//   parallelepiped ("box": up to six parallelograms — fused triangle pairs or quads — that are the faces of one
+//   parallelepiped, e.g. the Cornell boxes, or the room itself with its front face absent), TWO slots (96 B):
+//       r0..r2 = (n_i.x, n_i.y, n_i.z, c_i)   unit slab normals, c_i = n_i·centre          i = 0,1,2
+//       r3     = (h_0, h_1, h_2, face mask)   slab half-widths; mask bit 2i / 2i+1 = face at c_i -/+ h_i present
+//     one test = three slab pairs = at most two candidate hits (entry, exit) instead of six plane-form tests.
 //
 // The fp64 copies (Q,u,v as the host gave them) feed only the decision-exact harness kernels.
 #pragma once
@@ -32,6 +37,7 @@ struct HotPrim { f4 r0, r1, r2; };  // 48 B
 
 // ids of the user primitives behind one hot primitive: b >= 0 only for a fused triangle pair
 // (a = the triangle on the alpha >= beta side of the diagonal and the lower user id).
+// For a box slot: a = -1 - box index (its six per-face HotIds live in DevScene::box_faces[6*index + face]).
 struct HotIds { int a, b; };
 
 struct PrimInfo { int user_id, mat, tex, type; };  // per device primitive (device order: triangles, quads, spheres)
@@ -53,16 +59,17 @@ struct TextureRec {
 //   b0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   b1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
 //   b2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
 //   child[i] >= 0: inner node index.  child[i] < 0: leaf, first hot primitive = ~child[i],
-//   meta[i] = nq | nt << 8 | ns << 16  (quads+fused pairs, triangles, spheres; stored in that order)
+//   meta[i] = nq | nt << 8 | ns << 16 | nb << 24  (boxes first — two slots each — then quads+fused pairs,
+//   triangles, spheres)
 struct BvhNode {
 	f4 b0, b1, b2;
 	int child[2];
 	int meta[2];
 };
 
-// A contiguous run of hot primitives sorted by test kind: [first, first+nq) quad test, then nt triangle tests,
-// then ns sphere tests.  The brute-force list is one big range; every BVH leaf is a small one.
-struct HotRange { int first, nq, nt, ns; };
+// A contiguous run of hot primitives sorted by test kind: nb boxes (two slots each) from `first`, then nq quad
+// tests, nt triangle tests, ns sphere tests.  The brute-force list is one big range; every BVH leaf is a small one.
+struct HotRange { int first, nq, nt, ns, nb; };
 
 struct DevScene {
 	// --- fp32 render data ---
@@ -74,7 +81,8 @@ struct DevScene {
 	const BvhNode *nodes;
 	int n_nodes;
 	int root_leaf_meta;        // when the whole scene is one leaf (n_nodes == 0)
-	int n_hot;
+	int n_hot;                 // slots in the hot arrays (a box takes two)
+	const HotIds *box_faces;   // 6 per box: the fused pair / quad behind each face, {-1,-1} when the face is absent
 	// --- per device primitive ---
 	const PrimInfo *info;
 	const HotPrim *prim_plane; // plane form (or sphere record) of every user primitive, device order
@@ -99,6 +107,13 @@ struct DevScene {
 struct CamBasis {
 	double pos[3], fwd[3], right[3], up[3];
 	double sx, sy, lens_r, focus;
+	int jitter, pad_;
+};
+
+// the same basis rounded to fp32 once on the host: what the render kernels read (no F2F in the loop)
+struct CamF {
+	float pos[3], fwd[3], right[3], up[3];
+	float sx, sy, lens_r, focus;
 	int jitter, pad_;
 };
 

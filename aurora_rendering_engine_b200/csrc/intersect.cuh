@@ -77,11 +77,74 @@ __device__ __forceinline__ void test_sphere(float4 r0, float4 r1, V3<float> o, V
 	if (ok) { h.t = t; h.idx = idx; }
 }
 
+// ---- parallelepiped ("box") -----------------------------------------------------------------------------
+// Three slab pairs.  Per axis: s = n·d, e = c - n·o, m = e/s, k = h/|s|: the ray is inside the slab for t in
+// [m-k, m+k] (already ordered, no min/max), entering through face "-" when s > 0.  A line meets a convex body's
+// surface at most twice, so the only possible hits on the (two-sided) faces are the entry t_in = max(m-k) and the
+// exit t_out = min(m+k); each is accepted if it lies in the (tmin, best) window and its face is present.
+struct BoxSlabs {
+	float tn[3], tf[3], s[3];
+};
+__device__ __forceinline__ float nonzero(float s) {  // keep the sign, push |s| away from 0 so that 1/s stays finite
+	return __uint_as_float((__float_as_uint(fmaxf(fabsf(s), 1e-30f)) & 0x7fffffffu) | (__float_as_uint(s) & 0x80000000u));
+}
+__device__ __forceinline__ BoxSlabs box_slabs(float4 r0, float4 r1, float4 r2, float4 r3, V3<float> o, V3<float> d) {
+	BoxSlabs b;
+	const float4 r[3] = { r0, r1, r2 };
+	const float hw[3] = { r3.x, r3.y, r3.z };
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+		float s = nonzero(fmaf(r[i].x, d.x, fmaf(r[i].y, d.y, r[i].z * d.z)));
+		float e = fmaf(-r[i].x, o.x, fmaf(-r[i].y, o.y, fmaf(-r[i].z, o.z, r[i].w)));
+		float inv = rcp_fast(s);
+		float m = e * inv, k = hw[i] * fabsf(inv);
+		b.tn[i] = m - k;
+		b.tf[i] = m + k;
+		b.s[i] = s;
+	}
+	return b;
+}
+// face index (2*axis + side) the ray crosses at parameter t_in (entry) / t_out (exit)
+__device__ __forceinline__ int box_entry_face(const BoxSlabs &b) {
+	int ax = (b.tn[0] >= b.tn[1]) ? ((b.tn[0] >= b.tn[2]) ? 0 : 2) : ((b.tn[1] >= b.tn[2]) ? 1 : 2);
+	float s = ax == 0 ? b.s[0] : (ax == 1 ? b.s[1] : b.s[2]);
+	return 2 * ax + (s > 0.0f ? 0 : 1);
+}
+__device__ __forceinline__ int box_exit_face(const BoxSlabs &b) {
+	int ax = (b.tf[0] <= b.tf[1]) ? ((b.tf[0] <= b.tf[2]) ? 0 : 2) : ((b.tf[1] <= b.tf[2]) ? 1 : 2);
+	float s = ax == 0 ? b.s[0] : (ax == 1 ? b.s[1] : b.s[2]);
+	return 2 * ax + (s > 0.0f ? 1 : 0);
+}
+// The candidate hit of a box: returns t (NaN-free) and whether it is acceptable. A closed box (mask 63) skips the
+// face-presence logic inside the loop; the face is recovered for the winner afterwards (box_hit_face).
+__device__ __forceinline__ void test_box(float4 r0, float4 r1, float4 r2, float4 r3, V3<float> o, V3<float> d, float tmin, int idx, Hit &h) {
+	const BoxSlabs b = box_slabs(r0, r1, r2, r3, o, d);
+	const float t_in = fmaxf(fmaxf(b.tn[0], b.tn[1]), b.tn[2]), t_out = fminf(fminf(b.tf[0], b.tf[1]), b.tf[2]);
+	const unsigned mask = __float_as_uint(r3.w);
+	bool in_ok = t_in > tmin, out_ok = t_out > tmin;
+	if (mask != 63u) {  // warp-uniform: all lanes test the same primitive
+		in_ok = in_ok && ((mask >> box_entry_face(b)) & 1u);
+		out_ok = out_ok && ((mask >> box_exit_face(b)) & 1u);
+	}
+	const float t = in_ok ? t_in : t_out;
+	const bool ok = (t_in <= t_out) & (in_ok | out_ok) & (t < h.t);
+	if (ok) { h.t = t; h.idx = idx; }
+}
+// which face a winning box hit at distance t lies on (same arithmetic as test_box, so t compares exactly)
+__device__ __forceinline__ int box_hit_face(float4 r0, float4 r1, float4 r2, float4 r3, V3<float> o, V3<float> d, float t) {
+	const BoxSlabs b = box_slabs(r0, r1, r2, r3, o, d);
+	const float t_in = fmaxf(fmaxf(b.tn[0], b.tn[1]), b.tn[2]);
+	return (t == t_in) ? box_entry_face(b) : box_exit_face(b);
+}
+
 // Test a type-sorted run of hot primitives. LD = ldg4 (global / L2) or lds4 (shared-memory copy).
 template <float4 (*LD)(const f4 *)>
-__device__ __forceinline__ void intersect_range(const HotPrim *prims, int first, int nq, int nt, int ns, V3<float> o, V3<float> d, float tmin, Hit &h) {
+__device__ __forceinline__ void intersect_range(const HotPrim *prims, int first, int nq, int nt, int ns, int nb, V3<float> o, V3<float> d, float tmin, Hit &h) {
 	int i = first;
-	int end = first + nq;
+	int end = first + 2 * nb;
+#pragma unroll 2
+	for (; i < end; i += 2) test_box(LD(&prims[i].r0), LD(&prims[i].r1), LD(&prims[i].r2), LD(&prims[i + 1].r0), o, d, tmin, i, h);
+	end += nq;
 #pragma unroll 4
 	for (; i < end; ++i) test_plane<true>(LD(&prims[i].r0), LD(&prims[i].r1), LD(&prims[i].r2), o, d, tmin, i, h);
 	end += nt;
@@ -96,15 +159,15 @@ __device__ __forceinline__ void intersect_range(const HotPrim *prims, int first,
 #define ARE_BVH_STACK 48
 
 struct TravCounters {
-	unsigned long long nodes, quads, tris, spheres;
+	unsigned long long nodes, quads, tris, spheres, boxes;
 };
 
 template <bool COUNT>
 __device__ __forceinline__ void intersect_bvh(const DevScene &sc, V3<float> o, V3<float> d, float tmin, Hit &h, TravCounters *cnt) {
 	if (sc.n_nodes == 0) {
 		int m = sc.root_leaf_meta;
-		intersect_range<ldg4>(sc.bvh_prims, 0, m & 255, (m >> 8) & 255, (m >> 16) & 255, o, d, tmin, h);
-		if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; }
+		intersect_range<ldg4>(sc.bvh_prims, 0, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, tmin, h);
+		if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; cnt->boxes += (m >> 24) & 255; }
 		return;
 	}
 	// safe reciprocals: a zero component becomes a huge finite slope so the slab maths never sees 0*inf
@@ -134,15 +197,15 @@ __device__ __forceinline__ void intersect_bvh(const DevScene &sc, V3<float> o, V
 		// leaves are intersected immediately; inner children are ordered near-first
 		if (hit0 && cm.x < 0) {
 			int m = cm.z;
-			intersect_range<ldg4>(sc.bvh_prims, ~cm.x, m & 255, (m >> 8) & 255, (m >> 16) & 255, o, d, tmin, h);
-			if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; }
+			intersect_range<ldg4>(sc.bvh_prims, ~cm.x, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, tmin, h);
+			if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; cnt->boxes += (m >> 24) & 255; }
 			hit0 = false;
 		}
 		if (hit1 && cm.y < 0) {
 			if (t1n <= h.t) {
 				int m = cm.w;
-				intersect_range<ldg4>(sc.bvh_prims, ~cm.y, m & 255, (m >> 8) & 255, (m >> 16) & 255, o, d, tmin, h);
-				if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; }
+				intersect_range<ldg4>(sc.bvh_prims, ~cm.y, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, tmin, h);
+				if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; cnt->boxes += (m >> 24) & 255; }
 			}
 			hit1 = false;
 		}
@@ -165,31 +228,31 @@ struct Resolved {
 	int dev_prim;   // device primitive index (device order: triangles, quads, spheres)
 	float a, b;     // planar coordinates in that primitive's own frame (0 for spheres)
 };
-// hot = the array (shared or global) the winning index refers to; spheres carry no planar coordinates
-__device__ __forceinline__ Resolved resolve_hit(const DevScene &sc, const HotIds *ids, int idx, V3<float> P) {
+// `hot` = the array (shared or global) the winning index refers to — needed again only for boxes, whose face is
+// re-derived from the ray; spheres carry no planar coordinates.
+template <float4 (*LD)(const f4 *)>
+__device__ __forceinline__ Resolved resolve_hit(const DevScene &sc, const HotPrim *hot, const HotIds *ids, int idx, V3<float> o, V3<float> d, float t, V3<float> P) {
 	Resolved r;
-	const HotIds id = ids[idx];
+	HotIds id = ids[idx];
+	if (id.a < 0) {  // box: find the face, continue with the parallelogram (fused pair or quad) behind it
+		const int face = box_hit_face(LD(&hot[idx].r0), LD(&hot[idx].r1), LD(&hot[idx].r2), LD(&hot[idx + 1].r0), o, d, t);
+		id = sc.box_faces[6 * (-1 - id.a) + face];
+	}
 	r.dev_prim = id.a;
 	r.a = 0.0f;
 	r.b = 0.0f;
 	if (id.a < sc.n_tri + sc.n_quad) {
+		const HotPrim &ta = sc.prim_plane[id.a];
+		plane_coords(*reinterpret_cast<const float4 *>(&ta.r1), *reinterpret_cast<const float4 *>(&ta.r2), P, r.a, r.b);
 		if (id.b >= 0) {
-			// fused pair: the hot parallelogram is (d0; a - d0; b - d0) with triangle id.a on the alpha >= beta side.
-			// Both triangles are coplanar with it, so deciding on the pair's own coordinates = deciding on which side
-			// of the shared diagonal P lies; use triangle id.a's barycentrics: inside it <=> all three >= 0.
-			const HotPrim &ta = sc.prim_plane[id.a];
-			float a0, b0;
-			plane_coords(*reinterpret_cast<const float4 *>(&ta.r1), *reinterpret_cast<const float4 *>(&ta.r2), P, a0, b0);
-			const bool in_a = (a0 >= 0.0f) & (b0 >= 0.0f) & (a0 + b0 <= 1.0f);
-			if (in_a) { r.a = a0; r.b = b0; }
-			else {
+			// fused pair of coplanar triangles: P belongs to triangle id.a (the lower user id, which also owns the shared
+			// diagonal) iff its barycentrics there are all inside; otherwise to id.b
+			const bool in_a = (r.a >= 0.0f) & (r.b >= 0.0f) & (r.a + r.b <= 1.0f);
+			if (!in_a) {
 				r.dev_prim = id.b;
 				const HotPrim &tb = sc.prim_plane[id.b];
 				plane_coords(*reinterpret_cast<const float4 *>(&tb.r1), *reinterpret_cast<const float4 *>(&tb.r2), P, r.a, r.b);
 			}
-		} else {
-			const HotPrim &tp = sc.prim_plane[id.a];
-			plane_coords(*reinterpret_cast<const float4 *>(&tp.r1), *reinterpret_cast<const float4 *>(&tp.r2), P, r.a, r.b);
 		}
 	}
 	return r;

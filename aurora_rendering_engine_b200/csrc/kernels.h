@@ -11,6 +11,7 @@ namespace areb {
 struct RenderArgs {
 	DevScene sc;
 	CamBasis cam;
+	CamF camf;       // cam rounded to fp32 (path integrator)
 	RtCam rtcam;     // RT_AO integrator only
 	PhiloxKey key;   // the ten round keys of the render seed (constant-bank operands in the kernel)
 	int W, H;
@@ -20,10 +21,10 @@ struct RenderArgs {
 	float tmin;
 	float bg_bottom[3], bg_top[3];
 	float *accum;                    // W*H*3 floats, sample SUMS are added
-	unsigned long long *counters;    // [0] rays [1] node visits [2] quad tests [3] tri tests [4] sphere tests
+	unsigned long long *counters;    // [0] rays [1] node visits [2] quad tests [3] tri tests [4] sphere tests [5] box tests
 };
 
-enum { CNT_RAYS = 0, CNT_NODES = 1, CNT_QUADS = 2, CNT_TRIS = 3, CNT_SPHERES = 4, CNT_N = 8 };
+enum { CNT_RAYS = 0, CNT_NODES = 1, CNT_QUADS = 2, CNT_TRIS = 3, CNT_SPHERES = 4, CNT_BOXES = 5, CNT_N = 8 };
 
 // fp64 harness (harness64.cu, -fmad=false)
 void launch_hit64(const DevScene &sc, int n, const double *Q, const double *D, double tmin, int *prim, double *t, double *P, double *N, double *uv, cudaStream_t s);

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_path(const __grid_con
 	__syncthreads();
 	int x0, y0;
 	warp_tile_origin(A.W, x0, y0);
-	const CamT<float> cam = cam_from_basis<float>(A.cam);
+	const CamT<float> cam = cam_from_f32(A.camf);
 	const float inv_w = 1.0f / (float)A.W, inv_h = 1.0f / (float)A.H;
 	const HotRange br = A.sc.brute_range;
 	const HotIds *ids = BVH ? A.sc.bvh_ids : A.sc.brute_ids;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_path(const __grid_con
 	float su = 0.f, sv = 0.f;
 	int smat = 0, stex = 0;
 	unsigned int rays = 0;
-	TravCounters tc = { 0, 0, 0, 0 };
+	TravCounters tc = { 0, 0, 0, 0, 0 };
 
 	while (true) {
 		// ---- A. trace + classify ----------------------------------------------------------------------
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_path(const __grid_con
 			Hit h;
 			h.t = INFINITY; h.idx = -1;
 			if (BVH) intersect_bvh<COUNT>(A.sc, o, d, A.tmin, h, &tc);
-			else intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, o, d, A.tmin, h);
+			else intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, br.nb, o, d, A.tmin, h);
 			++rays;
 			F3 contrib = mk<float>(0.f, 0.f, 0.f);
 			bool done;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_path(const __grid_con
 				done = true;
 			} else {
 				sP = o + h.t * d;
-				const Resolved rs = resolve_hit(A.sc, ids, h.idx, sP);
+				const Resolved rs = BVH ? resolve_hit<ldg4>(A.sc, A.sc.bvh_prims, ids, h.idx, o, d, h.t, sP) : resolve_hit<lds4>(A.sc, s_prims, ids, h.idx, o, d, h.t, sP);
 				const PrimInfo pi = A.sc.info[rs.dev_prim];
 				surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, su, sv);
 				smat = pi.mat; stex = pi.tex;
@@ -178,9 +178,9 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_path(const __grid_con
 	for (int off = 16; off > 0; off >>= 1) r64 += __shfl_down_sync(0xffffffffu, r64, off);
 	if (lane == 0 && r64) atomicAdd(A.counters + CNT_RAYS, r64);
 	if (BVH && COUNT) {
-		unsigned long long c[4] = { tc.nodes, tc.quads, tc.tris, tc.spheres };
+		unsigned long long c[5] = { tc.nodes, tc.quads, tc.tris, tc.spheres, tc.boxes };
 #pragma unroll
-		for (int k = 0; k < 4; ++k) {
+		for (int k = 0; k < 5; ++k) {
 #pragma unroll
 			for (int off = 16; off > 0; off >>= 1) c[k] += __shfl_down_sync(0xffffffffu, c[k], off);
 			if (lane == 0 && c[k]) atomicAdd(A.counters + CNT_NODES + k, c[k]);
@@ -214,14 +214,14 @@ __global__ void k_hit32(DevScene sc, int n, const double *__restrict__ Q, const 
 	h.t = INFINITY; h.idx = -1;
 	TravCounters tc;
 	if (use_bvh) intersect_bvh<false>(sc, o, d, tmin, h, &tc);
-	else intersect_range<ldg4>(sc.brute, sc.brute_range.first, sc.brute_range.nq, sc.brute_range.nt, sc.brute_range.ns, o, d, tmin, h);
+	else intersect_range<ldg4>(sc.brute, sc.brute_range.first, sc.brute_range.nq, sc.brute_range.nt, sc.brute_range.ns, sc.brute_range.nb, o, d, tmin, h);
 	const float nan = nan_t<float>();
 	F3 x = mk<float>(nan, nan, nan), nn = x;
 	float cu = nan, cv = nan;
 	int uid = -1;
 	if (h.idx >= 0) {
 		x = o + h.t * d;
-		Resolved rs = resolve_hit(sc, use_bvh ? sc.bvh_ids : sc.brute_ids, h.idx, x);
+		Resolved rs = resolve_hit<ldg4>(sc, use_bvh ? sc.bvh_prims : sc.brute, use_bvh ? sc.bvh_ids : sc.brute_ids, h.idx, o, d, h.t, x);
 		uid = sc.info[rs.dev_prim].user_id;
 		surface_at(sc, rs.dev_prim, x, rs.a, rs.b, nn, cu, cv);
 	}

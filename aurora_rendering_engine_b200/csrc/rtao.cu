@@ -13,7 +13,8 @@
 // (rt.cpp:268-270 reflects the view vector, not the incoming direction), so it re-hits its own triangle at
 // t ~ EPS/cos — a decision that sits on the t > EPS threshold and flips with the last bit.  Only sinf/cosf/acosf
 // (AO and gather directions) may differ from glibc by an ulp; the random source is Philox instead of
-// mt19937(random_device), stream layout documented in oracle/are_oracle.c section (3).
+// mt19937(random_device); stream layout: counter = (pixel, sample, slot, stream) with stream 1 = AO
+// ray `slot`, stream 2 = gather sample/bounce `slot`.
 #include "dev_types.h"
 #include "kernels.h"
 #include "philox.cuh"

@@ -67,14 +67,22 @@ HotPrim sphere_form(D3 c, double r) {
 	return h;
 }
 
-enum HotKind { HK_QUAD = 0, HK_TRI = 1, HK_SPHERE = 2 };
+enum HotKind { HK_BOX = 0, HK_QUAD = 1, HK_TRI = 2, HK_SPHERE = 3, HK_KINDS = 4 };  // emission order inside a range
 struct HotItem {
 	int kind;
-	HotPrim rec;
+	HotPrim rec, rec2;  // rec2: second slot of a box
 	HotIds ids;
 	Box box;
 	double c[3];  // centroid
+	D3 gQ, gu, gv;  // parallelogram geometry (quads / fused pairs), for box detection
+	bool dead = false;  // absorbed into a box
 };
+inline void emit_item(const HotItem &it, std::vector<HotPrim> &prims, std::vector<HotIds> &ids) {
+	prims.push_back(it.rec);
+	ids.push_back(it.ids);
+	if (it.kind == HK_BOX) { prims.push_back(it.rec2); ids.push_back(it.ids); }
+}
+inline int pack_meta(const int cnt[HK_KINDS]) { return cnt[HK_QUAD] | (cnt[HK_TRI] << 8) | (cnt[HK_SPHERE] << 16) | (cnt[HK_BOX] << 24); }
 
 struct VKey {
 	uint64_t a[3];
@@ -139,18 +147,17 @@ struct Builder {
 	ChildRef make_leaf(int lo, int hi) {
 		ChildRef c;
 		c.box.reset();
-		int first = (int)out.bvh_prims.size(), cnt[3] = { 0, 0, 0 };
-		for (int kind = 0; kind < 3; ++kind)
+		int first = (int)out.bvh_prims.size(), cnt[HK_KINDS] = { 0, 0, 0, 0 };
+		for (int kind = 0; kind < HK_KINDS; ++kind)
 			for (int i = lo; i < hi; ++i) {
 				const HotItem &it = items[idx[i]];
 				if (it.kind != kind) continue;
-				out.bvh_prims.push_back(it.rec);
-				out.bvh_ids.push_back(it.ids);
+				emit_item(it, out.bvh_prims, out.bvh_ids);
 				c.box.grow(it.box);
 				cnt[kind]++;
 			}
 		c.ref = ~first;
-		c.meta = cnt[0] | (cnt[1] << 8) | (cnt[2] << 16);
+		c.meta = pack_meta(cnt);
 		return c;
 	}
 	ChildRef build(int lo, int hi, int depth) {
@@ -399,9 +406,10 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 	hot.reserve(order.size());
 	const int nt = out.n_tri;
 	std::vector<char> fused(nt, 0);
-	auto push_item = [&](int kind, const HotPrim &rec, HotIds ids, const Box &b) {
+	auto push_item = [&](int kind, const HotPrim &rec, HotIds ids, const Box &b, D3 gQ, D3 gu, D3 gv) {
 		HotItem it;
-		it.kind = kind; it.rec = rec; it.ids = ids; it.box = b;
+		it.kind = kind; it.rec = rec; it.rec2 = rec; it.ids = ids; it.box = b;
+		it.gQ = gQ; it.gu = gu; it.gv = gv;
 		for (int k = 0; k < 3; ++k) it.c[k] = 0.5 * (b.lo[k] + b.hi[k]);
 		hot.push_back(it);
 	};
@@ -435,7 +443,7 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 					HotPrim rec = plane_form(d0, va - d0, vb - d0);
 					Box bx = pbox[t];
 					bx.grow(pbox[j]);
-					push_item(HK_QUAD, rec, { ta, tb }, bx);
+					push_item(HK_QUAD, rec, { ta, tb }, bx, d0, va - d0, vb - d0);
 					fused[t] = fused[j] = 1;
 					out.n_fused_pairs++;
 					break;
@@ -447,23 +455,138 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 		int type = out.info[dp].type;
 		if (type == PT_TRIANGLE && fused[dp]) continue;
 		int kind = type == PT_TRIANGLE ? HK_TRI : (type == PT_QUAD ? HK_QUAD : HK_SPHERE);
-		push_item(kind, out.prim_plane[dp], { (int)dp, -1 }, pbox[dp]);
+		const HostPrim &hp = hs.prims[order[dp]];
+		push_item(kind, out.prim_plane[dp], { (int)dp, -1 }, pbox[dp], d3(hp.Q), d3(hp.u), d3(hp.v));
 	}
-	out.n_hot = (int)hot.size();
+	// ---- box detection: parallelograms that are faces of one parallelepiped become a single slab-test primitive ----
+	if (opt.fuse_boxes) {
+		std::vector<int> quads;
+		for (size_t i = 0; i < hot.size(); ++i)
+			if (hot[i].kind == HK_QUAD) quads.push_back((int)i);
+		if (quads.size() >= 4 && quads.size() <= 2048) {
+			auto corners = [&](const HotItem &q, D3 c[4]) { c[0] = q.gQ; c[1] = q.gQ + q.gu; c[2] = q.gQ + q.gv; c[3] = q.gQ + q.gu + q.gv; };
+			auto same_pt = [&](D3 a, D3 b, double tol) { return len(a - b) <= tol; };
+			auto find_face = [&](D3 B, D3 e1, D3 e2, double tol) -> int {  // live quad whose corner set is {B, B+e1, B+e2, B+e1+e2}
+				const D3 want[4] = { B, B + e1, B + e2, B + e1 + e2 };
+				for (int qi : quads) {
+					const HotItem &q = hot[qi];
+					if (q.dead) continue;
+					D3 c[4];
+					corners(q, c);
+					bool all = true;
+					for (int a = 0; a < 4 && all; ++a) {
+						bool found = false;
+						for (int b = 0; b < 4; ++b) found = found || same_pt(want[a], c[b], tol);
+						all = found;
+					}
+					if (all) return qi;
+				}
+				return -1;
+			};
+			for (int fi : quads) {
+				if (hot[fi].dead) continue;
+				D3 fc[4];
+				corners(hot[fi], fc);
+				// the four (base corner, edge, other edge) views of F
+				const D3 gu = hot[fi].gu, gv = hot[fi].gv, mu = -1.0 * gu, mv = -1.0 * gv;
+				const D3 bases[8] = { fc[0], fc[1], fc[2], fc[3], fc[0], fc[1], fc[2], fc[3] };
+				const D3 e1s[8] = { gu, mu, gu, mu, gv, gv, mv, mv };  // the edge shared with the neighbour G
+				const D3 e2s[8] = { gv, gv, mv, mv, gu, mu, gu, mu };
+				bool made = false;
+				for (int view = 0; view < 8 && !made; ++view) {
+					const D3 B = bases[view], a = e1s[view], b = e2s[view];
+					const double tol = 1e-9 * (len(a) + len(b));
+					const D3 fn = cross(a, b);
+					// a neighbour G sharing the edge (B, B+a) and leaving F's plane gives the third edge c
+					for (int gi : quads) {
+						if (gi == fi || hot[gi].dead) continue;
+						D3 gc[4];
+						corners(hot[gi], gc);
+						int iB = -1, iA = -1;
+						for (int k = 0; k < 4; ++k) {
+							if (same_pt(gc[k], B, tol)) iB = k;
+							if (same_pt(gc[k], B + a, tol)) iA = k;
+						}
+						if (iB < 0 || iA < 0) continue;
+						D3 c = { 0, 0, 0 };
+						bool have = false;
+						for (int k = 0; k < 4 && !have; ++k) {  // the corner adjacent to B other than B+a: B+c with B+a+c also in G
+							if (k == iB || k == iA) continue;
+							D3 cand = gc[k] - B;
+							for (int m = 0; m < 4; ++m)
+								if (m != k && m != iB && m != iA && same_pt(gc[m], B + a + cand, tol)) { c = cand; have = true; }
+						}
+						if (!have) continue;
+						if (std::fabs(dot(fn, c)) <= 1e-9 * len(fn) * len(c)) continue;  // coplanar neighbour: not a box
+						const double tol3 = 1e-9 * (len(a) + len(b) + len(c));
+						// faces: 0/1 = -a/+a (spanned by b,c), 2/3 = -b/+b (a,c), 4/5 = -c/+c (a,b)
+						const int face[6] = { find_face(B, b, c, tol3), find_face(B + a, b, c, tol3), find_face(B, a, c, tol3),
+							find_face(B + b, a, c, tol3), find_face(B, a, b, tol3), find_face(B + c, a, b, tol3) };
+						int present = 0;
+						bool distinct = true;
+						for (int k = 0; k < 6; ++k) {
+							if (face[k] >= 0) present++;
+							for (int m = 0; m < k; ++m)
+								if (face[k] >= 0 && face[k] == face[m]) distinct = false;
+						}
+						if (present < 4 || !distinct) continue;
+						const D3 edges[3] = { a, b, c };
+						const D3 centre = B + 0.5 * (a + b + c);
+						HotItem bx;
+						bx.kind = HK_BOX;
+						bx.ids = { -1 - out.n_boxes, -1 };
+						bx.box.reset();
+						f4 *slots[3] = { &bx.rec.r0, &bx.rec.r1, &bx.rec.r2 };
+						float hw[3];
+						for (int i = 0; i < 3; ++i) {
+							D3 n = cross(edges[(i + 1) % 3], edges[(i + 2) % 3]);
+							n = (1.0 / len(n)) * n;
+							if (dot(n, edges[i]) < 0) n = -1.0 * n;
+							*slots[i] = { (float)n.x, (float)n.y, (float)n.z, (float)dot(n, centre) };
+							hw[i] = (float)(0.5 * dot(n, edges[i]));
+						}
+						unsigned mask = 0;
+						for (int k = 0; k < 6; ++k) {
+							if (face[k] >= 0) {
+								mask |= 1u << k;
+								out.box_faces.push_back(hot[face[k]].ids);
+								bx.box.grow(hot[face[k]].box);
+								hot[face[k]].dead = true;
+							} else out.box_faces.push_back({ -1, -1 });
+						}
+						float maskf;
+						std::memcpy(&maskf, &mask, 4);
+						bx.rec2.r0 = { hw[0], hw[1], hw[2], maskf };
+						bx.rec2.r1 = { 0, 0, 0, 0 };
+						bx.rec2.r2 = { 0, 0, 0, 0 };
+						for (int k = 0; k < 3; ++k) bx.c[k] = 0.5 * (bx.box.lo[k] + bx.box.hi[k]);
+						bx.gQ = B; bx.gu = a; bx.gv = b;
+						hot.push_back(bx);
+						out.n_boxes++;
+						made = true;
+						break;
+					}
+				}
+			}
+			hot.erase(std::remove_if(hot.begin(), hot.end(), [](const HotItem &it) { return it.dead; }), hot.end());
+		}
+	}
+	out.n_hot = 0;
+	for (const HotItem &it : hot) out.n_hot += it.kind == HK_BOX ? 2 : 1;
 	// ---- brute list (type-sorted) ----
 	if (out.n_hot <= opt.brute_max) {
-		int cnt[3] = { 0, 0, 0 };
-		for (int kind = 0; kind < 3; ++kind)
+		int cnt[HK_KINDS] = { 0, 0, 0, 0 };
+		for (int kind = 0; kind < HK_KINDS; ++kind)
 			for (const HotItem &it : hot)
-				if (it.kind == kind) { out.brute.push_back(it.rec); out.brute_ids.push_back(it.ids); cnt[kind]++; }
-		out.brute_range = { 0, cnt[0], cnt[1], cnt[2] };
+				if (it.kind == kind) { emit_item(it, out.brute, out.brute_ids); cnt[kind]++; }
+		out.brute_range = { 0, cnt[HK_QUAD], cnt[HK_TRI], cnt[HK_SPHERE], cnt[HK_BOX] };
 	}
 	// ---- BVH ----
-	if (out.n_hot > 0) {
+	if (!hot.empty()) {
 		Builder b(hot, out, std::max(1, std::min(opt.leaf_size, 16)));
 		out.bvh_prims.reserve(hot.size());
 		out.bvh_ids.reserve(hot.size());
-		ChildRef root = b.build(0, out.n_hot, 0);
+		ChildRef root = b.build(0, (int)hot.size(), 0);
 		if (root.ref < 0) out.root_leaf_meta = root.meta;
 		out.bvh_depth = b.max_depth;
 	}

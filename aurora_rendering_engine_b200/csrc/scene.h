@@ -43,7 +43,9 @@ struct HostScene {
 struct CompiledScene {
 	std::vector<HotPrim> brute;
 	std::vector<HotIds> brute_ids;
-	HotRange brute_range = { 0, 0, 0, 0 };
+	HotRange brute_range = { 0, 0, 0, 0, 0 };
+	std::vector<HotIds> box_faces;  // 6 per box
+	int n_boxes = 0;
 	std::vector<HotPrim> bvh_prims;
 	std::vector<HotIds> bvh_ids;
 	std::vector<BvhNode> nodes;
@@ -63,6 +65,7 @@ struct CompiledScene {
 
 struct CompileOptions {
 	bool fuse_parallelograms = true;
+	bool fuse_boxes = true;
 	int leaf_size = 4;
 	int brute_max = 1024;
 };

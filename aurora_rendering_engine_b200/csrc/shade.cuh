@@ -225,6 +225,14 @@ __host__ __device__ __forceinline__ CamT<T> cam_from_basis(const CamBasis &b) {
 	c.jitter = b.jitter;
 	return c;
 }
+__device__ __forceinline__ CamT<float> cam_from_f32(const CamF &b) {
+	CamT<float> c;
+	c.pos = mk<float>(b.pos[0], b.pos[1], b.pos[2]); c.fwd = mk<float>(b.fwd[0], b.fwd[1], b.fwd[2]);
+	c.right = mk<float>(b.right[0], b.right[1], b.right[2]); c.up = mk<float>(b.up[0], b.up[1], b.up[2]);
+	c.sx = b.sx; c.sy = b.sy; c.lens_r = b.lens_r; c.focus = b.focus;
+	c.jitter = b.jitter;
+	return c;
+}
 // r = (sx, sy, lens r0, lens r1); the caller substitutes sx = sy = 0.5 when jitter is off
 template <typename T>
 __device__ __forceinline__ void cam_ray(const CamT<T> &c, T inv_w, T inv_h, int x, int y, Rnd4<T> r, V3<T> &o, V3<T> &d) {

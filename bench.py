@@ -36,6 +36,8 @@ UNIT = "Msamples/s"
 
 # SURVEY.md §8d algorithmic FLOP figures
 F_TRI, F_SPH, F_QUAD, F_AABB, F_SCATTER, F_PRIMARY = 51.0, 28.0, 45.0, 24.0, 40.0, 40.0
+# a parallelepiped test = three slab pairs with arbitrary normals: 3 x (two dots 10 + sub 1 + rcp 1 + 2 mul + 2 add) + 4 min/max
+F_BOX = 52.0
 
 
 def parse():
@@ -266,7 +268,7 @@ def run_b200(a):
     st = ctx.render_device(job.cam, job.params(sample_base(a.warmup), S), scratch.data_ptr(), want_stats=True, count_tests=True)
     rays_per_sample = st.rays / max(1, st.samples)
     use_bvh = st.node_visits > 0
-    flops = (F_TRI * st.tri_tests + F_SPH * st.sphere_tests + F_QUAD * st.quad_tests + F_AABB * 2 * st.node_visits
+    flops = (F_TRI * st.tri_tests + F_SPH * st.sphere_tests + F_QUAD * st.quad_tests + F_BOX * st.box_tests + F_AABB * 2 * st.node_visits
              + F_SCATTER * max(0, st.rays - st.samples) + F_PRIMARY * st.samples)
     kernel_ms = step_ms[0] if step_ms else st.kernel_ms
     avg_kernel_ms = sum(step_ms) / max(1, len(step_ms))
@@ -303,7 +305,7 @@ def run_b200(a):
                 "traffic": None, "peak_source": "measured on this GPU by are_cuda_measure_fp32_peak (register-resident FFMA loop); MEASURED_PEAKS.json has no FP32 figure",
                 "nominal_peak": nominal, "kernel": "k_render_path<%s>" % ("bvh" if use_bvh else "brute/smem"), "kernel_ms": avg_kernel_ms,
                 "flops_per_launch": flops, "counted": {"rays": st.rays, "tri_tests": st.tri_tests, "quad_tests": st.quad_tests,
-                                                        "sphere_tests": st.sphere_tests, "node_visits": st.node_visits},
+                                                        "sphere_tests": st.sphere_tests, "box_tests": st.box_tests, "node_visits": st.node_visits},
                 "hbm_algorithmic_gbs": (2.0 * W * H * 12) / (avg_kernel_ms * 1e-3) / 1e9}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": total_ms / max(1, a.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

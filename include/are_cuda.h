@@ -117,6 +117,7 @@ typedef struct are_render_stats {
 	uint64_t rays; /* every ray segment cast, incl. bounces / AO rays */
 	uint64_t tri_tests, quad_tests, sphere_tests; /* ray-primitive tests executed */
 	uint64_t node_visits; /* BVH node (AABB pair) visits */
+	uint64_t box_tests; /* parallelepiped (three slab pairs) tests: boxes detected among the scene's parallelograms */
 	double kernel_ms; /* device time of the render kernel(s), CUDA events on the launch stream */
 	uint64_t launches; /* kernels launched by this call */
 } are_render_stats;
@@ -147,6 +148,11 @@ int are_cuda_clear(are_cuda_ctx *ctx);
 int are_cuda_num_primitives(are_cuda_ctx *ctx);
 /* Flatten to SoA, build the BVH (host, binned SAH) and upload. Returns bytes uploaded via *h2d_bytes (may be NULL). */
 int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes);
+
+/* Host-only probe of the scene compiler (no GPU needed): flattens n_tri triangles exactly as are_cuda_commit would
+ * and reports out[8] = { hot slots, fused triangle pairs, boxes, BVH nodes, BVH depth, brute quads, brute triangles,
+ * brute boxes }.  Lets CPU-only test boxes check parallelogram fusion / box detection / BVH construction. */
+int are_cuda_compile_probe(int n_tri, const double *Q, const double *u, const double *v, int out[8]);
 
 /* ---- per-ray harness ----------------------------------------------------------------------------------- */
 /* Closest hit of n rays against the committed scene.  D is normalised first, as are::Ray's ctor does

@@ -358,7 +358,7 @@ typedef struct {
 	double background_bottom[3], background_top[3];
 } orc_params;
 typedef struct {
-	uint64_t samples, rays, tri_tests, quad_tests, sphere_tests, node_visits;
+	uint64_t samples, rays, tri_tests, quad_tests, sphere_tests, node_visits, box_tests;
 	double kernel_ms;
 	uint64_t launches;
 } orc_stats;

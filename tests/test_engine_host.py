@@ -85,3 +85,28 @@ def test_scene_feeds_the_cpu_twin(oracle):
     for sc in (scenes.rt_cornell(), scenes.cornell_box(), scenes.textured(width=8, height=8), scenes.stress(n_prims=100)):
         osc = sc.feed(oracle.scene())
         assert osc.num_primitives() == sc.num_prims
+
+
+def test_scene_compiler_fuses_parallelograms_and_boxes(lib):
+    """Host-only probe of the scene compiler: the 36-triangle Cornell box becomes 18 parallelograms, of which 17 are
+    faces of three parallelepipeds (the room with its front open, the two boxes); the light stays a quad."""
+    import numpy as np
+    from aurora_rendering_engine_b200 import capi
+
+    def tris(sc):
+        return (np.stack([t[0] for t in sc.tris]), np.stack([t[1] for t in sc.tris]), np.stack([t[2] for t in sc.tris]))
+
+    r = capi.compile_probe(*tris(scenes.cornell_box()))
+    assert (r["fused_pairs"], r["boxes"], r["brute_quads"], r["brute_tris"], r["brute_boxes"]) == (18, 3, 1, 0, 3)
+    assert r["hot_slots"] == 3 * 2 + 1 and r["bvh_nodes"] == 0
+    r = capi.compile_probe(*tris(scenes.rt_cornell()))
+    assert (r["fused_pairs"], r["boxes"], r["brute_quads"]) == (17, 3, 0)
+    # random triangles: nothing to fuse, a real hierarchy
+    r = capi.compile_probe(*tris(scenes.stress(n_prims=2000)))
+    assert r["fused_pairs"] == 0 and r["boxes"] == 0 and r["hot_slots"] == 1000 and r["bvh_nodes"] > 200 and 8 <= r["bvh_depth"] <= 40
+    # a lone parallelogram pair and an open book (two quads sharing an edge) are not boxes
+    Q = np.array([[0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0]], float)
+    u = np.array([[1, 0, 0], [1, 1, 0], [1, 0, 0], [1, 0, 1]], float)
+    v = np.array([[1, 1, 0], [0, 1, 0], [1, 0, 1], [0, 0, 1]], float)
+    r = capi.compile_probe(Q, u, v)
+    assert r["fused_pairs"] == 2 and r["boxes"] == 0 and r["brute_quads"] == 2

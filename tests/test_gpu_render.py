@@ -128,9 +128,22 @@ def test_counters_brute_and_bvh(ctx):
     sv = ctx.render_device(cam, capi.make_params(**sc.params_args(sample_count=4, traversal=2)), acc, want_stats=True, count_tests=True)
     ctx.free_accum(acc)
     assert sb.rays == sv.rays  # same arithmetic -> same paths
-    assert sb.quad_tests == sb.rays * 18 and sb.tri_tests == 0  # 36 triangles fused into 18 parallelograms
-    assert 0 < sv.quad_tests < sb.quad_tests and sv.node_visits > 0
+    # 36 triangles -> 18 fused parallelograms -> room (5 faces) + 2 boxes as slab-test primitives, + the light quad
+    assert sb.box_tests == sb.rays * 3 and sb.quad_tests == sb.rays and sb.tri_tests == 0
+    assert sv.box_tests == sb.box_tests and sv.node_visits == 0  # 4 hot primitives = one BVH leaf
     assert sb.launches == 1 and sb.kernel_ms > 0
+    # a scene with a real hierarchy
+    sc = scenes.rtiow_final(width=64, height=36)
+    cam = capi.make_camera(**sc.camera_args())
+    ctx.clear()
+    sc.feed(ctx)
+    ctx.commit()
+    acc = ctx.alloc_accum(64, 36)
+    sb = ctx.render_device(cam, capi.make_params(**sc.params_args(sample_count=2, traversal=1)), acc, want_stats=True)
+    sv = ctx.render_device(cam, capi.make_params(**sc.params_args(sample_count=2, traversal=2)), acc, want_stats=True, count_tests=True)
+    ctx.free_accum(acc)
+    assert sb.rays == sv.rays and sb.sphere_tests == sb.rays * sc.num_prims
+    assert 0 < sv.sphere_tests < sb.sphere_tests / 10 and sv.node_visits > sv.rays
 
 
 def test_rt_ao_integrator_matches_cpu_restatement(ctx, oracle):
