@@ -316,7 +316,7 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	if ((st = upload(ctx, cs.vec, &d.field, bytes)) != ARE_OK) return st;
 	UP(brute, brute) UP(brute_ids, brute_ids) UP(bvh_prims, bvh_prims) UP(bvh_ids, bvh_ids) UP(nodes, nodes)
 	UP(info, info) UP(prim_plane, prim_plane) UP(tri_uv, tri_uv) UP(tri64, tri64) UP(quad64, quad64) UP(sph64, sph64)
-	UP(tri_uv64, tri_uv64) UP(mats, mats) UP(texs, texs) UP(tex_data, tex_data) UP(rt_tris, rt_tris) UP(box_faces, box_faces)
+	UP(tri_uv64, tri_uv64) UP(mats, mats) UP(texs, texs) UP(tex_data, tex_data) UP(rt_tris, rt_tris) UP(box_faces, box_faces) UP(shade, shade)
 #undef UP
 	d.brute_range = cs.brute_range;
 	d.n_nodes = (int)cs.nodes.size();

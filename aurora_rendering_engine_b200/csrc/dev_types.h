@@ -37,10 +37,21 @@ struct HotPrim { f4 r0, r1, r2; };  // 48 B
 
 // ids of the user primitives behind one hot primitive: b >= 0 only for a fused triangle pair
 // (a = the triangle on the alpha >= beta side of the diagonal and the lower user id).
+// b <= -2 marks a pair whose two triangles shade identically (same material, same position-only texture, same
+// normal): the second triangle is -2 - b and the render loop need not find out which half was hit.
 // For a box slot: a = -1 - box index (its six per-face HotIds live in DevScene::box_faces[6*index + face]).
 struct HotIds { int a, b; };
 
 struct PrimInfo { int user_id, mat, tex, type; };  // per device primitive (device order: triangles, quads, spheres)
+
+// Everything the shading stage needs for the common case, 32 B per device primitive (two LDG.128 per hit instead
+// of ~10 dependent loads through info -> material -> texture tables):
+//   r0 = (N.x, N.y, N.z, bits)   geometric unit normal (spheres: unused), bits = material kind | SHADE_FAST << 8
+//   r1 = (c.r, c.g, c.b, p0)     albedo (emitted radiance for lights, already scaled); p0 = fuzz | ior
+// SHADE_FAST is set when the effective texture is a solid colour and the material is Diffuse / Lambertian / Metal /
+// Dielectric / DiffuseLight; other primitives take the general path (texture evaluation, Reflective lobe choice).
+struct ShadeRec { f4 r0, r1; };
+enum { SHADE_FAST = 1 };
 
 struct MaterialRec {
 	int kind, pad_;
@@ -85,6 +96,7 @@ struct DevScene {
 	const HotIds *box_faces;   // 6 per box: the fused pair / quad behind each face, {-1,-1} when the face is absent
 	// --- per device primitive ---
 	const PrimInfo *info;
+	const ShadeRec *shade;     // per device primitive
 	const HotPrim *prim_plane; // plane form (or sphere record) of every user primitive, device order
 	const float *tri_uv;       // 6 floats per triangle
 	// rt.cpp-style fp32 triangle records for the RT_AO integrator, 3 x float4 per triangle:

@@ -82,59 +82,43 @@ __device__ __forceinline__ void test_sphere(float4 r0, float4 r1, V3<float> o, V
 // [m-k, m+k] (already ordered, no min/max), entering through face "-" when s > 0.  A line meets a convex body's
 // surface at most twice, so the only possible hits on the (two-sided) faces are the entry t_in = max(m-k) and the
 // exit t_out = min(m+k); each is accepted if it lies in the (tmin, best) window and its face is present.
-struct BoxSlabs {
-	float tn[3], tf[3], s[3];
-};
-__device__ __forceinline__ float nonzero(float s) {  // keep the sign, push |s| away from 0 so that 1/s stays finite
-	return __uint_as_float((__float_as_uint(fmaxf(fabsf(s), 1e-30f)) & 0x7fffffffu) | (__float_as_uint(s) & 0x80000000u));
-}
-__device__ __forceinline__ BoxSlabs box_slabs(float4 r0, float4 r1, float4 r2, float4 r3, V3<float> o, V3<float> d) {
-	BoxSlabs b;
-	const float4 r[3] = { r0, r1, r2 };
-	const float hw[3] = { r3.x, r3.y, r3.z };
-#pragma unroll
-	for (int i = 0; i < 3; ++i) {
-		float s = nonzero(fmaf(r[i].x, d.x, fmaf(r[i].y, d.y, r[i].z * d.z)));
-		float e = fmaf(-r[i].x, o.x, fmaf(-r[i].y, o.y, fmaf(-r[i].z, o.z, r[i].w)));
-		float inv = rcp_fast(s);
-		float m = e * inv, k = hw[i] * fabsf(inv);
-		b.tn[i] = m - k;
-		b.tf[i] = m + k;
-		b.s[i] = s;
-	}
-	return b;
-}
-// face index (2*axis + side) the ray crosses at parameter t_in (entry) / t_out (exit)
-__device__ __forceinline__ int box_entry_face(const BoxSlabs &b) {
-	int ax = (b.tn[0] >= b.tn[1]) ? ((b.tn[0] >= b.tn[2]) ? 0 : 2) : ((b.tn[1] >= b.tn[2]) ? 1 : 2);
-	float s = ax == 0 ? b.s[0] : (ax == 1 ? b.s[1] : b.s[2]);
-	return 2 * ax + (s > 0.0f ? 0 : 1);
-}
-__device__ __forceinline__ int box_exit_face(const BoxSlabs &b) {
-	int ax = (b.tf[0] <= b.tf[1]) ? ((b.tf[0] <= b.tf[2]) ? 0 : 2) : ((b.tf[1] <= b.tf[2]) ? 1 : 2);
-	float s = ax == 0 ? b.s[0] : (ax == 1 ? b.s[1] : b.s[2]);
-	return 2 * ax + (s > 0.0f ? 1 : 0);
-}
-// The candidate hit of a box: returns t (NaN-free) and whether it is acceptable. A closed box (mask 63) skips the
-// face-presence logic inside the loop; the face is recovered for the winner afterwards (box_hit_face).
+// The 1e-30 folded into the dot product keeps s away from an exact zero (a direction lying exactly in a face plane
+// occurs with probability 2^-24 per cosine sample), so 1/s stays finite and the slab ordering below stays valid.
+//
+// An open box is stored with its one absent face on axis 2, "-" side (scene compiler): a ray enters through that
+// hole iff the entry is decided by axis 2 while moving along +n2, and leaves through it iff the exit is decided by
+// axis 2 while moving along -n2.
 __device__ __forceinline__ void test_box(float4 r0, float4 r1, float4 r2, float4 r3, V3<float> o, V3<float> d, float tmin, int idx, Hit &h) {
-	const BoxSlabs b = box_slabs(r0, r1, r2, r3, o, d);
-	const float t_in = fmaxf(fmaxf(b.tn[0], b.tn[1]), b.tn[2]), t_out = fminf(fminf(b.tf[0], b.tf[1]), b.tf[2]);
-	const unsigned mask = __float_as_uint(r3.w);
+	const float s0 = fmaf(r0.x, d.x, fmaf(r0.y, d.y, fmaf(r0.z, d.z, 1e-30f)));
+	const float s1 = fmaf(r1.x, d.x, fmaf(r1.y, d.y, fmaf(r1.z, d.z, 1e-30f)));
+	const float s2 = fmaf(r2.x, d.x, fmaf(r2.y, d.y, fmaf(r2.z, d.z, 1e-30f)));
+	const float e0 = fmaf(-r0.x, o.x, fmaf(-r0.y, o.y, fmaf(-r0.z, o.z, r0.w)));
+	const float e1 = fmaf(-r1.x, o.x, fmaf(-r1.y, o.y, fmaf(-r1.z, o.z, r1.w)));
+	const float e2 = fmaf(-r2.x, o.x, fmaf(-r2.y, o.y, fmaf(-r2.z, o.z, r2.w)));
+	const float i0 = rcp_fast(s0), i1 = rcp_fast(s1), i2 = rcp_fast(s2);
+	const float m0 = e0 * i0, m1 = e1 * i1, m2 = e2 * i2;
+	const float k0 = r3.x * fabsf(i0), k1 = r3.y * fabsf(i1), k2 = r3.z * fabsf(i2);
+	const float n2 = m2 - k2, f2 = m2 + k2;
+	const float t_in = fmaxf(fmaxf(m0 - k0, m1 - k1), n2), t_out = fminf(fminf(m0 + k0, m1 + k1), f2);
 	bool in_ok = t_in > tmin, out_ok = t_out > tmin;
-	if (mask != 63u) {  // warp-uniform: all lanes test the same primitive
-		in_ok = in_ok && ((mask >> box_entry_face(b)) & 1u);
-		out_ok = out_ok && ((mask >> box_exit_face(b)) & 1u);
+	if (r3.w != 0.0f) {  // warp-uniform: all lanes test the same primitive
+		in_ok = in_ok & !((n2 == t_in) & (s2 > 0.0f));
+		out_ok = out_ok & !((f2 == t_out) & (s2 < 0.0f));
 	}
 	const float t = in_ok ? t_in : t_out;
 	const bool ok = (t_in <= t_out) & (in_ok | out_ok) & (t < h.t);
 	if (ok) { h.t = t; h.idx = idx; }
 }
-// which face a winning box hit at distance t lies on (same arithmetic as test_box, so t compares exactly)
-__device__ __forceinline__ int box_hit_face(float4 r0, float4 r1, float4 r2, float4 r3, V3<float> o, V3<float> d, float t) {
-	const BoxSlabs b = box_slabs(r0, r1, r2, r3, o, d);
-	const float t_in = fmaxf(fmaxf(b.tn[0], b.tn[1]), b.tn[2]);
-	return (t == t_in) ? box_entry_face(b) : box_exit_face(b);
+// Which face (2*axis + side) of a box the hit point P lies on: the axis whose normalised slab coordinate
+// q_i = (n_i·P - c_i)/h_i is closest to +-1, i.e. largest in magnitude; rih = (1/h_0, 1/h_1, 1/h_2).
+__device__ __forceinline__ int box_hit_face(float4 r0, float4 r1, float4 r2, float4 rih, V3<float> P) {
+	const float q0 = fmaf(r0.x, P.x, fmaf(r0.y, P.y, fmaf(r0.z, P.z, -r0.w))) * rih.x;
+	const float q1 = fmaf(r1.x, P.x, fmaf(r1.y, P.y, fmaf(r1.z, P.z, -r1.w))) * rih.y;
+	const float q2 = fmaf(r2.x, P.x, fmaf(r2.y, P.y, fmaf(r2.z, P.z, -r2.w))) * rih.z;
+	const float a0 = fabsf(q0), a1 = fabsf(q1), a2 = fabsf(q2);
+	const int ax = (a0 >= a1) ? ((a0 >= a2) ? 0 : 2) : ((a1 >= a2) ? 1 : 2);
+	const float q = ax == 0 ? q0 : (ax == 1 ? q1 : q2);
+	return 2 * ax + (q > 0.0f ? 1 : 0);
 }
 
 // Test a type-sorted run of hot primitives. LD = ldg4 (global / L2) or lds4 (shared-memory copy).
@@ -228,29 +212,32 @@ struct Resolved {
 	int dev_prim;   // device primitive index (device order: triangles, quads, spheres)
 	float a, b;     // planar coordinates in that primitive's own frame (0 for spheres)
 };
-// `hot` = the array (shared or global) the winning index refers to — needed again only for boxes, whose face is
-// re-derived from the ray; spheres carry no planar coordinates.
+// The user primitives behind hot slot idx. `hot` = the array (shared or global) the index refers to — needed again
+// only for boxes, whose face is found from the hit point.
 template <float4 (*LD)(const f4 *)>
-__device__ __forceinline__ Resolved resolve_hit(const DevScene &sc, const HotPrim *hot, const HotIds *ids, int idx, V3<float> o, V3<float> d, float t, V3<float> P) {
-	Resolved r;
+__device__ __forceinline__ HotIds hit_ids(const DevScene &sc, const HotPrim *hot, const HotIds *ids, int idx, V3<float> P) {
 	HotIds id = ids[idx];
-	if (id.a < 0) {  // box: find the face, continue with the parallelogram (fused pair or quad) behind it
-		const int face = box_hit_face(LD(&hot[idx].r0), LD(&hot[idx].r1), LD(&hot[idx].r2), LD(&hot[idx + 1].r0), o, d, t);
+	if (id.a < 0) {  // box: continue with the parallelogram (fused pair or quad) behind the face that was hit
+		const int face = box_hit_face(LD(&hot[idx].r0), LD(&hot[idx].r1), LD(&hot[idx].r2), LD(&hot[idx + 1].r1), P);
 		id = sc.box_faces[6 * (-1 - id.a) + face];
 	}
+	return id;
+}
+// Exact owner + its planar coordinates: for a fused pair of coplanar triangles, P belongs to triangle id.a (the
+// lower user id, which also owns the shared diagonal) iff its barycentrics there are all inside, else to the other.
+__device__ __forceinline__ Resolved resolve_exact(const DevScene &sc, HotIds id, V3<float> P) {
+	Resolved r;
 	r.dev_prim = id.a;
 	r.a = 0.0f;
 	r.b = 0.0f;
 	if (id.a < sc.n_tri + sc.n_quad) {
 		const HotPrim &ta = sc.prim_plane[id.a];
 		plane_coords(*reinterpret_cast<const float4 *>(&ta.r1), *reinterpret_cast<const float4 *>(&ta.r2), P, r.a, r.b);
-		if (id.b >= 0) {
-			// fused pair of coplanar triangles: P belongs to triangle id.a (the lower user id, which also owns the shared
-			// diagonal) iff its barycentrics there are all inside; otherwise to id.b
+		if (id.b != -1) {
 			const bool in_a = (r.a >= 0.0f) & (r.b >= 0.0f) & (r.a + r.b <= 1.0f);
 			if (!in_a) {
-				r.dev_prim = id.b;
-				const HotPrim &tb = sc.prim_plane[id.b];
+				r.dev_prim = id.b >= 0 ? id.b : -2 - id.b;
+				const HotPrim &tb = sc.prim_plane[r.dev_prim];
 				plane_coords(*reinterpret_cast<const float4 *>(&tb.r1), *reinterpret_cast<const float4 *>(&tb.r2), P, r.a, r.b);
 			}
 		}

@@ -83,9 +83,9 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_path(const __grid_con
 	uint32_t pixel = 0, sample = 0;
 	F3 o = mk<float>(0.f, 0.f, 0.f), d = mk<float>(0.f, 0.f, 1.f), thr = o;
 	// surface interaction carried from the classify stage to the scatter stage
-	F3 sP = o, sN = o;
-	float su = 0.f, sv = 0.f;
-	int smat = 0, stex = 0;
+	F3 sP = o, sN = o, scol = o;
+	float sp0 = 0.f;
+	int sdev = 0, sbits = 0;
 	unsigned int rays = 0;
 	TravCounters tc = { 0, 0, 0, 0, 0 };
 
@@ -104,18 +104,36 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_path(const __grid_con
 				done = true;
 			} else {
 				sP = o + h.t * d;
-				const Resolved rs = BVH ? resolve_hit<ldg4>(A.sc, A.sc.bvh_prims, ids, h.idx, o, d, h.t, sP) : resolve_hit<lds4>(A.sc, s_prims, ids, h.idx, o, d, h.t, sP);
-				const PrimInfo pi = A.sc.info[rs.dev_prim];
-				surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, su, sv);
-				smat = pi.mat; stex = pi.tex;
-				const MaterialRec &m = A.sc.mats[smat];
-				if (m.kind == MK_LIGHT) {
-					contrib = thr * (m.pf[1] * tex_eval<float>(A.sc, mat_texture(m, stex), su, sv, sP));
+				const HotIds id = BVH ? hit_ids<ldg4>(A.sc, A.sc.bvh_prims, ids, h.idx, sP) : hit_ids<lds4>(A.sc, s_prims, ids, h.idx, sP);
+				// which half of a fused pair was hit only matters when the halves shade differently (id.b >= 0)
+				sdev = id.b >= 0 ? resolve_exact(A.sc, id, sP).dev_prim : id.a;
+				const float4 s0 = __ldg(reinterpret_cast<const float4 *>(&A.sc.shade[sdev].r0));
+				const float4 s1 = __ldg(reinterpret_cast<const float4 *>(&A.sc.shade[sdev].r1));
+				sbits = __float_as_int(s0.w);
+				sN = mk<float>(s0.x, s0.y, s0.z);
+				scol = mk<float>(s1.x, s1.y, s1.z);
+				sp0 = s1.w;
+				if (sdev >= A.sc.n_tri + A.sc.n_quad) {  // sphere: outward normal from (centre, radius)
+					const float4 c = __ldg(reinterpret_cast<const float4 *>(&A.sc.prim_plane[sdev].r0));
+					sN = (1.0f / c.w) * (sP - mk<float>(c.x, c.y, c.z));
+				}
+				const int kind = sbits & 255;
+				if (kind == MK_LIGHT) {
+					if (!(sbits >> 8)) {  // textured light: general path
+						const Resolved rs = resolve_exact(A.sc, id, sP);
+						const PrimInfo pi = A.sc.info[rs.dev_prim];
+						float u, v;
+						surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, u, v);
+						const MaterialRec &m = A.sc.mats[pi.mat];
+						scol = m.pf[1] * tex_eval<float>(A.sc, mat_texture(m, pi.tex), u, v, sP);
+					}
+					contrib = thr * scol;
 					done = true;
 				} else done = bounce >= A.max_depth;  // truncated path contributes nothing (RTIOW depth cut-off)
 			}
 			if (done) {
-				if (finite3(contrib)) {
+				const float csum = contrib.x + contrib.y + contrib.z;  // radiance is non-negative: 0 adds nothing, NaN / inf are dropped
+				if (csum > 0.0f && csum < INFINITY) {
 					float *acc = &s_acc[warp][pl * 3];
 					atomicAdd(acc, contrib.x); atomicAdd(acc + 1, contrib.y); atomicAdd(acc + 2, contrib.z);
 				}
@@ -153,8 +171,18 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_path(const __grid_con
 				bounce = 1;
 				ray_ok = true;
 			} else {
-				F3 wo, att, emit;
-				if (scatter<float>(A.sc, smat, stex, d, sN, sP, su, sv, r, wo, att, emit)) {
+				F3 wo, att = scol;
+				bool alive;
+				if (sbits >> 8) alive = scatter_dir<float>(sbits & 255, sp0, d, sN, r, wo);  // SHADE_FAST: solid colour, simple lobe
+				else {  // general path: textures, Reflective's lobe choice
+					const Resolved rs = resolve_exact(A.sc, HotIds{ sdev, -1 }, sP);
+					const PrimInfo pi = A.sc.info[rs.dev_prim];
+					float u, v;
+					F3 emit;
+					surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, u, v);
+					alive = scatter<float>(A.sc, pi.mat, pi.tex, d, sN, sP, u, v, r, wo, att, emit);
+				}
+				if (alive) {
 					thr = thr * att;
 					o = sP;
 					d = wo;
@@ -221,7 +249,8 @@ __global__ void k_hit32(DevScene sc, int n, const double *__restrict__ Q, const 
 	int uid = -1;
 	if (h.idx >= 0) {
 		x = o + h.t * d;
-		Resolved rs = resolve_hit<ldg4>(sc, use_bvh ? sc.bvh_prims : sc.brute, use_bvh ? sc.bvh_ids : sc.brute_ids, h.idx, o, d, h.t, x);
+		const HotIds id = hit_ids<ldg4>(sc, use_bvh ? sc.bvh_prims : sc.brute, use_bvh ? sc.bvh_ids : sc.brute_ids, h.idx, x);
+		Resolved rs = resolve_exact(sc, id, x);
 		uid = sc.info[rs.dev_prim].user_id;
 		surface_at(sc, rs.dev_prim, x, rs.a, rs.b, nn, cu, cv);
 	}

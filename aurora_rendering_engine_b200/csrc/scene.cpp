@@ -400,7 +400,39 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 			}
 		}
 		pbox[dp] = b;
+		{  // shading record: normal + material kind + solid colour / parameter, SHADE_FAST when that is all shading needs
+			const HostMaterial &m = hs.materials[p.mat];
+			int over = -1;
+			if (m.kind == MK_LAMBERTIAN || m.kind == MK_LIGHT) over = (int)m.p[0];
+			else if (m.kind == MK_METAL) over = (int)m.p[1];
+			const HostTexture &tx = hs.textures[over >= 0 ? over : p.tex];
+			const bool fast = tx.kind == TK_SOLID && m.kind != MK_REFLECTIVE;
+			const double scale = m.kind == MK_LIGHT ? m.p[1] : 1.0;
+			const double p0 = m.kind == MK_METAL ? m.p[0] : (m.kind == MK_DIELECTRIC ? m.p[0] : 0.0);
+			const unsigned bits = (unsigned)m.kind | (fast ? (unsigned)SHADE_FAST << 8 : 0u);
+			float bitsf;
+			std::memcpy(&bitsf, &bits, 4);
+			const HotPrim &pf = out.prim_plane.back();
+			ShadeRec sr;
+			sr.r0 = { pf.r0.x, pf.r0.y, pf.r0.z, bitsf };
+			sr.r1 = { (float)(scale * tx.p[0]), (float)(scale * tx.p[1]), (float)(scale * tx.p[2]), (float)p0 };
+			if (m.kind == MK_DIELECTRIC) sr.r1 = { 1.f, 1.f, 1.f, (float)p0 };
+			out.shade.push_back(sr);
+		}
 	}
+	// two triangles shade identically when nothing but the hit position enters their shading
+	auto same_shading = [&](int ta, int tb) {
+		const PrimInfo &ia = out.info[ta], &ib = out.info[tb];
+		if (ia.mat != ib.mat || ia.tex != ib.tex) return false;
+		const HostMaterial &m = hs.materials[ia.mat];
+		int over = -1;
+		if (m.kind == MK_LAMBERTIAN || m.kind == MK_LIGHT) over = (int)m.p[0];
+		else if (m.kind == MK_METAL) over = (int)m.p[1];
+		const int tk = hs.textures[over >= 0 ? over : ia.tex].kind;
+		if (tk != TK_SOLID && tk != TK_CHECKER_3D && tk != TK_NOISE) return false;
+		const HotPrim &pa = out.prim_plane[ta], &pb = out.prim_plane[tb];
+		return pa.r0.x * pb.r0.x + pa.r0.y * pb.r0.y + pa.r0.z * pb.r0.z > 0.0f;  // same orientation
+	};
 	// ---- hot list with parallelogram fusion ----
 	std::vector<HotItem> hot;
 	hot.reserve(order.size());
@@ -443,7 +475,7 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 					HotPrim rec = plane_form(d0, va - d0, vb - d0);
 					Box bx = pbox[t];
 					bx.grow(pbox[j]);
-					push_item(HK_QUAD, rec, { ta, tb }, bx, d0, va - d0, vb - d0);
+					push_item(HK_QUAD, rec, { ta, same_shading(ta, tb) ? -2 - tb : tb }, bx, d0, va - d0, vb - d0);
 					fused[t] = fused[j] = 1;
 					out.n_fused_pairs++;
 					break;
@@ -529,35 +561,53 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 							for (int m = 0; m < k; ++m)
 								if (face[k] >= 0 && face[k] == face[m]) distinct = false;
 						}
-						if (present < 4 || !distinct) continue;
+						if (present < 5 || !distinct) continue;  // closed, or open on exactly one face
 						const D3 edges[3] = { a, b, c };
 						const D3 centre = B + 0.5 * (a + b + c);
 						HotItem bx;
 						bx.kind = HK_BOX;
 						bx.ids = { -1 - out.n_boxes, -1 };
 						bx.box.reset();
-						f4 *slots[3] = { &bx.rec.r0, &bx.rec.r1, &bx.rec.r2 };
-						float hw[3];
+						// per axis: unit slab normal (pointing along +edge), centre offset, half-width, faces at -/+
+						D3 nrm3[3];
+						double cen[3], hw[3];
+						int fminus[3], fplus[3];
 						for (int i = 0; i < 3; ++i) {
 							D3 n = cross(edges[(i + 1) % 3], edges[(i + 2) % 3]);
 							n = (1.0 / len(n)) * n;
 							if (dot(n, edges[i]) < 0) n = -1.0 * n;
-							*slots[i] = { (float)n.x, (float)n.y, (float)n.z, (float)dot(n, centre) };
-							hw[i] = (float)(0.5 * dot(n, edges[i]));
+							nrm3[i] = n;
+							cen[i] = dot(n, centre);
+							hw[i] = 0.5 * dot(n, edges[i]);
+							fminus[i] = face[2 * i];
+							fplus[i] = face[2 * i + 1];
 						}
-						unsigned mask = 0;
-						for (int k = 0; k < 6; ++k) {
-							if (face[k] >= 0) {
-								mask |= 1u << k;
-								out.box_faces.push_back(hot[face[k]].ids);
-								bx.box.grow(hot[face[k]].box);
-								hot[face[k]].dead = true;
-							} else out.box_faces.push_back({ -1, -1 });
+						// canonical form of an open box: the absent face is axis 2, "-" side (the kernel tests only that one)
+						for (int i = 0; i < 3; ++i) {
+							if (fminus[i] >= 0 && fplus[i] >= 0) continue;
+							std::swap(nrm3[i], nrm3[2]); std::swap(cen[i], cen[2]); std::swap(hw[i], hw[2]);
+							std::swap(fminus[i], fminus[2]); std::swap(fplus[i], fplus[2]);
+							if (fplus[2] < 0) {  // flip the axis so that the hole is on the "-" side
+								nrm3[2] = -1.0 * nrm3[2];
+								cen[2] = -cen[2];
+								std::swap(fminus[2], fplus[2]);
+							}
+							break;
 						}
-						float maskf;
-						std::memcpy(&maskf, &mask, 4);
-						bx.rec2.r0 = { hw[0], hw[1], hw[2], maskf };
-						bx.rec2.r1 = { 0, 0, 0, 0 };
+						f4 *slots[3] = { &bx.rec.r0, &bx.rec.r1, &bx.rec.r2 };
+						for (int i = 0; i < 3; ++i) {
+							*slots[i] = { (float)nrm3[i].x, (float)nrm3[i].y, (float)nrm3[i].z, (float)cen[i] };
+							for (int side = 0; side < 2; ++side) {
+								const int f = side ? fplus[i] : fminus[i];
+								if (f >= 0) {
+									out.box_faces.push_back(hot[f].ids);
+									bx.box.grow(hot[f].box);
+									hot[f].dead = true;
+								} else out.box_faces.push_back({ -1, -1 });
+							}
+						}
+						bx.rec2.r0 = { (float)hw[0], (float)hw[1], (float)hw[2], present == 6 ? 0.0f : 1.0f };  // .w != 0: open at face 4
+						bx.rec2.r1 = { (float)(1.0 / hw[0]), (float)(1.0 / hw[1]), (float)(1.0 / hw[2]), 0 };
 						bx.rec2.r2 = { 0, 0, 0, 0 };
 						for (int k = 0; k < 3; ++k) bx.c[k] = 0.5 * (bx.box.lo[k] + bx.box.hi[k]);
 						bx.gQ = B; bx.gu = a; bx.gv = b;

@@ -53,6 +53,7 @@ struct CompiledScene {
 	int n_hot = 0, n_fused_pairs = 0;
 	std::vector<PrimInfo> info;
 	std::vector<HotPrim> prim_plane;
+	std::vector<ShadeRec> shade;
 	std::vector<float> tri_uv;
 	std::vector<f4> rt_tris;  // 3 per triangle: rt.cpp-style fp32 record (v0, e1, e2, n)
 	std::vector<double> tri64, quad64, sph64, tri_uv64;

@@ -124,7 +124,9 @@ __device__ __forceinline__ V3<T> cosine_dir(V3<T> n, T r1, T r2) {
 	V3<T> up = abs_t(n.z) < T(0.999) ? mk<T>(T(0), T(0), T(1)) : mk<T>(T(1), T(0), T(0));
 	V3<T> tangent = nrm(cross(n, up));
 	V3<T> bitangent = cross(n, tangent);
-	T lz = sqrt_t(max_t(T(0), T(1) - lx * lx - ly * ly));
+	// rt.cpp:54 rebuilds lz from lx, ly; lx^2 + ly^2 = r2 exactly, so sqrt(1 - r2) is the same quantity without
+	// the sin/cos rounding amplified at grazing directions
+	T lz = sqrt_t(max_t(T(0), T(1) - r2));
 	return lx * tangent + ly * bitangent + lz * n;
 }
 template <typename T>
@@ -141,13 +143,43 @@ __device__ __forceinline__ int mat_texture(const MaterialRec &m, int prim_tex) {
 	return o >= 0 ? o : prim_tex;
 }
 
-// Material response. wi unit incoming, Ng geometric unit normal (either side). Returns alive.
+// Direction sampling shared by the general path and the SHADE_FAST path of the render loop.
+// lobe: MK_DIELECTRIC (p0 = ior), MK_METAL (p0 = fuzz), MK_REFLECTIVE = perfect mirror, anything else = cosine lobe.
+// wi unit incoming, Ng geometric unit normal (either side). Returns alive; wo is unit length.
+template <typename T>
+__device__ __forceinline__ bool scatter_dir(int lobe, T p0, V3<T> wi, V3<T> Ng, Rnd4<T> r, V3<T> &wo) {
+	const bool front = dot(wi, Ng) < T(0);
+	const V3<T> nf = front ? Ng : -Ng;
+	if (lobe == MK_DIELECTRIC) {
+		T ri = front ? T(1) / p0 : p0;
+		T cos_t = min_t(dot(-wi, nf), T(1)), sin_t = sqrt_t(max_t(T(0), T(1) - cos_t * cos_t));
+		T r0 = (T(1) - ri) / (T(1) + ri);
+		r0 = r0 * r0;
+		T x = T(1) - cos_t, x2 = x * x;
+		T schlick = r0 + (T(1) - r0) * (x2 * x2 * x);
+		V3<T> d = (ri * sin_t > T(1) || schlick > r.x) ? reflect(wi, nf) : refract(wi, nf, ri);
+		wo = nrm(d);
+		return true;
+	}
+	if (lobe == MK_METAL) {
+		V3<T> d = nrm(reflect(wi, nf)) + p0 * sphere_dir<T>(r.x, r.y);
+		if (!(dot(d, nf) > T(0))) return false;
+		wo = nrm(d);
+		return true;
+	}
+	if (lobe == MK_REFLECTIVE) {
+		wo = nrm(reflect(wi, nf));
+		return true;
+	}
+	wo = nrm(cosine_dir<T>(nf, r.x, r.y));
+	return true;
+}
+
+// Material response, general path (any texture kind). Returns alive.
 template <typename T>
 __device__ bool scatter(const DevScene &sc, int mat, int tex, V3<T> wi, V3<T> Ng, V3<T> P, T u, T v, Rnd4<T> r,
 	V3<T> &wo, V3<T> &att, V3<T> &emit) {
 	const MaterialRec &m = sc.mats[mat];
-	const bool front = dot(wi, Ng) < T(0);
-	const V3<T> nf = front ? Ng : -Ng;
 	emit = mk<T>(T(0), T(0), T(0));
 	att = emit;
 	wo = mk<T>(nan_t<T>(), nan_t<T>(), nan_t<T>());
@@ -157,32 +189,15 @@ __device__ bool scatter(const DevScene &sc, int mat, int tex, V3<T> wi, V3<T> Ng
 		return false;
 	}
 	if (kind == MK_DIELECTRIC) {
-		T ior = mparam<T>(m, 0), ri = front ? T(1) / ior : ior;
-		T cos_t = min_t(dot(-wi, nf), T(1)), sin_t = sqrt_t(max_t(T(0), T(1) - cos_t * cos_t));
-		T r0 = (T(1) - ri) / (T(1) + ri);
-		r0 = r0 * r0;
-		T x = T(1) - cos_t, x2 = x * x;
-		T schlick = r0 + (T(1) - r0) * (x2 * x2 * x);
-		V3<T> d = (ri * sin_t > T(1) || schlick > r.x) ? reflect(wi, nf) : refract(wi, nf, ri);
-		wo = nrm(d);
 		att = mk<T>(T(1), T(1), T(1));
-		return true;
-	}
-	if (kind == MK_METAL) {
-		att = tex_eval<T>(sc, mat_texture(m, tex), u, v, P);
-		V3<T> d = nrm(reflect(wi, nf)) + mparam<T>(m, 0) * sphere_dir<T>(r.x, r.y);
-		if (!(dot(d, nf) > T(0))) return false;
-		wo = nrm(d);
-		return true;
+		return scatter_dir<T>(MK_DIELECTRIC, mparam<T>(m, 0), wi, Ng, r, wo);
 	}
 	if (kind == MK_REFLECTIVE && r.z < mparam<T>(m, 0)) {
-		wo = nrm(reflect(wi, nf));
 		att = mk<T>(mparam<T>(m, 1), mparam<T>(m, 2), mparam<T>(m, 3));
-		return true;
+		return scatter_dir<T>(MK_REFLECTIVE, T(0), wi, Ng, r, wo);
 	}
 	att = tex_eval<T>(sc, mat_texture(m, tex), u, v, P);
-	wo = nrm(cosine_dir<T>(nf, r.x, r.y));
-	return true;
+	return scatter_dir<T>(kind == MK_METAL ? MK_METAL : MK_LAMBERTIAN, kind == MK_METAL ? mparam<T>(m, 0) : T(0), wi, Ng, r, wo);
 }
 
 // ---- surface resolution -------------------------------------------------------------------------------
