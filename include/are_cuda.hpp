@@ -1,0 +1,170 @@
+// <are_cuda.hpp> — header-only C++ shim between the are:: class API and the C ABI of <are_cuda.h>.
+//
+// A host program written in the reference's style builds are::Texture / are::Material / are::Triangle objects, pushes
+// pointers into an are::ObjectSet, and then — instead of looping over pixels on the CPU — hands the set to
+// are::cuda::Renderer:
+//
+//     are::cuda::Renderer gpu;                     // one CUDA device, throws std::runtime_error if there is none
+//     gpu.upload(scene);                           // walks ObjectSet::triangles (+ quads, spheres), commits to the GPU
+//     are::Texture image = gpu.render(camera, 512, 512, settings);
+//     image.save_texture("out.ppm");               // the reference's own writer semantics
+//
+// Errors follow the reference's convention: what the C ABI reports as ARE_ERR_INVALID_ARGUMENT is re-thrown as
+// std::invalid_argument (are::Triangle's constructor checks), everything else as std::runtime_error.
+#pragma once
+
+#include <are_cuda.h>
+#include <camera.h>
+#include <object/object_set.h>
+#include <texture.h>
+
+#include <cstdint>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace are {
+namespace cuda {
+
+struct Settings {
+	int spp = 64;
+	int max_depth = 50;
+	std::uint64_t seed = 1;
+	double t_min = 1e-3;
+	Color3 background_bottom = Color3(1, 1, 1);
+	Color3 background_top = Color3(0.5, 0.7, 1.0);
+	int integrator = ARE_INTEGRATOR_PATH;  // ARE_INTEGRATOR_RT_AO = the shading of experiments/rt.cpp
+	int traversal = ARE_TRAVERSAL_AUTO;
+	int ao_samples = 32;
+	int sample_begin = 0;  // first global sample index (sample-sharded multi-GPU jobs)
+};
+
+class Renderer {
+public:
+	explicit Renderer(int device = 0) {
+		if (are_cuda_create(&ctx_, device) != ARE_OK) throw std::runtime_error(std::string("are_cuda_create: ") + are_cuda_last_error(nullptr));
+	}
+	~Renderer() { are_cuda_destroy(ctx_); }
+	Renderer(const Renderer &) = delete;
+	Renderer &operator=(const Renderer &) = delete;
+
+	/// Flatten the scene and upload it. May be called again after the scene changed.
+	void upload(const ObjectSet &set) {
+		check(are_cuda_clear(ctx_));
+		textures_.clear();
+		materials_.clear();
+		for (const Triangle *t : set.triangles) {
+			const int mat = material_id(t->material()), tex = texture_id(t->texture());
+			const int id = check(are_cuda_add_triangle(ctx_, t->origin().e(), t->edge_u().e(), t->edge_v().e(), mat, tex));
+			if (t->has_uv()) check(are_cuda_set_triangle_uv(ctx_, id, t->uv()));
+		}
+		for (const Quad *q : set.quads)
+			check(are_cuda_add_quad(ctx_, q->origin().e(), q->edge_u().e(), q->edge_v().e(), material_id(q->material()), texture_id(q->texture())));
+		for (const Sphere *s : set.spheres)
+			check(are_cuda_add_sphere(ctx_, s->center().e(), s->radius(), material_id(s->material()), texture_id(s->texture())));
+		std::uint64_t bytes = 0;
+		check(are_cuda_commit(ctx_, &bytes));
+		uploaded_bytes_ = bytes;
+	}
+
+	/// Render spp samples per pixel; the returned texture holds the mean linear radiance per pixel.
+	Texture render(const Camera &camera, int width, int height, const Settings &s = Settings()) {
+		std::vector<float> sums(static_cast<size_t>(width) * height * 3);
+		render_sums(camera, width, height, s, sums.data());
+		Texture out(width, height, Color3(0, 0, 0));
+		const double inv = s.spp > 0 ? 1.0 / s.spp : 0.0;
+		for (int y = 0; y < height; ++y)
+			for (int x = 0; x < width; ++x) {
+				const float *p = &sums[(static_cast<size_t>(y) * width + x) * 3];
+				out.pixel(x, y) = Color3(p[0] * inv, p[1] * inv, p[2] * inv);
+			}
+		return out;
+	}
+
+	/// Raw per-pixel sample SUMS (W*H*3 floats) — what a multi-GPU driver adds up across devices.
+	void render_sums(const Camera &camera, int width, int height, const Settings &s, float *sums) {
+		are_camera c = to_c(camera);
+		are_render_params p = to_c(width, height, s);
+		check(are_cuda_render(ctx_, &c, &p, sums, &stats_));
+	}
+
+	const are_render_stats &stats() const { return stats_; }
+	std::uint64_t uploaded_bytes() const { return uploaded_bytes_; }
+	are_cuda_ctx *context() { return ctx_; }
+
+	static are_camera to_c(const Camera &cam) {
+		are_camera c;
+		for (int i = 0; i < 3; ++i) {
+			c.pos[i] = cam.pos[i];
+			c.target[i] = cam.target[i];
+			c.up[i] = cam.up[i];
+		}
+		c.vfov_deg = cam.vfov_deg;
+		c.focus_dist = cam.focus_dist;
+		c.defocus_angle_deg = cam.defocus_angle_deg;
+		c.jitter = cam.jitter ? 1 : 0;
+		c.pad_ = 0;
+		return c;
+	}
+	static are_render_params to_c(int width, int height, const Settings &s) {
+		are_render_params p;
+		p.width = width;
+		p.height = height;
+		p.sample_begin = s.sample_begin;
+		p.sample_count = s.spp;
+		p.max_depth = s.max_depth;
+		p.integrator = s.integrator;
+		p.traversal = s.traversal;
+		p.ao_samples = s.ao_samples;
+		p.seed = s.seed;
+		p.t_min = s.t_min;
+		for (int i = 0; i < 3; ++i) {
+			p.background_bottom[i] = s.background_bottom[i];
+			p.background_top[i] = s.background_top[i];
+		}
+		return p;
+	}
+
+private:
+	int check(int status) {
+		if (status >= 0) return status;
+		const std::string msg = are_cuda_last_error(ctx_);
+		if (status == ARE_ERR_INVALID_ARGUMENT) throw std::invalid_argument(msg);
+		throw std::runtime_error(msg);
+	}
+	int texture_id(const Texture *t) {
+		if (!t) throw std::invalid_argument("Texture pointer cannot be null");
+		auto it = textures_.find(t);
+		if (it != textures_.end()) return it->second;
+		const int kind = t->kind();
+		const int id = kind == ARE_TEX_IMAGE ? check(are_cuda_add_texture(ctx_, kind, t->params(), t->data(), t->width_, t->height_))
+											 : check(are_cuda_add_texture(ctx_, kind, t->params(), nullptr, 0, 0));
+		textures_[t] = id;
+		return id;
+	}
+	int material_id(const Material *m) {
+		if (!m) throw std::invalid_argument("Material pointer cannot be null");
+		auto it = materials_.find(m);
+		if (it != materials_.end()) return it->second;
+		double p[8];
+		m->describe(p);
+		const int kind = m->kind();
+		const Texture *over = m->texture_override();
+		const double over_id = over ? texture_id(over) : -1.0;
+		if (kind == ARE_MAT_LAMBERTIAN || kind == ARE_MAT_DIFFUSE_LIGHT) p[0] = over_id;
+		else if (kind == ARE_MAT_METAL) p[1] = over_id;
+		const int id = check(are_cuda_add_material(ctx_, kind, p));
+		materials_[m] = id;
+		return id;
+	}
+
+	are_cuda_ctx *ctx_ = nullptr;
+	std::map<const Texture *, int> textures_;
+	std::map<const Material *, int> materials_;
+	are_render_stats stats_{};
+	std::uint64_t uploaded_bytes_ = 0;
+};
+
+}  // namespace cuda
+}  // namespace are
