@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libare_b200.so")
+LIB_PATH = os.environ.get("ARE_B200_LIB") or os.path.join(_HERE, "lib", "libare_b200.so")  # override: A/B of kernel builds
 
 ARE_OK = 0
 STATUS_NAMES = {0: "ARE_OK", -1: "ARE_ERR_INVALID_ARGUMENT", -2: "ARE_ERR_RUNTIME", -3: "ARE_ERR_CUDA",

@@ -23,7 +23,9 @@ namespace areb {
 
 typedef V3<float> F3;
 
-#define RENDER_THREADS 128
+#ifndef RENDER_THREADS
+#define RENDER_THREADS 128  // 4 warps = a 16x8 pixel tile per CTA
+#endif
 #define BRUTE_MAX_PRIMS 512  // 24 KB of shared memory; larger scenes traverse the BVH
 
 size_t brute_smem_limit_prims() { return BRUTE_MAX_PRIMS; }
@@ -37,11 +39,11 @@ __device__ __forceinline__ bool finite3(F3 v) { return isfinite(v.x) && isfinite
 
 // A warp owns an 8x4 pixel tile, a block (4 warps) a 16x8 tile: coherent primary rays and texture reads.
 __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
-	const int tiles_x = (W + 15) >> 4;
-	const int bx = blockIdx.x % tiles_x, by = blockIdx.x / tiles_x;
-	const int warp = threadIdx.x >> 5;
-	x0 = bx * 16 + (warp & 1) * 8;
-	y0 = by * 8 + (warp >> 1) * 4;
+	const int tiles_x = (W + 15) >> 4;  // 16x8 super-tiles of four warp tiles, so neighbouring warps share texels / BVH nodes in L1
+	const int gw = blockIdx.x * (RENDER_THREADS / 32) + (threadIdx.x >> 5);
+	const int st = gw >> 2, sub = gw & 3;
+	x0 = (st % tiles_x) * 16 + (sub & 1) * 8;
+	y0 = (st / tiles_x) * 8 + (sub >> 1) * 4;
 }
 
 // Path-tracing megakernel.
@@ -52,8 +54,11 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 // added to the tile's accumulators in shared memory (one RED.ADD.F32 x3 per sample).  Each trip = trace one ray
 // segment for every lane, classify, then ONE Philox call per lane that feeds either the camera (new path) or the
 // material scatter (continuing path).
+#ifndef RENDER_MIN_BLOCKS
+#define RENDER_MIN_BLOCKS 6
+#endif
 template <bool BVH, bool COUNT>
-__global__ void __launch_bounds__(RENDER_THREADS) k_render_path(const __grid_constant__ RenderArgs A) {
+__global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_path(const __grid_constant__ RenderArgs A) {
 	extern __shared__ float4 s_raw[];
 	__shared__ float s_acc[RENDER_THREADS / 32][96];
 	const HotPrim *s_prims = reinterpret_cast<const HotPrim *>(s_raw);
@@ -217,7 +222,8 @@ __global__ void __launch_bounds__(RENDER_THREADS) k_render_path(const __grid_con
 }
 
 int launch_render_path(const RenderArgs &a, bool use_bvh, bool count_tests, cudaStream_t s) {
-	const int tiles = ((a.W + 15) / 16) * ((a.H + 7) / 8);
+	const int warps = ((a.W + 15) / 16) * ((a.H + 7) / 8) * 4;  // one warp per 8x4 tile
+	const int tiles = (warps + RENDER_THREADS / 32 - 1) / (RENDER_THREADS / 32);
 	if (tiles <= 0) return -1;
 	if (use_bvh) {
 		if (count_tests) k_render_path<true, true><<<tiles, RENDER_THREADS, 0, s>>>(a);

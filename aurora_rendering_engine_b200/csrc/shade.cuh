@@ -26,6 +26,11 @@ template <> __device__ __forceinline__ float tparam<float>(const TextureRec &t, 
 __device__ __forceinline__ V3<double> nrm(V3<double> a) { return normalized(a); }
 __device__ __forceinline__ V3<float> nrm(V3<float> a) { return rsqrtf(len2(a)) * a; }
 
+// A combination lx*T + ly*B + lz*N of an orthonormal frame with lx^2 + ly^2 + lz^2 = 1 is already unit length up to
+// rounding: fp64 normalises anyway (literal to the oracle), fp32 keeps the 1e-7 deviation and saves a MUFU + 6 ops.
+__device__ __forceinline__ V3<double> renorm(V3<double> a) { return normalized(a); }
+__device__ __forceinline__ V3<float> renorm(V3<float> a) { return a; }
+
 template <typename T> struct Pi { static constexpr T value = T(3.14159265358979323846); };
 
 // ---- textures -----------------------------------------------------------------------------------------
@@ -171,7 +176,7 @@ __device__ __forceinline__ bool scatter_dir(int lobe, T p0, V3<T> wi, V3<T> Ng, 
 		wo = nrm(reflect(wi, nf));
 		return true;
 	}
-	wo = nrm(cosine_dir<T>(nf, r.x, r.y));
+	wo = renorm(cosine_dir<T>(nf, r.x, r.y));
 	return true;
 }
 

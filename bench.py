@@ -301,8 +301,18 @@ def run_b200(a):
         peak = ctx.measure_fp32_peak()
         nominal = peak["sm_count"] * 128 * 2 * (clk["sm_max_mhz"] or 1965.0) * 1e6 / 1e12 if clk else None
         achieved = flops / (avg_kernel_ms * 1e-3) / 1e12
+        # what the reference's algorithm (every ray tests every primitive of the ObjectSet, 51 FLOP per Moeller-Trumbore
+        # test, 28 per sphere, 45 per quad) would have executed for the same rays — the kernel does less (fusion, boxes, BVH)
+        ref_flops = st.rays * (F_TRI * len(sc.tris) + F_QUAD * len(sc.quads) + F_SPH * len(sc.spheres)) + F_SCATTER * max(0, st.rays - st.samples) + F_PRIMARY * st.samples
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this launch size, from the committed ncu capture
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_render_path_full.json")))
+            if prof.get("width") == W and prof.get("height") == H and prof.get("spp_per_step") == S:
+                traffic = prof.get("dram_bytes")
+        except Exception:
+            pass
         roof = {"bound": "fp32", "achieved": achieved, "peak": peak["tflops"], "unit": "TFLOP/s", "frac": achieved / peak["tflops"] if peak["tflops"] else None,
-                "traffic": None, "peak_source": "measured on this GPU by are_cuda_measure_fp32_peak (register-resident FFMA loop); MEASURED_PEAKS.json has no FP32 figure",
+                "traffic": traffic, "reference_equivalent_tflops": ref_flops / (avg_kernel_ms * 1e-3) / 1e12, "peak_source": "measured on this GPU by are_cuda_measure_fp32_peak (register-resident FFMA loop); MEASURED_PEAKS.json has no FP32 figure",
                 "nominal_peak": nominal, "kernel": "k_render_path<%s>" % ("bvh" if use_bvh else "brute/smem"), "kernel_ms": avg_kernel_ms,
                 "flops_per_launch": flops, "counted": {"rays": st.rays, "tri_tests": st.tri_tests, "quad_tests": st.quad_tests,
                                                         "sphere_tests": st.sphere_tests, "box_tests": st.box_tests, "node_visits": st.node_visits},
