@@ -16,8 +16,9 @@
 namespace areb {
 
 struct Hit {
-	float t;   // closest distance so far (INFINITY = none)
-	int idx;   // index into the hot array traversed (-1 = miss)
+	float t;    // closest distance so far (INFINITY = none)
+	int idx;    // index into the hot array traversed (-1 = miss)
+	int orig;   // in: hot index of the primitive the ray starts ON (-1: none, e.g. camera rays)
 };
 
 __device__ __forceinline__ float4 ldg4(const f4 *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
@@ -73,7 +74,13 @@ __device__ __forceinline__ void test_sphere(float4 r0, float4 r1, V3<float> o, V
 	float sq = sqrt_fast(fmaxf(disc, 0.0f));
 	float t0 = hh - sq, t1 = hh + sq;
 	float t = (t0 > tmin) ? t0 : t1;  // nearest root inside the window (t0 <= t1)
-	bool ok = (disc >= 0.0f) & (t > tmin) & (t < h.t);
+	// A ray that starts ON this sphere has the exact roots 0 and 2(oc·d): leaving it (oc·d < 0) it cannot come back,
+	// entering it the far side is at 2(oc·d).  Evaluating that case through r^2 - |l|^2 would decide on rounding noise
+	// (|oc|^2 carries 0.06 absolute error for a radius-1000 ground sphere) and lets grazing rays leak INSIDE the
+	// sphere, where a two-sided Lambertian surface traps them until max_depth.
+	const bool self = idx == h.orig;
+	t = self ? 2.0f * hh : t;
+	bool ok = ((disc >= 0.0f) | self) & (t > tmin) & (t < h.t);
 	if (ok) { h.t = t; h.idx = idx; }
 }
 

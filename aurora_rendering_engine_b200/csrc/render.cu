@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 	F3 sP = o, sN = o, scol = o;
 	float sp0 = 0.f;
 	int sdev = 0, sbits = 0;
+	int orig = -1;  // hot slot of the primitive the current ray starts on
 	unsigned int rays = 0;
 	TravCounters tc = { 0, 0, 0, 0, 0 };
 
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 		// ---- A. trace + classify ----------------------------------------------------------------------
 		if (ray_ok) {
 			Hit h;
-			h.t = INFINITY; h.idx = -1;
+			h.t = INFINITY; h.idx = -1; h.orig = orig;
 			if (BVH) intersect_bvh<COUNT>(A.sc, o, d, A.tmin, h, &tc);
 			else intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, br.nb, o, d, A.tmin, h);
 			++rays;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 				done = true;
 			} else {
 				sP = o + h.t * d;
+				orig = h.idx;
 				const HotIds id = BVH ? hit_ids<ldg4>(A.sc, A.sc.bvh_prims, ids, h.idx, sP) : hit_ids<lds4>(A.sc, s_prims, ids, h.idx, sP);
 				// which half of a fused pair was hit only matters when the halves shade differently (id.b >= 0)
 				sdev = id.b >= 0 ? resolve_exact(A.sc, id, sP).dev_prim : id.a;
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 			if (bounce == 0) {
 				if (!cam.jitter) { r.x = 0.5f; r.y = 0.5f; }
 				cam_ray<float>(cam, inv_w, inv_h, px, py, r, o, d);
+				orig = -1;
 				thr = mk<float>(1.f, 1.f, 1.f);
 				bounce = 1;
 				ray_ok = true;
@@ -245,7 +248,7 @@ __global__ void k_hit32(DevScene sc, int n, const double *__restrict__ Q, const 
 	if (i >= n) return;
 	F3 o = ld3<float>(Q + 3 * i), d = nrm(ld3<float>(D + 3 * i));
 	Hit h;
-	h.t = INFINITY; h.idx = -1;
+	h.t = INFINITY; h.idx = -1; h.orig = -1;
 	TravCounters tc;
 	if (use_bvh) intersect_bvh<false>(sc, o, d, tmin, h, &tc);
 	else intersect_range<ldg4>(sc.brute, sc.brute_range.first, sc.brute_range.nq, sc.brute_range.nt, sc.brute_range.ns, sc.brute_range.nb, o, d, tmin, h);

@@ -72,6 +72,17 @@ def test_scene_matches_cpu_twin(ctx, oracle, name, kw, spp, traversal):
     assert p >= PSNR_MIN, f"{name}: PSNR {p:.1f} dB"
 
 
+@pytest.mark.parametrize("traversal", [1, 2])
+def test_no_rays_trapped_inside_spheres_at_depth_50(ctx, oracle, traversal):
+    """Regression: a ray leaving the radius-1000 ground sphere at a grazing angle used to re-hit it through fp32
+    rounding of |oc|^2 - r^2, end up INSIDE the sphere and bounce there until max_depth (+20 % rays at depth 50).
+    A ray that starts on a sphere is now resolved with the exact roots {0, 2 oc·d}."""
+    sc = scenes.rtiow_final(width=96, height=54)
+    img, st, oimg, ost = _render_both(sc, ctx, oracle, spp=8, traversal=traversal, max_depth=50)
+    assert abs(int(st.rays) - int(ost.rays)) < 5e-3 * ost.rays, (st.rays, ost.rays)
+    assert abs(img.mean() - oimg.mean()) < 2e-3 * oimg.mean()
+
+
 def test_stress_scene_bvh_equals_brute_and_matches_cpu_twin(ctx, oracle):
     """Config-4 style scene scaled to 500 primitives so the brute-force list still fits: BVH and brute force run the
     same per-primitive arithmetic, so their images must be IDENTICAL; both must match the CPU twin."""
@@ -230,3 +241,35 @@ def test_render_job_driver_chunks_and_ppm(lib, tmp_path):
     raw = (tmp_path / "job.ppm").read_bytes()
     assert raw.startswith(b"P6\n64 48\n255\n") and raw[len(b"P6\n64 48\n255\n"):] == rgb8.tobytes()
     job.close()
+
+
+def test_rt_ao_matches_the_real_reference_renderer(ctx, tmp_path):
+    """config 0 against the REAL reference: oracle/_ref/rt_ref is experiments/rt.cpp compiled unmodified; it writes
+    out_diffuse.ppm (512x512, gamma 2.2) using mt19937(random_device), i.e. one noisy 32-AO-ray estimate per pixel.
+    The GPU renders the same scene with the RT_AO integrator, averages 64 independent estimates per pixel and encodes
+    with the same formula.  Two reference runs agree with each other to 38.5 dB; a noise-free image must
+    agree with one reference run ~3 dB better."""
+    import os
+    import subprocess
+    from oracle_binding import RT_REF
+    if not os.path.exists(RT_REF):
+        pytest.skip("oracle/_ref/rt_ref not present")
+    subprocess.run([RT_REF], cwd=tmp_path, check=True, capture_output=True, timeout=300)
+    raw = (tmp_path / "out_diffuse.ppm").read_bytes()
+    hdr = b"P6\n512 512\n255\n"
+    assert raw.startswith(hdr)
+    ref = np.frombuffer(raw[len(hdr):], np.uint8).reshape(512, 512, 3).astype(np.float64) / 255.0
+    sc = scenes.rt_cornell()
+    cam = capi.make_camera(**sc.camera_args())
+    sc.feed(ctx)
+    ctx.commit()
+    n = 64
+    acc = ctx.alloc_accum(512, 512)
+    st = ctx.render_device(cam, capi.make_params(**sc.params_args(sample_count=n)), acc, want_stats=True)
+    gpu8 = ctx.tonemap(acc, 512, 512, 1.0 / n, encoder=0).astype(np.float64) / 255.0
+    ctx.free_accum(acc)
+    p = psnr(gpu8, ref)
+    rays_per_px = st.rays / st.samples
+    print(f"[rt_ao vs rt_ref] PSNR {p:.1f} dB, {rays_per_px:.2f} rays per pixel-sample (reference: 34.19)")
+    assert abs(rays_per_px - 34.19) < 0.1   # 8 963 385 rays / 262 144 pixels measured on the reference (BASELINE.md)
+    assert p >= 40.0, f"PSNR {p:.1f} dB"
