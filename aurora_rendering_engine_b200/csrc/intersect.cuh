@@ -153,65 +153,82 @@ struct TravCounters {
 	unsigned long long nodes, quads, tris, spheres, boxes;
 };
 
+// Ray constants of the slab test: reciprocal direction (a zero component becomes a huge finite slope so the slab
+// maths never sees 0*inf) and origin * reciprocal.
+struct RaySlopes {
+	float idx, idy, idz, oxi, oyi, ozi;
+};
+__device__ __forceinline__ RaySlopes ray_slopes(V3<float> o, V3<float> d) {
+	const float big = 1e30f;
+	RaySlopes r;
+	r.idx = fabsf(d.x) > 1e-30f ? 1.0f / d.x : (d.x < 0 ? -big : big);
+	r.idy = fabsf(d.y) > 1e-30f ? 1.0f / d.y : (d.y < 0 ? -big : big);
+	r.idz = fabsf(d.z) > 1e-30f ? 1.0f / d.z : (d.z < 0 ? -big : big);
+	r.oxi = o.x * r.idx; r.oyi = o.y * r.idy; r.ozi = o.z * r.idz;
+	return r;
+}
+
+// One traversal step: visit inner node `node` (both children's boxes, leaves intersected on the spot, the nearer
+// inner child next, the farther pushed).  Returns false when the traversal is complete.  The cursor (node, sp, stack)
+// and the best hit live in the caller, so a traversal can be suspended and resumed — the megakernel runs traversals
+// in slices and lets lanes whose ray is finished go on to shading while long rays keep their place.
+template <bool COUNT>
+__device__ __forceinline__ bool bvh_visit(const DevScene &sc, V3<float> o, V3<float> d, float tmin, const RaySlopes &rs, int &node, int &sp, int *stack, Hit &h, TravCounters *cnt) {
+	const BvhNode *n = sc.nodes + node;
+	const float4 b0 = ldg4(&n->b0), b1 = ldg4(&n->b1), b2 = ldg4(&n->b2);
+	const int4 cm = __ldg(reinterpret_cast<const int4 *>(&n->child[0]));
+	if (COUNT) cnt->nodes++;
+	const float c0lox = fmaf(b0.x, rs.idx, -rs.oxi), c0hix = fmaf(b0.y, rs.idx, -rs.oxi), c0loy = fmaf(b0.z, rs.idy, -rs.oyi), c0hiy = fmaf(b0.w, rs.idy, -rs.oyi);
+	const float c0loz = fmaf(b2.x, rs.idz, -rs.ozi), c0hiz = fmaf(b2.y, rs.idz, -rs.ozi);
+	const float c1lox = fmaf(b1.x, rs.idx, -rs.oxi), c1hix = fmaf(b1.y, rs.idx, -rs.oxi), c1loy = fmaf(b1.z, rs.idy, -rs.oyi), c1hiy = fmaf(b1.w, rs.idy, -rs.oyi);
+	const float c1loz = fmaf(b2.z, rs.idz, -rs.ozi), c1hiz = fmaf(b2.w, rs.idz, -rs.ozi);
+	const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin));
+	const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
+	const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
+	const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
+	bool hit0 = t0n <= t0f, hit1 = t1n <= t1f;
+	if (hit0 && cm.x < 0) {
+		const int m = cm.z;
+		intersect_range<ldg4>(sc.bvh_prims, ~cm.x, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, tmin, h);
+		if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; cnt->boxes += (m >> 24) & 255; }
+		hit0 = false;
+	}
+	if (hit1 && cm.y < 0) {
+		if (t1n <= h.t) {
+			const int m = cm.w;
+			intersect_range<ldg4>(sc.bvh_prims, ~cm.y, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, tmin, h);
+			if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; cnt->boxes += (m >> 24) & 255; }
+		}
+		hit1 = false;
+	}
+	int next = -1;
+	if (hit0 && hit1) {
+		const bool near0 = t0n <= t1n;
+		next = near0 ? cm.x : cm.y;
+		if (sp < ARE_BVH_STACK) stack[sp++] = near0 ? cm.y : cm.x;
+	} else if (hit0) next = cm.x;
+	else if (hit1) next = cm.y;
+	if (next < 0) {
+		if (sp == 0) return false;
+		next = stack[--sp];
+	}
+	node = next;
+	return true;
+}
+
+// Whole traversal in one go (per-ray harness).
 template <bool COUNT>
 __device__ __forceinline__ void intersect_bvh(const DevScene &sc, V3<float> o, V3<float> d, float tmin, Hit &h, TravCounters *cnt) {
 	if (sc.n_nodes == 0) {
-		int m = sc.root_leaf_meta;
+		const int m = sc.root_leaf_meta;
 		intersect_range<ldg4>(sc.bvh_prims, 0, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, tmin, h);
 		if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; cnt->boxes += (m >> 24) & 255; }
 		return;
 	}
-	// safe reciprocals: a zero component becomes a huge finite slope so the slab maths never sees 0*inf
-	const float big = 1e30f;
-	float idx = fabsf(d.x) > 1e-30f ? 1.0f / d.x : (d.x < 0 ? -big : big);
-	float idy = fabsf(d.y) > 1e-30f ? 1.0f / d.y : (d.y < 0 ? -big : big);
-	float idz = fabsf(d.z) > 1e-30f ? 1.0f / d.z : (d.z < 0 ? -big : big);
-	float oxi = o.x * idx, oyi = o.y * idy, ozi = o.z * idz;
+	const RaySlopes rs = ray_slopes(o, d);
 	int stack[ARE_BVH_STACK];
-	int sp = 0;
-	int node = 0;
-	while (true) {
-		const BvhNode *n = sc.nodes + node;
-		float4 b0 = ldg4(&n->b0), b1 = ldg4(&n->b1), b2 = ldg4(&n->b2);
-		int4 cm = __ldg(reinterpret_cast<const int4 *>(&n->child[0]));
-		if (COUNT) cnt->nodes++;
-		float c0lox = fmaf(b0.x, idx, -oxi), c0hix = fmaf(b0.y, idx, -oxi), c0loy = fmaf(b0.z, idy, -oyi), c0hiy = fmaf(b0.w, idy, -oyi);
-		float c0loz = fmaf(b2.x, idz, -ozi), c0hiz = fmaf(b2.y, idz, -ozi);
-		float c1lox = fmaf(b1.x, idx, -oxi), c1hix = fmaf(b1.y, idx, -oxi), c1loy = fmaf(b1.z, idy, -oyi), c1hiy = fmaf(b1.w, idy, -oyi);
-		float c1loz = fmaf(b2.z, idz, -ozi), c1hiz = fmaf(b2.w, idz, -ozi);
-		float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin));
-		float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
-		float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
-		float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
-		bool hit0 = t0n <= t0f, hit1 = t1n <= t1f;
-		int next = -1;  // inner node to descend into
-		// leaves are intersected immediately; inner children are ordered near-first
-		if (hit0 && cm.x < 0) {
-			int m = cm.z;
-			intersect_range<ldg4>(sc.bvh_prims, ~cm.x, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, tmin, h);
-			if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; cnt->boxes += (m >> 24) & 255; }
-			hit0 = false;
-		}
-		if (hit1 && cm.y < 0) {
-			if (t1n <= h.t) {
-				int m = cm.w;
-				intersect_range<ldg4>(sc.bvh_prims, ~cm.y, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, tmin, h);
-				if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; cnt->boxes += (m >> 24) & 255; }
-			}
-			hit1 = false;
-		}
-		if (hit0 && hit1) {
-			bool near0 = t0n <= t1n;
-			next = near0 ? cm.x : cm.y;
-			if (sp < ARE_BVH_STACK) stack[sp++] = near0 ? cm.y : cm.x;
-		} else if (hit0) next = cm.x;
-		else if (hit1) next = cm.y;
-		if (next < 0) {
-			if (sp == 0) break;
-			next = stack[--sp];
-		}
-		node = next;
-	}
+	int sp = 0, node = 0;
+	while (bvh_visit<COUNT>(sc, o, d, tmin, rs, node, sp, stack, h, cnt)) {}
 }
 
 // ---- map a hot hit back to the user primitive ---------------------------------------------------------

@@ -57,6 +57,9 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #ifndef RENDER_MIN_BLOCKS
 #define RENDER_MIN_BLOCKS 6
 #endif
+#ifndef TRAV_MIN_LANES
+#define TRAV_MIN_LANES 20  // BVH slices end when fewer lanes than this are still traversing and others are waiting
+#endif
 template <bool BVH, bool COUNT>
 __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_path(const __grid_constant__ RenderArgs A) {
 	extern __shared__ float4 s_raw[];
@@ -92,17 +95,47 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 	float sp0 = 0.f;
 	int sdev = 0, sbits = 0;
 	int orig = -1;  // hot slot of the primitive the current ray starts on
+	Hit h;          // best hit of the ray in flight (BVH: survives across trips while its traversal is suspended)
+	h.t = INFINITY; h.idx = -1; h.orig = -1;
+	bool trav = false;  // BVH: traversal in progress
+	int node = 0, sp = 0;
+	int stack[BVH ? ARE_BVH_STACK : 1];
 	unsigned int rays = 0;
 	TravCounters tc = { 0, 0, 0, 0, 0 };
 
 	while (true) {
 		// ---- A. trace + classify ----------------------------------------------------------------------
-		if (ray_ok) {
-			Hit h;
+		// Brute force: every lane with a ray finishes it in this trip.  BVH: traversals run in SLICES — all lanes step
+		// through their hierarchy until fewer than TRAV_MIN_LANES are still traversing while finished lanes wait; the
+		// unfinished ones keep their cursor (node, stack, best hit) and resume next trip, the finished ones go on to
+		// shading and regeneration.  Long rays no longer hold 31 idle lanes hostage.
+		bool finished = ray_ok;
+		if (BVH) {
+			if (ray_ok && !trav) {  // a fresh ray
+				h.t = INFINITY; h.idx = -1; h.orig = orig;
+				++rays;
+				if (A.sc.n_nodes == 0) {  // the whole scene is one leaf
+					const int m = A.sc.root_leaf_meta;
+					intersect_range<ldg4>(A.sc.bvh_prims, 0, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, A.tmin, h);
+					if (COUNT) { tc.quads += m & 255; tc.tris += (m >> 8) & 255; tc.spheres += (m >> 16) & 255; tc.boxes += (m >> 24) & 255; }
+				} else { node = 0; sp = 0; trav = true; }
+			}
+			const int n_rays = __popc(__ballot_sync(full, ray_ok));
+			if (__any_sync(full, trav)) {
+				const RaySlopes rs = ray_slopes(o, d);
+				while (true) {
+					if (trav) trav = bvh_visit<COUNT>(A.sc, o, d, A.tmin, rs, node, sp, stack, h, &tc);
+					const int n_trav = __popc(__ballot_sync(full, trav));
+					if (n_trav == 0 || (n_trav < TRAV_MIN_LANES && n_trav < n_rays)) break;
+				}
+			}
+			finished = ray_ok && !trav;
+		} else if (ray_ok) {
 			h.t = INFINITY; h.idx = -1; h.orig = orig;
-			if (BVH) intersect_bvh<COUNT>(A.sc, o, d, A.tmin, h, &tc);
-			else intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, br.nb, o, d, A.tmin, h);
+			intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, br.nb, o, d, A.tmin, h);
 			++rays;
+		}
+		if (finished) {
 			F3 contrib = mk<float>(0.f, 0.f, 0.f);
 			bool done;
 			if (h.idx < 0) {
@@ -168,8 +201,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 			next += __popc(m);
 		}
 		// ---- C. one Philox draw per lane: camera ray for a new path, scatter for a continuing one -------
-		ray_ok = false;
-		if (task >= 0) {
+		if (!trav) ray_ok = false;  // a suspended traversal keeps its ray
+		if (task >= 0 && !trav) {
 			Rnd4<float> r = rnd4<float>(A.key, pixel, sample, (uint32_t)bounce, 0u);
 			if (bounce == 0) {
 				if (!cam.jitter) { r.x = 0.5f; r.y = 0.5f; }
