@@ -103,6 +103,7 @@ SIGNATURES = {
     "are_cuda_render_device": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _vp, C.POINTER(RenderStats), C.c_int]),
     "are_cuda_render": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _fp, C.POINTER(RenderStats)]),
     "are_cuda_tonemap": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_uint8)]),
+    "are_cuda_texture_paste": (C.c_int, [_vp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _ip]),
     "are_cuda_write_ppm": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint8)]),
     "are_cuda_alloc_accum": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "are_cuda_zero_accum": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
@@ -305,6 +306,14 @@ class Context:
         self._ck(self.lib.are_cuda_tonemap(self.h, _vp(accum_ptr), int(width), int(height), float(inv_spp), int(encoder),
                                            _ptr(out, C.POINTER(C.c_uint8))))
         return out
+
+    def texture_paste(self, dst: np.ndarray, src: np.ndarray, corners):
+        """In-place are::Texture::paste of src (h,w,3 float64) into dst; corners = (lt, rt, lb, rb) integer pixel pairs."""
+        assert dst.dtype == np.float64 and dst.flags.c_contiguous
+        src = np.ascontiguousarray(src, np.float64)
+        c = np.ascontiguousarray(np.asarray(corners, np.int32).reshape(8))
+        self._ck(self.lib.are_cuda_texture_paste(self.h, _ptr(dst), dst.shape[1], dst.shape[0], _ptr(src), src.shape[1], src.shape[0], _ptr(c, _ip)))
+        return dst
 
     def write_ppm(self, path, rgb8: np.ndarray):
         rgb8 = np.ascontiguousarray(rgb8, np.uint8)

@@ -6,6 +6,7 @@
 // src/texture.cpp:13-79).  There is no CPU implementation behind any of these calls.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -596,6 +597,80 @@ int are_cuda_tonemap(are_cuda_ctx *ctx, const float *accum, int width, int heigh
 	launch_tonemap(accum, width, height, inv_spp, encoder, d.as<uint8_t>(), ctx->stream);
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(out_host, d.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
+// Host part of Texture::paste: the homography through the four corner correspondences (8x8 Gauss-Jordan with partial
+// pivoting, pivot threshold GEOMETRY_EPSILON) and its 3x3 inverse by cofactors — same elimination order as the
+// reference (src/texture.cpp:196-300), so the coefficients handed to the kernel are the reference's bit for bit.
+static bool paste_homography(const double sxy[4][2], const double dxy[4][2], double hinv[9]) {
+	const double eps = 1e-12;
+	double M[8][9];
+	for (int k = 0; k < 4; ++k) {
+		const double x = sxy[k][0], y = sxy[k][1], u = dxy[k][0], v = dxy[k][1];
+		const double r0[9] = { x, y, 1.0, 0.0, 0.0, 0.0, -u * x, -u * y, u }, r1[9] = { 0.0, 0.0, 0.0, x, y, 1.0, -v * x, -v * y, v };
+		std::memcpy(M[2 * k], r0, sizeof r0);
+		std::memcpy(M[2 * k + 1], r1, sizeof r1);
+	}
+	for (int col = 0; col < 8; ++col) {
+		int pivot = col;
+		double best = std::fabs(M[col][col]);
+		for (int r = col + 1; r < 8; ++r)
+			if (std::fabs(M[r][col]) > best) { best = std::fabs(M[r][col]); pivot = r; }
+		if (best < eps) return false;
+		if (pivot != col)
+			for (int c = col; c < 9; ++c) std::swap(M[col][c], M[pivot][c]);
+		const double div = M[col][col];
+		for (int c = col; c < 9; ++c) M[col][c] /= div;
+		for (int r = 0; r < 8; ++r) {
+			if (r == col) continue;
+			const double factor = M[r][col];
+			if (std::fabs(factor) < eps) continue;
+			for (int c = col; c < 9; ++c) M[r][c] -= factor * M[col][c];
+		}
+	}
+	const double a = M[0][8], b = M[1][8], c = M[2][8], d = M[3][8], e = M[4][8], f = M[5][8], g = M[6][8], h = M[7][8], i = 1.0;
+	const double A = (e * i - f * h), B = -(d * i - f * g), C = (d * h - e * g), D = -(b * i - c * h), E = (a * i - c * g), F = -(a * h - b * g);
+	const double G = (b * f - c * e), Hc = -(a * f - c * d), I = (a * e - b * d);
+	const double det = a * A + b * B + c * C;
+	if (std::fabs(det) < eps) return false;
+	const double inv_det = 1.0 / det;
+	const double out[9] = { A * inv_det, D * inv_det, G * inv_det, B * inv_det, E * inv_det, Hc * inv_det, C * inv_det, F * inv_det, I * inv_det };
+	std::memcpy(hinv, out, sizeof out);
+	return true;
+}
+
+int are_cuda_texture_paste(are_cuda_ctx *ctx, double *dst_rgb, int dst_w, int dst_h, const double *src_rgb, int src_w, int src_h, const int corners[8]) {
+	if (!ctx || !corners) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	if (!dst_rgb || dst_w <= 0 || dst_h <= 0) return fail(ctx, ARE_ERR_RUNTIME, "Texture is not initialized.");  // texture.cpp:90-92
+	if (src_w <= 0 || src_h <= 0 || !src_rgb) return ARE_OK;                                                       // texture.cpp:93-95
+	// corners arrive as LT, RT, LB, RB; the polygon test walks LT, RT, RB, LB
+	const double lt[2] = { (double)corners[0], (double)corners[1] }, rt[2] = { (double)corners[2], (double)corners[3] };
+	const double lb[2] = { (double)corners[4], (double)corners[5] }, rb[2] = { (double)corners[6], (double)corners[7] };
+	PasteArgs a;
+	const double qx[4] = { lt[0], rt[0], rb[0], lb[0] }, qy[4] = { lt[1], rt[1], rb[1], lb[1] };
+	std::memcpy(a.qx, qx, sizeof qx);
+	std::memcpy(a.qy, qy, sizeof qy);
+	const double min_x = std::min(std::min(qx[0], qx[1]), std::min(qx[2], qx[3])), max_x = std::max(std::max(qx[0], qx[1]), std::max(qx[2], qx[3]));
+	const double min_y = std::min(std::min(qy[0], qy[1]), std::min(qy[2], qy[3])), max_y = std::max(std::max(qy[0], qy[1]), std::max(qy[2], qy[3]));
+	if (max_x < 0.0 || max_y < 0.0 || min_x > (double)(dst_w - 1) || min_y > (double)(dst_h - 1)) return ARE_OK;
+	a.x0 = std::max(0, (int)std::floor(min_x)); a.x1 = std::min(dst_w - 1, (int)std::ceil(max_x));
+	a.y0 = std::max(0, (int)std::floor(min_y)); a.y1 = std::min(dst_h - 1, (int)std::ceil(max_y));
+	const double sw = (double)src_w, sh = (double)src_h;
+	const double sxy[4][2] = { { 0.0, 0.0 }, { sw - 1.0, 0.0 }, { 0.0, sh - 1.0 }, { sw - 1.0, sh - 1.0 } };
+	const double dxy[4][2] = { { lt[0], lt[1] }, { rt[0], rt[1] }, { lb[0], lb[1] }, { rb[0], rb[1] } };
+	if (!paste_homography(sxy, dxy, a.hinv)) return ARE_OK;  // degenerate mapping: nothing pasted
+	Bind b(ctx);
+	const size_t dbytes = (size_t)dst_w * dst_h * 3 * sizeof(double), sbytes = (size_t)src_w * src_h * 3 * sizeof(double);
+	Tmp ddst, dsrc;
+	TMP_IN(ddst, dst_rgb, dbytes);
+	TMP_IN(dsrc, src_rgb, sbytes);
+	a.dst = ddst.as<double>(); a.src = dsrc.as<double>();
+	a.dw = dst_w; a.dh = dst_h; a.sw = src_w; a.sh = src_h;
+	launch_paste(a, ctx->stream);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(dst_rgb, ddst.p, dbytes, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	return ARE_OK;
 }

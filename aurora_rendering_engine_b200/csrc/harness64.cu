@@ -177,3 +177,49 @@ void launch_philox(int n, uint64_t seed, const uint32_t *ctr, uint32_t *out, cud
 }
 
 }  // namespace areb
+
+// =========================================================================================================
+// Texture::paste on the device (reference src/texture.cpp:85-360): one thread per destination pixel of the clipped
+// bounding box — even-odd point-in-quad at the pixel centre, inverse homography, bilinear fetch, all in fp64 with the
+// reference's operation order (this TU is built with -fmad=false), so the pasted texels are bit-identical.
+// The 8x8 solve and 3x3 inverse are done once on the host (api.cu).
+// =========================================================================================================
+namespace areb {
+
+__global__ void k_paste(PasteArgs a) {
+	const int x = a.x0 + blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = a.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+	if (x > a.x1 || y > a.y1) return;
+	const double X = (double)x + 0.5, Y = (double)y + 0.5;
+	bool inside = false;
+	for (int i = 0, j = 3; i < 4; j = i++) {  // boundary order LT, RT, RB, LB
+		const double xi = a.qx[i], yi = a.qy[i], xj = a.qx[j], yj = a.qy[j];
+		const bool cross = ((yi > Y) != (yj > Y)) && (X < (xj - xi) * (Y - yi) / ((yj - yi) == 0.0 ? 1e-30 : (yj - yi)) + xi);
+		inside ^= cross;
+	}
+	if (!inside) return;
+	const double denom = a.hinv[6] * X + a.hinv[7] * Y + a.hinv[8];
+	if (fabs(denom) < LIB_EPS) return;
+	double sx = (a.hinv[0] * X + a.hinv[1] * Y + a.hinv[2]) / denom;
+	double sy = (a.hinv[3] * X + a.hinv[4] * Y + a.hinv[5]) / denom;
+	const double sw = (double)a.sw, sh = (double)a.sh;
+	if (sx < 0.0 || sy < 0.0 || sx > sw - 1.0 || sy > sh - 1.0) return;
+	sx = fmin(fmax(sx, 0.0), sw - 1.0);
+	sy = fmin(fmax(sy, 0.0), sh - 1.0);
+	const int ix = (int)floor(sx), iy = (int)floor(sy);
+	const int ix1 = min(ix + 1, a.sw - 1), iy1 = min(iy + 1, a.sh - 1);
+	const double tx = sx - (double)ix, ty = sy - (double)iy;
+	const double w00 = (1.0 - tx) * (1.0 - ty), w10 = tx * (1.0 - ty), w01 = (1.0 - tx) * ty, w11 = tx * ty;
+	const double *c00 = a.src + ((size_t)iy * a.sw + ix) * 3, *c10 = a.src + ((size_t)iy * a.sw + ix1) * 3;
+	const double *c01 = a.src + ((size_t)iy1 * a.sw + ix) * 3, *c11 = a.src + ((size_t)iy1 * a.sw + ix1) * 3;
+	double *out = a.dst + ((size_t)y * a.dw + x) * 3;
+	for (int k = 0; k < 3; ++k) out[k] = w00 * c00[k] + w10 * c10[k] + w01 * c01[k] + w11 * c11[k];
+}
+
+void launch_paste(const PasteArgs &a, cudaStream_t s) {
+	if (a.x1 < a.x0 || a.y1 < a.y0) return;
+	dim3 block(32, 8), grid((a.x1 - a.x0 + 32) / 32, (a.y1 - a.y0 + 8) / 8);
+	k_paste<<<grid, block, 0, s>>>(a);
+}
+
+}  // namespace areb

@@ -34,6 +34,17 @@ void launch_texture64(const DevScene &sc, int n, const int *tex, const double *u
 void launch_camera64(const CamBasis &cb, int W, int H, int n, const int *px, const int *py, const double *rnd, double *Q, double *D, cudaStream_t s);
 void launch_philox(int n, uint64_t seed, const uint32_t *ctr, uint32_t *out, cudaStream_t s);
 
+// Texture::paste (harness64.cu): destination / source images as w*h*3 doubles on the device
+struct PasteArgs {
+	double *dst;
+	const double *src;
+	int dw, dh, sw, sh;
+	int x0, y0, x1, y1;       // clipped bounding box, inclusive
+	double qx[4], qy[4];      // destination quad in boundary order LT, RT, RB, LB
+	double hinv[9];           // inverse homography (destination -> source), row-major
+};
+void launch_paste(const PasteArgs &a, cudaStream_t s);
+
 // fp32 harness: the render kernels' own device routines (render.cu)
 void launch_hit32(const DevScene &sc, int n, const double *Q, const double *D, double tmin, bool use_bvh, int *prim, double *t, double *P, double *N, double *uv, cudaStream_t s);
 void launch_scatter32(const DevScene &sc, int n, const int *mat, const int *tex, const double *wi, const double *N, const double *P, const double *uv,

@@ -200,6 +200,14 @@ int are_cuda_tonemap(are_cuda_ctx *ctx, const float *accum_rgb_device, int width
 /* Write a binary P6 file exactly as the reference does ("P6\n%d %d\n255\n" + payload). */
 int are_cuda_write_ppm(const char *path, int width, int height, const uint8_t *rgb8);
 
+/* are::Texture::paste on the GPU (reference src/texture.cpp:85-360): warps the src image into the quad
+ * (left_top, right_top, left_bottom, right_bottom) of the dst image — 4-corner homography, even-odd point-in-quad at
+ * pixel centres, bilinear fetch, fp64; only pixels inside the quad whose pre-image lies inside src are overwritten.
+ * dst_rgb (in/out) and src_rgb are host arrays of w*h*3 doubles, rows as are::Texture holds them.
+ * corners = { lt.x, lt.y, rt.x, rt.y, lb.x, lb.y, rb.x, rb.y }.  Degenerate mappings leave dst untouched (ARE_OK). */
+int are_cuda_texture_paste(are_cuda_ctx *ctx, double *dst_rgb, int dst_w, int dst_h, const double *src_rgb, int src_w, int src_h,
+	const int corners[8]);
+
 /* Device scratch owned by the context (so hosts without a CUDA allocator can still drive render_device). */
 int are_cuda_alloc_accum(are_cuda_ctx *ctx, int width, int height, float **accum_rgb_device);
 int are_cuda_zero_accum(are_cuda_ctx *ctx, float *accum_rgb_device, int width, int height);

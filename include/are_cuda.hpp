@@ -166,5 +166,16 @@ private:
 	std::uint64_t uploaded_bytes_ = 0;
 };
 
+/// are::Texture::paste on the GPU (bit-identical to the CPU member function): warps `src` into the quad of `dst`.
+inline void paste(Renderer &gpu, Texture &dst, const Texture &src, const std::pair<int, int> &left_top, const std::pair<int, int> &right_top,
+	const std::pair<int, int> &left_bottom, const std::pair<int, int> &right_bottom) {
+	if (dst.width_ <= 0 || dst.height_ <= 0 || !dst.data()) throw std::runtime_error("Texture is not initialized.");
+	const int corners[8] = { left_top.first, left_top.second, right_top.first, right_top.second, left_bottom.first, left_bottom.second,
+		right_bottom.first, right_bottom.second };
+	double *d = dst.pixel(0, 0).e();  // contiguous w*h*3 doubles
+	const int st = are_cuda_texture_paste(gpu.context(), d, dst.width_, dst.height_, src.data(), src.width_, src.height_, corners);
+	if (st < 0) throw std::runtime_error(are_cuda_last_error(gpu.context()));
+}
+
 }  // namespace cuda
 }  // namespace are

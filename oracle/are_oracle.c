@@ -278,6 +278,81 @@ int lib_texture_save(const char *path, int w, int h, const double *rgb) {
 	fclose(fp);
 	return 1;
 }
+/* src/texture.cpp:85-360 — Texture::paste: warp src into the quad (lt, rt, lb, rb) of dst through the 4-corner
+ * homography (8x8 Gauss-Jordan with partial pivoting, 3x3 inverse by cofactors), even-odd point-in-quad at pixel
+ * centres, bilinear fetch.  dst/src = w*h*3 doubles, corners = {lt.x, lt.y, rt.x, rt.y, lb.x, lb.y, rb.x, rb.y}. */
+void lib_texture_paste(double *dst, int dw, int dh, const double *src, int sw_i, int sh_i, const int *corners) {
+	if (!dst || sw_i <= 0 || sh_i <= 0) return;
+	const double lt[2] = { corners[0], corners[1] }, rt[2] = { corners[2], corners[3] }, lb[2] = { corners[4], corners[5] }, rb[2] = { corners[6], corners[7] };
+	const double qx[4] = { lt[0], rt[0], rb[0], lb[0] }, qy[4] = { lt[1], rt[1], rb[1], lb[1] };
+	double min_x = fmin(fmin(qx[0], qx[1]), fmin(qx[2], qx[3])), max_x = fmax(fmax(qx[0], qx[1]), fmax(qx[2], qx[3]));
+	double min_y = fmin(fmin(qy[0], qy[1]), fmin(qy[2], qy[3])), max_y = fmax(fmax(qy[0], qy[1]), fmax(qy[2], qy[3]));
+	if (max_x < 0.0 || max_y < 0.0 || min_x > (double)(dw - 1) || min_y > (double)(dh - 1)) return;
+	int x0 = (int)floor(min_x), x1 = (int)ceil(max_x), y0 = (int)floor(min_y), y1 = (int)ceil(max_y);
+	if (x0 < 0) x0 = 0;
+	if (x1 > dw - 1) x1 = dw - 1;
+	if (y0 < 0) y0 = 0;
+	if (y1 > dh - 1) y1 = dh - 1;
+	const double sw = sw_i, sh = sh_i;
+	const double sxy[4][2] = { { 0.0, 0.0 }, { sw - 1.0, 0.0 }, { 0.0, sh - 1.0 }, { sw - 1.0, sh - 1.0 } };
+	const double dxy[4][2] = { { lt[0], lt[1] }, { rt[0], rt[1] }, { lb[0], lb[1] }, { rb[0], rb[1] } };
+	double M[8][9];
+	for (int k = 0; k < 4; ++k) {
+		double x = sxy[k][0], y = sxy[k][1], u = dxy[k][0], v = dxy[k][1];
+		double r0[9] = { x, y, 1.0, 0.0, 0.0, 0.0, -u * x, -u * y, u }, r1[9] = { 0.0, 0.0, 0.0, x, y, 1.0, -v * x, -v * y, v };
+		memcpy(M[2 * k], r0, sizeof r0);
+		memcpy(M[2 * k + 1], r1, sizeof r1);
+	}
+	for (int col = 0; col < 8; ++col) {
+		int pivot = col;
+		double best = fabs(M[col][col]);
+		for (int r = col + 1; r < 8; ++r)
+			if (fabs(M[r][col]) > best) { best = fabs(M[r][col]); pivot = r; }
+		if (best < LIB_EPS) return;
+		if (pivot != col)
+			for (int c = col; c < 9; ++c) { double t = M[col][c]; M[col][c] = M[pivot][c]; M[pivot][c] = t; }
+		double div = M[col][col];
+		for (int c = col; c < 9; ++c) M[col][c] /= div;
+		for (int r = 0; r < 8; ++r) {
+			if (r == col) continue;
+			double factor = M[r][col];
+			if (fabs(factor) < LIB_EPS) continue;
+			for (int c = col; c < 9; ++c) M[r][c] -= factor * M[col][c];
+		}
+	}
+	const double a = M[0][8], b = M[1][8], c = M[2][8], d = M[3][8], e = M[4][8], f = M[5][8], g = M[6][8], h = M[7][8], i = 1.0;
+	const double A = (e * i - f * h), B = -(d * i - f * g), C = (d * h - e * g), D = -(b * i - c * h), E = (a * i - c * g), F = -(a * h - b * g);
+	const double G = (b * f - c * e), Hc = -(a * f - c * d), I = (a * e - b * d);
+	const double det = a * A + b * B + c * C;
+	if (fabs(det) < LIB_EPS) return;
+	const double id = 1.0 / det;
+	const double hi[9] = { A * id, D * id, G * id, B * id, E * id, Hc * id, C * id, F * id, I * id };
+	for (int y = y0; y <= y1; ++y)
+		for (int x = x0; x <= x1; ++x) {
+			const double X = (double)x + 0.5, Y = (double)y + 0.5;
+			int inside = 0;
+			for (int p = 0, q = 3; p < 4; q = p++) {
+				const double xi = qx[p], yi = qy[p], xj = qx[q], yj = qy[q];
+				const int cross = ((yi > Y) != (yj > Y)) && (X < (xj - xi) * (Y - yi) / ((yj - yi) == 0.0 ? 1e-30 : (yj - yi)) + xi);
+				inside ^= cross;
+			}
+			if (!inside) continue;
+			const double denom = hi[6] * X + hi[7] * Y + hi[8];
+			if (fabs(denom) < LIB_EPS) continue;
+			double sx = (hi[0] * X + hi[1] * Y + hi[2]) / denom, sy = (hi[3] * X + hi[4] * Y + hi[5]) / denom;
+			if (sx < 0.0 || sy < 0.0 || sx > sw - 1.0 || sy > sh - 1.0) continue;
+			sx = sx < 0.0 ? 0.0 : (sw - 1.0 < sx ? sw - 1.0 : sx);
+			sy = sy < 0.0 ? 0.0 : (sh - 1.0 < sy ? sh - 1.0 : sy);
+			int ix = (int)floor(sx), iy = (int)floor(sy);
+			int ix1 = ix + 1 < sw_i - 1 ? ix + 1 : sw_i - 1, iy1 = iy + 1 < sh_i - 1 ? iy + 1 : sh_i - 1;
+			double tx = sx - (double)ix, ty = sy - (double)iy;
+			double w00 = (1.0 - tx) * (1.0 - ty), w10 = tx * (1.0 - ty), w01 = (1.0 - tx) * ty, w11 = tx * ty;
+			const double *c00 = src + ((size_t)iy * sw_i + ix) * 3, *c10 = src + ((size_t)iy * sw_i + ix1) * 3;
+			const double *c01 = src + ((size_t)iy1 * sw_i + ix) * 3, *c11 = src + ((size_t)iy1 * sw_i + ix1) * 3;
+			double *out = dst + ((size_t)y * dw + x) * 3;
+			for (int k = 0; k < 3; ++k) out[k] = w00 * c00[k] + w10 * c10[k] + w01 * c01[k] + w11 * c11[k];
+		}
+}
 /* experiments/rt.cpp:72-76,383-386: clamp to [0,1] (fmax/fmin), (unsigned char)(powf(c, 1/2.2f) * 255) in fp32 */
 void lib_encode_gamma22(long n, const float *c, unsigned char *out) {
 	for (long i = 0; i < n; ++i) {

@@ -295,6 +295,25 @@ int ref_texture_save(const char *path, int w, int h, const double *rgb) {
 	}
 }
 
+// Texture::paste (src/texture.cpp:85-360) on images given as w*h*3 doubles; dst is updated in place.
+// corners = { lt.x, lt.y, rt.x, rt.y, lb.x, lb.y, rb.x, rb.y }.  Returns 0, or 1 on runtime_error.
+int ref_texture_paste(double *dst, int dw, int dh, const double *src, int sw, int sh, const int *corners) {
+	try {
+		std::unique_ptr<are::Texture> d(new are::Texture(dw, dh, are::Color3(0, 0, 0)));
+		std::unique_ptr<are::Texture> s(new are::Texture(sw, sh, are::Color3(0, 0, 0)));
+		for (int y = 0; y < dh; ++y)
+			for (int x = 0; x < dw; ++x) d->pixel(x, y) = ld(dst + ((size_t)y * dw + x) * 3);
+		for (int y = 0; y < sh; ++y)
+			for (int x = 0; x < sw; ++x) s->pixel(x, y) = ld(src + ((size_t)y * sw + x) * 3);
+		d->paste(*s, { corners[0], corners[1] }, { corners[2], corners[3] }, { corners[4], corners[5] }, { corners[6], corners[7] });
+		for (int y = 0; y < dh; ++y)
+			for (int x = 0; x < dw; ++x) st(dst + ((size_t)y * dw + x) * 3, d->pixel(x, y));
+		return 0;
+	} catch (const std::runtime_error &) {
+		return 1;
+	}
+}
+
 // Texture(w,h,fill) ctor error behaviour: 0 ok, 1 runtime_error.
 int ref_texture_fill_ctor(int w, int h) {
 	try {

@@ -186,6 +186,32 @@ int main(int argc, char **argv) {
 		try { empty.pixel(0, 0); std::printf("pixel ok\n"); } catch (const std::runtime_error &e) { std::printf("pixel runtime_error: %s\n", e.what()); }
 		try { empty.save_texture(tmp + "/e.ppm"); std::printf("esave ok\n"); } catch (const std::runtime_error &e) { std::printf("esave runtime_error: %s\n", e.what()); }
 	}
+	// ---- Texture::paste ----
+	{
+		Texture src(7, 5, Color3(0, 0, 0));
+		for (int y = 0; y < 5; ++y)
+			for (int x = 0; x < 7; ++x) {
+				double r = rnd(), g = rnd(), b = rnd();
+				src.pixel(x, y) = Color3(r, g, b);
+			}
+		const int cases[5][8] = { { 2, 3, 27, 1, 1, 19, 29, 17 }, { -6, -4, 40, 3, 2, 30, 31, 23 }, { 5, 5, 5, 5, 5, 20, 5, 20 },
+			{ 20, 2, 3, 4, 25, 21, 1, 18 }, { 0, 0, 31, 0, 0, 23, 31, 23 } };
+		for (const int(&c)[8] : cases) {
+			Texture dst(32, 24, Color3(0.5, 0.25, 0.125));
+			dst.paste(src, { c[0], c[1] }, { c[2], c[3] }, { c[4], c[5] }, { c[6], c[7] });
+			int changed = 0;
+			double sum = 0;
+			for (int y = 0; y < 24; ++y)
+				for (int x = 0; x < 32; ++x) {
+					const Color3 &q = dst.pixel(x, y);
+					if (q.x() != 0.5 || q.y() != 0.25 || q.z() != 0.125) ++changed;
+					sum += q.x() * (1 + x) + q.y() * (1 + y) + q.z();
+				}
+			std::printf("paste changed %d checksum %.17g ", changed, sum); show("centre", dst.pixel(15, 11));
+		}
+		Texture empty;
+		try { empty.paste(src, { 0, 0 }, { 1, 0 }, { 0, 1 }, { 1, 1 }); std::printf("epaste ok\n"); } catch (const std::runtime_error &e) { std::printf("epaste runtime_error: %s\n", e.what()); }
+	}
 	for (Triangle *t : owned) delete t;
 	return 0;
 }

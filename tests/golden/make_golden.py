@@ -116,6 +116,12 @@ def main():
         g["tex_load_p3"] = np.array([ref.texture_load(os.path.join(d, "p3.ppm"))[0]])
         open(os.path.join(d, "short.ppm"), "wb").write(b"P6\n2 2\n255\n" + bytes(5))
         g["tex_load_short"] = np.array([ref.texture_load(os.path.join(d, "short.ppm"))[0]])
+    # Texture::paste (src/texture.cpp:85-360): general quad, partly outside, degenerate, flipped, full-frame
+    pdst, psrc = rng.uniform(0, 1, (40, 56, 3)), rng.uniform(0, 1, (9, 13, 3))
+    pcorners = np.array([[3, 4, 50, 2, 2, 33, 52, 30], [-9, -6, 70, 5, 4, 50, 55, 39], [5, 5, 5, 5, 5, 20, 5, 20],
+                         [40, 3, 6, 7, 45, 36, 2, 31], [0, 0, 55, 0, 0, 39, 55, 39], [200, 200, 260, 200, 200, 260, 260, 260]], np.int32)
+    g["paste_dst"], g["paste_src"], g["paste_corners"] = pdst, psrc, pcorners
+    g["paste_out"] = np.stack([ref.texture_paste(pdst, psrc, c.reshape(4, 2)) for c in pcorners])
     g["tex_fill_ctor"] = np.array([ref.texture_fill_ctor(4, 4), ref.texture_fill_ctor(0, 4), ref.texture_fill_ctor(4, -1)])
     g["sizeof"] = np.array(ref.sizeof())
     g["geometry_epsilon"] = np.array([ref.geometry_epsilon()])

@@ -121,6 +121,14 @@ class _VecLib:
         st = fn(os.fsencode(path), C.byref(w), C.byref(h), _p(rgb), C.c_long(rgb.size))
         return st, rgb
 
+    def texture_paste(self, dst, src, corners):
+        """are::Texture::paste; returns the updated copy of dst (h,w,3). corners = (lt, rt, lb, rb) integer pixel pairs."""
+        out = np.array(dst, dtype=np.float64, order="C", copy=True)
+        src = _d(src)
+        c = np.ascontiguousarray(np.asarray(corners, np.int32).reshape(8))
+        self._f("texture_paste")(_p(out), C.c_int(out.shape[1]), C.c_int(out.shape[0]), _p(src), C.c_int(src.shape[1]), C.c_int(src.shape[0]), _p(c, _ip))
+        return out
+
     def texture_save(self, path, rgb):
         rgb = _d(rgb)
         fn = self._f("texture_save")

@@ -108,3 +108,38 @@ def test_reference_style_host_program_renders_on_gpu(tmp_path, lib, ctx):
     mean = sums.astype(np.float64) * (1.0 / spp)
     exp = np.clip(mean * 255.0, 0.0, 255.0).astype(np.uint8)
     assert np.array_equal(px, exp)
+
+
+def test_paste_restatement_matches_reference_golden(oracle):
+    """oracle lib_texture_paste vs outputs of the real are::Texture::paste recorded in the golden file."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+    changed = 0
+    for c, want in zip(g["paste_corners"], g["paste_out"]):
+        got = oracle.texture_paste(g["paste_dst"], g["paste_src"], c.reshape(4, 2))
+        assert np.array_equal(got, want)
+        changed += int((want != g["paste_dst"]).any(axis=2).sum())
+    assert changed > 3000  # the cases really paste something
+    assert np.array_equal(g["paste_out"][2], g["paste_dst"]) and np.array_equal(g["paste_out"][5], g["paste_dst"])  # degenerate / off-image
+
+
+@pytest.mark.gpu
+def test_gpu_paste_is_bit_identical(ctx, oracle):
+    """are_cuda_texture_paste (fp64 kernel, -fmad=false) against the reference's outputs and against the restatement
+    on fresh random quads."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+    for c, want in zip(g["paste_corners"], g["paste_out"]):
+        got = ctx.texture_paste(g["paste_dst"].copy(), g["paste_src"], c.reshape(4, 2))
+        assert np.array_equal(got, want)
+    rng = np.random.RandomState(11)
+    pasted = 0
+    for trial in range(30):
+        dw, dh, sw, sh = rng.randint(16, 300), rng.randint(16, 300), rng.randint(1, 64), rng.randint(1, 64)
+        dst, src = rng.uniform(0, 1, (dh, dw, 3)), rng.uniform(0, 1, (sh, sw, 3))
+        corners = [tuple(int(v) for v in rng.randint(-20, max(dw, dh) + 20, 2)) for _ in range(4)]
+        if trial % 3 == 0:
+            corners = [(3, 2), (dw - 5, 4), (1, dh - 4), (dw - 2, dh - 3)]
+        want = oracle.texture_paste(dst, src, corners)
+        got = ctx.texture_paste(dst.copy(), src, corners)
+        assert np.array_equal(got, want), (trial, corners)
+        pasted += int((want != dst).any(axis=2).sum())
+    assert pasted > 100_000
