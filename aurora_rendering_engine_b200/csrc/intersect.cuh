@@ -168,15 +168,46 @@ __device__ __forceinline__ RaySlopes ray_slopes(V3<float> o, V3<float> d) {
 	return r;
 }
 
-// One traversal step: visit inner node `node` (both children's boxes, leaves intersected on the spot, the nearer
-// inner child next, the farther pushed).  Returns false when the traversal is complete.  The cursor (node, sp, stack)
-// and the best hit live in the caller, so a traversal can be suspended and resumed — the megakernel runs traversals
-// in slices and lets lanes whose ray is finished go on to shading while long rays keep their place.
+// BVH leaves hold ONE hot primitive each; a negative child reference encodes it completely:
+//   ref = ~(slot | kind << 29),  kind: 0 box (two slots), 1 quad / fused pair, 2 triangle, 3 sphere.
+// No per-leaf loops, no counts to fetch: a leaf test is one switch on the kind.
+__device__ __forceinline__ int leaf_slot(int ref) { return (~ref) & 0x1fffffff; }
 template <bool COUNT>
-__device__ __forceinline__ bool bvh_visit(const DevScene &sc, V3<float> o, V3<float> d, float tmin, const RaySlopes &rs, int &node, int &sp, int *stack, Hit &h, TravCounters *cnt) {
+__device__ __forceinline__ void test_leaf(const DevScene &sc, int ref, V3<float> o, V3<float> d, float tmin, Hit &h, TravCounters *cnt) {
+	const unsigned code = (unsigned)~ref;
+	const int slot = (int)(code & 0x1fffffffu), kind = (int)(code >> 29);
+	const HotPrim *p = sc.bvh_prims + slot;
+	const float4 r0 = ldg4(&p->r0), r1 = ldg4(&p->r1);
+	if (kind == 3) {
+		test_sphere(r0, r1, o, d, tmin, slot, h);
+		if (COUNT) cnt->spheres++;
+	} else {
+		const float4 r2 = ldg4(&p->r2);
+		if (kind == 1) { test_plane<true>(r0, r1, r2, o, d, tmin, slot, h); if (COUNT) cnt->quads++; }
+		else if (kind == 2) { test_plane<false>(r0, r1, r2, o, d, tmin, slot, h); if (COUNT) cnt->tris++; }
+		else { test_box(r0, r1, r2, ldg4(&p[1].r0), o, d, tmin, slot, h); if (COUNT) cnt->boxes++; }
+	}
+}
+
+// Traversal cursor kept by the caller (so a traversal can be suspended and resumed): `node` >= 0 is the inner node to
+// visit next, `pend` != 0 a leaf waiting to be tested (leaf tests are postponed so that many lanes run them together),
+// the stack holds inner nodes and leaves alike.
+__device__ __forceinline__ void trav_set(int x, int &node, int &pend) {
+	if (x < 0) { pend = x; node = -1; }
+	else node = x;
+}
+__device__ __forceinline__ bool trav_pop(int &sp, const int *stack, int &node, int &pend) {
+	if (sp == 0) { node = -1; return false; }
+	trav_set(stack[--sp], node, pend);
+	return true;
+}
+// Visit inner node `node`: slab-test both children, continue with the nearer one that is hit, push the farther.
+// Returns false when nothing is left to do.
+template <bool COUNT>
+__device__ __forceinline__ bool bvh_visit(const DevScene &sc, float tmin, const RaySlopes &rs, int &node, int &pend, int &sp, int *stack, const Hit &h, TravCounters *cnt) {
 	const BvhNode *n = sc.nodes + node;
 	const float4 b0 = ldg4(&n->b0), b1 = ldg4(&n->b1), b2 = ldg4(&n->b2);
-	const int4 cm = __ldg(reinterpret_cast<const int4 *>(&n->child[0]));
+	const int2 ch = __ldg(reinterpret_cast<const int2 *>(&n->child[0]));
 	if (COUNT) cnt->nodes++;
 	const float c0lox = fmaf(b0.x, rs.idx, -rs.oxi), c0hix = fmaf(b0.y, rs.idx, -rs.oxi), c0loy = fmaf(b0.z, rs.idy, -rs.oyi), c0hiy = fmaf(b0.w, rs.idy, -rs.oyi);
 	const float c0loz = fmaf(b2.x, rs.idz, -rs.ozi), c0hiz = fmaf(b2.y, rs.idz, -rs.ozi);
@@ -186,49 +217,38 @@ __device__ __forceinline__ bool bvh_visit(const DevScene &sc, V3<float> o, V3<fl
 	const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
 	const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
 	const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
-	bool hit0 = t0n <= t0f, hit1 = t1n <= t1f;
-	if (hit0 && cm.x < 0) {
-		const int m = cm.z;
-		intersect_range<ldg4>(sc.bvh_prims, ~cm.x, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, tmin, h);
-		if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; cnt->boxes += (m >> 24) & 255; }
-		hit0 = false;
-	}
-	if (hit1 && cm.y < 0) {
-		if (t1n <= h.t) {
-			const int m = cm.w;
-			intersect_range<ldg4>(sc.bvh_prims, ~cm.y, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, tmin, h);
-			if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; cnt->boxes += (m >> 24) & 255; }
-		}
-		hit1 = false;
-	}
-	int next = -1;
+	const bool hit0 = t0n <= t0f, hit1 = t1n <= t1f;
 	if (hit0 && hit1) {
 		const bool near0 = t0n <= t1n;
-		next = near0 ? cm.x : cm.y;
-		if (sp < ARE_BVH_STACK) stack[sp++] = near0 ? cm.y : cm.x;
-	} else if (hit0) next = cm.x;
-	else if (hit1) next = cm.y;
-	if (next < 0) {
-		if (sp == 0) return false;
-		next = stack[--sp];
+		if (sp < ARE_BVH_STACK) stack[sp++] = near0 ? ch.y : ch.x;
+		trav_set(near0 ? ch.x : ch.y, node, pend);
+		return true;
 	}
-	node = next;
-	return true;
+	if (hit0 || hit1) {
+		trav_set(hit0 ? ch.x : ch.y, node, pend);
+		return true;
+	}
+	return trav_pop(sp, stack, node, pend);
 }
 
 // Whole traversal in one go (per-ray harness).
 template <bool COUNT>
 __device__ __forceinline__ void intersect_bvh(const DevScene &sc, V3<float> o, V3<float> d, float tmin, Hit &h, TravCounters *cnt) {
 	if (sc.n_nodes == 0) {
-		const int m = sc.root_leaf_meta;
-		intersect_range<ldg4>(sc.bvh_prims, 0, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, tmin, h);
-		if (COUNT) { cnt->quads += m & 255; cnt->tris += (m >> 8) & 255; cnt->spheres += (m >> 16) & 255; cnt->boxes += (m >> 24) & 255; }
+		if (sc.root_leaf_meta != 0) test_leaf<COUNT>(sc, sc.root_leaf_meta, o, d, tmin, h, cnt);  // a one-primitive scene
 		return;
 	}
 	const RaySlopes rs = ray_slopes(o, d);
 	int stack[ARE_BVH_STACK];
-	int sp = 0, node = 0;
-	while (bvh_visit<COUNT>(sc, o, d, tmin, rs, node, sp, stack, h, cnt)) {}
+	int sp = 0, node = 0, pend = 0;
+	bool more = true;
+	while (more) {
+		if (pend != 0) {
+			test_leaf<COUNT>(sc, pend, o, d, tmin, h, cnt);
+			pend = 0;
+			more = trav_pop(sp, stack, node, pend);
+		} else more = bvh_visit<COUNT>(sc, tmin, rs, node, pend, sp, stack, h, cnt);
+	}
 }
 
 // ---- map a hot hit back to the user primitive ---------------------------------------------------------

@@ -58,7 +58,10 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #define RENDER_MIN_BLOCKS 6
 #endif
 #ifndef TRAV_MIN_LANES
-#define TRAV_MIN_LANES 20  // BVH slices end when fewer lanes than this are still traversing and others are waiting
+#define TRAV_MIN_LANES 6   // BVH slices end when fewer lanes than this are still traversing and others are waiting
+#endif
+#ifndef LEAF_MIN_LANES
+#define LEAF_MIN_LANES 1   // leaf tests run once this many lanes hold one (measured: 1 is best on RTIOW and on the 1 M-primitive stress scene)
 #endif
 template <bool BVH, bool COUNT>
 __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_path(const __grid_constant__ RenderArgs A) {
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 	Hit h;          // best hit of the ray in flight (BVH: survives across trips while its traversal is suspended)
 	h.t = INFINITY; h.idx = -1; h.orig = -1;
 	bool trav = false;  // BVH: traversal in progress
-	int node = 0, sp = 0;
+	int node = 0, pend = 0, sp = 0;
 	int stack[BVH ? ARE_BVH_STACK : 1];
 	unsigned int rays = 0;
 	TravCounters tc = { 0, 0, 0, 0, 0 };
@@ -114,17 +117,27 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 			if (ray_ok && !trav) {  // a fresh ray
 				h.t = INFINITY; h.idx = -1; h.orig = orig;
 				++rays;
-				if (A.sc.n_nodes == 0) {  // the whole scene is one leaf
-					const int m = A.sc.root_leaf_meta;
-					intersect_range<ldg4>(A.sc.bvh_prims, 0, m & 255, (m >> 8) & 255, (m >> 16) & 255, (m >> 24) & 255, o, d, A.tmin, h);
-					if (COUNT) { tc.quads += m & 255; tc.tris += (m >> 8) & 255; tc.spheres += (m >> 16) & 255; tc.boxes += (m >> 24) & 255; }
-				} else { node = 0; sp = 0; trav = true; }
+				if (A.sc.n_nodes == 0) {  // zero or one primitive
+					if (A.sc.root_leaf_meta != 0) test_leaf<COUNT>(A.sc, A.sc.root_leaf_meta, o, d, A.tmin, h, &tc);
+				} else { node = 0; pend = 0; sp = 0; trav = true; }
 			}
 			const int n_rays = __popc(__ballot_sync(full, ray_ok));
 			if (__any_sync(full, trav)) {
 				const RaySlopes rs = ray_slopes(o, d);
 				while (true) {
-					if (trav) trav = bvh_visit<COUNT>(A.sc, o, d, A.tmin, rs, node, sp, stack, h, &tc);
+					// node phase: every traversing lane that has no leaf waiting visits one inner node
+					if (trav && pend == 0) trav = bvh_visit<COUNT>(A.sc, A.tmin, rs, node, pend, sp, stack, h, &tc);
+					// leaf phase, postponed until LEAF_MIN_LANES lanes hold a leaf (or nobody can do anything else): the
+					// primitive tests then run with many lanes instead of one or two
+					const unsigned m_leaf = __ballot_sync(full, trav && pend != 0);
+					const unsigned m_node = __ballot_sync(full, trav && pend == 0);
+					if (m_leaf != 0u && (__popc(m_leaf) >= LEAF_MIN_LANES || m_node == 0u)) {
+						if (trav && pend != 0) {
+							test_leaf<COUNT>(A.sc, pend, o, d, A.tmin, h, &tc);
+							pend = 0;
+							trav = trav_pop(sp, stack, node, pend);
+						}
+					}
 					const int n_trav = __popc(__ballot_sync(full, trav));
 					if (n_trav == 0 || (n_trav < TRAV_MIN_LANES && n_trav < n_rays)) break;
 				}

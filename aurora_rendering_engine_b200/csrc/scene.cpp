@@ -82,7 +82,6 @@ inline void emit_item(const HotItem &it, std::vector<HotPrim> &prims, std::vecto
 	ids.push_back(it.ids);
 	if (it.kind == HK_BOX) { prims.push_back(it.rec2); ids.push_back(it.ids); }
 }
-inline int pack_meta(const int cnt[HK_KINDS]) { return cnt[HK_QUAD] | (cnt[HK_TRI] << 8) | (cnt[HK_SPHERE] << 16) | (cnt[HK_BOX] << 24); }
 
 struct VKey {
 	uint64_t a[3];
@@ -144,20 +143,15 @@ struct Builder {
 		zlo = lo[2];
 		zhi = hi[2];
 	}
-	ChildRef make_leaf(int lo, int hi) {
+	ChildRef make_leaf(int lo, int hi) {  // exactly one item per leaf: ref = ~(slot | kind << 29)
 		ChildRef c;
-		c.box.reset();
-		int first = (int)out.bvh_prims.size(), cnt[HK_KINDS] = { 0, 0, 0, 0 };
-		for (int kind = 0; kind < HK_KINDS; ++kind)
-			for (int i = lo; i < hi; ++i) {
-				const HotItem &it = items[idx[i]];
-				if (it.kind != kind) continue;
-				emit_item(it, out.bvh_prims, out.bvh_ids);
-				c.box.grow(it.box);
-				cnt[kind]++;
-			}
-		c.ref = ~first;
-		c.meta = pack_meta(cnt);
+		const HotItem &it = items[idx[lo]];
+		(void)hi;
+		const int slot = (int)out.bvh_prims.size();
+		emit_item(it, out.bvh_prims, out.bvh_ids);
+		c.box = it.box;
+		c.ref = ~(slot | (it.kind << 29));
+		c.meta = 0;
 		return c;
 	}
 	ChildRef build(int lo, int hi, int depth) {
@@ -633,11 +627,11 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 	}
 	// ---- BVH ----
 	if (!hot.empty()) {
-		Builder b(hot, out, std::max(1, std::min(opt.leaf_size, 16)));
+		Builder b(hot, out, 1);  // one hot primitive per leaf (the traversal kernel relies on it)
 		out.bvh_prims.reserve(hot.size());
 		out.bvh_ids.reserve(hot.size());
 		ChildRef root = b.build(0, (int)hot.size(), 0);
-		if (root.ref < 0) out.root_leaf_meta = root.meta;
+		if (root.ref < 0) out.root_leaf_meta = root.ref;  // a one-primitive scene: the root IS the leaf reference
 		out.bvh_depth = b.max_depth;
 	}
 	return true;

@@ -93,7 +93,10 @@ def test_stress_scene_bvh_equals_brute_and_matches_cpu_twin(ctx, oracle):
     spp = 8
     ib, sb = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=spp, traversal=1)))
     iv, sv = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=spp, traversal=2)))
-    assert sb.rays == sv.rays and np.array_equal(ib, iv)
+    # every (pixel, sample) path is the same set of rays either way; only the order in which finished samples reach
+    # the tile accumulators differs (BVH traversals are sliced), i.e. float summation order
+    assert sb.rays == sv.rays, (sb.rays, sv.rays)
+    assert np.allclose(ib, iv, rtol=1e-5, atol=1e-6), float(np.abs(ib - iv).max())
     osc = sc.feed(oracle.scene())
     oimg, ost = osc.render(cam, capi.make_params(**sc.params_args(sample_count=spp)))
     p = psnr(np.clip(iv / spp, 0, 1), np.clip(oimg / spp, 0, 1))
@@ -141,7 +144,7 @@ def test_counters_brute_and_bvh(ctx):
     assert sb.rays == sv.rays  # same arithmetic -> same paths
     # 36 triangles -> 18 fused parallelograms -> room (5 faces) + 2 boxes as slab-test primitives, + the light quad
     assert sb.box_tests == sb.rays * 3 and sb.quad_tests == sb.rays and sb.tri_tests == 0
-    assert sv.box_tests == sb.box_tests and sv.node_visits == 0  # 4 hot primitives = one BVH leaf
+    assert 0 < sv.box_tests <= sb.box_tests and sv.node_visits >= sv.rays  # 4 hot primitives = 3 inner nodes, one primitive per leaf
     assert sb.launches == 1 and sb.kernel_ms > 0
     # a scene with a real hierarchy
     sc = scenes.rtiow_final(width=64, height=36)
