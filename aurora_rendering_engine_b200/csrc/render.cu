@@ -90,11 +90,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 	int task = -1;         // this lane's task, -1 = needs one
 	bool exhausted = false;
 	bool ray_ok = false;
-	int pl = lane, px = 0, py = 0, bounce = 0;
-	uint32_t pixel = 0, sample = 0;
+	int bounce = 0;
 	F3 o = mk<float>(0.f, 0.f, 0.f), d = mk<float>(0.f, 0.f, 1.f), thr = o;
 	// surface interaction carried from the classify stage to the scatter stage
-	F3 sP = o, sN = o, scol = o;
+	F3 sP = o, sN = o;
 	float sp0 = 0.f;
 	int sdev = 0, sbits = 0;
 	int orig = -1;  // hot slot of the primitive the current ray starts on
@@ -164,7 +163,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 				const float4 s1 = __ldg(reinterpret_cast<const float4 *>(&A.sc.shade[sdev].r1));
 				sbits = __float_as_int(s0.w);
 				sN = mk<float>(s0.x, s0.y, s0.z);
-				scol = mk<float>(s1.x, s1.y, s1.z);
+				F3 scol = mk<float>(s1.x, s1.y, s1.z);
 				sp0 = s1.w;
 				if (sdev >= A.sc.n_tri + A.sc.n_quad) {  // sphere: outward normal from (centre, radius)
 					const float4 c = __ldg(reinterpret_cast<const float4 *>(&A.sc.prim_plane[sdev].r0));
@@ -182,12 +181,15 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 					}
 					contrib = thr * scol;
 					done = true;
-				} else done = bounce >= A.max_depth;  // truncated path contributes nothing (RTIOW depth cut-off)
+				} else {
+					done = bounce >= A.max_depth;  // truncated path contributes nothing (RTIOW depth cut-off)
+					if (sbits >> 8) thr = thr * scol;  // SHADE_FAST: the attenuation is the solid colour, apply it now
+				}
 			}
 			if (done) {
 				const float csum = contrib.x + contrib.y + contrib.z;  // radiance is non-negative: 0 adds nothing, NaN / inf are dropped
 				if (csum > 0.0f && csum < INFINITY) {
-					float *acc = &s_acc[warp][pl * 3];
+					float *acc = &s_acc[warp][(task & 31) * 3];
 					atomicAdd(acc, contrib.x); atomicAdd(acc + 1, contrib.y); atomicAdd(acc + 2, contrib.z);
 				}
 				task = -1;
@@ -201,12 +203,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 			if (need) {
 				const int k = next + __popc(m & lt_mask);
 				if (k < total) {
-					pl = k & 31;
-					px = x0 + (pl & 7); py = y0 + (pl >> 3);
-					if (px < A.W && py < A.H) {
+					if (x0 + (k & 7) < A.W && y0 + ((k >> 3) & 3) < A.H) {  // tiles on the image border own pixels outside it
 						task = k;
-						sample = (uint32_t)(A.s_begin + (k >> 5));
-						pixel = (uint32_t)(py * A.W + px);
 						bounce = 0;
 					}
 				} else exhausted = true;
@@ -216,6 +214,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 		// ---- C. one Philox draw per lane: camera ray for a new path, scatter for a continuing one -------
 		if (!trav) ray_ok = false;  // a suspended traversal keeps its ray
 		if (task >= 0 && !trav) {
+			// task -> (pixel of the tile, sample): recomputed here instead of living in four registers across the trip
+			const int px = x0 + (task & 7), py = y0 + ((task >> 3) & 3);
+			const uint32_t pixel = (uint32_t)(py * A.W + px), sample = (uint32_t)(A.s_begin + (task >> 5));
 			Rnd4<float> r = rnd4<float>(A.key, pixel, sample, (uint32_t)bounce, 0u);
 			if (bounce == 0) {
 				if (!cam.jitter) { r.x = 0.5f; r.y = 0.5f; }
@@ -225,19 +226,19 @@ __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_pa
 				bounce = 1;
 				ray_ok = true;
 			} else {
-				F3 wo, att = scol;
+				F3 wo;
 				bool alive;
 				if (sbits >> 8) alive = scatter_dir<float>(sbits & 255, sp0, d, sN, r, wo);  // SHADE_FAST: solid colour, simple lobe
 				else {  // general path: textures, Reflective's lobe choice
 					const Resolved rs = resolve_exact(A.sc, HotIds{ sdev, -1 }, sP);
 					const PrimInfo pi = A.sc.info[rs.dev_prim];
 					float u, v;
-					F3 emit;
+					F3 att, emit;
 					surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, u, v);
 					alive = scatter<float>(A.sc, pi.mat, pi.tex, d, sN, sP, u, v, r, wo, att, emit);
+					thr = thr * att;
 				}
 				if (alive) {
-					thr = thr * att;
 					o = sP;
 					d = wo;
 					++bounce;
