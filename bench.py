@@ -146,7 +146,7 @@ def run_reference(a):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": twin.threads, "kind": "port",
                              "sample": what + "; the reference ships no renderer for this config (SURVEY.md §0), so its CPU path is the fp64 twin in oracle/are_oracle.c"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -304,15 +304,19 @@ def run_b200(a):
         # what the reference's algorithm (every ray tests every primitive of the ObjectSet, 51 FLOP per Moeller-Trumbore
         # test, 28 per sphere, 45 per quad) would have executed for the same rays — the kernel does less (fusion, boxes, BVH)
         ref_flops = st.rays * (F_TRI * len(sc.tris) + F_QUAD * len(sc.quads) + F_SPH * len(sc.spheres)) + F_SCATTER * max(0, st.rays - st.samples) + F_PRIMARY * st.samples
-        traffic = None
+        traffic, ncu = None, None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this launch size, from the committed ncu capture
             prof = json.load(open(os.path.join(ROOT, "profiles", "r01_render_path_full.json")))
             if prof.get("width") == W and prof.get("height") == H and prof.get("spp_per_step") == S:
                 traffic = prof.get("dram_bytes")
+                # the resource that actually binds this kernel (not measured live: copied from the committed capture)
+                ncu = {"issue_slot_utilisation_pct": prof.get("issue_slot_utilisation_pct"),
+                       "active_threads_per_instruction": prof.get("active_threads_per_instruction"),
+                       "source": "profiles/r01_render_path_full.json (ncu --set full, same launch size)"}
         except Exception:
             pass
         roof = {"bound": "fp32", "achieved": achieved, "peak": peak["tflops"], "unit": "TFLOP/s", "frac": achieved / peak["tflops"] if peak["tflops"] else None,
-                "traffic": traffic, "reference_equivalent_tflops": ref_flops / (avg_kernel_ms * 1e-3) / 1e12, "peak_source": "measured on this GPU by are_cuda_measure_fp32_peak (register-resident FFMA loop); MEASURED_PEAKS.json has no FP32 figure",
+                "traffic": traffic, "reference_equivalent_tflops": ref_flops / (avg_kernel_ms * 1e-3) / 1e12, "ncu": ncu, "peak_source": "measured on this GPU by are_cuda_measure_fp32_peak (register-resident FFMA loop); MEASURED_PEAKS.json has no FP32 figure",
                 "nominal_peak": nominal, "kernel": "k_render_path<%s>" % ("bvh" if use_bvh else "brute/smem"), "kernel_ms": avg_kernel_ms,
                 "flops_per_launch": flops, "counted": {"rays": st.rays, "tri_tests": st.tri_tests, "quad_tests": st.quad_tests,
                                                         "sphere_tests": st.sphere_tests, "box_tests": st.box_tests, "node_visits": st.node_visits},
@@ -324,14 +328,33 @@ def run_b200(a):
                 "roofline": roof}
         if not a.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(sc, a.cpu_seconds)
-        print(json.dumps(line), flush=True)
+        emit(line)
     job.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     a = parse()
+    # Libraries chat on stdout at the C level (NCCL prints "NCCL version ..." on communicator creation): keep the
+    # process's stdout for the JSON line only and send everything else to stderr.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
