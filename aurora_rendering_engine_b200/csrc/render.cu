@@ -57,14 +57,20 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #ifndef RENDER_MIN_BLOCKS
 #define RENDER_MIN_BLOCKS 6
 #endif
+#ifndef RENDER_MIN_BLOCKS_BIG
+#define RENDER_MIN_BLOCKS_BIG 12  // hierarchies that live in L2 (not L1) are latency-bound: 48 resident warps/SM at 40 registers (with spills)
+#endif                            // beat 24 at 80 — measured on the 1 M-primitive scene: 467 -> 577 Msamples/s; RTIOW (L1-resident) loses 5 %
+#ifndef BVH_BIG_NODES
+#define BVH_BIG_NODES 16384       // 1 MiB of 64 B nodes: beyond this the high-occupancy build is launched
+#endif
 #ifndef TRAV_MIN_LANES
 #define TRAV_MIN_LANES 6   // BVH slices end when fewer lanes than this are still traversing and others are waiting
 #endif
 #ifndef LEAF_MIN_LANES
 #define LEAF_MIN_LANES 1   // leaf tests run once this many lanes hold one (measured: 1 is best on RTIOW and on the 1 M-primitive stress scene)
 #endif
-template <bool BVH, bool COUNT>
-__global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_path(const __grid_constant__ RenderArgs A) {
+template <bool BVH, bool COUNT, bool BIG = false>
+__global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : RENDER_MIN_BLOCKS) k_render_path(const __grid_constant__ RenderArgs A) {
 	extern __shared__ float4 s_raw[];
 	__shared__ float s_acc[RENDER_THREADS / 32][96];
 	const HotPrim *s_prims = reinterpret_cast<const HotPrim *>(s_raw);
@@ -276,8 +282,14 @@ int launch_render_path(const RenderArgs &a, bool use_bvh, bool count_tests, cuda
 	const int tiles = (warps + RENDER_THREADS / 32 - 1) / (RENDER_THREADS / 32);
 	if (tiles <= 0) return -1;
 	if (use_bvh) {
-		if (count_tests) k_render_path<true, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
-		else k_render_path<true, false><<<tiles, RENDER_THREADS, 0, s>>>(a);
+		const bool big = a.sc.n_nodes > BVH_BIG_NODES;
+		if (count_tests) {
+			if (big) k_render_path<true, true, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
+			else k_render_path<true, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
+		} else {
+			if (big) k_render_path<true, false, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
+			else k_render_path<true, false><<<tiles, RENDER_THREADS, 0, s>>>(a);
+		}
 	} else {
 		if (!a.sc.brute || a.sc.n_hot > BRUTE_MAX_PRIMS) return -1;
 		size_t smem = (size_t)a.sc.n_hot * sizeof(HotPrim);
