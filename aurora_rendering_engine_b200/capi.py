@@ -62,6 +62,45 @@ def make_params(width, height, sample_begin=0, sample_count=1, max_depth=50, int
     return p
 
 
+class PatchSceneC(C.Structure):
+    _fields_ = [("n_tri", C.c_int32), ("n_mat", C.c_int32), ("P", C.POINTER(C.c_double)), ("UV", C.POINTER(C.c_double)),
+                ("material", C.POINTER(C.c_int32)), ("mat_type", C.POINTER(C.c_int32)), ("mat_albedo", C.POINTER(C.c_double)),
+                ("mat_metalness", C.POINTER(C.c_double))]
+
+
+class PatchConfig(C.Structure):
+    _fields_ = [("max_depth", C.c_int32), ("max_tex_res", C.c_int32), ("min_tex_res", C.c_int32), ("pad_", C.c_int32),
+                ("min_area_px", C.c_double), ("env", C.c_double * 3), ("gamma", C.c_double)]
+
+
+class PatchStats(C.Structure):
+    _fields_ = [("nodes", C.c_uint64), ("node_texels", C.c_uint64), ("ops", C.c_uint64), ("levels", C.c_uint64), ("launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("plan_ms", C.c_double), ("kernel_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class _PatchArgs:
+    """Keeps the numpy arrays behind an are_patch_scene alive for the duration of a call."""
+
+    def __init__(self, ps):
+        self.P = np.ascontiguousarray(ps.P, np.float64)
+        self.UV = np.ascontiguousarray(ps.UV, np.float64)
+        self.M = np.ascontiguousarray(ps.material, np.int32)
+        self.T = np.ascontiguousarray(ps.mat_type, np.int32)
+        self.A = np.ascontiguousarray(ps.mat_albedo, np.float64)
+        self.Mt = np.ascontiguousarray(ps.mat_metalness, np.float64)
+        i32 = C.POINTER(C.c_int32)
+        self.scene = PatchSceneC(len(self.M), len(self.T), self.P.ctypes.data_as(_dp), self.UV.ctypes.data_as(_dp), self.M.ctypes.data_as(i32),
+                                 self.T.ctypes.data_as(i32), self.A.ctypes.data_as(_dp), self.Mt.ctypes.data_as(_dp))
+        self.cfg = PatchConfig(int(ps.max_depth), int(ps.max_tex_res), int(ps.min_tex_res), 0, float(ps.min_area_px),
+                               (C.c_double * 3)(*[float(x) for x in ps.env]), float(ps.gamma))
+        self.origin = np.ascontiguousarray(ps.origin, np.float64)
+        self.vp_P = np.ascontiguousarray(ps.vp_P, np.float64)
+        self.vp_UV = np.ascontiguousarray(ps.vp_UV, np.float64)
+
+
 class AreCudaError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__(f"{STATUS_NAMES.get(status, status)}: {msg}")
@@ -104,6 +143,11 @@ SIGNATURES = {
     "are_cuda_render": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _fp, C.POINTER(RenderStats)]),
     "are_cuda_tonemap": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_uint8)]),
     "are_cuda_texture_paste": (C.c_int, [_vp, _dp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, _ip]),
+    "are_cuda_patch_render": (C.c_int, [_vp, C.POINTER(PatchSceneC), _dp, _dp, _dp, C.c_int, C.c_int, C.POINTER(PatchConfig), _dp,
+                                        C.POINTER(C.c_uint8), C.POINTER(PatchStats)]),
+    "are_cuda_patch_trace_texture": (C.c_int, [_vp, C.POINTER(PatchSceneC), _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(PatchConfig), _dp,
+                                               _ip, C.POINTER(PatchStats)]),
+    "are_cuda_patch_plan_probe": (C.c_int, [C.POINTER(PatchSceneC), _dp, _dp, _dp, C.c_int, C.c_int, C.POINTER(PatchConfig), C.POINTER(C.c_uint64)]),
     "are_cuda_write_ppm": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint8)]),
     "are_cuda_alloc_accum": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "are_cuda_zero_accum": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
@@ -130,6 +174,17 @@ def load_library(path: str | None = None):
     if path is None:
         _lib = lib
     return lib
+
+
+def patch_plan_probe(ps) -> dict:
+    """Host-only planner probe (no GPU): node / texel / warp-triangle counts of a PatchScene's camera render."""
+    lib = load_library()
+    a = _PatchArgs(ps)
+    out = (C.c_uint64 * 6)()
+    st = lib.are_cuda_patch_plan_probe(C.byref(a.scene), _ptr(a.origin), _ptr(a.vp_P), _ptr(a.vp_UV), int(ps.width), int(ps.height), C.byref(a.cfg), out)
+    if st < 0:
+        raise AreCudaError(st, "patch_plan_probe")
+    return dict(zip(("nodes", "node_texels", "ops", "levels", "ops_a", "ops_b"), [int(x) for x in out]))
 
 
 def compile_probe(Q, u, v) -> dict:
@@ -314,6 +369,29 @@ class Context:
         c = np.ascontiguousarray(np.asarray(corners, np.int32).reshape(8))
         self._ck(self.lib.are_cuda_texture_paste(self.h, _ptr(dst), dst.shape[1], dst.shape[0], _ptr(src), src.shape[1], src.shape[0], _ptr(c, _ip)))
         return dst
+
+    def patch_render(self, ps, want_rgb=True, want_rgb8=True):
+        """The reference's patch-as-viewport renderer (experiments/rt10.cpp) for a scenes.PatchScene:
+        -> (rgb float64 (H,W,3) | None, rgb8 uint8 (H,W,3) | None, PatchStats)."""
+        a = _PatchArgs(ps)
+        rgb = np.empty((ps.height, ps.width, 3), np.float64) if want_rgb else None
+        rgb8 = np.empty((ps.height, ps.width, 3), np.uint8) if want_rgb8 else None
+        st = PatchStats()
+        self._ck(self.lib.are_cuda_patch_render(self.h, C.byref(a.scene), _ptr(a.origin), _ptr(a.vp_P), _ptr(a.vp_UV), int(ps.width), int(ps.height),
+                                                C.byref(a.cfg), _ptr(rgb) if want_rgb else None,
+                                                _ptr(rgb8, C.POINTER(C.c_uint8)) if want_rgb8 else None, C.byref(st)))
+        return rgb, rgb8, st
+
+    def patch_trace_texture(self, ps, origin, current, tex_w, tex_h, est_area_px=0.0):
+        """Object::trace_texture for triangle `current` of a PatchScene seen from `origin` -> (texture (h,w,3) float64, PatchStats)."""
+        a = _PatchArgs(ps)
+        o = np.ascontiguousarray(origin, np.float64)
+        out = np.empty(int(ps.max_tex_res) ** 2 * 3, np.float64)
+        wh = np.zeros(2, np.int32)
+        st = PatchStats()
+        self._ck(self.lib.are_cuda_patch_trace_texture(self.h, C.byref(a.scene), _ptr(o), int(current), int(tex_w), int(tex_h), float(est_area_px),
+                                                       C.byref(a.cfg), _ptr(out), _ptr(wh, _ip), C.byref(st)))
+        return out[: int(wh[0]) * int(wh[1]) * 3].reshape(int(wh[1]), int(wh[0]), 3).copy(), st
 
     def write_ppm(self, path, rgb8: np.ndarray):
         rgb8 = np.ascontiguousarray(rgb8, np.uint8)

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -16,6 +17,7 @@
 #include "../../include/are_cuda.h"
 #include "dev_types.h"
 #include "kernels.h"
+#include "patch.h"
 #include "scene.h"
 
 using namespace areb;
@@ -35,6 +37,7 @@ struct are_cuda_ctx {
 	size_t own_accum_elems = 0;
 	int sm_count = 0;
 	CompileOptions opt;
+	PatchWorkspace patch_ws;
 };
 
 static std::string g_create_error;
@@ -184,6 +187,7 @@ void are_cuda_destroy(are_cuda_ctx *ctx) {
 	Bind b(ctx);
 	cudaStreamSynchronize(ctx->stream);
 	free_scene_allocs(ctx);
+	ctx->patch_ws.release();
 	if (ctx->own_accum) cudaFree(ctx->own_accum);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -672,6 +676,91 @@ int are_cuda_texture_paste(are_cuda_ctx *ctx, double *dst_rgb, int dst_w, int ds
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(dst_rgb, ddst.p, dbytes, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
+// ---- patch-as-viewport renderer (patch.cu) ------------------------------------------------------------------
+static const char *patch_check(const are_patch_scene *sc, const are_patch_config *cfg) {
+	if (!sc || !cfg) return "null argument";
+	if (sc->n_tri < 0 || sc->n_mat < 0) return "negative count";
+	if (sc->n_tri > 0 && (!sc->P || !sc->UV)) return "scene arrays missing";
+	if (sc->n_mat > 0 && (!sc->mat_type || !sc->mat_albedo || !sc->mat_metalness)) return "material arrays missing";
+	if (cfg->min_tex_res < 1 || cfg->max_tex_res < cfg->min_tex_res || cfg->max_tex_res > 16384) return "texture resolution limits out of range";
+	if (cfg->max_depth < 0 || cfg->max_depth > 64) return "max_depth out of range";
+	if (!(cfg->gamma > 0.0)) return "gamma must be positive";
+	return nullptr;
+}
+static PatchSceneView patch_view(const are_patch_scene *sc) {
+	PatchSceneView v;
+	v.n_tri = sc->n_tri; v.n_mat = sc->n_mat; v.P = sc->P; v.UV = sc->UV; v.material = sc->material;
+	v.mat_type = sc->mat_type; v.mat_albedo = sc->mat_albedo; v.mat_metalness = sc->mat_metalness;
+	return v;
+}
+static PatchCfg patch_cfg(const are_patch_config *c) {
+	PatchCfg o;
+	o.max_depth = c->max_depth; o.min_area_px = c->min_area_px; o.max_res = c->max_tex_res; o.min_res = c->min_tex_res;
+	std::memcpy(o.env, c->env, sizeof o.env);
+	o.gamma = c->gamma;
+	return o;
+}
+static void patch_stats_out(are_patch_stats *out, const PatchStats &st) {
+	if (!out) return;
+	out->nodes = st.nodes; out->node_texels = st.node_texels; out->ops = st.ops; out->levels = st.levels; out->launches = st.launches;
+	out->h2d_bytes = st.h2d_bytes; out->d2h_bytes = st.d2h_bytes; out->plan_ms = st.plan_ms; out->kernel_ms = st.kernel_ms;
+}
+static double ms_since(const std::chrono::steady_clock::time_point &t0) {
+	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+int are_cuda_patch_render(are_cuda_ctx *ctx, const are_patch_scene *scene, const double origin[3], const double viewport_P[18],
+	const double viewport_UV[12], int width, int height, const are_patch_config *cfg, double *out_rgb, uint8_t *out_rgb8, are_patch_stats *stats) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	if (const char *why = patch_check(scene, cfg)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, why);
+	if (!origin || !viewport_P || !viewport_UV || width < 2 || height < 2) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "camera arguments missing or image smaller than 2x2");
+	Bind b(ctx);
+	PatchStats st;
+	PatchPlan plan;
+	const auto t0 = std::chrono::steady_clock::now();
+	patch_plan_camera(patch_view(scene), origin, viewport_P, viewport_UV, width, height, patch_cfg(cfg), plan);
+	st.plan_ms = ms_since(t0);
+	std::string err;
+	if (patch_run_camera(ctx->patch_ws, plan, viewport_UV, width, height, patch_cfg(cfg), out_rgb, out_rgb8, st, ctx->stream, err)) return fail(ctx, ARE_ERR_CUDA, err);
+	patch_stats_out(stats, st);
+	return ARE_OK;
+}
+
+int are_cuda_patch_trace_texture(are_cuda_ctx *ctx, const are_patch_scene *scene, const double origin[3], int current, int tex_w, int tex_h,
+	double est_area_px, const are_patch_config *cfg, double *out_tex, int out_wh[2], are_patch_stats *stats) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	if (const char *why = patch_check(scene, cfg)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, why);
+	if (!origin || !out_tex || !out_wh || current < 0 || current >= scene->n_tri) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "bad triangle index or null output");
+	Bind b(ctx);
+	PatchStats st;
+	PatchPlan plan;
+	const auto t0 = std::chrono::steady_clock::now();
+	patch_plan_texture(patch_view(scene), origin, current, tex_w, tex_h, est_area_px, patch_cfg(cfg), plan);
+	st.plan_ms = ms_since(t0);
+	out_wh[0] = plan.root_w;
+	out_wh[1] = plan.root_h;
+	std::string err;
+	if (patch_run_texture(ctx->patch_ws, plan, patch_cfg(cfg), out_tex, st, ctx->stream, err)) return fail(ctx, ARE_ERR_CUDA, err);
+	patch_stats_out(stats, st);
+	return ARE_OK;
+}
+
+int are_cuda_patch_plan_probe(const are_patch_scene *scene, const double origin[3], const double viewport_P[18], const double viewport_UV[12],
+	int width, int height, const are_patch_config *cfg, uint64_t out[6]) {
+	if (patch_check(scene, cfg) || !origin || !viewport_P || !viewport_UV || !out || width < 2 || height < 2) return ARE_ERR_INVALID_ARGUMENT;
+	PatchPlan plan;
+	patch_plan_camera(patch_view(scene), origin, viewport_P, viewport_UV, width, height, patch_cfg(cfg), plan);
+	out[0] = plan.nodes.size();
+	out[1] = (uint64_t)plan.arena_texels;
+	out[2] = plan.ops.size();
+	uint64_t lv = 0;
+	for (const auto &l : plan.level_nodes) lv += !l.empty();
+	out[3] = lv;
+	out[4] = (uint64_t)(plan.vp_op_end[0] - plan.vp_op_begin[0]);
+	out[5] = (uint64_t)(plan.vp_op_end[1] - plan.vp_op_begin[1]);
 	return ARE_OK;
 }
 

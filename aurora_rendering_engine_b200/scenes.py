@@ -334,3 +334,133 @@ def stress(n_prims=1_000_000, width=3840, height=2160, spp=256, seed=4, extent=5
 def by_name(name, **kw):
     return {"rt_cornell": rt_cornell, "cornell_box": cornell_box, "rtiow_final": rtiow_final, "textured": textured,
             "stress": stress}[name](**kw)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# patch-as-viewport renderer: scenes for are_cuda_patch_render
+# ---------------------------------------------------------------------------------------------------------
+PATCH_DIFFUSE, PATCH_REFLECTIVE = 0, 1
+
+
+@dataclass
+class PatchScene:
+    """Input of the reference's patch renderer (/root/reference/experiments/rt10.cpp): uv-mapped triangles with
+    (type, albedo, metalness) materials, an eye point, a two-triangle viewport and RenderConfig (rt10.cpp:536-542)."""
+    name: str
+    P: np.ndarray            # (n,3,3) vertices
+    UV: np.ndarray           # (n,3,2) texture coordinates
+    material: np.ndarray     # (n,) int32 material index, -1 = none (white, diffuse)
+    mat_type: np.ndarray     # (m,) int32 PATCH_DIFFUSE | PATCH_REFLECTIVE
+    mat_albedo: np.ndarray   # (m,3)
+    mat_metalness: np.ndarray  # (m,)
+    origin: np.ndarray       # (3,)
+    vp_P: np.ndarray         # (2,3,3) the two viewport triangles
+    vp_UV: np.ndarray        # (2,3,2)
+    width: int = 900
+    height: int = 650
+    max_depth: int = 4
+    min_area_px: float = 6.0
+    max_tex_res: int = 256
+    min_tex_res: int = 16
+    env: tuple = (0.06, 0.07, 0.09)
+    gamma: float = 2.2
+
+    def cfg8(self):
+        return np.array([self.max_depth, self.min_area_px, self.max_tex_res, self.min_tex_res, *self.env, self.gamma], dtype=np.float64)
+
+
+class _PatchBuilder:
+    def __init__(self):
+        self.P, self.UV, self.M = [], [], []
+
+    def quad(self, p00, p10, p11, p01, mat):  # rt10.cpp:778-800: two triangles, uv (0,0)-(1,1) per quad
+        self.P += [[p00, p10, p01], [p10, p11, p01]]
+        self.UV += [[(0, 0), (1, 0), (0, 1)], [(1, 0), (1, 1), (0, 1)]]
+        self.M += [mat, mat]
+
+    def box(self, lo, hi, mat):  # rt10.cpp:802-830, faces -X +X -Y +Y -Z +Z
+        x0, y0, z0 = lo
+        x1, y1, z1 = hi
+        p = {(i, j, k): ((x0, x1)[i], (y0, y1)[j], (z0, z1)[k]) for i in (0, 1) for j in (0, 1) for k in (0, 1)}
+        self.quad(p[0, 0, 0], p[0, 0, 1], p[0, 1, 1], p[0, 1, 0], mat)
+        self.quad(p[1, 0, 0], p[1, 1, 0], p[1, 1, 1], p[1, 0, 1], mat)
+        self.quad(p[0, 0, 0], p[1, 0, 0], p[1, 0, 1], p[0, 0, 1], mat)
+        self.quad(p[0, 1, 0], p[0, 1, 1], p[1, 1, 1], p[1, 1, 0], mat)
+        self.quad(p[0, 0, 0], p[0, 1, 0], p[1, 1, 0], p[1, 0, 0], mat)
+        self.quad(p[0, 0, 1], p[1, 0, 1], p[1, 1, 1], p[0, 1, 1], mat)
+
+    def arrays(self):
+        return (np.array(self.P, dtype=np.float64).reshape(-1, 3, 3), np.array(self.UV, dtype=np.float64).reshape(-1, 3, 2),
+                np.array(self.M, dtype=np.int32))
+
+
+def _patch_viewport(width, height, center, vp_h):
+    """The camera of rt10.cpp:895-921: viewport rectangle in the plane z = center.z, u right, v down."""
+    aspect = float(width) / float(height)
+    vp_w = vp_h * aspect
+    cx, cy, cz = center
+    TL = (cx - vp_w * 0.5, cy - vp_h * 0.5, cz)
+    TR = (cx + vp_w * 0.5, cy - vp_h * 0.5, cz)
+    BL = (cx - vp_w * 0.5, cy + vp_h * 0.5, cz)
+    BR = (cx + vp_w * 0.5, cy + vp_h * 0.5, cz)
+    vp_P = np.array([[TL, TR, BL], [TR, BR, BL]], dtype=np.float64)
+    vp_UV = np.array([[(0, 0), (1, 0), (0, 1)], [(1, 0), (1, 1), (0, 1)]], dtype=np.float64)
+    return vp_P, vp_UV
+
+
+def patch_rt10(width=900, height=650, max_depth=4):
+    """The scene hard-wired into the reference program (rt10.cpp:832-925): open-front Cornell room x[-1,1] y[0,2] z[0,2],
+    a blue and a yellow metal box, eye (0,1,-3), viewport plane z=-2 of world height 1.6.  At the defaults the
+    reference's output is its shipped experiments/output_rt10.ppm."""
+    b = _PatchBuilder()
+    white, red, green, blue, yellow = 0, 1, 2, 3, 4
+    b.quad((-1, 0, 0), (1, 0, 0), (1, 0, 2), (-1, 0, 2), white)
+    b.quad((-1, 2, 0), (-1, 2, 2), (1, 2, 2), (1, 2, 0), white)
+    b.quad((-1, 0, 2), (1, 0, 2), (1, 2, 2), (-1, 2, 2), white)
+    b.quad((-1, 0, 0), (-1, 0, 2), (-1, 2, 2), (-1, 2, 0), red)
+    b.quad((1, 0, 0), (1, 2, 0), (1, 2, 2), (1, 0, 2), green)
+    b.box((-0.70, 0.0, 0.80), (-0.15, 0.60, 1.30), blue)
+    b.box((0.15, 0.0, 1.00), (0.70, 1.10, 1.65), yellow)
+    P, UV, M = b.arrays()
+    vp_P, vp_UV = _patch_viewport(width, height, (0.0, 1.0, -2.0), 1.6)
+    return PatchScene("patch_rt10", P, UV, M,
+                      mat_type=np.array([0, 0, 0, 1, 1], dtype=np.int32),
+                      mat_albedo=np.array([[0.85, 0.85, 0.85], [0.85, 0.25, 0.25], [0.25, 0.85, 0.25], [0.25, 0.45, 1.0], [1.0, 0.92, 0.20]]),
+                      mat_metalness=np.array([0.0, 0.0, 0.0, 0.90, 0.92]),
+                      origin=np.array([0.0, 1.0, -3.0]), vp_P=vp_P, vp_UV=vp_UV, width=width, height=height, max_depth=max_depth)
+
+
+def patch_random(seed, n_boxes=3, n_loose=6, width=160, height=120, max_depth=3, mirror_walls=False):
+    """Random rooms for parity tests: the rt10 room with random boxes (random metal / diffuse materials), a few loose
+    triangles (some without a material), optional mirror walls (mirror facing mirror: exercises the cycle guard and the
+    depth / area cut-offs)."""
+    rng = np.random.RandomState(seed)
+    n_mat = 6
+    mat_type = rng.randint(0, 2, n_mat).astype(np.int32)
+    mat_type[0], mat_type[1] = 0, 1
+    mat_albedo = rng.uniform(0.1, 1.0, (n_mat, 3))
+    mat_metal = rng.uniform(-0.1, 1.1, n_mat)  # outside [0,1] on purpose: the renderer clamps (rt10.cpp:651)
+    b = _PatchBuilder()
+    wall = 1 if mirror_walls else 0
+    b.quad((-1, 0, 0), (1, 0, 0), (1, 0, 2), (-1, 0, 2), 0)
+    b.quad((-1, 2, 0), (-1, 2, 2), (1, 2, 2), (1, 2, 0), int(rng.randint(0, n_mat)))
+    b.quad((-1, 0, 2), (1, 0, 2), (1, 2, 2), (-1, 2, 2), int(rng.randint(0, n_mat)))
+    b.quad((-1, 0, 0), (-1, 0, 2), (-1, 2, 2), (-1, 2, 0), wall)
+    b.quad((1, 0, 0), (1, 2, 0), (1, 2, 2), (1, 0, 2), wall)
+    for _ in range(n_boxes):
+        lo = np.array([rng.uniform(-0.9, 0.4), 0.0, rng.uniform(0.3, 1.3)])
+        hi = lo + np.array([rng.uniform(0.2, 0.5), rng.uniform(0.2, 1.2), rng.uniform(0.2, 0.5)])
+        b.box(tuple(lo), tuple(hi), int(rng.randint(0, n_mat)))
+    P, UV, M = b.arrays()
+    if n_loose:
+        c = rng.uniform([-0.8, 0.2, 0.3], [0.8, 1.8, 1.8], (n_loose, 1, 3))
+        LP = c + rng.uniform(-0.35, 0.35, (n_loose, 3, 3))
+        LUV = rng.uniform(0, 1, (n_loose, 3, 2))
+        LM = rng.randint(-1, n_mat, n_loose).astype(np.int32)
+        P, UV, M = np.concatenate([P, LP]), np.concatenate([UV, LUV]), np.concatenate([M, LM])
+    vp_P, vp_UV = _patch_viewport(width, height, (rng.uniform(-0.1, 0.1), 1.0 + rng.uniform(-0.1, 0.1), -2.0), 1.6)
+    origin = np.array([rng.uniform(-0.3, 0.3), 1.0 + rng.uniform(-0.2, 0.2), -3.0])
+    return PatchScene(f"patch_random_{seed}", P, UV, M.astype(np.int32), mat_type, mat_albedo, mat_metal, origin, vp_P, vp_UV,
+                      width=width, height=height, max_depth=max_depth, min_area_px=float(rng.choice([2.0, 6.0, 20.0])),
+                      max_tex_res=int(rng.choice([64, 128, 256])), min_tex_res=int(rng.choice([4, 16])),
+                      env=tuple(rng.uniform(0, 0.2, 3)), gamma=2.2)

@@ -208,6 +208,57 @@ int are_cuda_write_ppm(const char *path, int width, int height, const uint8_t *r
 int are_cuda_texture_paste(are_cuda_ctx *ctx, double *dst_rgb, int dst_w, int dst_h, const double *src_rgb, int src_w, int src_h,
 	const int corners[8]);
 
+/* ---- patch-as-viewport renderer ------------------------------------------------------------------------ */
+/* The reference's OWN rendering algorithm (not ray tracing): what are::Object::trace_texture(object_set,
+ * viewport_origin) -> Texture is declared for (reference include/object/object.h:37-38; never defined there) and
+ * what its prototype experiments/rt10.cpp implements: a reflective triangle is a viewport seen from the eye point
+ * mirrored across its plane (are::Reflective::reflect, src/material/reflective.cpp:9-26); the triangles visible
+ * through it are projected, clipped, painted far-to-near into its texture, recursively (rt10.cpp:551-664), and the
+ * camera is a two-triangle viewport (rt10.cpp:677-772).  The host plans footprints, the GPU produces every texel in
+ * fp64 with the reference's operation order: output is bit-identical to rt10.cpp (its shipped
+ * experiments/output_rt10.ppm reproduces byte for byte). */
+typedef struct are_patch_scene {
+	int32_t n_tri, n_mat;
+	const double *P; /* n_tri*9: three vertices per triangle                       rt10.cpp:152-156 */
+	const double *UV; /* n_tri*6: texture coordinates of the vertices */
+	const int32_t *material; /* n_tri: material index; out of range = none (white, diffuse) */
+	const int32_t *mat_type; /* n_mat: 0 = Diffuse, 1 = Reflective                         rt10.cpp:140-149 */
+	const double *mat_albedo; /* n_mat*3 */
+	const double *mat_metalness; /* n_mat: reflection / base colour mix, clamped to [0,1] */
+} are_patch_scene;
+
+typedef struct are_patch_config { /* RenderConfig, rt10.cpp:536-542 */
+	int32_t max_depth;
+	int32_t max_tex_res, min_tex_res;
+	int32_t pad_;
+	double min_area_px; /* footprints smaller than this (in pixels) are not recursed into */
+	double env[3]; /* colour where nothing is reflected */
+	double gamma; /* 8-bit encode: lround(255*pow(clamp(c,0,1), 1/gamma))     rt10.cpp:118-143 */
+} are_patch_config;
+
+typedef struct are_patch_stats {
+	uint64_t nodes, node_texels, ops, levels, launches;
+	uint64_t h2d_bytes, d2h_bytes;
+	double plan_ms; /* host: footprint planning */
+	double kernel_ms; /* device: all launches of the call, CUDA events on the context's stream */
+} are_patch_stats;
+
+/* Camera::render (rt10.cpp:755-772).  viewport_P[18] / viewport_UV[12]: the two viewport triangles.  Outputs (host,
+ * either may be NULL): out_rgb = W*H*3 doubles (linear, clamped to [0,1]); out_rgb8 = W*H*3 bytes, the P6 payload. */
+int are_cuda_patch_render(are_cuda_ctx *ctx, const are_patch_scene *scene, const double origin[3], const double viewport_P[18],
+	const double viewport_UV[12], int width, int height, const are_patch_config *cfg, double *out_rgb, uint8_t *out_rgb8, are_patch_stats *stats);
+
+/* renderTriangleWithTriangle (rt10.cpp:551-664) = Object::trace_texture for scene triangle `current` seen from
+ * `origin`.  The texture size is clamped to [min_tex_res, max_tex_res] and returned in out_wh; out_tex must hold
+ * max_tex_res^2*3 doubles.  est_area_px: projected size hint (0 = unknown; < min_area_px stops the recursion). */
+int are_cuda_patch_trace_texture(are_cuda_ctx *ctx, const are_patch_scene *scene, const double origin[3], int current, int tex_w, int tex_h,
+	double est_area_px, const are_patch_config *cfg, double *out_tex, int out_wh[2], are_patch_stats *stats);
+
+/* Host-only probe of the planner (no GPU needed): out[6] = { reflective nodes, node texels, warp triangles, levels,
+ * warp triangles of viewport A, of viewport B }. */
+int are_cuda_patch_plan_probe(const are_patch_scene *scene, const double origin[3], const double viewport_P[18], const double viewport_UV[12],
+	int width, int height, const are_patch_config *cfg, uint64_t out[6]);
+
 /* Device scratch owned by the context (so hosts without a CUDA allocator can still drive render_device). */
 int are_cuda_alloc_accum(are_cuda_ctx *ctx, int width, int height, float **accum_rgb_device);
 int are_cuda_zero_accum(are_cuda_ctx *ctx, float *accum_rgb_device, int width, int height);

@@ -354,3 +354,63 @@ def psnr(a, b, peak=1.0):
     if mse == 0:
         return float("inf")
     return 10.0 * np.log10(peak * peak / mse)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# patch-as-viewport renderer (experiments/rt10.cpp): restatement (oracle/libpatch_oracle.so) and the real thing
+# (oracle/_ref/librt10_ref.so)
+# ---------------------------------------------------------------------------------------------------------
+_ip = C.POINTER(C.c_int)
+
+
+class _PatchLib:
+    def __init__(self, path, prefix):
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+
+    def _scene_args(self, ps):
+        self._keep = [_d(ps.P), _d(ps.UV), np.ascontiguousarray(ps.material, dtype=np.int32), np.ascontiguousarray(ps.mat_type, dtype=np.int32),
+                      _d(ps.mat_albedo), _d(ps.mat_metalness)]
+        P, UV, M, T, A, Mt = self._keep
+        return [C.c_int(len(M)), _p(P), _p(UV), _p(M, _ip), C.c_int(len(T)), _p(T, _ip), _p(A), _p(Mt)]
+
+    def render(self, ps, want_counters=False):
+        """-> (rgb (H,W,3) float64 linear, rgb8 (H,W,3) uint8 gamma-encoded P6 payload[, counters])"""
+        rgb = np.zeros((ps.height, ps.width, 3), dtype=np.float64)
+        rgb8 = np.zeros((ps.height, ps.width, 3), dtype=np.uint8)
+        o, vP, vUV, cfg = _d(ps.origin), _d(ps.vp_P), _d(ps.vp_UV), ps.cfg8()
+        args = self._scene_args(ps) + [_p(o), _p(vP), _p(vUV), C.c_int(ps.width), C.c_int(ps.height), _p(cfg), _p(rgb),
+                                       rgb8.ctypes.data_as(C.POINTER(C.c_uint8))]
+        cnt = np.zeros(3, dtype=np.uint64)
+        if self.prefix == "orc":
+            args.append(cnt.ctypes.data_as(C.POINTER(C.c_uint64)))
+        rc = getattr(self.lib, self.prefix + "_patch_render")(*args)
+        assert rc == 0, rc
+        return (rgb, rgb8, cnt) if want_counters else (rgb, rgb8)
+
+    def trace_texture(self, ps, origin, current, tex_w, tex_h, est_area_px=0.0):
+        out = np.zeros((ps.max_tex_res * ps.max_tex_res * 3 + 3), dtype=np.float64)
+        wh = np.zeros(2, dtype=np.int32)
+        o, cfg = _d(origin), ps.cfg8()
+        rc = getattr(self.lib, self.prefix + "_patch_trace_texture")(*self._scene_args(ps), _p(o), C.c_int(current), C.c_int(tex_w), C.c_int(tex_h),
+                                                                     C.c_double(est_area_px), _p(cfg), _p(out), _p(wh, _ip))
+        assert rc == 0, rc
+        return out[: wh[0] * wh[1] * 3].reshape(wh[1], wh[0], 3).copy()
+
+
+class PatchOracle(_PatchLib):
+    def __init__(self):
+        build_oracle()
+        super().__init__(os.path.join(ORACLE_DIR, "libpatch_oracle.so"), "orc")
+
+
+class PatchReference(_PatchLib):
+    """The real experiments/rt10.cpp; only available where oracle/_ref/librt10_ref.so was built."""
+    PATH = os.path.join(ORACLE_DIR, "_ref", "librt10_ref.so")
+
+    def __init__(self):
+        super().__init__(self.PATH, "ref")
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(cls.PATH)
