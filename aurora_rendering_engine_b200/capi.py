@@ -134,6 +134,7 @@ SIGNATURES = {
     "are_cuda_num_primitives": (C.c_int, [_vp]),
     "are_cuda_commit": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "are_cuda_compile_probe": (C.c_int, [C.c_int, _dp, _dp, _dp, _ip]),
+    "are_cuda_compile_probe_digest": (C.c_int, [C.c_int, _dp, _dp, _dp, _ip, C.POINTER(C.c_uint64)]),
     "are_cuda_hit_batch": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_double, C.c_int, C.c_int, _ip, _dp, _dp, _dp, _dp]),
     "are_cuda_scatter_batch": (C.c_int, [_vp, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _ip]),
     "are_cuda_texture_batch": (C.c_int, [_vp, C.c_int, _ip, _dp, _dp, C.c_int, _dp]),
@@ -192,11 +193,15 @@ def compile_probe(Q, u, v) -> dict:
     lib = load_library()
     Q, u, v = (np.ascontiguousarray(x, dtype=np.float64) for x in (Q, u, v))
     out = np.zeros(8, np.int32)
-    st = lib.are_cuda_compile_probe(len(Q), Q.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp), out.ctypes.data_as(_ip))
+    digest = C.c_uint64(0)
+    st = lib.are_cuda_compile_probe_digest(len(Q), Q.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp), out.ctypes.data_as(_ip),
+                                           C.byref(digest))
     if st != ARE_OK:
         raise AreCudaError(st, "compile probe rejected the triangles")
     keys = ("hot_slots", "fused_pairs", "boxes", "bvh_nodes", "bvh_depth", "brute_quads", "brute_tris", "brute_boxes")
-    return dict(zip(keys, (int(x) for x in out)))
+    d = dict(zip(keys, (int(x) for x in out)))
+    d["digest"] = int(digest.value)
+    return d
 
 
 def _d(a, shape=None):

@@ -310,7 +310,6 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	ctx->opt.brute_max = (int)brute_smem_limit_prims();
 	if (const char *e = getenv("ARE_CUDA_NO_FUSE")) ctx->opt.fuse_parallelograms = !(e[0] == '1');
 	if (const char *e = getenv("ARE_CUDA_NO_BOXES")) ctx->opt.fuse_boxes = !(e[0] == '1');
-	if (const char *e = getenv("ARE_CUDA_LEAF_SIZE")) ctx->opt.leaf_size = atoi(e);
 	if (!compile_scene(ctx->scene, ctx->opt, ctx->cs, err)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, err);
 	const CompiledScene &cs = ctx->cs;
 	DevScene d;
@@ -336,7 +335,17 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	return ARE_OK;
 }
 
+static uint64_t fnv1a(uint64_t h, const void *data, size_t bytes) {
+	const unsigned char *p = static_cast<const unsigned char *>(data);
+	for (size_t i = 0; i < bytes; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+	return h;
+}
+
 int are_cuda_compile_probe(int n_tri, const double *Q, const double *u, const double *v, int out[8]) {
+	return are_cuda_compile_probe_digest(n_tri, Q, u, v, out, nullptr);
+}
+
+int are_cuda_compile_probe_digest(int n_tri, const double *Q, const double *u, const double *v, int out[8], uint64_t *digest) {
 	if (n_tri < 0 || !out || (n_tri && (!Q || !u || !v))) return ARE_ERR_INVALID_ARGUMENT;
 	HostScene hs;
 	hs.textures.emplace_back();
@@ -357,6 +366,13 @@ int are_cuda_compile_probe(int n_tri, const double *Q, const double *u, const do
 	if (!compile_scene(hs, opt, cs, err)) return ARE_ERR_INVALID_ARGUMENT;
 	const int r[8] = { cs.n_hot, cs.n_fused_pairs, cs.n_boxes, (int)cs.nodes.size(), cs.bvh_depth, cs.brute_range.nq, cs.brute_range.nt, cs.brute_range.nb };
 	std::memcpy(out, r, sizeof r);
+	if (digest) {
+		uint64_t h = 0xcbf29ce484222325ull;
+		h = fnv1a(h, cs.nodes.data(), cs.nodes.size() * sizeof(BvhNode));
+		h = fnv1a(h, cs.bvh_prims.data(), cs.bvh_prims.size() * sizeof(HotPrim));
+		h = fnv1a(h, cs.bvh_ids.data(), cs.bvh_ids.size() * sizeof(HotIds));
+		*digest = h;
+	}
 	return ARE_OK;
 }
 

@@ -67,7 +67,6 @@ struct CompiledScene {
 struct CompileOptions {
 	bool fuse_parallelograms = true;
 	bool fuse_boxes = true;
-	int leaf_size = 4;
 	int brute_max = 1024;
 };
 

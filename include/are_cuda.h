@@ -153,6 +153,9 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes);
  * and reports out[8] = { hot slots, fused triangle pairs, boxes, BVH nodes, BVH depth, brute quads, brute triangles,
  * brute boxes }.  Lets CPU-only test boxes check parallelogram fusion / box detection / BVH construction. */
 int are_cuda_compile_probe(int n_tri, const double *Q, const double *u, const double *v, int out[8]);
+/* Same, plus an FNV-1a digest of the compiled hierarchy (nodes, leaf-ordered primitives, ids): the BVH is built by
+ * several host threads (ARE_CUDA_BUILD_THREADS overrides the count) and must not depend on how many. */
+int are_cuda_compile_probe_digest(int n_tri, const double *Q, const double *u, const double *v, int out[8], uint64_t *digest);
 
 /* ---- per-ray harness ----------------------------------------------------------------------------------- */
 /* Closest hit of n rays against the committed scene.  D is normalised first, as are::Ray's ctor does
