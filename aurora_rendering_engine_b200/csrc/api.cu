@@ -38,6 +38,7 @@ struct are_cuda_ctx {
 	int sm_count = 0;
 	CompileOptions opt;
 	PatchWorkspace patch_ws;
+	int wide_min_nodes = 0x7fffffff;  // AUTO never picks the compressed 8-wide BVH (measured slower); ARE_CUDA_WIDE_MIN_NODES overrides
 };
 
 static std::string g_create_error;
@@ -108,13 +109,18 @@ struct Tmp {
 		if (host) CK(cudaMemcpyAsync((host), (tmp).p, (bytes), cudaMemcpyDeviceToHost, ctx->stream));      \
 	} while (0)
 
-bool resolve_traversal(are_cuda_ctx *ctx, int traversal, bool &use_bvh) {
-	const bool brute_ok = ctx->dev.brute != nullptr;
+// -> kernel mode: 0 brute force (shared memory), 1 BVH2, 2 compressed 8-wide BVH
+bool resolve_traversal(are_cuda_ctx *ctx, int traversal, int &mode) {
+	const bool brute_ok = ctx->dev.brute != nullptr, wide_ok = ctx->dev.wnodes != nullptr;
 	if (traversal == ARE_TRAVERSAL_BRUTE) {
 		if (!brute_ok) return false;
-		use_bvh = false;
-	} else if (traversal == ARE_TRAVERSAL_BVH) use_bvh = true;
-	else use_bvh = !(brute_ok && ctx->cs.n_hot <= 32);
+		mode = 0;
+	} else if (traversal == ARE_TRAVERSAL_BVH) mode = 1;
+	else if (traversal == ARE_TRAVERSAL_WIDE) mode = wide_ok ? 2 : 1;  // a single-primitive scene has no wide hierarchy
+	else if (traversal == ARE_TRAVERSAL_AUTO) {
+		if (brute_ok && ctx->cs.n_hot <= 32) mode = 0;
+		else mode = (wide_ok && (int)ctx->cs.nodes.size() > ctx->wide_min_nodes) ? 2 : 1;
+	} else return false;
 	return true;
 }
 
@@ -310,6 +316,7 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	ctx->opt.brute_max = (int)brute_smem_limit_prims();
 	if (const char *e = getenv("ARE_CUDA_NO_FUSE")) ctx->opt.fuse_parallelograms = !(e[0] == '1');
 	if (const char *e = getenv("ARE_CUDA_NO_BOXES")) ctx->opt.fuse_boxes = !(e[0] == '1');
+	if (const char *e = getenv("ARE_CUDA_WIDE")) ctx->opt.build_wide = e[0] == '1';
 	if (!compile_scene(ctx->scene, ctx->opt, ctx->cs, err)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, err);
 	const CompiledScene &cs = ctx->cs;
 	DevScene d;
@@ -319,11 +326,14 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 #define UP(vec, field)                                                     \
 	if ((st = upload(ctx, cs.vec, &d.field, bytes)) != ARE_OK) return st;
 	UP(brute, brute) UP(brute_ids, brute_ids) UP(bvh_prims, bvh_prims) UP(bvh_ids, bvh_ids) UP(nodes, nodes)
+	if (cs.wide_depth <= 32) { UP(wnodes, wnodes) UP(wide_prims, wide_prims) UP(wide_ids, wide_ids) UP(wide_kinds, wide_kinds) }  // 32 = ARE_WIDE_STACK
 	UP(info, info) UP(prim_plane, prim_plane) UP(tri_uv, tri_uv) UP(tri64, tri64) UP(quad64, quad64) UP(sph64, sph64)
 	UP(tri_uv64, tri_uv64) UP(mats, mats) UP(texs, texs) UP(tex_data, tex_data) UP(rt_tris, rt_tris) UP(box_faces, box_faces) UP(shade, shade)
 #undef UP
 	d.brute_range = cs.brute_range;
 	d.n_nodes = (int)cs.nodes.size();
+	d.n_wnodes = d.wnodes ? (int)cs.wnodes.size() : 0;
+	if (const char *e = getenv("ARE_CUDA_WIDE_MIN_NODES")) ctx->wide_min_nodes = atoi(e);
 	d.root_leaf_meta = cs.root_leaf_meta;
 	d.n_hot = cs.n_hot;
 	d.n_tri = cs.n_tri; d.n_quad = cs.n_quad; d.n_sph = cs.n_sph;
@@ -392,9 +402,9 @@ int are_cuda_hit_batch(are_cuda_ctx *ctx, int n, const double *ray_Q, const doub
 	TMP_OUT(dprim, n * sizeof(int)); TMP_OUT(dt, n * sizeof(double)); TMP_OUT(dP, n3); TMP_OUT(dN, n3); TMP_OUT(duv, (size_t)n * 2 * sizeof(double));
 	if (precision == 64) launch_hit64(ctx->dev, n, dQ.as<double>(), dD.as<double>(), t_min, dprim.as<int>(), dt.as<double>(), dP.as<double>(), dN.as<double>(), duv.as<double>(), ctx->stream);
 	else {
-		bool use_bvh;
-		if (!resolve_traversal(ctx, traversal, use_bvh)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "scene too large for brute-force traversal");
-		launch_hit32(ctx->dev, n, dQ.as<double>(), dD.as<double>(), t_min, use_bvh, dprim.as<int>(), dt.as<double>(), dP.as<double>(), dN.as<double>(), duv.as<double>(), ctx->stream);
+		int mode;
+		if (!resolve_traversal(ctx, traversal, mode)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown traversal, or scene too large for brute-force traversal");
+		launch_hit32(ctx->dev, n, dQ.as<double>(), dD.as<double>(), t_min, mode, dprim.as<int>(), dt.as<double>(), dP.as<double>(), dN.as<double>(), duv.as<double>(), ctx->stream);
 	}
 	CK(cudaGetLastError());
 	GET_OUT(prim, dprim, n * sizeof(int)); GET_OUT(t, dt, n * sizeof(double)); GET_OUT(P, dP, n3); GET_OUT(N, dN, n3); GET_OUT(uv, duv, (size_t)n * 2 * sizeof(double));
@@ -509,19 +519,19 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 	for (int k = 0; k < 3; ++k) { a.bg_bottom[k] = (float)p->background_bottom[k]; a.bg_top[k] = (float)p->background_top[k]; }
 	a.accum = accum;
 	a.counters = ctx->d_counters;
-	bool use_bvh = false;
+	int mode = 0;
 	if (p->integrator == ARE_INTEGRATOR_RT_AO) {
 		// experiments/rt.cpp knows triangles only, tested by linear scan from shared memory
 		if (ctx->cs.n_tri == 0 || ctx->cs.n_quad != 0 || ctx->cs.n_sph != 0 || ctx->cs.n_tri > 1000)
 			return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "RT_AO integrator renders triangle-only scenes of at most 1000 triangles");
 		make_rt_cam(cam->pos, cam->target, cam->up, cam->vfov_deg, p->width, p->height, a.rtcam);
 	} else if (p->integrator != ARE_INTEGRATOR_PATH) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown integrator");
-	else if (!resolve_traversal(ctx, p->traversal, use_bvh)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "scene too large for brute-force traversal");
+	else if (!resolve_traversal(ctx, p->traversal, mode)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown traversal, or scene too large for brute-force traversal");
 	CK(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * sizeof(unsigned long long), ctx->stream));
 	if (stats) CK(cudaEventRecord(ctx->ev0, ctx->stream));
 	int launched = 0;
 	if (p->sample_count > 0) {
-		launched = p->integrator == ARE_INTEGRATOR_RT_AO ? launch_render_rtao(a, ctx->stream) : launch_render_path(a, use_bvh, count_tests != 0, ctx->stream);
+		launched = p->integrator == ARE_INTEGRATOR_RT_AO ? launch_render_rtao(a, ctx->stream) : launch_render_path(a, mode, count_tests != 0, ctx->stream);
 		if (launched < 0) return fail(ctx, ARE_ERR_CUDA, "render launch configuration rejected");
 		CK(cudaGetLastError());
 	}
@@ -535,7 +545,7 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 		std::memset(stats, 0, sizeof *stats);
 		stats->samples = (uint64_t)p->width * p->height * p->sample_count;
 		stats->rays = c[CNT_RAYS];
-		if (use_bvh) {
+		if (mode != 0) {
 			stats->node_visits = c[CNT_NODES]; stats->quad_tests = c[CNT_QUADS]; stats->tri_tests = c[CNT_TRIS]; stats->sphere_tests = c[CNT_SPHERES];
 			stats->box_tests = c[CNT_BOXES];
 		} else {  // brute force: every ray tests every hot primitive — exact by construction

@@ -78,6 +78,24 @@ struct BvhNode {
 	int meta[2];
 };
 
+// Compressed 8-wide BVH node, 80 B = five 16-byte loads (layout after Ylitie, Karras, Laine, "Efficient incoherent
+// ray traversal on GPUs through compressed wide BVHs", HPG 2017): child boxes are 8-bit offsets on a per-node grid
+// origin + 2^e per axis, so 1 M primitives need ~20 MB of nodes instead of 64 MB of BVH2 nodes and a ray makes
+// a third of the dependent memory round trips.
+//   n0 = (origin.x, origin.y, origin.z, e_x | e_y << 8 | e_z << 16 | imask << 24)   e_k = biased float exponent of the grid step
+//   n1 = (first inner child node, first leaf primitive slot, meta[0..3], meta[4..7])
+//        meta byte: 0 = empty slot; bit 5 = present; bits 0-4 = bit position of the child in the hit mask:
+//        inner child in slot s -> 24 + s (slot order = spatial octant order, so XOR with the ray octant gives a
+//        front-to-back visiting order), leaf -> offset of its primitive from the node's first slot (0..23)
+//   n2 = (qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7])   n3 = (qlo.z.., qlo.z.., qhi.x.., qhi.x..)
+//   n4 = (qhi.y[0..3], qhi.y[4..7], qhi.z[0..3], qhi.z[4..7])
+// imask bit s = slot s holds an inner node; inner children are stored contiguously in slot order.
+struct u4 { unsigned x, y, z, w; };
+struct WideNode {
+	f4 n0;
+	u4 n1, n2, n3, n4;
+};
+
 // A contiguous run of hot primitives sorted by test kind: nb boxes (two slots each) from `first`, then nq quad
 // tests, nt triangle tests, ns sphere tests.  The brute-force list is one big range; every BVH leaf is a small one.
 struct HotRange { int first, nq, nt, ns, nb; };
@@ -92,6 +110,11 @@ struct DevScene {
 	const BvhNode *nodes;
 	int n_nodes;
 	int root_leaf_meta;        // when the whole scene is one leaf (n_nodes == 0)
+	const WideNode *wnodes;    // compressed 8-wide hierarchy over the same hot items (nullptr when n_nodes == 0)
+	const HotPrim *wide_prims; // its leaf-ordered primitives, ids and test kinds (0 box, 1 quad / fused pair, 2 triangle, 3 sphere)
+	const HotIds *wide_ids;
+	const unsigned char *wide_kinds;
+	int n_wnodes;
 	int n_hot;                 // slots in the hot arrays (a box takes two)
 	const HotIds *box_faces;   // 6 per box: the fused pair / quad behind each face, {-1,-1} when the face is absent
 	// --- per device primitive ---

@@ -46,14 +46,15 @@ struct PasteArgs {
 void launch_paste(const PasteArgs &a, cudaStream_t s);
 
 // fp32 harness: the render kernels' own device routines (render.cu)
-void launch_hit32(const DevScene &sc, int n, const double *Q, const double *D, double tmin, bool use_bvh, int *prim, double *t, double *P, double *N, double *uv, cudaStream_t s);
+void launch_hit32(const DevScene &sc, int n, const double *Q, const double *D, double tmin, int mode, int *prim, double *t, double *P, double *N, double *uv, cudaStream_t s);
 void launch_scatter32(const DevScene &sc, int n, const int *mat, const int *tex, const double *wi, const double *N, const double *P, const double *uv,
 	const double *rnd, double *wo, double *att, double *emit, int *alive, cudaStream_t s);
 void launch_texture32(const DevScene &sc, int n, const int *tex, const double *uv, const double *P, double *rgb, cudaStream_t s);
 void launch_camera32(const CamBasis &cb, int W, int H, int n, const int *px, const int *py, const double *rnd, double *Q, double *D, cudaStream_t s);
 
 // render kernels. Returns the number of kernels launched, <0 on a launch-configuration error.
-int launch_render_path(const RenderArgs &a, bool use_bvh, bool count_tests, cudaStream_t s);
+// mode: 0 brute force (shared memory), 1 BVH2, 2 compressed 8-wide BVH
+int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStream_t s);
 int launch_render_rtao(const RenderArgs &a, cudaStream_t s);
 void launch_tonemap(const float *accum, int W, int H, double inv_spp, int encoder, uint8_t *out, cudaStream_t s);
 // register-resident FFMA loop; returns FLOPs executed per launch

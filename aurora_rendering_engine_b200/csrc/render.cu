@@ -18,6 +18,7 @@
 #include "philox.cuh"
 #include "shade.cuh"
 #include "vec.cuh"
+#include "wide.cuh"
 
 namespace areb {
 
@@ -69,8 +70,10 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #ifndef LEAF_MIN_LANES
 #define LEAF_MIN_LANES 1   // leaf tests run once this many lanes hold one (measured: 1 is best on RTIOW and on the 1 M-primitive stress scene)
 #endif
-template <bool BVH, bool COUNT, bool BIG = false>
+// MODE: 0 = brute force from shared memory, 1 = BVH2, 2 = compressed 8-wide BVH
+template <int MODE, bool COUNT, bool BIG = false>
 __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : RENDER_MIN_BLOCKS) k_render_path(const __grid_constant__ RenderArgs A) {
+	constexpr bool BVH = MODE != 0, WIDE = MODE == 2;
 	extern __shared__ float4 s_raw[];
 	__shared__ float s_acc[RENDER_THREADS / 32][96];
 	const HotPrim *s_prims = reinterpret_cast<const HotPrim *>(s_raw);
@@ -87,7 +90,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 	const CamT<float> cam = cam_from_f32(A.camf);
 	const float inv_w = 1.0f / (float)A.W, inv_h = 1.0f / (float)A.H;
 	const HotRange br = A.sc.brute_range;
-	const HotIds *ids = BVH ? A.sc.bvh_ids : A.sc.brute_ids;
+	const HotIds *ids = WIDE ? A.sc.wide_ids : (BVH ? A.sc.bvh_ids : A.sc.brute_ids);
+	const HotPrim *tree_prims = WIDE ? A.sc.wide_prims : A.sc.bvh_prims;
 	const unsigned full = 0xffffffffu;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const int total = (x0 < A.W && y0 < A.H) ? 32 * A.s_count : 0;
@@ -107,7 +111,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 	h.t = INFINITY; h.idx = -1; h.orig = -1;
 	bool trav = false;  // BVH: traversal in progress
 	int node = 0, pend = 0, sp = 0;
-	int stack[BVH ? ARE_BVH_STACK : 1];
+	int stack[MODE == 1 ? ARE_BVH_STACK : 1];
+	uint2 ng = make_uint2(0u, 0u), tg = ng;  // wide-BVH cursor
+	uint2 wstack[WIDE ? ARE_WIDE_STACK : 1];
 	unsigned int rays = 0;
 	TravCounters tc = { 0, 0, 0, 0, 0 };
 
@@ -118,7 +124,30 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 		// unfinished ones keep their cursor (node, stack, best hit) and resume next trip, the finished ones go on to
 		// shading and regeneration.  Long rays no longer hold 31 idle lanes hostage.
 		bool finished = ray_ok;
-		if (BVH) {
+		if (WIDE) {
+			if (ray_ok && !trav) {  // a fresh ray
+				h.t = INFINITY; h.idx = -1; h.orig = orig;
+				++rays;
+				wide_start(ng, tg, sp);
+				trav = true;
+			}
+			const int n_rays = __popc(__ballot_sync(full, ray_ok));
+			if (__any_sync(full, trav)) {
+				const WideRay wr = wide_ray(o, d);
+				while (true) {
+					// node phase: every traversing lane with no leaf primitive waiting decodes one wide node
+					if (trav && tg.y == 0u) trav = wide_node_step<COUNT>(A.sc, wr, A.tmin, h.t, ng, tg, sp, wstack, &tc);
+					// leaf phase: a wide node step is ~6x a primitive test, so every lane drains the primitives its node
+					// produced before the next node phase — all traversing lanes then take part in every node step
+					while (__any_sync(full, trav && tg.y != 0u)) {
+						if (trav && tg.y != 0u) wide_leaf_step<COUNT>(A.sc, o, d, A.tmin, tg, h, &tc);
+					}
+					const int n_trav = __popc(__ballot_sync(full, trav));
+					if (n_trav == 0 || (n_trav < TRAV_MIN_LANES && n_trav < n_rays)) break;
+				}
+			}
+			finished = ray_ok && !trav;
+		} else if (BVH) {
 			if (ray_ok && !trav) {  // a fresh ray
 				h.t = INFINITY; h.idx = -1; h.orig = orig;
 				++rays;
@@ -162,7 +191,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 			} else {
 				sP = o + h.t * d;
 				orig = h.idx;
-				const HotIds id = BVH ? hit_ids<ldg4>(A.sc, A.sc.bvh_prims, ids, h.idx, sP) : hit_ids<lds4>(A.sc, s_prims, ids, h.idx, sP);
+				const HotIds id = BVH ? hit_ids<ldg4>(A.sc, tree_prims, ids, h.idx, sP) : hit_ids<lds4>(A.sc, s_prims, ids, h.idx, sP);
 				// which half of a fused pair was hit only matters when the halves shade differently (id.b >= 0)
 				sdev = id.b >= 0 ? resolve_exact(A.sc, id, sP).dev_prim : id.a;
 				const float4 s0 = __ldg(reinterpret_cast<const float4 *>(&A.sc.shade[sdev].r0));
@@ -277,23 +306,33 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 	}
 }
 
-int launch_render_path(const RenderArgs &a, bool use_bvh, bool count_tests, cudaStream_t s) {
+int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStream_t s) {
+	const bool use_bvh = mode != 0;
 	const int warps = ((a.W + 15) / 16) * ((a.H + 7) / 8) * 4;  // one warp per 8x4 tile
 	const int tiles = (warps + RENDER_THREADS / 32 - 1) / (RENDER_THREADS / 32);
 	if (tiles <= 0) return -1;
 	if (use_bvh) {
 		const bool big = a.sc.n_nodes > BVH_BIG_NODES;
-		if (count_tests) {
-			if (big) k_render_path<true, true, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
-			else k_render_path<true, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
+		if (mode == 2) {
+			if (!a.sc.wnodes) return -1;
+			if (count_tests) {
+				if (big) k_render_path<2, true, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
+				else k_render_path<2, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
+			} else {
+				if (big) k_render_path<2, false, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
+				else k_render_path<2, false><<<tiles, RENDER_THREADS, 0, s>>>(a);
+			}
+		} else if (count_tests) {
+			if (big) k_render_path<1, true, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
+			else k_render_path<1, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
 		} else {
-			if (big) k_render_path<true, false, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
-			else k_render_path<true, false><<<tiles, RENDER_THREADS, 0, s>>>(a);
+			if (big) k_render_path<1, false, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
+			else k_render_path<1, false><<<tiles, RENDER_THREADS, 0, s>>>(a);
 		}
 	} else {
 		if (!a.sc.brute || a.sc.n_hot > BRUTE_MAX_PRIMS) return -1;
 		size_t smem = (size_t)a.sc.n_hot * sizeof(HotPrim);
-		k_render_path<false, false><<<tiles, RENDER_THREADS, smem, s>>>(a);
+		k_render_path<0, false><<<tiles, RENDER_THREADS, smem, s>>>(a);
 	}
 	return 1;
 }
@@ -309,7 +348,8 @@ __global__ void k_hit32(DevScene sc, int n, const double *__restrict__ Q, const 
 	Hit h;
 	h.t = INFINITY; h.idx = -1; h.orig = -1;
 	TravCounters tc;
-	if (use_bvh) intersect_bvh<false>(sc, o, d, tmin, h, &tc);
+	if (use_bvh == 2) intersect_wide<false>(sc, o, d, tmin, h, &tc);
+	else if (use_bvh) intersect_bvh<false>(sc, o, d, tmin, h, &tc);
 	else intersect_range<ldg4>(sc.brute, sc.brute_range.first, sc.brute_range.nq, sc.brute_range.nt, sc.brute_range.ns, sc.brute_range.nb, o, d, tmin, h);
 	const float nan = nan_t<float>();
 	F3 x = mk<float>(nan, nan, nan), nn = x;
@@ -317,7 +357,8 @@ __global__ void k_hit32(DevScene sc, int n, const double *__restrict__ Q, const 
 	int uid = -1;
 	if (h.idx >= 0) {
 		x = o + h.t * d;
-		const HotIds id = hit_ids<ldg4>(sc, use_bvh ? sc.bvh_prims : sc.brute, use_bvh ? sc.bvh_ids : sc.brute_ids, h.idx, x);
+		const HotIds id = hit_ids<ldg4>(sc, use_bvh == 2 ? sc.wide_prims : (use_bvh ? sc.bvh_prims : sc.brute),
+			use_bvh == 2 ? sc.wide_ids : (use_bvh ? sc.bvh_ids : sc.brute_ids), h.idx, x);
 		Resolved rs = resolve_exact(sc, id, x);
 		uid = sc.info[rs.dev_prim].user_id;
 		surface_at(sc, rs.dev_prim, x, rs.a, rs.b, nn, cu, cv);
@@ -357,8 +398,8 @@ __global__ void k_camera32(CamBasis cb, int W, int H, int n, const int *px, cons
 
 static inline int blocks(int n) { return (n + 127) / 128; }
 
-void launch_hit32(const DevScene &sc, int n, const double *Q, const double *D, double tmin, bool use_bvh, int *prim, double *t, double *P, double *N, double *uv, cudaStream_t s) {
-	if (n > 0) k_hit32<<<blocks(n), 128, 0, s>>>(sc, n, Q, D, (float)tmin, use_bvh ? 1 : 0, prim, t, P, N, uv);
+void launch_hit32(const DevScene &sc, int n, const double *Q, const double *D, double tmin, int mode, int *prim, double *t, double *P, double *N, double *uv, cudaStream_t s) {
+	if (n > 0) k_hit32<<<blocks(n), 128, 0, s>>>(sc, n, Q, D, (float)tmin, mode, prim, t, P, N, uv);
 }
 void launch_scatter32(const DevScene &sc, int n, const int *mat, const int *tex, const double *wi, const double *N, const double *P, const double *uv,
 	const double *rnd, double *wo, double *att, double *emit, int *alive, cudaStream_t s) {

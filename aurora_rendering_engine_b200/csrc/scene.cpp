@@ -279,6 +279,160 @@ struct Builder {
 	}
 };
 
+// ---- BVH2 -> compressed 8-wide collapse (WideNode, dev_types.h) -----------------------------------------
+// Greedy: a wide node starts from a BVH2 node's two children and keeps opening the inner child with the largest
+// surface area until it has eight (or only leaves are left).  Children go to the slot whose octant direction
+// (+/-,+/-,+/-) they lie furthest along, so that slot XOR ray-octant orders them front to back during traversal.
+struct WideBuilder {
+	const CompiledScene &src;   // the BVH2 (nodes + leaf-ordered prims)
+	CompiledScene &out;
+	int max_depth = 0;
+	struct Entry { int ref; float lo[3], hi[3]; };
+	WideBuilder(const CompiledScene &s, CompiledScene &o) : src(s), out(o) {}
+	static Entry child_of(const BvhNode &n, int which) {
+		Entry e;
+		e.ref = n.child[which];
+		const f4 &bxy = which ? n.b1 : n.b0;
+		e.lo[0] = bxy.x; e.hi[0] = bxy.y; e.lo[1] = bxy.z; e.hi[1] = bxy.w;
+		e.lo[2] = which ? n.b2.z : n.b2.x; e.hi[2] = which ? n.b2.w : n.b2.y;
+		return e;
+	}
+	static double area(const Entry &e) {
+		const double dx = (double)e.hi[0] - e.lo[0], dy = (double)e.hi[1] - e.lo[1], dz = (double)e.hi[2] - e.lo[2];
+		return dx * dy + dy * dz + dz * dx;
+	}
+	void build() {
+		out.wnodes.clear(); out.wide_prims.clear(); out.wide_ids.clear(); out.wide_kinds.clear();
+		if (src.nodes.empty()) return;
+		out.wnodes.reserve(src.nodes.size() / 3 + 8);
+		out.wide_prims.reserve(src.bvh_prims.size());
+		out.wide_ids.reserve(src.bvh_ids.size());
+		out.wide_kinds.reserve(src.bvh_prims.size());
+		out.wnodes.push_back(WideNode());
+		// explicit stack (depth-first): (BVH2 node, wide node index, depth)
+		struct Job { int bvh2, wide, depth; };
+		std::vector<Job> jobs;
+		jobs.push_back({ 0, 0, 1 });
+		while (!jobs.empty()) {
+			const Job job = jobs.back();
+			jobs.pop_back();
+			max_depth = std::max(max_depth, job.depth);
+			Entry kids[8];
+			int nk = 2;
+			kids[0] = child_of(src.nodes[job.bvh2], 0);
+			kids[1] = child_of(src.nodes[job.bvh2], 1);
+			while (nk < 8) {
+				int best = -1;
+				double best_area = -1.0;
+				for (int i = 0; i < nk; ++i)
+					if (kids[i].ref >= 0 && area(kids[i]) > best_area) { best_area = area(kids[i]); best = i; }
+				if (best < 0) break;
+				const BvhNode &open = src.nodes[kids[best].ref];
+				kids[best] = child_of(open, 0);
+				kids[nk++] = child_of(open, 1);
+			}
+			// node bounds, quantisation grid
+			float lo[3], hi[3];
+			for (int k = 0; k < 3; ++k) { lo[k] = kids[0].lo[k]; hi[k] = kids[0].hi[k]; }
+			for (int i = 1; i < nk; ++i)
+				for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], kids[i].lo[k]); hi[k] = std::max(hi[k], kids[i].hi[k]); }
+			int ebits[3];
+			double step[3];
+			for (int k = 0; k < 3; ++k) {
+				const double ext = (double)hi[k] - (double)lo[k];
+				int e = -126;
+				if (ext > 0.0) {
+					int fe;
+					std::frexp(ext / 255.0, &fe);  // ext/255 = m * 2^fe, m in [0.5,1)  =>  2^fe >= ext/255
+					e = std::max(-126, std::min(126, fe));
+				}
+				for (;; ++e) {  // the ceil() of the upper bounds must still fit 8 bits
+					step[k] = std::ldexp(1.0, e);
+					bool fits = true;
+					for (int i = 0; i < nk && fits; ++i) fits = std::ceil(((double)kids[i].hi[k] - (double)lo[k]) / step[k]) <= 255.0;
+					if (fits || e >= 126) break;
+				}
+				ebits[k] = e + 127;
+			}
+			// slot assignment: greedy on cost(child, slot) = (centroid - node centre) . (+/-1, +/-1, +/-1)
+			int slot_of[8], child_in[8];
+			for (int i = 0; i < 8; ++i) { slot_of[i] = -1; child_in[i] = -1; }
+			double cost[8][8];
+			for (int i = 0; i < nk; ++i)
+				for (int sl = 0; sl < 8; ++sl) {
+					double c = 0.0;
+					for (int k = 0; k < 3; ++k) {
+						const double rel = 0.5 * ((double)kids[i].lo[k] + kids[i].hi[k]) - 0.5 * ((double)lo[k] + hi[k]);
+						c += ((sl >> k) & 1) ? rel : -rel;
+					}
+					cost[i][sl] = c;
+				}
+			for (int round = 0; round < nk; ++round) {
+				int bi = -1, bs = -1;
+				double bc = -std::numeric_limits<double>::infinity();
+				for (int i = 0; i < nk; ++i) {
+					if (slot_of[i] >= 0) continue;
+					for (int sl = 0; sl < 8; ++sl)
+						if (child_in[sl] < 0 && cost[i][sl] > bc) { bc = cost[i][sl]; bi = i; bs = sl; }
+				}
+				slot_of[bi] = bs;
+				child_in[bs] = bi;
+			}
+			// emit
+			unsigned char meta[8] = { 0 }, q[6][8];
+			std::memset(q, 0, sizeof q);
+			unsigned imask = 0;
+			const int child_base = (int)out.wnodes.size(), prim_base = (int)out.wide_prims.size();
+			int n_inner = 0, prim_off = 0;
+			for (int sl = 0; sl < 8; ++sl) {
+				const int i = child_in[sl];
+				if (i < 0) continue;
+				const Entry &e = kids[i];
+				for (int k = 0; k < 3; ++k) {
+					q[k][sl] = (unsigned char)std::max(0.0, std::min(255.0, std::floor(((double)e.lo[k] - (double)lo[k]) / step[k])));
+					q[3 + k][sl] = (unsigned char)std::max(0.0, std::min(255.0, std::ceil(((double)e.hi[k] - (double)lo[k]) / step[k])));
+				}
+				if (e.ref >= 0) {
+					imask |= 1u << sl;
+					meta[sl] = (unsigned char)(0x20 | (24 + sl));
+					++n_inner;
+				} else {
+					const unsigned code = (unsigned)~e.ref;
+					const int slot = (int)(code & 0x1fffffffu), kind = (int)(code >> 29);
+					meta[sl] = (unsigned char)(0x20 | prim_off);
+					const int span = kind == HK_BOX ? 2 : 1;
+					for (int m = 0; m < span; ++m) {
+						out.wide_prims.push_back(src.bvh_prims[slot + m]);
+						out.wide_ids.push_back(src.bvh_ids[slot + m]);
+						out.wide_kinds.push_back((unsigned char)kind);
+					}
+					prim_off += span;
+				}
+			}
+			out.wnodes.resize(out.wnodes.size() + n_inner);
+			int rel = 0;
+			for (int sl = 0; sl < 8; ++sl) {
+				const int i = child_in[sl];
+				if (i < 0 || kids[i].ref < 0) continue;
+				jobs.push_back({ kids[i].ref, child_base + rel, job.depth + 1 });
+				++rel;
+			}
+			WideNode w;
+			unsigned ew = (unsigned)ebits[0] | (unsigned)ebits[1] << 8 | (unsigned)ebits[2] << 16 | imask << 24;
+			float ewf;
+			std::memcpy(&ewf, &ew, 4);
+			w.n0 = { lo[0], lo[1], lo[2], ewf };
+			auto pack = [](const unsigned char *b) { return (unsigned)b[0] | (unsigned)b[1] << 8 | (unsigned)b[2] << 16 | (unsigned)b[3] << 24; };
+			w.n1 = { (unsigned)child_base, (unsigned)prim_base, pack(meta), pack(meta + 4) };
+			w.n2 = { pack(q[0]), pack(q[0] + 4), pack(q[1]), pack(q[1] + 4) };
+			w.n3 = { pack(q[2]), pack(q[2] + 4), pack(q[3]), pack(q[3] + 4) };
+			w.n4 = { pack(q[4]), pack(q[4] + 4), pack(q[5]), pack(q[5] + 4) };
+			out.wnodes[job.wide] = w;
+		}
+		out.wide_depth = max_depth;
+	}
+};
+
 }  // namespace
 
 const char *validate_edges(const double u[3], const double v[3]) {
@@ -695,8 +849,13 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 		ChildRef root = b.build(0, (int)hot.size(), 0, 0, 0);
 		if (root.ref < 0) out.root_leaf_meta = root.ref;  // a one-primitive scene: the root IS the leaf reference
 		out.bvh_depth = root.depth;
+		phase("BVH build");
+		// The compressed 8-wide hierarchy is an alternative traversal structure (ARE_TRAVERSAL_WIDE), measured slower than
+		// BVH2 on B200 for this kernel: built for small scenes (cheap) and on request for large ones.
+		if (opt.build_wide || out.nodes.size() <= 65536) WideBuilder(out, out).build();
 	}
-	phase("BVH build");
+	phase("wide BVH collapse");
+	if (verbose) fprintf(stderr, "[are_cuda compile] %zu hot items, BVH2 %zu nodes depth %d, wide %zu nodes depth %d\n", hot.size(), out.nodes.size(), out.bvh_depth, out.wnodes.size(), out.wide_depth);
 	return true;
 }
 

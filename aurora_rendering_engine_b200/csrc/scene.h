@@ -49,6 +49,11 @@ struct CompiledScene {
 	std::vector<HotPrim> bvh_prims;
 	std::vector<HotIds> bvh_ids;
 	std::vector<BvhNode> nodes;
+	std::vector<WideNode> wnodes;  // compressed 8-wide collapse of `nodes` (empty when the scene has a single hot item)
+	std::vector<HotPrim> wide_prims;
+	std::vector<HotIds> wide_ids;
+	std::vector<unsigned char> wide_kinds;
+	int wide_depth = 0;
 	int root_leaf_meta = 0;
 	int n_hot = 0, n_fused_pairs = 0;
 	std::vector<PrimInfo> info;
@@ -68,6 +73,7 @@ struct CompileOptions {
 	bool fuse_parallelograms = true;
 	bool fuse_boxes = true;
 	int brute_max = 1024;
+	bool build_wide = false;  // also build the compressed 8-wide BVH for scenes beyond 65536 BVH2 nodes
 };
 
 // Validation mirroring are::Triangle's ctor (src/object/triangle.cpp:22-36): returns nullptr when fine, else the

@@ -69,9 +69,10 @@ typedef enum are_integrator {
 } are_integrator;
 
 typedef enum are_traversal {
-	ARE_TRAVERSAL_AUTO = 0, /* brute force from shared memory for small scenes, BVH otherwise */
+	ARE_TRAVERSAL_AUTO = 0, /* brute force from shared memory for small scenes, BVH2 for mid-size, compressed wide BVH for large ones */
 	ARE_TRAVERSAL_BRUTE = 1,
-	ARE_TRAVERSAL_BVH = 2
+	ARE_TRAVERSAL_BVH = 2, /* binary BVH, 64-byte nodes with both children's boxes */
+	ARE_TRAVERSAL_WIDE = 3 /* compressed 8-wide BVH, 80-byte nodes with 8-bit child boxes (large scenes) */
 } are_traversal;
 
 typedef enum are_encoder {
@@ -116,7 +117,7 @@ typedef struct are_render_stats {
 	uint64_t samples; /* W*H*sample_count */
 	uint64_t rays; /* every ray segment cast, incl. bounces / AO rays */
 	uint64_t tri_tests, quad_tests, sphere_tests; /* ray-primitive tests executed */
-	uint64_t node_visits; /* BVH node (AABB pair) visits */
+	uint64_t node_visits; /* BVH child-box PAIRS tested: 1 per BVH2 node visit, 4 per 8-wide node visit */
 	uint64_t box_tests; /* parallelepiped (three slab pairs) tests: boxes detected among the scene's parallelograms */
 	double kernel_ms; /* device time of the render kernel(s), CUDA events on the launch stream */
 	uint64_t launches; /* kernels launched by this call */

@@ -91,7 +91,7 @@ def test_hit64_bit_exact_mixed_primitives(ctx, oracle):
         assert np.allclose(uv[hit], ouv[hit], rtol=0, atol=1e-12)  # acos/atan2 last-ulp differences only
 
 
-@pytest.mark.parametrize("traversal", [1, 2])
+@pytest.mark.parametrize("traversal", [1, 2, 3])
 @pytest.mark.parametrize("scene_name", ["rt_cornell", "cornell_box", "mixed"])
 def test_hit32_within_tolerance(ctx, oracle, scene_name, traversal):
     sc = _mixed_scene() if scene_name == "mixed" else scenes.by_name(scene_name)
@@ -144,6 +144,29 @@ def test_bvh_and_brute_agree(ctx, oracle):
     assert (pb >= 0).mean() > 0.5
     assert np.array_equal(pb, pv)
     assert np.array_equal(tb[pb >= 0], tv[pv >= 0])  # same arithmetic, different visiting order
+    pw, tw, *_ = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=3)  # compressed 8-wide hierarchy
+    assert np.array_equal(pb, pw)
+    assert np.array_equal(tb[pb >= 0], tw[pw >= 0])
+
+
+def test_wide_bvh_agrees_on_a_deep_hierarchy(ctx):
+    """20 k random spheres + triangles (BVH2 depth ~17, several levels of wide nodes, octant-ordered slots): the
+    compressed 8-wide traversal must return exactly the BVH2 result for rays from every octant."""
+    sc = scenes.stress(n_prims=20_000, width=8, height=8)
+    sc.feed(ctx)
+    ctx.commit()
+    rng = np.random.RandomState(3)
+    n = 300_000
+    Q = rng.uniform(-12, 12, (n, 3))   # inside the cloud (extent ~13.6 at this density)
+    D = rng.normal(size=(n, 3))
+    D[:1000, 0] = 0.0   # axis-parallel components: the huge-finite-slope path
+    D[1000:2000, 1] = 0.0
+    pv, tv, Pv, Nv, uvv = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=2)
+    pw, tw, Pw, Nw, uvw = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=3)
+    assert 0.01 < (pv >= 0).mean() < 0.99
+    assert np.array_equal(pv, pw)
+    hit = pv >= 0
+    assert np.array_equal(tv[hit], tw[hit]) and np.array_equal(Pv[hit], Pw[hit]) and np.array_equal(uvv[hit], uvw[hit])
 
 
 def _scatter_inputs(sc, n, seed):

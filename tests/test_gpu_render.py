@@ -61,6 +61,7 @@ def test_cornell_quads_equal_triangles(ctx):
 @pytest.mark.parametrize("name,kw,spp,traversal", [
     ("rtiow_final", dict(width=160, height=90), 8, 2),
     ("rtiow_final", dict(width=96, height=54), 4, 1),
+    ("rtiow_final", dict(width=128, height=72), 8, 3),
     ("textured", dict(width=160, height=90), 16, 0),
 ])
 def test_scene_matches_cpu_twin(ctx, oracle, name, kw, spp, traversal):
@@ -97,6 +98,9 @@ def test_stress_scene_bvh_equals_brute_and_matches_cpu_twin(ctx, oracle):
     # the tile accumulators differs (BVH traversals are sliced), i.e. float summation order
     assert sb.rays == sv.rays, (sb.rays, sv.rays)
     assert np.allclose(ib, iv, rtol=1e-5, atol=1e-6), float(np.abs(ib - iv).max())
+    iw, sw = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=spp, traversal=3)))  # compressed 8-wide BVH
+    assert sb.rays == sw.rays, (sb.rays, sw.rays)
+    assert np.allclose(ib, iw, rtol=1e-5, atol=1e-6), float(np.abs(ib - iw).max())
     osc = sc.feed(oracle.scene())
     oimg, ost = osc.render(cam, capi.make_params(**sc.params_args(sample_count=spp)))
     p = psnr(np.clip(iv / spp, 0, 1), np.clip(oimg / spp, 0, 1))
@@ -158,6 +162,10 @@ def test_counters_brute_and_bvh(ctx):
     ctx.free_accum(acc)
     assert sb.rays == sv.rays and sb.sphere_tests == sb.rays * sc.num_prims
     assert 0 < sv.sphere_tests < sb.sphere_tests / 10 and sv.node_visits > sv.rays
+    acc = ctx.alloc_accum(64, 36)
+    sw = ctx.render_device(cam, capi.make_params(**sc.params_args(sample_count=2, traversal=3)), acc, want_stats=True, count_tests=True)
+    ctx.free_accum(acc)
+    assert sw.rays == sb.rays and 0 < sw.sphere_tests < sb.sphere_tests / 10 and sw.node_visits % 4 == 0
 
 
 def test_rt_ao_integrator_matches_cpu_restatement(ctx, oracle):
