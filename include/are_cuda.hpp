@@ -15,6 +15,7 @@
 
 #include <are_cuda.h>
 #include <camera.h>
+#include <material/reflective.h>
 #include <object/object_set.h>
 #include <texture.h>
 
@@ -22,6 +23,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace are {
@@ -175,6 +177,125 @@ inline void paste(Renderer &gpu, Texture &dst, const Texture &src, const std::pa
 	double *d = dst.pixel(0, 0).e();  // contiguous w*h*3 doubles
 	const int st = are_cuda_texture_paste(gpu.context(), d, dst.width_, dst.height_, src.data(), src.width_, src.height_, corners);
 	if (st < 0) throw std::runtime_error(are_cuda_last_error(gpu.context()));
+}
+
+// ---- the reference's own algorithm: patch-as-viewport rendering ------------------------------------------------
+// are::Object::trace_texture(object_set, viewport_origin) is what the reference declares for it
+// (include/object/object.h:37-38) and never defines; experiments/rt10.cpp is its prototype.  These wrappers map the
+// class API onto are_cuda_patch_*: a triangle's vertices are get_vertices(), its uv are Triangle::uv(), its material is
+// Diffuse (type 0) or Reflective (type 1, metalness = reflectivity_), its albedo the colour of its (solid) Texture.
+struct PatchSettings {  // RenderConfig, rt10.cpp:536-542
+	int max_depth = 4;
+	double min_area_px = 4.0;
+	int max_tex_res = 256, min_tex_res = 16;
+	Color3 env = Color3(0.08, 0.08, 0.10);
+	double gamma = 2.2;
+};
+struct PatchViewport {  // one viewport triangle of the camera (rt10.cpp:899-915)
+	Point3 p[3];
+	double uv[3][2];
+};
+
+class PatchScene {
+public:
+	explicit PatchScene(const ObjectSet &set) {
+		std::map<std::pair<const Material *, const Texture *>, int> ids;
+		for (const Triangle *t : set.triangles) {
+			const std::vector<Point3> &v = t->get_vertices();
+			for (int k = 0; k < 3; ++k)
+				for (int c = 0; c < 3; ++c) P_.push_back(v[k][c]);
+			UV_.insert(UV_.end(), t->uv(), t->uv() + 6);
+			const auto key = std::make_pair(static_cast<const Material *>(t->material()), static_cast<const Texture *>(t->texture()));
+			auto it = ids.find(key);
+			if (it == ids.end()) {
+				it = ids.insert({ key, static_cast<int>(type_.size()) }).first;
+				const Reflective *mirror = dynamic_cast<const Reflective *>(t->material());
+				type_.push_back(mirror ? 1 : 0);
+				metal_.push_back(mirror ? mirror->reflectivity_ : 0.0);
+				const Texture *tex = t->texture();
+				const Color3 c = tex->data() ? const_cast<Texture *>(tex)->pixel(0, 0) : Color3(tex->params()[0], tex->params()[1], tex->params()[2]);
+				for (int k = 0; k < 3; ++k) albedo_.push_back(c[k]);
+			}
+			material_.push_back(it->second);
+			index_[t] = static_cast<int>(material_.size()) - 1;
+		}
+		c_.n_tri = static_cast<int32_t>(material_.size());
+		c_.n_mat = static_cast<int32_t>(type_.size());
+		c_.P = P_.data(); c_.UV = UV_.data(); c_.material = material_.data();
+		c_.mat_type = type_.data(); c_.mat_albedo = albedo_.data(); c_.mat_metalness = metal_.data();
+	}
+	PatchScene(const PatchScene &) = delete;
+	PatchScene &operator=(const PatchScene &) = delete;
+	const are_patch_scene *c() const { return &c_; }
+	int index_of(const Triangle &t) const {
+		auto it = index_.find(&t);
+		if (it == index_.end()) throw std::invalid_argument("triangle is not part of the object set");
+		return it->second;
+	}
+	static are_patch_config to_c(const PatchSettings &s) {
+		are_patch_config c;
+		c.max_depth = s.max_depth; c.max_tex_res = s.max_tex_res; c.min_tex_res = s.min_tex_res; c.pad_ = 0;
+		c.min_area_px = s.min_area_px;
+		for (int k = 0; k < 3; ++k) c.env[k] = s.env[k];
+		c.gamma = s.gamma;
+		return c;
+	}
+
+private:
+	std::vector<double> P_, UV_, albedo_, metal_;
+	std::vector<int32_t> material_, type_;
+	std::map<const Triangle *, int> index_;
+	are_patch_scene c_{};
+};
+
+/// Object::trace_texture on the GPU: the texture of `current` (a triangle of `set`) seen from `viewport_origin`, with
+/// everything visible through it painted in (renderTriangleWithTriangle, rt10.cpp:551-664).  The size is clamped to
+/// [min_tex_res, max_tex_res] as the reference clamps it.
+inline Texture trace_texture(Renderer &gpu, const ObjectSet &set, const Triangle &current, const Point3 &viewport_origin, int tex_w, int tex_h,
+	const PatchSettings &s = PatchSettings()) {
+	PatchScene scene(set);
+	const are_patch_config cfg = PatchScene::to_c(s);
+	std::vector<double> tex(static_cast<size_t>(s.max_tex_res) * s.max_tex_res * 3);
+	int wh[2] = { 0, 0 };
+	const int st = are_cuda_patch_trace_texture(gpu.context(), scene.c(), viewport_origin.e(), scene.index_of(current), tex_w, tex_h, 0.0, &cfg, tex.data(),
+		wh, nullptr);
+	if (st == ARE_ERR_INVALID_ARGUMENT) throw std::invalid_argument(are_cuda_last_error(gpu.context()));
+	if (st < 0) throw std::runtime_error(are_cuda_last_error(gpu.context()));
+	Texture out(wh[0], wh[1], Color3(0, 0, 0));
+	for (int y = 0; y < wh[1]; ++y)
+		for (int x = 0; x < wh[0]; ++x) {
+			const double *p = &tex[(static_cast<size_t>(y) * wh[0] + x) * 3];
+			out.pixel(x, y) = Color3(p[0], p[1], p[2]);
+		}
+	return out;
+}
+
+/// Camera::render of rt10.cpp:755-772: the scene seen from `origin` through the two viewport triangles.  Returns the
+/// linear image; rgb8 (optional, W*H*3) receives the gamma-encoded P6 payload of Image::writePPM (rt10.cpp:118-143).
+inline Texture patch_render(Renderer &gpu, const ObjectSet &set, const Point3 &origin, const PatchViewport &a, const PatchViewport &b, int width, int height,
+	const PatchSettings &s = PatchSettings(), std::vector<std::uint8_t> *rgb8 = nullptr, are_patch_stats *stats = nullptr) {
+	PatchScene scene(set);
+	const are_patch_config cfg = PatchScene::to_c(s);
+	double vp_P[18], vp_UV[12];
+	const PatchViewport *vp[2] = { &a, &b };
+	for (int v = 0; v < 2; ++v)
+		for (int k = 0; k < 3; ++k) {
+			for (int c = 0; c < 3; ++c) vp_P[9 * v + 3 * k + c] = vp[v]->p[k][c];
+			vp_UV[6 * v + 2 * k] = vp[v]->uv[k][0];
+			vp_UV[6 * v + 2 * k + 1] = vp[v]->uv[k][1];
+		}
+	std::vector<double> rgb(static_cast<size_t>(width) * height * 3);
+	if (rgb8) rgb8->resize(rgb.size());
+	const int st = are_cuda_patch_render(gpu.context(), scene.c(), origin.e(), vp_P, vp_UV, width, height, &cfg, rgb.data(), rgb8 ? rgb8->data() : nullptr, stats);
+	if (st == ARE_ERR_INVALID_ARGUMENT) throw std::invalid_argument(are_cuda_last_error(gpu.context()));
+	if (st < 0) throw std::runtime_error(are_cuda_last_error(gpu.context()));
+	Texture out(width, height, Color3(0, 0, 0));
+	for (int y = 0; y < height; ++y)
+		for (int x = 0; x < width; ++x) {
+			const double *p = &rgb[(static_cast<size_t>(y) * width + x) * 3];
+			out.pixel(x, y) = Color3(p[0], p[1], p[2]);
+		}
+	return out;
 }
 
 }  // namespace cuda

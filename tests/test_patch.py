@@ -184,3 +184,35 @@ def test_gpu_full_size_properties(ctx, porc):
     again = ctx.patch_render(ps)
     assert np.array_equal(again[0], rgb)  # deterministic: no atomics, no order dependence
     print(f"[patch 4K] plan {st.plan_ms:.3f} ms, kernels {st.kernel_ms:.3f} ms, {st.node_texels} node texels, {st.ops} warp triangles")
+
+
+@pytest.mark.gpu
+def test_reference_style_host_program_patch_renders_on_gpu(tmp_path, lib, ctx, golden):
+    """examples/patch_host.cpp builds the rt10 room from are::Triangle / Diffuse / Reflective / Texture objects and renders
+    it through are::cuda::patch_render / trace_texture (include/are_cuda.hpp).  are::Triangle stores (Q, u, v), so its
+    vertices are Q + (P - Q): the Python-driven render of exactly those vertices must be identical, and the image is the
+    reference's shipped one up to that one-ulp vertex perturbation."""
+    import subprocess
+    libdir = os.path.dirname(capi.LIB_PATH)
+    exe = tmp_path / "patch_host"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "patch_host.cpp"),
+                    "-L", libdir, "-lare_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    ppm, raw, tex = tmp_path / "out.ppm", tmp_path / "rgb.f64", tmp_path / "tex.f64"
+    r = subprocess.run([str(exe), str(ppm), "900", "650", str(raw), str(tex)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ps = scenes.patch_rt10()
+    P = ps.P.copy()
+    P[:, 1] = P[:, 0] + (P[:, 1] - P[:, 0])
+    P[:, 2] = P[:, 0] + (P[:, 2] - P[:, 0])
+    ps = dataclasses.replace(ps, P=P)
+    rgb, rgb8, _ = ctx.patch_render(ps)
+    got = np.fromfile(raw, np.float64).reshape(650, 900, 3)
+    assert np.array_equal(got, rgb)
+    blob = ppm.read_bytes()
+    assert blob == b"P6\n900 650\n255\n" + rgb8.tobytes()
+    shipped_rows = golden["rt10_rows"]
+    diff = (rgb8[golden["rt10_row_index"]].astype(int) - shipped_rows.astype(int))
+    assert (diff != 0).mean() < 1e-3  # one-ulp vertex differences may move a few edge pixels, nothing more
+    t, _ = ctx.patch_trace_texture(ps, ps.origin, 18, 200, 200, 0.0)
+    got_t = np.fromfile(tex, np.float64).reshape(t.shape)
+    assert np.array_equal(got_t, t) and t.std() > 0.01  # a mirror face with the room painted into it
