@@ -414,10 +414,16 @@ typedef struct {
 	v3 Q, u, v; /* sphere: Q = centre, u.x = radius */
 	double uv[6];
 } orc_prim;
+/* CPU-side acceleration (NEW, test infrastructure): median-split AABB tree over the primitives, built on first use for
+ * scenes of more than ORC_BVH_MIN primitives.  It only prunes: every surviving primitive goes through the same
+ * tri_test / quad_test / sphere_test as the linear scan, and ties in t go to the lower primitive index exactly as the
+ * scan resolves them, so closest_hit returns the same (primitive, t, a, b) with or without it. */
+typedef struct { double lo[3], hi[3]; int left, right, first, count; } orc_node; /* leaf: count > 0 */
 typedef struct {
 	orc_texture *tex; int ntex, ctex;
 	orc_material *mat; int nmat, cmat;
 	orc_prim *prim; int nprim, cprim;
+	orc_node *node; int nnode, cnode; int *order; double *pb; int bvh_nprim; /* tree valid for the first bvh_nprim primitives; pb = 6 bounds per primitive */
 } orc_scene;
 
 /* identical field order to are_camera / are_render_params in include/are_cuda.h */
@@ -442,7 +448,7 @@ orc_scene *orc_scene_create(void) { return (orc_scene *)calloc(1, sizeof(orc_sce
 void orc_scene_destroy(orc_scene *s) {
 	if (!s) return;
 	for (int i = 0; i < s->ntex; ++i) { free(s->tex[i].rgb); free(s->tex[i].ranvec); free(s->tex[i].perm); }
-	free(s->tex); free(s->mat); free(s->prim); free(s);
+	free(s->tex); free(s->mat); free(s->prim); free(s->node); free(s->order); free(s->pb); free(s);
 }
 #define GROW(arr, n, c, T) do { if ((n) == (c)) { (c) = (c) ? 2 * (c) : 16; (arr) = (T *)realloc((arr), (size_t)(c) * sizeof(T)); } } while (0)
 
@@ -563,18 +569,119 @@ static inline int sphere_test(const orc_prim *p, v3 o, v3 d, double tmin, double
 	*t = root;
 	return 1;
 }
+#define ORC_BVH_MIN 256
+static inline int prim_test(const orc_prim *p, v3 o, v3 d, double tmin, double tmax, double *t, double *a, double *b, orc_stats *st) {
+	*a = 0; *b = 0;
+	if (p->type == PRIM_TRIANGLE) { if (st) st->tri_tests++; return tri_test(p, o, d, tmin, tmax, t, a, b); }
+	if (p->type == PRIM_QUAD) { if (st) st->quad_tests++; return quad_test(p, o, d, tmin, tmax, t, a, b); }
+	if (st) st->sphere_tests++;
+	return sphere_test(p, o, d, tmin, tmax, t);
+}
+static void prim_bounds(const orc_prim *p, double lo[3], double hi[3]) {
+	v3 c[4];
+	int n = 0;
+	if (p->type == PRIM_SPHERE) {
+		double r = fabs(p->u.x);
+		c[0] = V(p->Q.x - r, p->Q.y - r, p->Q.z - r); c[1] = V(p->Q.x + r, p->Q.y + r, p->Q.z + r);
+		n = 2;
+	} else {
+		c[0] = p->Q; c[1] = vadd(p->Q, p->u); c[2] = vadd(p->Q, p->v);
+		n = 3;
+		if (p->type == PRIM_QUAD) c[n++] = vadd(vadd(p->Q, p->u), p->v);
+	}
+	lo[0] = hi[0] = c[0].x; lo[1] = hi[1] = c[0].y; lo[2] = hi[2] = c[0].z;
+	for (int i = 1; i < n; ++i) {
+		lo[0] = fmin(lo[0], c[i].x); hi[0] = fmax(hi[0], c[i].x);
+		lo[1] = fmin(lo[1], c[i].y); hi[1] = fmax(hi[1], c[i].y);
+		lo[2] = fmin(lo[2], c[i].z); hi[2] = fmax(hi[2], c[i].z);
+	}
+	for (int k = 0; k < 3; ++k) { /* outward pad: the tree must never cut off a hit the scan would find (the tests carry eps slack) */
+		double pad = 1e-9 * (fabs(lo[k]) + fabs(hi[k]) + (hi[k] - lo[k])) + 1e-9;
+		lo[k] -= pad; hi[k] += pad;
+	}
+}
+static const orc_scene *g_sort_scene;
+static int g_sort_axis;
+static int cmp_centroid(const void *a, const void *b) {
+	const double *pa = g_sort_scene->pb + 6 * (size_t)*(const int *)a, *pc = g_sort_scene->pb + 6 * (size_t)*(const int *)b;
+	const double ca = pa[g_sort_axis] + pa[3 + g_sort_axis], cb = pc[g_sort_axis] + pc[3 + g_sort_axis];
+	return ca < cb ? -1 : (ca > cb ? 1 : (*(const int *)a - *(const int *)b));
+}
+static int bvh_build(orc_scene *s, int first, int count) {
+	GROW(s->node, s->nnode, s->cnode, orc_node);
+	int me = s->nnode++;
+	orc_node nd;
+	for (int k = 0; k < 3; ++k) { nd.lo[k] = INFINITY; nd.hi[k] = -INFINITY; }
+	for (int i = first; i < first + count; ++i) {
+		const double *b = s->pb + 6 * (size_t)s->order[i];
+		for (int k = 0; k < 3; ++k) { nd.lo[k] = fmin(nd.lo[k], b[k]); nd.hi[k] = fmax(nd.hi[k], b[3 + k]); }
+	}
+	nd.first = first; nd.count = count; nd.left = nd.right = -1;
+	if (count > 4) {
+		int ax = 0;
+		for (int k = 1; k < 3; ++k) if (nd.hi[k] - nd.lo[k] > nd.hi[ax] - nd.lo[ax]) ax = k;
+		g_sort_scene = s; g_sort_axis = ax;
+		qsort(s->order + first, (size_t)count, sizeof(int), cmp_centroid);
+		nd.count = 0;
+		s->node[me] = nd;
+		int l = bvh_build(s, first, count / 2), r = bvh_build(s, first + count / 2, count - count / 2);
+		nd.left = l; nd.right = r;
+	}
+	s->node[me] = nd;
+	return me;
+}
+/* not thread-safe: called from the single-threaded entry points before any worker starts */
+static void ensure_bvh(const orc_scene *cs) {
+	orc_scene *s = (orc_scene *)cs;
+	if (s->nprim <= ORC_BVH_MIN || s->bvh_nprim == s->nprim) return;
+	free(s->order);
+	s->order = (int *)malloc((size_t)s->nprim * sizeof(int));
+	free(s->pb);
+	s->pb = (double *)malloc((size_t)s->nprim * 6 * sizeof(double));
+	for (int i = 0; i < s->nprim; ++i) { s->order[i] = i; prim_bounds(&s->prim[i], s->pb + 6 * (size_t)i, s->pb + 6 * (size_t)i + 3); }
+	s->nnode = 0;
+	bvh_build(s, 0, s->nprim);
+	s->bvh_nprim = s->nprim;
+}
+static inline int box_overlaps(const orc_node *n, v3 o, v3 inv, double tmin, double tmax) {
+	double t0 = tmin, t1 = tmax;
+	const double oo[3] = { o.x, o.y, o.z }, ii[3] = { inv.x, inv.y, inv.z };
+	for (int k = 0; k < 3; ++k) {
+		double a = (n->lo[k] - oo[k]) * ii[k], b = (n->hi[k] - oo[k]) * ii[k];
+		if (a != a || b != b) continue; /* 0 * inf: the origin lies on a slab plane of an axis-parallel ray — do not prune */
+		if (a > b) { double c = a; a = b; b = c; }
+		if (a > t0) t0 = a;
+		if (b < t1) t1 = b;
+	}
+	return t0 <= t1 * (1.0 + 1e-12) + 1e-12;
+}
 static orc_hit closest_hit(const orc_scene *s, v3 o, v3 d, double tmin, orc_stats *st) {
 	orc_hit best = { -1, INFINITY, 0, 0 };
-	for (int i = 0; i < s->nprim; ++i) {
-		const orc_prim *p = &s->prim[i];
-		double t, a = 0, b = 0;
-		int ok;
-		if (p->type == PRIM_TRIANGLE) { ok = tri_test(p, o, d, tmin, best.t, &t, &a, &b); if (st) st->tri_tests++; }
-		else if (p->type == PRIM_QUAD) { ok = quad_test(p, o, d, tmin, best.t, &t, &a, &b); if (st) st->quad_tests++; }
-		else { ok = sphere_test(p, o, d, tmin, best.t, &t); if (st) st->sphere_tests++; }
-		if (ok) { best.prim = i; best.t = t; best.a = a; best.b = b; }
-	}
 	if (st) st->rays++;
+	if (s->nprim <= ORC_BVH_MIN || s->bvh_nprim != s->nprim) { /* linear scan: the hittable list (include/object/object_set.h:10-12) */
+		for (int i = 0; i < s->nprim; ++i) {
+			double t, a, b;
+			if (prim_test(&s->prim[i], o, d, tmin, best.t, &t, &a, &b, st)) { best.prim = i; best.t = t; best.a = a; best.b = b; }
+		}
+		return best;
+	}
+	const v3 inv = V(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+	int stack[128], sp = 0;
+	stack[sp++] = 0;
+	while (sp > 0) {
+		const orc_node *n = &s->node[stack[--sp]];
+		if (st) st->node_visits++;
+		if (!box_overlaps(n, o, inv, tmin, best.t)) continue;
+		if (n->count > 0) {
+			for (int k = n->first; k < n->first + n->count; ++k) {
+				const int i = s->order[k];
+				double t, a, b;
+				/* window closed at best.t so that a tie reaches the index comparison: the scan keeps the lower index */
+				if (!prim_test(&s->prim[i], o, d, tmin, nextafter(best.t, INFINITY), &t, &a, &b, st)) continue;
+				if (t < best.t || (t == best.t && i < best.prim)) { best.prim = i; best.t = t; best.a = a; best.b = b; }
+			}
+		} else if (sp + 2 <= 128) { stack[sp++] = n->left; stack[sp++] = n->right; }
+	}
 	return best;
 }
 /* any hit in (tmin, tmax) — occlusion query */
@@ -612,6 +719,7 @@ static void surface_at(const orc_scene *s, const orc_hit *h, v3 P, v3 *N, double
 
 void orc_hit_batch(const orc_scene *s, int n, const double *Q, const double *D, double tmin,
 	int *prim, double *t, double *P, double *N, double *uv) {
+	ensure_bvh(s);
 	for (int i = 0; i < n; ++i) {
 		v3 o = vld(Q + 3 * i), d = vnormalized(vld(D + 3 * i));
 		orc_hit h = closest_hit(s, o, d, tmin, 0);
@@ -1047,6 +1155,7 @@ int orc_render_window(const orc_scene *s, const orc_camera *c, const orc_params 
 	double *accum, int nthreads, orc_stats *stats) {
 	if (nthreads < 1) nthreads = 1;
 	if (nthreads > 256) nthreads = 256;
+	ensure_bvh(s);
 	job_t j;
 	memset(&j, 0, sizeof j);
 	j.s = s; j.c = c; j.p = p; j.accum = accum; j.x0 = x0; j.x1 = x1; j.y0 = y0; j.y1 = y1; j.next_row = y0;

@@ -284,3 +284,26 @@ def test_rt_ao_matches_the_real_reference_renderer(ctx, tmp_path):
     print(f"[rt_ao vs rt_ref] PSNR {p:.1f} dB, {rays_per_px:.2f} rays per pixel-sample (reference: 34.19)")
     assert abs(rays_per_px - 34.19) < 0.1   # 8 963 385 rays / 262 144 pixels measured on the reference
     assert p >= 40.0, f"PSNR {p:.1f} dB"
+
+
+def test_large_stress_scene_matches_cpu_twin(ctx, oracle):
+    """Config-4 style scene at 60 000 primitives (BVH2 depth ~19; the CPU twin prunes with its own AABB tree, proven equal
+    to its linear scan in tests/test_oracle_vs_reference.py): image vs the CPU twin on the same Philox samples, and the
+    fp32 closest-hit harness vs the fp64 twin on rays through the cloud."""
+    sc = scenes.stress(n_prims=60_000, width=160, height=90)
+    img, st, oimg, ost = _render_both(sc, ctx, oracle, spp=8)
+    p = psnr(np.clip(img, 0, 1), np.clip(oimg, 0, 1))
+    print(f"[stress 60k] PSNR {p:.1f} dB, rays gpu/cpu {st.rays}/{ost.rays}")
+    assert abs(int(st.rays) - int(ost.rays)) < 1e-2 * ost.rays
+    assert p >= PSNR_MIN
+    rng = np.random.RandomState(9)
+    n = 100_000
+    Q = rng.uniform(-15, 15, (n, 3))
+    D = rng.normal(size=(n, 3))
+    osc = sc.feed(oracle.scene())
+    oprim, ot, *_ = osc.hit_batch(Q, D, 1e-3)
+    for trav in (2, 3):
+        prim, t, *_ = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=trav)
+        hit = (oprim >= 0) & (prim == oprim)
+        assert (prim != oprim).mean() < 5e-4, (trav, (prim != oprim).mean())   # grazing rays only
+        assert hit.sum() > 1000 and np.percentile(np.abs(t[hit] - ot[hit]) / np.maximum(np.abs(ot[hit]), np.abs(Q[hit]).max(axis=1)), 99.9) < 1e-5

@@ -185,3 +185,33 @@ def test_survey_million_ray_hit_count(oracle, reference):
     ts.close()
     assert rn == on and same(rp, op_) and same(rt, ot)
     assert 0.80 < rn / 1e6 < 0.87  # the survey measured 83.4 % with its generator
+
+
+def test_cpu_twin_tree_equals_linear_scan(oracle):
+    """The CPU twin prunes large scenes with an AABB tree; it must return exactly what its linear scan over the hittable
+    list returns (same primitive — ties to the lower index —, same t, point, normal, uv).  The scan result is assembled
+    from sub-scenes small enough (<= 256 primitives) to be scanned linearly."""
+    import copy
+    from aurora_rendering_engine_b200 import scenes
+    sc = scenes.stress(n_prims=3000, width=8, height=8)
+    # duplicate a few primitives so that exact ties in t exist
+    sc.order = sc.order + sc.order[:40]
+    osc = sc.feed(oracle.scene())
+    rng = np.random.RandomState(1)
+    n = 20000
+    Q = rng.uniform(-6, 6, (n, 3))
+    D = rng.normal(size=(n, 3))
+    D[:50, 0] = 0.0
+    D[50:100, 1] = 0.0
+    prim, t, P, N, uv = osc.hit_batch(Q, D, t_min=1e-3)
+    best_t, best_p = np.full(n, np.inf), np.full(n, -1)
+    chunk = 250
+    for c0 in range(0, len(sc.order), chunk):
+        sub = copy.copy(sc)
+        sub.order = sc.order[c0:c0 + chunk]
+        p2, t2, *_ = sub.feed(oracle.scene()).hit_batch(Q, D, t_min=1e-3)
+        m = (p2 >= 0) & (t2 < best_t)   # strict: an equal t later in the list does not replace an earlier one
+        best_t[m], best_p[m] = t2[m], p2[m] + c0
+    assert (prim >= 0).sum() > 300
+    assert np.array_equal(best_p, prim)
+    assert np.array_equal(best_t[prim >= 0], t[prim >= 0])
