@@ -1,0 +1,32 @@
+#!/bin/bash
+# tools/sanitize.sh — compute-sanitizer (memcheck, racecheck, initcheck) over one small invocation of every kernel family:
+# smoke() (megakernel brute force + fp64 harness), a BVH2 / wide-BVH render, the RT_AO integrator, Texture::paste and
+# the patch renderer.  Writes gpurun_out/sanitizer_<tool>.log; exit status 0 only if every tool reports 0 errors.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+cat > /tmp/are_sanitize_workload.py <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import numpy as np
+from aurora_rendering_engine_b200 import capi, scenes
+with capi.Context(0) as ctx:
+    for name, kw, trav in (("cornell_box", dict(width=48, height=48), 0), ("rtiow_final", dict(width=48, height=27), 2), ("rtiow_final", dict(width=48, height=27), 3),
+                           ("textured", dict(width=48, height=27), 0), ("rt_cornell", dict(width=48, height=48), 0), ("stress", dict(n_prims=30000, width=48, height=27), 0)):
+        sc = scenes.by_name(name, **kw)
+        ctx.clear(); sc.feed(ctx); ctx.commit()
+        img, st = ctx.render(capi.make_camera(**sc.camera_args()), capi.make_params(**sc.params_args(sample_count=2, traversal=trav, max_depth=min(sc.max_depth, 8))))
+        assert np.isfinite(img).all()
+        Q = np.random.RandomState(0).uniform(-1, 1, (2000, 3)); D = np.random.RandomState(1).normal(size=(2000, 3))
+        ctx.hit_batch(Q, D, precision=64); ctx.hit_batch(Q, D, precision=32, traversal=trav)
+    ps = scenes.patch_random(1, width=64, height=48, mirror_walls=True)
+    ctx.patch_render(ps); ctx.patch_trace_texture(ps, ps.origin, 12, 40, 40)
+    dst = np.zeros((40, 50, 3)); src = np.random.RandomState(2).uniform(size=(20, 30, 3))
+    ctx.texture_paste(dst, src, [(5, 5), (40, 8), (8, 30), (45, 35)])
+print("workload ok")
+PY
+rc=0
+for tool in memcheck racecheck initcheck; do
+  compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/are_sanitize_workload.py > gpurun_out/sanitizer_$tool.log 2>&1 || rc=1
+  echo "== $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer_$tool.log | tail -1) $(grep -c 'workload ok' gpurun_out/sanitizer_$tool.log) run(s) completed"
+done
+exit $rc
