@@ -209,6 +209,7 @@ public:
 			const P2 p0 = { op.px[0], op.py[0] }, p1 = { op.px[1], op.py[1] }, p2 = { op.px[2], op.py[2] };
 			op.area = cross2(p1 - p0, p2 - p0);
 			if (std::fabs(op.area) < 1e-12) continue;
+			op.inv_area = 1.0 / op.area;
 			op.src_off = src.off;
 			op.src_w = src.w;
 			op.src_h = src.h;
@@ -368,8 +369,16 @@ __device__ __forceinline__ bool painted(const PatchOp *__restrict__ ops, int beg
 		const PatchOp &op = ops[i];
 		if (x < op.x0 || x > op.x1 || y < op.y0 || y > op.y1) continue;
 		const P2 p0 = { op.px[0], op.py[0] }, p1 = { op.px[1], op.py[1] }, p2 = { op.px[2], op.py[2] };
-		const double w0 = cross2(p1 - c, p2 - c) / op.area;
-		const double w1 = cross2(p2 - c, p0 - c) / op.area;
+		const double c0 = cross2(p1 - c, p2 - c), c1 = cross2(p2 - c, p0 - c);
+		{  // Conservative early reject without the two fp64 divisions: c*inv_area is within 3 ulp of c/area, so a barycentric
+			// that misses the reference's -1e-6 threshold by more than the margin below misses it exactly as well.  Every
+			// pixel that might be covered still takes the exact test, and only exact quotients reach the image.
+			const double q0 = c0 * op.inv_area, q1 = c1 * op.inv_area;
+			const double slack = 1e-12 * (1.0 + fabs(q0) + fabs(q1));
+			if (q0 < -1e-6 - slack || q1 < -1e-6 - slack || 1.0 - q0 - q1 < -1e-6 - slack) continue;
+		}
+		const double w0 = c0 / op.area;
+		const double w1 = c1 / op.area;
 		const double w2 = 1.0 - w0 - w1;
 		if (w0 < -1e-6 || w1 < -1e-6 || w2 < -1e-6) continue;
 		const P2 s0 = { op.su[0], op.sv[0] }, s1 = { op.su[1], op.sv[1] }, s2 = { op.su[2], op.sv[2] };

@@ -44,10 +44,11 @@ struct PatchStats {
 };
 
 // One warp triangle: destination triangle in pixel space of the texture being painted, source uv per vertex, and where
-// the source texels are (arena offset in texels, or a solid colour).  152 bytes, read-only, broadcast across a warp.
+// the source texels are (arena offset in texels, or a solid colour).  160 bytes, read-only, broadcast across a warp.
 struct PatchOp {
 	double px[3], py[3];    // destination vertices (pixels)
 	double area;            // cross(p1-p0, p2-p0)
+	double inv_area;        // 1/area: only for the conservative early reject, never for a value that reaches the image
 	double su[3], sv[3];    // source uv of the vertices
 	double solid[3];        // colour of a solid source
 	long long src_off;      // first texel of the source texture in the arena, -1 = solid
