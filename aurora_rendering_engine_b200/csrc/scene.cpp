@@ -32,6 +32,22 @@ inline bool near_zero(D3 a) {  // are::Vec3::near_zero, src/basic/vec3.cpp:143-1
 	return std::fabs(a.x) < s && std::fabs(a.y) < s && std::fabs(a.z) < s;
 }
 
+// Host threads for the data-parallel phases of the scene compiler (ARE_CUDA_BUILD_THREADS overrides the count).
+inline unsigned host_threads() {
+	unsigned hw = std::thread::hardware_concurrency();
+	if (const char *e = getenv("ARE_CUDA_BUILD_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+	return std::max(1u, std::min(hw, 64u));
+}
+// fn(begin, end) over [0,n) in contiguous chunks, one per thread; results must not depend on the chunking
+template <typename F>
+void parallel_chunks(size_t n, size_t min_chunk, F fn) {
+	const unsigned T = (unsigned)std::min<size_t>(host_threads(), std::max<size_t>(1, n / std::max<size_t>(1, min_chunk)));
+	if (T <= 1) { fn((size_t)0, n); return; }
+	std::vector<std::thread> th;
+	for (unsigned t = 0; t < T; ++t) th.emplace_back([=] { fn(n * t / T, n * (t + 1) / T); });
+	for (auto &x : th) x.join();
+}
+
 struct Box {
 	double lo[3], hi[3];
 	void reset() {
@@ -130,16 +146,25 @@ struct ChildRef {
 // before it is built: subtrees are built by independent threads straight into the preallocated output (no stitching),
 // and the result is identical to the serial build whatever the thread count.
 struct Builder {
-	std::vector<HotItem> &items;
-	std::vector<int> idx;
+	// what the builder touches per item, 80 bytes, physically partitioned with the ranges so that every subtree scans
+	// contiguous memory (the full HotItem is 256 bytes and would be visited through a permutation)
+	struct Ref {
+		Box box;
+		double c[3];  // centroid
+		int item;
+	};
+	const std::vector<HotItem> &items;
+	std::vector<Ref> refs;
 	CompiledScene &out;
 	bool any_box = false;
 	int spawn_depth = 0;  // subtrees above this depth (and big enough) hand their left half to a new thread
-	Builder(std::vector<HotItem> &it, CompiledScene &o) : items(it), out(o) {
-		idx.resize(items.size());
+	Builder(const std::vector<HotItem> &it, CompiledScene &o) : items(it), out(o) {
+		refs.resize(items.size());
 		size_t slots = 0;
-		for (size_t i = 0; i < idx.size(); ++i) {
-			idx[i] = (int)i;
+		for (size_t i = 0; i < refs.size(); ++i) {
+			refs[i].box = items[i].box;
+			for (int k = 0; k < 3; ++k) refs[i].c[k] = items[i].c[k];
+			refs[i].item = (int)i;
 			any_box |= items[i].kind == HK_BOX;
 			slots += items[i].kind == HK_BOX ? 2 : 1;
 		}
@@ -168,12 +193,12 @@ struct Builder {
 	int slots_of(int lo, int hi) const {
 		if (!any_box) return hi - lo;
 		int n = 0;
-		for (int i = lo; i < hi; ++i) n += items[idx[i]].kind == HK_BOX ? 2 : 1;
+		for (int i = lo; i < hi; ++i) n += items[refs[i].item].kind == HK_BOX ? 2 : 1;
 		return n;
 	}
 	ChildRef make_leaf(int at, int slot) {  // ref = ~(slot | kind << 29)
 		ChildRef c;
-		const HotItem &it = items[idx[at]];
+		const HotItem &it = items[refs[at].item];
 		out.bvh_prims[slot] = it.rec;
 		out.bvh_ids[slot] = it.ids;
 		if (it.kind == HK_BOX) { out.bvh_prims[slot + 1] = it.rec2; out.bvh_ids[slot + 1] = it.ids; }
@@ -183,64 +208,68 @@ struct Builder {
 		c.depth = 0;
 		return c;
 	}
-	// Subtree over idx[lo,hi): inner nodes go to out.nodes[node_base ...), items to slots [slot_base ...).
+	// Subtree over refs[lo,hi): inner nodes go to out.nodes[node_base ...), items to slots [slot_base ...).
 	ChildRef build(int lo, int hi, int depth, int node_base, int slot_base) {
 		const int n = hi - lo;
 		if (n <= 1) return make_leaf(lo, slot_base);
-		Box bounds, cb;
-		bounds.reset();
+		Box cb;
 		cb.reset();
-		for (int i = lo; i < hi; ++i) {
-			const HotItem &it = items[idx[i]];
-			bounds.grow(it.box);
-			cb.grow(D3{ it.c[0], it.c[1], it.c[2] });
-		}
+		for (int i = lo; i < hi; ++i) cb.grow(D3{ refs[i].c[0], refs[i].c[1], refs[i].c[2] });
 		int mid = -1;
 		if (depth < 40) {
 			const int NB = 16;
 			double best_cost = std::numeric_limits<double>::infinity();
 			int best_axis = -1, best_split = -1;
+			// one pass fills the bins of all three axes
+			Box bb[3][NB];
+			int bc[3][NB];
+			double scale[3];
+			bool live[3];
 			for (int ax = 0; ax < 3; ++ax) {
-				double ext = cb.hi[ax] - cb.lo[ax];
-				if (!(ext > 0.0)) continue;
-				Box bb[NB];
-				int bc[NB] = { 0 };
-				for (int b = 0; b < NB; ++b) bb[b].reset();
-				const double scale = NB / ext;
-				for (int i = lo; i < hi; ++i) {
-					const HotItem &it = items[idx[i]];
-					int b = std::min(NB - 1, (int)((it.c[ax] - cb.lo[ax]) * scale));
-					bb[b].grow(it.box);
-					bc[b]++;
+				const double ext = cb.hi[ax] - cb.lo[ax];
+				live[ax] = ext > 0.0;
+				scale[ax] = live[ax] ? NB / ext : 0.0;
+				for (int b = 0; b < NB; ++b) { bb[ax][b].reset(); bc[ax][b] = 0; }
+			}
+			for (int i = lo; i < hi; ++i) {
+				const Ref &r = refs[i];
+				for (int ax = 0; ax < 3; ++ax) {
+					if (!live[ax]) continue;
+					const int b = std::min(NB - 1, (int)((r.c[ax] - cb.lo[ax]) * scale[ax]));
+					bb[ax][b].grow(r.box);
+					bc[ax][b]++;
 				}
+			}
+			for (int ax = 0; ax < 3; ++ax) {
+				if (!live[ax]) continue;
 				double right_area[NB];
 				int right_cnt[NB];
 				Box acc;
 				acc.reset();
 				int c = 0;
 				for (int b = NB - 1; b > 0; --b) {
-					acc.grow(bb[b]);
-					c += bc[b];
+					acc.grow(bb[ax][b]);
+					c += bc[ax][b];
 					right_area[b] = acc.area();
 					right_cnt[b] = c;
 				}
 				acc.reset();
 				c = 0;
 				for (int b = 0; b < NB - 1; ++b) {
-					acc.grow(bb[b]);
-					c += bc[b];
+					acc.grow(bb[ax][b]);
+					c += bc[ax][b];
 					if (c == 0 || right_cnt[b + 1] == 0) continue;
 					double cost = acc.area() * c + right_area[b + 1] * right_cnt[b + 1];
 					if (cost < best_cost) { best_cost = cost; best_axis = ax; best_split = b; }
 				}
 			}
 			if (best_axis >= 0) {
-				const double ext = cb.hi[best_axis] - cb.lo[best_axis], scale = NB / ext, clo = cb.lo[best_axis];
-				auto it = std::partition(idx.begin() + lo, idx.begin() + hi, [&](int id) {
-					int b = std::min(NB - 1, (int)((items[id].c[best_axis] - clo) * scale));
+				const double sc = scale[best_axis], clo = cb.lo[best_axis];
+				auto it = std::partition(refs.begin() + lo, refs.begin() + hi, [&](const Ref &r) {
+					int b = std::min(NB - 1, (int)((r.c[best_axis] - clo) * sc));
 					return b <= best_split;
 				});
-				mid = (int)(it - idx.begin());
+				mid = (int)(it - refs.begin());
 				if (mid == lo || mid == hi) mid = -1;
 			}
 		}
@@ -249,7 +278,8 @@ struct Builder {
 			for (int k = 1; k < 3; ++k)
 				if (cb.hi[k] - cb.lo[k] > cb.hi[ax] - cb.lo[ax]) ax = k;
 			mid = lo + n / 2;
-			std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) { return items[a].c[ax] < items[b].c[ax]; });
+			std::nth_element(refs.begin() + lo, refs.begin() + mid, refs.begin() + hi,
+				[&](const Ref &a, const Ref &b) { return a.c[ax] != b.c[ax] ? a.c[ax] < b.c[ax] : a.item < b.item; });
 		}
 		// depth-first layout: this node, the left subtree's (mid-lo)-1 nodes, then the right subtree's
 		const int me = node_base, left_nodes = node_base + 1, right_nodes = node_base + (mid - lo);
@@ -650,9 +680,27 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 			return k == 0 ? Q : (k == 1 ? Q + d3(q + 3) : Q + d3(q + 6));
 		};
 		std::vector<EdgeUse> edges((size_t)nt * 3);
-		for (int t = 0; t < nt; ++t)
-			for (int k = 0; k < 3; ++k) edges[3 * (size_t)t + k] = { EHash()(ekey(vert(t, (k + 1) % 3), vert(t, (k + 2) % 3))), t, k };
-		std::sort(edges.begin(), edges.end(), [](const EdgeUse &a, const EdgeUse &b) { return a.h != b.h ? a.h < b.h : (a.tri != b.tri ? a.tri < b.tri : a.opp < b.opp); });
+		parallel_chunks((size_t)nt, 4096, [&](size_t t0, size_t t1) {
+			for (size_t t = t0; t < t1; ++t)
+				for (int k = 0; k < 3; ++k) edges[3 * t + k] = { EHash()(ekey(vert((int)t, (k + 1) % 3), vert((int)t, (k + 2) % 3))), (int)t, k };
+		});
+		{  // sort by (hash, triangle, edge): scatter into 256 buckets on the top hash byte, then sort the buckets in parallel
+			const auto less = [](const EdgeUse &a, const EdgeUse &b) { return a.h != b.h ? a.h < b.h : (a.tri != b.tri ? a.tri < b.tri : a.opp < b.opp); };
+			if (edges.size() < 65536) std::sort(edges.begin(), edges.end(), less);
+			else {
+				size_t start[257] = { 0 };
+				for (const EdgeUse &e : edges) ++start[(e.h >> 56) + 1];
+				for (int b = 0; b < 256; ++b) start[b + 1] += start[b];
+				std::vector<EdgeUse> tmp(edges.size());
+				size_t fill[256];
+				std::memcpy(fill, start, sizeof fill);
+				for (const EdgeUse &e : edges) tmp[fill[e.h >> 56]++] = e;
+				edges.swap(tmp);
+				parallel_chunks(256, 1, [&](size_t b0, size_t b1) {
+					for (size_t b = b0; b < b1; ++b) std::sort(edges.begin() + start[b], edges.begin() + start[b + 1], less);
+				});
+			}
+		}
 		// runs of equal hash = candidate shared edges; every (triangle, edge) remembers its run, lone edges get none
 		struct Range { int first, second; };
 		std::vector<Range> run_of((size_t)nt * 3, Range{ 0, 0 });
