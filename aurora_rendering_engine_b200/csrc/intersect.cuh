@@ -196,14 +196,26 @@ __device__ __forceinline__ void trav_set(int x, int &node, int &pend) {
 	if (x < 0) { pend = x; node = -1; }
 	else node = x;
 }
+// BRANCHY selects the formulation of the continuation logic (measured, profiles/r01_scenes.md): plain branches win in
+// the high-occupancy 40-register build used for hierarchies that live in L2 (latency-bound, and the select-heavy
+// form spills), the branch-free form wins in the 80-register build used for L1-resident hierarchies (issue-bound).
+template <bool BRANCHY = false>
 __device__ __forceinline__ bool trav_pop(int &sp, const int *stack, int &node, int &pend) {
-	if (sp == 0) { node = -1; return false; }
-	trav_set(stack[--sp], node, pend);
-	return true;
+	if (BRANCHY) {
+		if (sp == 0) { node = -1; return false; }
+		trav_set(stack[--sp], node, pend);
+		return true;
+	}
+	const bool has = sp > 0;
+	int x = 0;
+	if (has) x = stack[--sp];
+	pend = (has & (x < 0)) ? x : 0;
+	node = (has & (x >= 0)) ? x : -1;
+	return has;
 }
 // Visit inner node `node`: slab-test both children, continue with the nearer one that is hit, push the farther.
 // Returns false when nothing is left to do.
-template <bool COUNT>
+template <bool COUNT, bool BRANCHY = false>
 __device__ __forceinline__ bool bvh_visit(const DevScene &sc, float tmin, const RaySlopes &rs, int &node, int &pend, int &sp, int *stack, const Hit &h, TravCounters *cnt) {
 	const BvhNode *n = sc.nodes + node;
 	const float4 b0 = ldg4(&n->b0), b1 = ldg4(&n->b1), b2 = ldg4(&n->b2);
@@ -218,17 +230,34 @@ __device__ __forceinline__ bool bvh_visit(const DevScene &sc, float tmin, const 
 	const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
 	const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
 	const bool hit0 = t0n <= t0f, hit1 = t1n <= t1f;
-	if (hit0 && hit1) {
-		const bool near0 = t0n <= t1n;
-		if (sp < ARE_BVH_STACK) stack[sp++] = near0 ? ch.y : ch.x;
-		trav_set(near0 ? ch.x : ch.y, node, pend);
-		return true;
+	// Branch-free continuation (the three outcomes — both / one / none — are otherwise three divergent paths run by 4-6
+	// lanes each, ~30 % of the warp instructions of a traversal-bound launch): push the farther child when both are
+	// hit, continue with the nearer hit child, else pop.  Short predicated bodies, one local store / load at most.
+	if (BRANCHY) {
+		if (hit0 && hit1) {
+			const bool near0 = t0n <= t1n;
+			if (sp < ARE_BVH_STACK) stack[sp++] = near0 ? ch.y : ch.x;
+			trav_set(near0 ? ch.x : ch.y, node, pend);
+			return true;
+		}
+		if (hit0 || hit1) {
+			trav_set(hit0 ? ch.x : ch.y, node, pend);
+			return true;
+		}
+		return trav_pop<true>(sp, stack, node, pend);
 	}
-	if (hit0 || hit1) {
-		trav_set(hit0 ? ch.x : ch.y, node, pend);
-		return true;
-	}
-	return trav_pop(sp, stack, node, pend);
+	const bool both = hit0 & hit1, any = hit0 | hit1;
+	const bool near0 = t0n <= t1n;
+	const int farc = near0 ? ch.y : ch.x;
+	const int first = (hit0 & (near0 | !hit1)) ? ch.x : ch.y;
+	if (both & (sp < ARE_BVH_STACK)) stack[sp++] = farc;
+	const bool pop = !any & (sp > 0);
+	int x = first;
+	if (pop) x = stack[--sp];
+	const bool alive = any | pop;
+	pend = (alive & (x < 0)) ? x : 0;  // a leaf reference waits in `pend` for the leaf phase
+	node = (alive & (x >= 0)) ? x : -1;
+	return alive;
 }
 
 // Whole traversal in one go (per-ray harness).

@@ -160,17 +160,19 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 				const RaySlopes rs = ray_slopes(o, d);
 				while (true) {
 					// node phase: every traversing lane that has no leaf waiting visits one inner node
-					if (trav && pend == 0) trav = bvh_visit<COUNT>(A.sc, A.tmin, rs, node, pend, sp, stack, h, &tc);
-					// leaf phase, postponed until LEAF_MIN_LANES lanes hold a leaf (or nobody can do anything else): the
-					// primitive tests then run with many lanes instead of one or two
-					const unsigned m_leaf = __ballot_sync(full, trav && pend != 0);
-					const unsigned m_node = __ballot_sync(full, trav && pend == 0);
-					if (m_leaf != 0u && (__popc(m_leaf) >= LEAF_MIN_LANES || m_node == 0u)) {
-						if (trav && pend != 0) {
-							test_leaf<COUNT>(A.sc, pend, o, d, A.tmin, h, &tc);
-							pend = 0;
-							trav = trav_pop(sp, stack, node, pend);
-						}
+					if (trav && pend == 0) trav = bvh_visit<COUNT, BIG>(A.sc, A.tmin, rs, node, pend, sp, stack, h, &tc);
+					// leaf phase.  LEAF_MIN_LANES > 1 postpones it until that many lanes hold a leaf (or nobody can do anything
+					// else) so the primitive tests run with more lanes; measured best is 1, which needs no votes at all.
+					bool leaf_now = true;
+					if (LEAF_MIN_LANES > 1) {
+						const unsigned m_leaf = __ballot_sync(full, trav && pend != 0);
+						const unsigned m_node = __ballot_sync(full, trav && pend == 0);
+						leaf_now = m_leaf != 0u && (__popc(m_leaf) >= LEAF_MIN_LANES || m_node == 0u);
+					}
+					if (leaf_now && trav && pend != 0) {
+						test_leaf<COUNT>(A.sc, pend, o, d, A.tmin, h, &tc);
+						pend = 0;
+						trav = trav_pop<BIG>(sp, stack, node, pend);
 					}
 					const int n_trav = __popc(__ballot_sync(full, trav));
 					if (n_trav == 0 || (n_trav < TRAV_MIN_LANES && n_trav < n_rays)) break;
