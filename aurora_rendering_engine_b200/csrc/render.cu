@@ -67,6 +67,9 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #ifndef TRAV_MIN_LANES
 #define TRAV_MIN_LANES 6   // BVH slices end when fewer lanes than this are still traversing and others are waiting
 #endif
+#ifndef TRAV_STEPS_PER_VOTE
+#define TRAV_STEPS_PER_VOTE 4  // measured 1 / 2 / 4 / 8: RTIOW 3498 / 3582 / 3596 / 3417, 1 M primitives 584 / 591 / 602 / 607 Msamples/s
+#endif
 #ifndef LEAF_MIN_LANES
 #define LEAF_MIN_LANES 1   // leaf tests run once this many lanes hold one (measured: 1 is best on RTIOW and on the 1 M-primitive stress scene)
 #endif
@@ -159,20 +162,23 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 			if (__any_sync(full, trav)) {
 				const RaySlopes rs = ray_slopes(o, d);
 				while (true) {
-					// node phase: every traversing lane that has no leaf waiting visits one inner node
-					if (trav && pend == 0) trav = bvh_visit<COUNT, BIG>(A.sc, A.tmin, rs, node, pend, sp, stack, h, &tc);
-					// leaf phase.  LEAF_MIN_LANES > 1 postpones it until that many lanes hold a leaf (or nobody can do anything
-					// else) so the primitive tests run with more lanes; measured best is 1, which needs no votes at all.
-					bool leaf_now = true;
-					if (LEAF_MIN_LANES > 1) {
-						const unsigned m_leaf = __ballot_sync(full, trav && pend != 0);
-						const unsigned m_node = __ballot_sync(full, trav && pend == 0);
-						leaf_now = m_leaf != 0u && (__popc(m_leaf) >= LEAF_MIN_LANES || m_node == 0u);
-					}
-					if (leaf_now && trav && pend != 0) {
-						test_leaf<COUNT>(A.sc, pend, o, d, A.tmin, h, &tc);
-						pend = 0;
-						trav = trav_pop<BIG>(sp, stack, node, pend);
+#pragma unroll 1
+					for (int rep = 0; rep < TRAV_STEPS_PER_VOTE; ++rep) {  // several steps between the warp votes that decide the end of the slice
+						// node phase: every traversing lane that has no leaf waiting visits one inner node
+						if (trav && pend == 0) trav = bvh_visit<COUNT, BIG>(A.sc, A.tmin, rs, node, pend, sp, stack, h, &tc);
+						// leaf phase.  LEAF_MIN_LANES > 1 postpones it until that many lanes hold a leaf (or nobody can do anything
+						// else) so the primitive tests run with more lanes; measured best is 1, which needs no votes at all.
+						bool leaf_now = true;
+						if (LEAF_MIN_LANES > 1) {
+							const unsigned m_leaf = __ballot_sync(full, trav && pend != 0);
+							const unsigned m_node = __ballot_sync(full, trav && pend == 0);
+							leaf_now = m_leaf != 0u && (__popc(m_leaf) >= LEAF_MIN_LANES || m_node == 0u);
+						}
+						if (leaf_now && trav && pend != 0) {
+							test_leaf<COUNT>(A.sc, pend, o, d, A.tmin, h, &tc);
+							pend = 0;
+							trav = trav_pop<BIG>(sp, stack, node, pend);
+						}
 					}
 					const int n_trav = __popc(__ballot_sync(full, trav));
 					if (n_trav == 0 || (n_trav < TRAV_MIN_LANES && n_trav < n_rays)) break;
