@@ -545,7 +545,9 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 		std::memset(stats, 0, sizeof *stats);
 		stats->samples = (uint64_t)p->width * p->height * p->sample_count;
 		stats->rays = c[CNT_RAYS];
-		if (mode != 0) {
+		if (p->integrator == ARE_INTEGRATOR_RT_AO) {  // rt.cpp's linear scan: every ray tests every triangle (rt.cpp:209-218)
+			stats->tri_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.n_tri;
+		} else if (mode != 0) {
 			stats->node_visits = c[CNT_NODES]; stats->quad_tests = c[CNT_QUADS]; stats->tri_tests = c[CNT_TRIS]; stats->sphere_tests = c[CNT_SPHERES];
 			stats->box_tests = c[CNT_BOXES];
 		} else {  // brute force: every ray tests every hot primitive — exact by construction
