@@ -66,9 +66,9 @@ struct TextureRec {
 	float pf[8];
 };
 
-// BVH2 node, 64 B, both children's boxes inline (one node fetch = 4 x LDG.128):
-//   b0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   b1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
-//   b2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
+// BVH2 node, 64 B, both children's boxes inline (one node fetch = 4 x LDG.128), each axis as (centre, half-extent):
+//   b0 = (c0.cx, c0.hx, c0.cy, c0.hy)   b1 = (c1.cx, c1.hx, c1.cy, c1.hy)   b2 = (c0.cz, c0.hz, c1.cz, c1.hz)
+//   slab distances = centre*inv -/+ half*|inv|: FMA-pipe work only, no per-axis min/max on the (binding) ALU pipe
 //   child[i] >= 0: inner node index.  child[i] < 0: leaf, first hot primitive = ~child[i],
 //   meta[i] = nq | nt << 8 | ns << 16 | nb << 24  (boxes first — two slots each — then quads+fused pairs,
 //   triangles, spheres)

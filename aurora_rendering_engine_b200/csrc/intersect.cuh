@@ -157,6 +157,7 @@ struct TravCounters {
 // maths never sees 0*inf) and origin * reciprocal.
 struct RaySlopes {
 	float idx, idy, idz, oxi, oyi, ozi;
+	float ax, ay, az;  // |reciprocal direction|
 };
 __device__ __forceinline__ RaySlopes ray_slopes(V3<float> o, V3<float> d) {
 	const float big = 1e30f;
@@ -165,6 +166,7 @@ __device__ __forceinline__ RaySlopes ray_slopes(V3<float> o, V3<float> d) {
 	r.idy = fabsf(d.y) > 1e-30f ? 1.0f / d.y : (d.y < 0 ? -big : big);
 	r.idz = fabsf(d.z) > 1e-30f ? 1.0f / d.z : (d.z < 0 ? -big : big);
 	r.oxi = o.x * r.idx; r.oyi = o.y * r.idy; r.ozi = o.z * r.idz;
+	r.ax = fabsf(r.idx); r.ay = fabsf(r.idy); r.az = fabsf(r.idz);
 	return r;
 }
 
@@ -221,14 +223,13 @@ __device__ __forceinline__ bool bvh_visit(const DevScene &sc, float tmin, const 
 	const float4 b0 = ldg4(&n->b0), b1 = ldg4(&n->b1), b2 = ldg4(&n->b2);
 	const int2 ch = __ldg(reinterpret_cast<const int2 *>(&n->child[0]));
 	if (COUNT) cnt->nodes++;
-	const float c0lox = fmaf(b0.x, rs.idx, -rs.oxi), c0hix = fmaf(b0.y, rs.idx, -rs.oxi), c0loy = fmaf(b0.z, rs.idy, -rs.oyi), c0hiy = fmaf(b0.w, rs.idy, -rs.oyi);
-	const float c0loz = fmaf(b2.x, rs.idz, -rs.ozi), c0hiz = fmaf(b2.y, rs.idz, -rs.ozi);
-	const float c1lox = fmaf(b1.x, rs.idx, -rs.oxi), c1hix = fmaf(b1.y, rs.idx, -rs.oxi), c1loy = fmaf(b1.z, rs.idy, -rs.oyi), c1hiy = fmaf(b1.w, rs.idy, -rs.oyi);
-	const float c1loz = fmaf(b2.z, rs.idz, -rs.ozi), c1hiz = fmaf(b2.w, rs.idz, -rs.ozi);
-	const float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin));
-	const float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), h.t));
-	const float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
-	const float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), h.t));
+	// per axis: distance to the slab centre, then -/+ the half-width scaled by |1/d|: near and far are ordered by construction
+	const float c0x = fmaf(b0.x, rs.idx, -rs.oxi), c0y = fmaf(b0.z, rs.idy, -rs.oyi), c0z = fmaf(b2.x, rs.idz, -rs.ozi);
+	const float c1x = fmaf(b1.x, rs.idx, -rs.oxi), c1y = fmaf(b1.z, rs.idy, -rs.oyi), c1z = fmaf(b2.z, rs.idz, -rs.ozi);
+	const float t0n = fmaxf(fmaxf(fmaf(-b0.y, rs.ax, c0x), fmaf(-b0.w, rs.ay, c0y)), fmaxf(fmaf(-b2.y, rs.az, c0z), tmin));
+	const float t0f = fminf(fminf(fmaf(b0.y, rs.ax, c0x), fmaf(b0.w, rs.ay, c0y)), fminf(fmaf(b2.y, rs.az, c0z), h.t));
+	const float t1n = fmaxf(fmaxf(fmaf(-b1.y, rs.ax, c1x), fmaf(-b1.w, rs.ay, c1y)), fmaxf(fmaf(-b2.w, rs.az, c1z), tmin));
+	const float t1f = fminf(fminf(fmaf(b1.y, rs.ax, c1x), fmaf(b1.w, rs.ay, c1y)), fminf(fmaf(b2.w, rs.az, c1z), h.t));
 	const bool hit0 = t0n <= t0f, hit1 = t1n <= t1f;
 	// Branch-free continuation (the three outcomes — both / one / none — are otherwise three divergent paths run by 4-6
 	// lanes each, ~30 % of the warp instructions of a traversal-bound launch): push the farther child when both are

@@ -177,18 +177,21 @@ struct Builder {
 		if (hw > 1) spawn_depth += 2;  // 4 tasks per core: SAH splits are uneven
 		else spawn_depth = 0;
 	}
-	static void put_box(f4 &bxy, float &zlo, float &zhi, const Box &b) {
-		// pad outwards: fp32 rounding of the bounds and of the slab arithmetic must never cut a primitive off
-		float lo[3], hi[3];
+	// Child boxes are stored as (centre, half-extent) per axis: the slab distances are then centre*inv -/+ half*|inv|,
+	// three FMA-pipe operations per axis and no per-axis min/max (the ALU pipe is what binds the traversal kernels).
+	static void put_box(f4 &bxy, float &zc, float &zh, const Box &b) {
+		float c[3], h[3];
 		for (int k = 0; k < 3; ++k) {
-			double m = std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
-			double pad = 1e-5 * (m + (b.hi[k] - b.lo[k])) + 1e-7;
-			lo[k] = (float)(b.lo[k] - pad);
-			hi[k] = (float)(b.hi[k] + pad);
+			// pad outwards: fp32 rounding of the bounds and of the slab arithmetic must never cut a primitive off
+			const double m = std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k]));
+			const double pad = 1e-5 * (m + (b.hi[k] - b.lo[k])) + 1e-7;
+			const double lo = b.lo[k] - pad, hi = b.hi[k] + pad;
+			c[k] = (float)(0.5 * (lo + hi));
+			h[k] = std::nextafter((float)std::max(hi - (double)c[k], (double)c[k] - lo), std::numeric_limits<float>::infinity());
 		}
-		bxy = { lo[0], hi[0], lo[1], hi[1] };
-		zlo = lo[2];
-		zhi = hi[2];
+		bxy = { c[0], h[0], c[1], h[1] };
+		zc = c[2];
+		zh = h[2];
 	}
 	int slots_of(int lo, int hi) const {
 		if (!any_box) return hi - lo;
@@ -323,8 +326,11 @@ struct WideBuilder {
 		Entry e;
 		e.ref = n.child[which];
 		const f4 &bxy = which ? n.b1 : n.b0;
-		e.lo[0] = bxy.x; e.hi[0] = bxy.y; e.lo[1] = bxy.z; e.hi[1] = bxy.w;
-		e.lo[2] = which ? n.b2.z : n.b2.x; e.hi[2] = which ? n.b2.w : n.b2.y;
+		const float c[3] = { bxy.x, bxy.z, which ? n.b2.z : n.b2.x }, h[3] = { bxy.y, bxy.w, which ? n.b2.w : n.b2.y };
+		for (int k = 0; k < 3; ++k) {  // (centre, half-extent) -> conservative bounds
+			e.lo[k] = std::nextafter(c[k] - h[k], -std::numeric_limits<float>::infinity());
+			e.hi[k] = std::nextafter(c[k] + h[k], std::numeric_limits<float>::infinity());
+		}
 		return e;
 	}
 	static double area(const Entry &e) {
