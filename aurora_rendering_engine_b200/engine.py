@@ -41,6 +41,43 @@ def chunk_ranges(begin: int, count: int, chunk: int):
     return out
 
 
+def merge_ranges(ranges):
+    """Union of half-open sample ranges given as (begin, count), sorted and coalesced."""
+    iv = sorted((int(b), int(b) + int(c)) for b, c in ranges if c > 0)
+    out = []
+    for b, e in iv:
+        if out and b <= out[-1][1]:
+            out[-1][1] = max(out[-1][1], e)
+        else:
+            out.append([b, e])
+    return [(b, e - b) for b, e in out]
+
+
+def missing_ranges(begin: int, count: int, done):
+    """Sample ranges of [begin, begin+count) NOT covered by ``done`` — what a resumed job, or the rank that takes over
+    from a failed one, still has to render.  The Philox counter is the GLOBAL sample index, so any rank can render any
+    range and the result is the same set of samples."""
+    out, s, end = [], begin, begin + count
+    for b, c in merge_ranges(done):
+        e = b + c
+        if e <= s:
+            continue
+        if b >= end:
+            break
+        if b > s:
+            out.append((s, b - s))
+        s = max(s, e)
+    if s < end:
+        out.append((s, end - s))
+    return out
+
+
+def overlapping(ranges) -> bool:
+    """True when two ranges share a sample (a double-counted sample would bias the image)."""
+    iv = sorted((int(b), int(b) + int(c)) for b, c in ranges if c > 0)
+    return any(iv[i][0] < iv[i - 1][1] for i in range(1, len(iv)))
+
+
 def dist_env():
     """(rank, local_rank, world) from the torchrun environment (1-process defaults)."""
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -80,6 +117,7 @@ class RenderJob:
         self.traversal = traversal
         self.accum = torch.zeros((scene_desc.height, scene_desc.width, 3), dtype=torch.float32, device=f"cuda:{device_index}")
         self.result = JobResult(self.accum)
+        self.done = []  # (begin, count) sample ranges already in the accumulator
 
     def params(self, begin, count, **over):
         return capi.make_params(**self.sc.params_args(sample_begin=begin, sample_count=count, traversal=self.traversal, **over))
@@ -88,6 +126,7 @@ class RenderJob:
         st = self.ctx.render_device(self.cam, self.params(begin, count, **over), self.accum.data_ptr(), want_stats=want_stats)
         self.result.launches += 1
         self.result.samples += self.sc.width * self.sc.height * count
+        self.done.append((int(begin), int(count)))
         if st is not None:
             self.result.rays += st.rays
             self.result.kernel_ms += st.kernel_ms
@@ -105,12 +144,37 @@ class RenderJob:
         self.ctx.write_ppm(path, rgb8)
         return rgb8
 
+    # -- checkpoint / resume: the accumulator holds plain sample sums and the RNG is counter-based, so a job is fully
+    #    described by (accumulator, which global sample ranges are in it)
+    def signature(self) -> str:
+        sc = self.sc
+        return f"{sc.name}|{sc.width}x{sc.height}|{sc.num_prims}|depth{sc.max_depth}|integrator{sc.integrator}"
+
+    def save_checkpoint(self, path: str):
+        self.torch.cuda.current_stream().synchronize()
+        tmp = path + ".tmp.npz"
+        np.savez(tmp, accum=self.accum.cpu().numpy(), done=np.array(merge_ranges(self.done), dtype=np.int64).reshape(-1, 2),
+                 signature=np.array(self.signature()))
+        os.replace(tmp, path)
+
+    def load_checkpoint(self, path: str):
+        """Restore accumulator + progress; raises ValueError for a checkpoint of another job."""
+        ck = np.load(path)
+        if str(ck["signature"]) != self.signature():
+            raise ValueError(f"checkpoint belongs to {ck['signature']}, this job is {self.signature()}")
+        self.accum.copy_(self.torch.from_numpy(ck["accum"]))
+        self.done = [(int(b), int(c)) for b, c in ck["done"]]
+        return self.done
+
     def close(self):
         self.ctx.close()
 
 
-def render_job(scene_desc, spp: int, chunk: int = 64, traversal: int = 0, want_stats: bool = False):
-    """Whole job on this rank (call under torchrun for N GPUs): shard, render in chunks, reduce. Returns RenderJob."""
+def render_job(scene_desc, spp: int, chunk: int = 64, traversal: int = 0, want_stats: bool = False, checkpoint: str | None = None,
+               checkpoint_every: int = 0):
+    """Whole job on this rank (call under torchrun for N GPUs): shard, render in chunks, reduce. Returns RenderJob.
+    With ``checkpoint`` (a path; ``{rank}`` is substituted) the rank resumes from that file when it exists and rewrites
+    it every ``checkpoint_every`` launches (0 = only at the end of its shard)."""
     import torch
     rank, local_rank, world = dist_env()
     if world > 1:
@@ -119,7 +183,17 @@ def render_job(scene_desc, spp: int, chunk: int = 64, traversal: int = 0, want_s
             dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     job = RenderJob(scene_desc, local_rank, traversal)
     begin, count = shard_samples(spp, world, rank)
-    for b, c in chunk_ranges(begin, count, chunk):
-        job.render_range(b, c, want_stats=want_stats)
+    ck = checkpoint.format(rank=rank) if checkpoint else None
+    if ck and os.path.exists(ck):
+        job.load_checkpoint(ck)
+    n = 0
+    for mb, mc in missing_ranges(begin, count, job.done):
+        for b, c in chunk_ranges(mb, mc, chunk):
+            job.render_range(b, c, want_stats=want_stats)
+            n += 1
+            if ck and checkpoint_every and n % checkpoint_every == 0:
+                job.save_checkpoint(ck)
+    if ck:
+        job.save_checkpoint(ck)
     job.finish(world)
     return job

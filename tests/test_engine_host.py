@@ -130,3 +130,27 @@ def test_parallel_bvh_build_is_independent_of_thread_count(lib, monkeypatch):
     box = scenes.cornell_box()
     r = capi.compile_probe(*(np.stack([t[k] for t in box.tris]) for k in range(3)))
     assert (r["fused_pairs"], r["boxes"]) == (18, 3)
+
+
+def test_resume_and_takeover_bookkeeping():
+    """Checkpoint / failed-rank recovery is pure interval arithmetic on GLOBAL sample indices."""
+    from aurora_rendering_engine_b200 import engine
+    assert engine.merge_ranges([(8, 4), (0, 4), (4, 4), (20, 2), (21, 3)]) == [(0, 12), (20, 4)]
+    assert engine.missing_ranges(0, 16, []) == [(0, 16)]
+    assert engine.missing_ranges(0, 16, [(0, 16)]) == []
+    assert engine.missing_ranges(4, 10, [(0, 6), (8, 2), (30, 5)]) == [(6, 2), (10, 4)]
+    assert engine.missing_ranges(0, 8, [(2, 2), (2, 3)]) == [(0, 2), (5, 3)]
+    assert not engine.overlapping([(0, 4), (4, 4)]) and engine.overlapping([(0, 5), (4, 4)])
+    # 4 ranks render 1000 spp; rank 2 dies after 100 of its samples: what is missing is exactly the rest of its shard,
+    # and re-sharding it over the 3 survivors covers it without overlap
+    spp, world = 1000, 4
+    shards = [engine.shard_samples(spp, world, r) for r in range(world)]
+    done = [s for r, s in enumerate(shards) if r != 2] + [(shards[2][0], 100)]
+    miss = engine.missing_ranges(0, spp, done)
+    assert miss == [(shards[2][0] + 100, shards[2][1] - 100)]
+    redo = []
+    for mb, mc in miss:
+        for r in range(3):
+            b, c = engine.shard_samples(mc, 3, r)
+            redo.append((mb + b, c))
+    assert not engine.overlapping(done + redo) and engine.merge_ranges(done + redo) == [(0, spp)]
