@@ -14,6 +14,11 @@
 #include <string>
 #include <vector>
 
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
+#define ARE_NVTX 1
+#endif
+
 #include "../../include/are_cuda.h"
 #include "dev_types.h"
 #include "kernels.h"
@@ -55,6 +60,15 @@ int fail(are_cuda_ctx *c, int status, const std::string &msg) {
 		cudaError_t e_ = (call);                                                                              \
 		if (e_ != cudaSuccess) return fail(ctx, ARE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
 	} while (0)
+
+struct Range {  // NVTX range around one C-ABI call (tracing hooks)
+#ifdef ARE_NVTX
+	explicit Range(const char *name) { nvtxRangePushA(name); }
+	~Range() { nvtxRangePop(); }
+#else
+	explicit Range(const char *) {}
+#endif
+};
 
 struct Bind {  // make the context's device current for the duration of a call
 	int prev = -1;
@@ -308,6 +322,7 @@ int are_cuda_clear(are_cuda_ctx *ctx) {
 int are_cuda_num_primitives(are_cuda_ctx *ctx) { return ctx ? (int)ctx->scene.prims.size() : ARE_ERR_INVALID_ARGUMENT; }
 
 int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
+	Range nvtx_range("are_cuda_commit (scene compile + upload)");
 	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
 	Bind b(ctx);
 	CK(cudaStreamSynchronize(ctx->stream));
@@ -389,6 +404,7 @@ int are_cuda_compile_probe_digest(int n_tri, const double *Q, const double *u, c
 // ---- per-ray harness -------------------------------------------------------------------------------------
 int are_cuda_hit_batch(are_cuda_ctx *ctx, int n, const double *ray_Q, const double *ray_D, double t_min, int precision, int traversal,
 	int *prim, double *t, double *P, double *N, double *uv) {
+	Range nvtx_range("are_cuda_hit_batch");
 	int st = need_commit(ctx);
 	if (st) return st;
 	if (n < 0 || (n && (!ray_Q || !ray_D))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null ray arrays");
@@ -493,6 +509,7 @@ int are_cuda_philox_batch(are_cuda_ctx *ctx, int n, uint64_t seed, const uint32_
 
 // ---- rendering -------------------------------------------------------------------------------------------
 int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_render_params *p, float *accum, are_render_stats *stats, int count_tests) {
+	Range nvtx_range("are_cuda_render_device");
 	int st = need_commit(ctx);
 	if (st) return st;
 	if (!cam || !p || !accum) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
@@ -620,6 +637,7 @@ int are_cuda_render(are_cuda_ctx *ctx, const are_camera *cam, const are_render_p
 }
 
 int are_cuda_tonemap(are_cuda_ctx *ctx, const float *accum, int width, int height, double inv_spp, int encoder, uint8_t *out_host) {
+	Range nvtx_range("are_cuda_tonemap");
 	if (!ctx || !accum || !out_host || width <= 0 || height <= 0) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "bad argument");
 	if (encoder < ARE_ENCODE_GAMMA22_TRUNC || encoder > ARE_ENCODE_SQRT_TRUNC) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown encoder");
 	Bind b(ctx);
@@ -674,6 +692,7 @@ static bool paste_homography(const double sxy[4][2], const double dxy[4][2], dou
 }
 
 int are_cuda_texture_paste(are_cuda_ctx *ctx, double *dst_rgb, int dst_w, int dst_h, const double *src_rgb, int src_w, int src_h, const int corners[8]) {
+	Range nvtx_range("are_cuda_texture_paste");
 	if (!ctx || !corners) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
 	if (!dst_rgb || dst_w <= 0 || dst_h <= 0) return fail(ctx, ARE_ERR_RUNTIME, "Texture is not initialized.");  // texture.cpp:90-92
 	if (src_w <= 0 || src_h <= 0 || !src_rgb) return ARE_OK;                                                       // texture.cpp:93-95
@@ -742,6 +761,7 @@ static double ms_since(const std::chrono::steady_clock::time_point &t0) {
 
 int are_cuda_patch_render(are_cuda_ctx *ctx, const are_patch_scene *scene, const double origin[3], const double viewport_P[18],
 	const double viewport_UV[12], int width, int height, const are_patch_config *cfg, double *out_rgb, uint8_t *out_rgb8, are_patch_stats *stats) {
+	Range nvtx_range("are_cuda_patch_render (plan + levels + camera)");
 	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
 	if (const char *why = patch_check(scene, cfg)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, why);
 	if (!origin || !viewport_P || !viewport_UV || width < 2 || height < 2) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "camera arguments missing or image smaller than 2x2");
