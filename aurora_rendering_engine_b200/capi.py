@@ -139,6 +139,9 @@ SIGNATURES = {
     "are_cuda_scatter_batch": (C.c_int, [_vp, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _ip]),
     "are_cuda_texture_batch": (C.c_int, [_vp, C.c_int, _ip, _dp, _dp, C.c_int, _dp]),
     "are_cuda_camera_rays": (C.c_int, [_vp, C.POINTER(Camera), C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, C.c_int, _dp, _dp]),
+    "are_cuda_plane_batch": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp, _ip, _dp]),
+    "are_cuda_point_in_batch": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, _dp, _ip]),
+    "are_cuda_material_reflect_batch": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _ip, _dp]),
     "are_cuda_philox_batch": (C.c_int, [_vp, C.c_int, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "are_cuda_render_device": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _vp, C.POINTER(RenderStats), C.c_int]),
     "are_cuda_render": (C.c_int, [_vp, C.POINTER(Camera), C.POINTER(RenderParams), _fp, C.POINTER(RenderStats)]),
@@ -339,6 +342,29 @@ class Context:
         self._ck(self.lib.are_cuda_camera_rays(self.h, C.byref(cam), int(width), int(height), n, _ptr(px, _ip), _ptr(py, _ip),
                                                _ptr(rnd), int(precision), _ptr(Q), _ptr(D)))
         return Q, D
+
+    def plane_batch(self, plane4, Q, D):
+        """are::Plane::intersect_ray for n (plane, ray) pairs -> (hit int32[n], P float64[n,3])."""
+        plane4, Q, D = _d(plane4), _d(Q), _d(D)
+        n = len(Q)
+        hit, P = np.zeros(n, np.int32), np.zeros((n, 3))
+        self._ck(self.lib.are_cuda_plane_batch(self.h, n, _ptr(plane4), _ptr(Q), _ptr(D), _ptr(hit, _ip), _ptr(P)))
+        return hit, P
+
+    def point_in_batch(self, Q, u, v, pts):
+        """are::Triangle(Q,u,v).point_in for n points -> int32[n]."""
+        Q, u, v, pts = _d(Q), _d(u), _d(v), _d(pts)
+        inside = np.zeros(len(pts), np.int32)
+        self._ck(self.lib.are_cuda_point_in_batch(self.h, _ptr(Q), _ptr(u), _ptr(v), len(pts), _ptr(pts), _ptr(inside, _ip)))
+        return inside
+
+    def material_reflect_batch(self, kind, plane4, origin):
+        """are::Material::reflect (kind 0 Diffuse, 1 Reflective) -> (ok int32[n], new_origin float64[n,3])."""
+        plane4, origin = _d(plane4), _d(origin)
+        n = len(origin)
+        ok, out = np.zeros(n, np.int32), np.zeros((n, 3))
+        self._ck(self.lib.are_cuda_material_reflect_batch(self.h, int(kind), n, _ptr(plane4), _ptr(origin), _ptr(ok, _ip), _ptr(out)))
+        return ok, out
 
     def philox_batch(self, seed, counters):
         c = np.ascontiguousarray(counters, np.uint32)

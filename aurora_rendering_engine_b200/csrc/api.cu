@@ -493,6 +493,60 @@ int are_cuda_camera_rays(are_cuda_ctx *ctx, const are_camera *cam, int width, in
 	return ARE_OK;
 }
 
+int are_cuda_plane_batch(are_cuda_ctx *ctx, int n, const double *plane4, const double *ray_Q, const double *ray_D, int *hit, double *P) {
+	if (!ctx || n < 0 || (n && (!plane4 || !ray_Q || !ray_D))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	if (n == 0) return ARE_OK;
+	Bind b(ctx);
+	Tmp dpl, dQ, dD, dhit, dP;
+	TMP_IN(dpl, plane4, (size_t)n * 4 * sizeof(double));
+	TMP_IN(dQ, ray_Q, (size_t)n * 3 * sizeof(double));
+	TMP_IN(dD, ray_D, (size_t)n * 3 * sizeof(double));
+	TMP_OUT(dhit, (size_t)n * sizeof(int));
+	TMP_OUT(dP, (size_t)n * 3 * sizeof(double));
+	launch_plane64(n, dpl.as<double>(), dQ.as<double>(), dD.as<double>(), dhit.as<int>(), dP.as<double>(), ctx->stream);
+	CK(cudaGetLastError());
+	GET_OUT(hit, dhit, (size_t)n * sizeof(int));
+	GET_OUT(P, dP, (size_t)n * 3 * sizeof(double));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
+int are_cuda_point_in_batch(are_cuda_ctx *ctx, const double Q[3], const double u[3], const double v[3], int n, const double *points, int *inside) {
+	if (!ctx || n < 0 || !Q || !u || !v || (n && (!points || !inside))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	if (const char *why = validate_edges(u, v)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, why);  // are::Triangle's ctor checks
+	if (n == 0) return ARE_OK;
+	Bind b(ctx);
+	double tri9[9];
+	std::memcpy(tri9, Q, 24); std::memcpy(tri9 + 3, u, 24); std::memcpy(tri9 + 6, v, 24);
+	Tmp dtri, dpts, din;
+	TMP_IN(dtri, tri9, sizeof tri9);
+	TMP_IN(dpts, points, (size_t)n * 3 * sizeof(double));
+	TMP_OUT(din, (size_t)n * sizeof(int));
+	launch_point_in64(n, dtri.as<double>(), dpts.as<double>(), din.as<int>(), ctx->stream);
+	CK(cudaGetLastError());
+	GET_OUT(inside, din, (size_t)n * sizeof(int));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
+int are_cuda_material_reflect_batch(are_cuda_ctx *ctx, int kind, int n, const double *plane4, const double *origin, int *ok, double *new_origin) {
+	if (!ctx || n < 0 || (n && (!plane4 || !origin))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	if (kind != ARE_MAT_DIFFUSE && kind != ARE_MAT_REFLECTIVE) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "the reference has two materials: Diffuse and Reflective");
+	if (n == 0) return ARE_OK;
+	Bind b(ctx);
+	Tmp dpl, dorg, dok, dout;
+	TMP_IN(dpl, plane4, (size_t)n * 4 * sizeof(double));
+	TMP_IN(dorg, origin, (size_t)n * 3 * sizeof(double));
+	TMP_OUT(dok, (size_t)n * sizeof(int));
+	TMP_OUT(dout, (size_t)n * 3 * sizeof(double));
+	launch_material_reflect64(kind, n, dpl.as<double>(), dorg.as<double>(), dok.as<int>(), dout.as<double>(), ctx->stream);
+	CK(cudaGetLastError());
+	GET_OUT(ok, dok, (size_t)n * sizeof(int));
+	GET_OUT(new_origin, dout, (size_t)n * 3 * sizeof(double));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return ARE_OK;
+}
+
 int are_cuda_philox_batch(are_cuda_ctx *ctx, int n, uint64_t seed, const uint32_t *counter, uint32_t *out) {
 	if (!ctx || n < 0 || (n && (!counter || !out))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
 	if (n == 0) return ARE_OK;

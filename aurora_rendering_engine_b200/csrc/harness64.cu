@@ -216,6 +216,73 @@ __global__ void k_paste(PasteArgs a) {
 	for (int k = 0; k < 3; ++k) out[k] = w00 * c00[k] + w10 * c10[k] + w01 * c01[k] + w11 * c11[k];
 }
 
+// ---- library routines of SURVEY §8a that are not on the render loop, as fp64 batches (bit-exact, -fmad=false) ----
+// are::Plane::intersect_ray, src/basic/plane.cpp:13-27 (the ray direction is normalised first, as are::Ray's ctor does)
+__global__ void k_plane64(int n, const double *__restrict__ plane4, const double *__restrict__ Q, const double *__restrict__ D, int *__restrict__ hit,
+	double *__restrict__ P) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const D3 pn = ld3<double>(plane4 + 4 * i), q = ld3<double>(Q + 3 * i), d = normalized(ld3<double>(D + 3 * i));
+	const double pd = plane4[4 * i + 3];
+	const double nan = nan_t<double>();
+	D3 x = mk<double>(nan, nan, nan);
+	int ok = 0;
+	const double denom = dot(pn, d);
+	if (!(fabs(denom) < LIB_EPS)) {
+		const double t = -(dot(pn, q) + pd) / denom;
+		if (!(t < LIB_EPS)) { x = q + t * d; ok = 1; }
+	}
+	hit[i] = ok;
+	st3(P + 3 * i, x);
+}
+// are::Triangle::point_in, src/object/triangle.cpp:49-79
+__global__ void k_point_in64(int n, const double *__restrict__ tri9, const double *__restrict__ pts, int *__restrict__ inside) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const D3 Q = ld3<double>(tri9), u = ld3<double>(tri9 + 3), v = ld3<double>(tri9 + 6), p = ld3<double>(pts + 3 * i);
+	const D3 v0 = v, v1 = u, v2 = p - Q;
+	const double d00 = dot(v0, v0), d01 = dot(v0, v1), d02 = dot(v0, v2), d11 = dot(v1, v1), d12 = dot(v1, v2);
+	double inv = d00 * d11 - d01 * d01;
+	int ok = 0;
+	if (!(fabs(inv) < LIB_EPS)) {
+		inv = 1.0 / inv;
+		const double alpha = (d11 * d02 - d01 * d12) * inv, beta = (d00 * d12 - d01 * d02) * inv;
+		ok = alpha >= -LIB_EPS && beta >= -LIB_EPS && alpha + beta <= 1.0 + LIB_EPS;
+	}
+	inside[i] = ok;
+}
+// are::Material::reflect: Diffuse declines (src/material/diffuse.cpp:5-7), Reflective mirrors the viewport origin across
+// the plane, o' = o - 2 (n.o + d)/|n|^2 n (src/material/reflective.cpp:9-26)
+__global__ void k_material_reflect64(int kind, int n, const double *__restrict__ plane4, const double *__restrict__ origin, int *__restrict__ ok,
+	double *__restrict__ out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double nan = nan_t<double>();
+	D3 o = mk<double>(nan, nan, nan);
+	int good = 0;
+	if (kind == MK_REFLECTIVE) {
+		const D3 pn = ld3<double>(plane4 + 4 * i), org = ld3<double>(origin + 3 * i);
+		const double denom = len2(pn);
+		if (!(denom < LIB_EPS)) {
+			const double numer = dot(pn, org) + plane4[4 * i + 3];
+			const double k = 2.0 * numer / denom;
+			o = org - k * pn;
+			good = 1;
+		}
+	}
+	ok[i] = good;
+	st3(out + 3 * i, o);
+}
+void launch_plane64(int n, const double *plane4, const double *Q, const double *D, int *hit, double *P, cudaStream_t s) {
+	if (n > 0) k_plane64<<<(n + 127) / 128, 128, 0, s>>>(n, plane4, Q, D, hit, P);
+}
+void launch_point_in64(int n, const double *tri9, const double *pts, int *inside, cudaStream_t s) {
+	if (n > 0) k_point_in64<<<(n + 127) / 128, 128, 0, s>>>(n, tri9, pts, inside);
+}
+void launch_material_reflect64(int kind, int n, const double *plane4, const double *origin, int *ok, double *out, cudaStream_t s) {
+	if (n > 0) k_material_reflect64<<<(n + 127) / 128, 128, 0, s>>>(kind, n, plane4, origin, ok, out);
+}
+
 void launch_paste(const PasteArgs &a, cudaStream_t s) {
 	if (a.x1 < a.x0 || a.y1 < a.y0) return;
 	dim3 block(32, 8), grid((a.x1 - a.x0 + 32) / 32, (a.y1 - a.y0 + 8) / 8);

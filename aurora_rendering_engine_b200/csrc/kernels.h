@@ -34,6 +34,11 @@ void launch_texture64(const DevScene &sc, int n, const int *tex, const double *u
 void launch_camera64(const CamBasis &cb, int W, int H, int n, const int *px, const int *py, const double *rnd, double *Q, double *D, cudaStream_t s);
 void launch_philox(int n, uint64_t seed, const uint32_t *ctr, uint32_t *out, cudaStream_t s);
 
+// library routines off the render loop, fp64 bit-exact batches (harness64.cu)
+void launch_plane64(int n, const double *plane4, const double *Q, const double *D, int *hit, double *P, cudaStream_t s);
+void launch_point_in64(int n, const double *tri9, const double *pts, int *inside, cudaStream_t s);
+void launch_material_reflect64(int kind, int n, const double *plane4, const double *origin, int *ok, double *out, cudaStream_t s);
+
 // Texture::paste (harness64.cu): destination / source images as w*h*3 doubles on the device
 struct PasteArgs {
 	double *dst;

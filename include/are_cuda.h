@@ -182,6 +182,18 @@ int are_cuda_texture_batch(are_cuda_ctx *ctx, int n, const int *texture_id, cons
 int are_cuda_camera_rays(are_cuda_ctx *ctx, const are_camera *cam, int width, int height, int n,
 	const int *px, const int *py, const double *rnd, int precision, double *ray_Q, double *ray_D);
 
+/* Library routines that are not on the render loop, as fp64 batches with the reference's decisions bit for bit
+ * (SURVEY.md §8a rows a5, a8, a10).  None needs a committed scene.
+ *   plane_batch            are::Plane::intersect_ray        src/basic/plane.cpp:13-27   plane4 = (normal, d) per ray;
+ *                          D is normalised first; hit[n], P[3n] (NaN on a miss)
+ *   point_in_batch         are::Triangle::point_in          src/object/triangle.cpp:49-79   one triangle (Q,u,v), n points
+ *   material_reflect_batch are::Material::reflect           src/material/diffuse.cpp:5-7, reflective.cpp:9-26
+ *                          kind = ARE_MAT_DIFFUSE (always declines) or ARE_MAT_REFLECTIVE (mirrors the viewport origin
+ *                          across the plane); ok[n], new_origin[3n] (NaN when declined) */
+int are_cuda_plane_batch(are_cuda_ctx *ctx, int n, const double *plane4, const double *ray_Q, const double *ray_D, int *hit, double *P);
+int are_cuda_point_in_batch(are_cuda_ctx *ctx, const double Q[3], const double u[3], const double v[3], int n, const double *points, int *inside);
+int are_cuda_material_reflect_batch(are_cuda_ctx *ctx, int kind, int n, const double *plane4, const double *origin, int *ok, double *new_origin);
+
 /* The counter-based generator itself: out[4n] = Philox4x32-10(key = seed, counter[4n]). */
 int are_cuda_philox_batch(are_cuda_ctx *ctx, int n, uint64_t seed, const uint32_t *counter, uint32_t *out);
 

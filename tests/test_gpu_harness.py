@@ -321,3 +321,46 @@ def test_error_behaviour(ctx):
     ctx.commit()
     prim, t, *_ = ctx.hit_batch(np.zeros((4, 3)), np.ones((4, 3)))
     assert (prim == -1).all() and np.isnan(t).all()
+
+
+def test_library_routines_off_the_render_loop_are_bit_exact(ctx, oracle):
+    """SURVEY §8a rows a5 / a8 / a10 on the device: are::Plane::intersect_ray, are::Triangle::point_in and
+    are::Material::reflect as fp64 batches, against outputs of the REAL reference (tests/golden/reference_vectors.npz)
+    and against the restatement on fresh random inputs (NaN outputs compared as NaN)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+
+    def same(a, b):
+        return a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+    hit, P = ctx.plane_batch(g["plane4"], g["plane_rayQ"], g["plane_rayD"])
+    assert same(hit, g["plane_hit"]) and same(P, g["plane_P"])
+    TQ, Tu, Tv = g["cornell_TQ"], g["cornell_Tu"], g["cornell_Tv"]
+    assert same(ctx.point_in_batch(TQ[3], Tu[3], Tv[3], g["pointin_pts"]), g["pointin"])
+    ok, out = ctx.material_reflect_batch(1, g["mat_planes"], g["mat_origin"])
+    assert same(ok, g["mat_refl_ok"]) and same(out, g["mat_refl_out"])
+    ok, out = ctx.material_reflect_batch(0, g["mat_planes"], g["mat_origin"])
+    assert same(ok, g["mat_diff_ok"]) and same(out, g["mat_diff_out"]) and not ok.any()
+    # fresh inputs, larger batch, degenerate cases included
+    rng = np.random.RandomState(77)
+    n = 100_000
+    planes = np.concatenate([rng.normal(size=(n, 3)), rng.uniform(-2, 2, (n, 1))], axis=1)
+    planes[:10, :3] = 0.0                      # degenerate normal: Reflective declines
+    planes[10:20, :3] *= 1e-7
+    Q, D = rng.uniform(-3, 3, (n, 3)), rng.normal(size=(n, 3))
+    D[20:40] = np.cross(planes[20:40, :3], rng.normal(size=(20, 3)))  # rays parallel to their plane
+    hit, P = ctx.plane_batch(planes, Q, D)
+    ohit, oP = oracle.plane_intersect(planes, Q, D)
+    assert same(hit, ohit) and same(P, oP) and 0.2 < hit.mean() < 0.8
+    ok, out = ctx.material_reflect_batch(1, planes, Q)
+    ook, oout = oracle.material_reflect(1, 0.5, planes, Q)
+    assert same(ok, ook) and same(out, oout) and not ok[:10].any()
+    tq, tu, tv = np.array([0.1, -0.2, 0.3]), np.array([1.0, 0.2, 0.0]), np.array([0.1, 0.9, 0.4])
+    a, b = rng.uniform(-0.3, 1.3, n), rng.uniform(-0.3, 1.3, n)
+    pts = tq + a[:, None] * tu + b[:, None] * tv + rng.choice([0.0, 0.0, 1e-13, 1e-3], n)[:, None] * np.cross(tu, tv)
+    pts[:100] = tq + np.outer(np.linspace(0, 1, 100), tu)  # exactly on an edge
+    inside = ctx.point_in_batch(tq, tu, tv, pts)
+    oin = oracle.triset_point_in(tq[None], tu[None], tv[None], 0, pts)
+    assert same(inside, oin) and 0.1 < inside.mean() < 0.9
+    with pytest.raises(capi.AreCudaError):
+        ctx.point_in_batch(tq, tu, 2 * tu, pts[:4])   # collinear edges: what are::Triangle's ctor rejects
