@@ -363,28 +363,62 @@ __device__ __forceinline__ C3 sample_source(const PatchOp &op, const double *__r
 // wins (rt10.cpp:420-436, overwrite mode), so a texel only needs the LAST op that covers it — walk backwards, stop
 // at the first hit.  Coverage test = the reference's: inside the clamped integer bounding box and all three
 // pixel-centre barycentrics >= -1e-6.
-__device__ __forceinline__ bool painted(const PatchOp *__restrict__ ops, int begin, int end, const double *__restrict__ arena, int x, int y, C3 &out) {
-	const P2 c = { (double)x + 0.5, (double)y + 0.5 };
-	for (int i = end - 1; i >= begin; --i) {
-		const PatchOp &op = ops[i];
-		if (x < op.x0 || x > op.x1 || y < op.y0 || y > op.y1) continue;
-		const P2 p0 = { op.px[0], op.py[0] }, p1 = { op.px[1], op.py[1] }, p2 = { op.px[2], op.py[2] };
-		const double c0 = cross2(p1 - c, p2 - c), c1 = cross2(p2 - c, p0 - c);
-		{  // Conservative early reject without the two fp64 divisions: c*inv_area is within 3 ulp of c/area, so a barycentric
-			// that misses the reference's -1e-6 threshold by more than the margin below misses it exactly as well.  Every
-			// pixel that might be covered still takes the exact test, and only exact quotients reach the image.
-			const double q0 = c0 * op.inv_area, q1 = c1 * op.inv_area;
-			const double slack = 1e-12 * (1.0 + fabs(q0) + fabs(q1));
-			if (q0 < -1e-6 - slack || q1 < -1e-6 - slack || 1.0 - q0 - q1 < -1e-6 - slack) continue;
+// One op against one texel: the reference's coverage test and fetch.
+__device__ __forceinline__ bool paint_one(const PatchOp &op, const double *__restrict__ arena, int x, int y, P2 c, C3 &out) {
+	if (x < op.x0 || x > op.x1 || y < op.y0 || y > op.y1) return false;
+	const P2 p0 = { op.px[0], op.py[0] }, p1 = { op.px[1], op.py[1] }, p2 = { op.px[2], op.py[2] };
+	const double c0 = cross2(p1 - c, p2 - c), c1 = cross2(p2 - c, p0 - c);
+	{  // Conservative early reject without the two fp64 divisions: c*inv_area is within 3 ulp of c/area, so a barycentric
+		// that misses the reference's -1e-6 threshold by more than the margin below misses it exactly as well.  Every
+		// pixel that might be covered still takes the exact test, and only exact quotients reach the image.
+		const double q0 = c0 * op.inv_area, q1 = c1 * op.inv_area;
+		const double slack = 1e-12 * (1.0 + fabs(q0) + fabs(q1));
+		if (q0 < -1e-6 - slack || q1 < -1e-6 - slack || 1.0 - q0 - q1 < -1e-6 - slack) return false;
+	}
+	const double w0 = c0 / op.area;
+	const double w1 = c1 / op.area;
+	const double w2 = 1.0 - w0 - w1;
+	if (w0 < -1e-6 || w1 < -1e-6 || w2 < -1e-6) return false;
+	const P2 s0 = { op.su[0], op.sv[0] }, s1 = { op.su[1], op.sv[1] }, s2 = { op.su[2], op.sv[2] };
+	const P2 suv = s0 * w0 + s1 * w1 + s2 * w2;
+	out = sample_source(op, arena, suv.x, suv.y);
+	return true;
+}
+
+// Per-tile op culling: the CTA marks, in a shared bit set, the ops of [begin, end) whose bounding box touches its
+// 16x16 tile; a texel then visits only those (typically 5-10 of ~60), still in the reference's order.
+#define PATCH_CULL_WORDS 64  // up to 2048 ops per list through the bit set; longer lists fall back to the plain walk
+__device__ __forceinline__ void cull_ops(const PatchOp *__restrict__ ops, int begin, int end, int tx0, int ty0, unsigned *bits) {
+	const int n = end - begin;
+	for (int w = threadIdx.x; w < PATCH_CULL_WORDS; w += blockDim.x) bits[w] = 0u;
+	__syncthreads();
+	if (n <= 32 * PATCH_CULL_WORDS)
+		for (int i = threadIdx.x; i < n; i += blockDim.x) {
+			const PatchOp &op = ops[begin + i];
+			if (op.x1 >= tx0 && op.x0 <= tx0 + 15 && op.y1 >= ty0 && op.y0 <= ty0 + 15) atomicOr(&bits[i >> 5], 1u << (i & 31));
 		}
-		const double w0 = c0 / op.area;
-		const double w1 = c1 / op.area;
-		const double w2 = 1.0 - w0 - w1;
-		if (w0 < -1e-6 || w1 < -1e-6 || w2 < -1e-6) continue;
-		const P2 s0 = { op.su[0], op.sv[0] }, s1 = { op.su[1], op.sv[1] }, s2 = { op.su[2], op.sv[2] };
-		const P2 suv = s0 * w0 + s1 * w1 + s2 * w2;
-		out = sample_source(op, arena, suv.x, suv.y);
-		return true;
+	__syncthreads();
+}
+// The painter's loop turned inside out: the reference paints ops [begin,end) in order and the last writer of a texel
+// wins (rt10.cpp:420-436, overwrite mode), so a texel only needs the LAST op that covers it — walk backwards, stop
+// at the first hit.  Coverage test = the reference's: inside the clamped integer bounding box and all three
+// pixel-centre barycentrics >= -1e-6.
+__device__ __forceinline__ bool painted(const PatchOp *__restrict__ ops, int begin, int end, const unsigned *bits, const double *__restrict__ arena, int x,
+	int y, C3 &out) {
+	const P2 c = { (double)x + 0.5, (double)y + 0.5 };
+	const int n = end - begin;
+	if (n > 32 * PATCH_CULL_WORDS) {
+		for (int i = end - 1; i >= begin; --i)
+			if (paint_one(ops[i], arena, x, y, c, out)) return true;
+		return false;
+	}
+	for (int w = (n - 1) >> 5; w >= 0; --w) {
+		unsigned m = bits[w];
+		while (m) {
+			const int b = 31 - __clz(m);
+			m &= ~(1u << b);
+			if (paint_one(ops[begin + (w << 5) + b], arena, x, y, c, out)) return true;
+		}
 	}
 	return false;
 }
@@ -393,12 +427,14 @@ __device__ __forceinline__ bool painted(const PatchOp *__restrict__ ops, int beg
 // (rt10.cpp:650-661).
 __global__ void __launch_bounds__(256) k_patch_nodes(const PatchOp *__restrict__ ops, const PatchNode *__restrict__ nodes, const PatchTile *__restrict__ tiles,
 	double *__restrict__ arena, double env_r, double env_g, double env_b) {
+	__shared__ unsigned s_bits[PATCH_CULL_WORDS];
 	const PatchTile t = tiles[blockIdx.x];
 	const PatchNode &nd = nodes[t.node];
 	const int x = t.tx * 16 + (threadIdx.x & 15), y = t.ty * 16 + (threadIdx.x >> 4);
+	cull_ops(ops, nd.op_begin, nd.op_end, t.tx * 16, t.ty * 16, s_bits);
 	if (x >= nd.w || y >= nd.h) return;
 	C3 r = { env_r, env_g, env_b };
-	painted(ops, nd.op_begin, nd.op_end, arena, x, y, r);
+	painted(ops, nd.op_begin, nd.op_end, s_bits, arena, x, y, r);
 	const double m = nd.metal, k = 1.0 - m;
 	const C3 tint = { r.r * nd.base[0], r.g * nd.base[1], r.b * nd.base[2] };
 	double *o = arena + 3 * (nd.off + (long long)y * nd.w + x);
@@ -433,14 +469,17 @@ __device__ __forceinline__ uint8_t encode8(double c, double inv_gamma) {  // Ima
 // (rt10.cpp:744-772), plus the gamma-encoded P6 payload.
 __global__ void __launch_bounds__(256) k_patch_camera(const PatchOp *__restrict__ ops, const double *__restrict__ arena, CameraArgs a, double *__restrict__ rgb,
 	uint8_t *__restrict__ rgb8) {
+	__shared__ unsigned s_bits[2][PATCH_CULL_WORDS];
 	const int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 16 + (threadIdx.x >> 4);
+	cull_ops(ops, a.op_begin[0], a.op_end[0], blockIdx.x * 16, blockIdx.y * 16, s_bits[0]);
+	cull_ops(ops, a.op_begin[1], a.op_end[1], blockIdx.x * 16, blockIdx.y * 16, s_bits[1]);
 	if (x >= a.W || y >= a.H) return;
 	const P2 uv = { (double)x / (a.W - 1), (double)y / (a.H - 1) };
 	C3 part[2];
 #pragma unroll
 	for (int v = 0; v < 2; ++v) {
 		C3 c = { a.env[0], a.env[1], a.env[2] };
-		painted(ops, a.op_begin[v], a.op_end[v], arena, x, y, c);
+		painted(ops, a.op_begin[v], a.op_end[v], s_bits[v], arena, x, y, c);
 		if (!in_uv_triangle(uv, a.uv[v], 1e-10)) c = { 0.0, 0.0, 0.0 };
 		part[v] = c;
 	}
