@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <limits>
 
 namespace areb {
 
@@ -448,7 +449,7 @@ struct CameraArgs {
 	int op_begin[2], op_end[2];
 	double uv[2][6];    // the two viewport triangles' uv
 	double env[3];
-	double inv_gamma;   // 1.0 / gamma, computed on the host as the reference does (rt10.cpp:131)
+	const double *thresholds;  // 255 doubles: thresholds[v-1] = smallest c with encode(c) >= v (see encode_thresholds)
 };
 
 // pointInTriangle2D, rt10.cpp:202-218
@@ -459,10 +460,20 @@ __device__ __forceinline__ bool in_uv_triangle(P2 q, const double *uv, double ep
 	const bool pos = (c0 > eps) || (c1 > eps) || (c2 > eps);
 	return !(neg && pos);
 }
-__device__ __forceinline__ uint8_t encode8(double c, double inv_gamma) {  // Image::writePPM, rt10.cpp:124-141
+// Image::writePPM's 8-bit encode, rt10.cpp:124-141: lround(255 * pow(clamp(c,0,1), 1/gamma)).  The byte only depends on
+// which of 255 thresholds c has passed, and those thresholds are found on the HOST with the very libm pow the reference
+// calls (encode_thresholds below), so the device neither needs a pow (three per pixel were ~40 % of the kernel) nor has
+// to agree with glibc's pow to the last ulp: encode(c) = number of thresholds <= c, an 8-step binary search.
+__device__ __forceinline__ uint8_t encode8(double c, const double *__restrict__ thr) {
 	c = clampd(c, 0.0, 1.0);
-	c = pow(c, inv_gamma);
-	return (uint8_t)clampi((int)lround(c * 255.0), 0, 255);
+	int lo = 0, hi = 255;  // invariant: thr[0..lo) <= c, thr[hi..255) > c
+#pragma unroll
+	for (int step = 0; step < 8; ++step) {
+		const int mid = (lo + hi) >> 1;
+		if (lo < hi && __ldg(thr + mid) <= c) lo = mid + 1;
+		else hi = lo < hi ? mid : hi;
+	}
+	return (uint8_t)lo;
 }
 
 // Camera image: both viewport triangles per pixel (each black outside its own triangle), summed and clamped
@@ -486,13 +497,33 @@ __global__ void __launch_bounds__(256) k_patch_camera(const PatchOp *__restrict_
 	const double r = clampd(part[0].r + part[1].r, 0.0, 1.0), g = clampd(part[0].g + part[1].g, 0.0, 1.0), b = clampd(part[0].b + part[1].b, 0.0, 1.0);
 	const size_t i = ((size_t)y * a.W + x) * 3;
 	if (rgb) { rgb[i] = r; rgb[i + 1] = g; rgb[i + 2] = b; }
-	if (rgb8) { rgb8[i] = encode8(r, a.inv_gamma); rgb8[i + 1] = encode8(g, a.inv_gamma); rgb8[i + 2] = encode8(b, a.inv_gamma); }
+	if (rgb8) { rgb8[i] = encode8(r, a.thresholds); rgb8[i + 1] = encode8(g, a.thresholds); rgb8[i + 2] = encode8(b, a.thresholds); }
 }
 
 __global__ void k_patch_fill(double *__restrict__ out, long long texels, double r, double g, double b) {
 	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= texels) return;
 	out[3 * i] = r; out[3 * i + 1] = g; out[3 * i + 2] = b;
+}
+
+// thresholds[v-1] = the smallest double c in [0,1] whose reference encode is >= v, v = 1..255, by bisection over the bit
+// patterns of the non-negative doubles (monotone in the value) with the host's pow — the function the reference calls.
+void encode_thresholds(double gamma, double *thr255) {
+	const double inv_gamma = 1.0 / gamma;  // rt10.cpp:131
+	auto enc = [&](double c) { return clampi((int)std::lround(std::pow(clampd(c, 0.0, 1.0), inv_gamma) * 255.0), 0, 255); };
+	auto as_bits = [](double d) { uint64_t u; std::memcpy(&u, &d, 8); return u; };
+	auto as_double = [](uint64_t u) { double d; std::memcpy(&d, &u, 8); return d; };
+	const uint64_t one = as_bits(1.0);
+	for (int v = 1; v <= 255; ++v) {
+		if (enc(1.0) < v) { thr255[v - 1] = std::numeric_limits<double>::infinity(); continue; }  // never reached
+		uint64_t lo = 0, hi = one;  // enc(as_double(hi)) >= v; enc(0) = 0 < v
+		while (hi - lo > 1) {
+			const uint64_t mid = lo + (hi - lo) / 2;
+			if (enc(as_double(mid)) >= v) hi = mid;
+			else lo = mid;
+		}
+		thr255[v - 1] = as_double(hi);
+	}
 }
 
 int grow(void **p, size_t *cap, size_t bytes, std::string &err) {
@@ -553,7 +584,8 @@ int run_levels(PatchWorkspace &ws, const PatchPlan &plan, const PatchCfg &cfg, P
 }  // namespace
 
 void PatchWorkspace::release() {
-	void **bufs[] = { &d_ops, &d_nodes, &d_tiles, &d_arena, &d_rgb, &d_rgb8 };
+	void **bufs[] = { &d_ops, &d_nodes, &d_tiles, &d_arena, &d_rgb, &d_rgb8, &d_thr };
+	thr_gamma = 0.0;
 	for (void **b : bufs) {
 		if (*b) cudaFree(*b);
 		*b = nullptr;
@@ -580,7 +612,18 @@ int patch_run_camera(PatchWorkspace &ws, const PatchPlan &plan, const double *vp
 		std::memcpy(a.uv[v], vp_UV + 6 * v, 6 * sizeof(double));
 	}
 	std::memcpy(a.env, cfg.env, sizeof a.env);
-	a.inv_gamma = 1.0 / cfg.gamma;
+	if (out_rgb8) {
+		if (!ws.d_thr || ws.thr_gamma != cfg.gamma) {  // 255 x ~62 host pow calls: once per gamma value, kept in the workspace
+			double thr[256];
+			encode_thresholds(cfg.gamma, thr);
+			thr[255] = std::numeric_limits<double>::infinity();  // sentinel: the search may look one past the last threshold
+			if (!ws.d_thr) PCK(cudaMalloc(&ws.d_thr, sizeof thr));
+			PCK(cudaMemcpyAsync(ws.d_thr, thr, sizeof thr, cudaMemcpyHostToDevice, s));
+			PCK(cudaStreamSynchronize(s));  // thr lives on this stack frame
+			ws.thr_gamma = cfg.gamma;
+		}
+	}
+	a.thresholds = static_cast<const double *>(ws.d_thr);
 	const dim3 grid((W + 15) / 16, (H + 15) / 16);
 	k_patch_camera<<<grid, 256, 0, s>>>(static_cast<const PatchOp *>(ws.d_ops), static_cast<const double *>(ws.d_arena), a,
 		out_rgb ? static_cast<double *>(ws.d_rgb) : nullptr, out_rgb8 ? static_cast<uint8_t *>(ws.d_rgb8) : nullptr);

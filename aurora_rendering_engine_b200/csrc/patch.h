@@ -86,6 +86,8 @@ void patch_plan_texture(const PatchSceneView &sc, const double origin[3], int cu
 // Grow-only device / pinned workspace owned by the context.
 struct PatchWorkspace {
 	void *d_ops = nullptr, *d_nodes = nullptr, *d_tiles = nullptr, *d_arena = nullptr, *d_rgb = nullptr, *d_rgb8 = nullptr;
+	void *d_thr = nullptr;   // 255 encode thresholds of thr_gamma (8-bit output)
+	double thr_gamma = 0.0;
 	size_t cap_ops = 0, cap_nodes = 0, cap_tiles = 0, cap_arena = 0, cap_rgb = 0, cap_rgb8 = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	void release();
