@@ -43,6 +43,7 @@ struct are_cuda_ctx {
 	int sm_count = 0;
 	CompileOptions opt;
 	PatchWorkspace patch_ws;
+	float *d_gamma_thr = nullptr;  // thresholds of the rt.cpp gamma-2.2 encode (built on first use)
 	int wide_min_nodes = 0x7fffffff;  // AUTO never picks the compressed 8-wide BVH (measured slower); ARE_CUDA_WIDE_MIN_NODES overrides
 };
 
@@ -208,6 +209,7 @@ void are_cuda_destroy(are_cuda_ctx *ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	free_scene_allocs(ctx);
 	ctx->patch_ws.release();
+	if (ctx->d_gamma_thr) cudaFree(ctx->d_gamma_thr);
 	if (ctx->own_accum) cudaFree(ctx->own_accum);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -690,15 +692,41 @@ int are_cuda_render(are_cuda_ctx *ctx, const are_camera *cam, const are_render_p
 	return ARE_OK;
 }
 
+// thr[v-1] = the smallest float c in [0,1] with (unsigned char)(powf(c, 1/2.2f) * 255) >= v (experiments/rt.cpp:383-386),
+// by bisection over the bit patterns of the non-negative floats with the host's powf — what rt.cpp itself calls.
+static void gamma22_thresholds(float thr[256]) {
+	auto enc = [](float c) { return (int)(unsigned char)(powf(fmaxf(0.0f, fminf(1.0f, c)), 1 / 2.2f) * 255); };
+	auto as_float = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+	uint32_t one;
+	const float f1 = 1.0f;
+	std::memcpy(&one, &f1, 4);
+	for (int v = 1; v <= 255; ++v) {
+		uint32_t lo = 0, hi = one;  // enc(0) = 0 < v <= 255 = enc(1)
+		while (hi - lo > 1) {
+			const uint32_t mid = lo + (hi - lo) / 2;
+			if (enc(as_float(mid)) >= v) hi = mid;
+			else lo = mid;
+		}
+		thr[v - 1] = as_float(hi);
+	}
+	thr[255] = INFINITY;
+}
+
 int are_cuda_tonemap(are_cuda_ctx *ctx, const float *accum, int width, int height, double inv_spp, int encoder, uint8_t *out_host) {
 	Range nvtx_range("are_cuda_tonemap");
 	if (!ctx || !accum || !out_host || width <= 0 || height <= 0) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "bad argument");
 	if (encoder < ARE_ENCODE_GAMMA22_TRUNC || encoder > ARE_ENCODE_SQRT_TRUNC) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown encoder");
 	Bind b(ctx);
 	const size_t n = (size_t)width * height * 3;
+	if (encoder == ARE_ENCODE_GAMMA22_TRUNC && !ctx->d_gamma_thr) {
+		float thr[256];
+		gamma22_thresholds(thr);
+		CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_gamma_thr), sizeof thr));
+		CK(cudaMemcpy(ctx->d_gamma_thr, thr, sizeof thr, cudaMemcpyHostToDevice));
+	}
 	Tmp d;
 	TMP_OUT(d, n);
-	launch_tonemap(accum, width, height, inv_spp, encoder, d.as<uint8_t>(), ctx->stream);
+	launch_tonemap(accum, width, height, inv_spp, encoder, ctx->d_gamma_thr, d.as<uint8_t>(), ctx->stream);
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(out_host, d.p, n, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));

@@ -61,7 +61,8 @@ void launch_camera32(const CamBasis &cb, int W, int H, int n, const int *px, con
 // mode: 0 brute force (shared memory), 1 BVH2, 2 compressed 8-wide BVH
 int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStream_t s);
 int launch_render_rtao(const RenderArgs &a, cudaStream_t s);
-void launch_tonemap(const float *accum, int W, int H, double inv_spp, int encoder, uint8_t *out, cudaStream_t s);
+// gamma_thr: 256 floats, [v-1] = smallest c with the rt.cpp gamma encode >= v (v = 1..255), [255] = +inf (encoder 0 only)
+void launch_tonemap(const float *accum, int W, int H, double inv_spp, int encoder, const float *gamma_thr, uint8_t *out, cudaStream_t s);
 // register-resident FFMA loop; returns FLOPs executed per launch
 double launch_fp32_peak(float *sink, int sm_count, int iters, cudaStream_t s);
 

@@ -423,7 +423,7 @@ void launch_camera32(const CamBasis &cb, int W, int H, int n, const int *px, con
 // =========================================================================================================
 // output encoders
 // =========================================================================================================
-__global__ void k_tonemap(const float *__restrict__ accum, long n, double inv_spp, int encoder, uint8_t *__restrict__ out) {
+__global__ void k_tonemap(const float *__restrict__ accum, long n, double inv_spp, int encoder, const float *__restrict__ gamma_thr, uint8_t *__restrict__ out) {
 	long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	if (encoder == 1) {  // src/texture.cpp:384-386 in fp64: (unsigned char)clamp(c*255, 0, 255)
@@ -433,18 +433,27 @@ __global__ void k_tonemap(const float *__restrict__ accum, long n, double inv_sp
 		out[i] = (uint8_t)v;
 	} else if (encoder == 2) {
 		float c = accum[i] * (float)inv_spp;
-		float g = c > 0.f ? sqrtf(c) : 0.f;
+		float g = c > 0.f ? __fsqrt_rn(c) : 0.f;  // IEEE square root (this file is built with -prec-sqrt=false)
 		g = g < 0.f ? 0.f : (g > 0.999f ? 0.999f : g);
 		out[i] = (uint8_t)(256.0f * g);
-	} else {  // rt.cpp:72-76,383-386 in fp32
+	} else {  // rt.cpp:72-76,383-386 in fp32: (unsigned char)(powf(clamp(c,0,1), 1/2.2f) * 255)
+		// The byte depends on c only through 255 thresholds, bisected on the host with libm's powf — the function rt.cpp
+		// calls — so the encode is byte-identical to the reference's instead of "device powf within one ulp of it".
 		float c = accum[i] * (float)inv_spp;
 		c = fmaxf(0.0f, fminf(1.0f, c));
-		out[i] = (uint8_t)(powf(c, 1 / 2.2f) * 255);
+		int lo = 0, hi = 255;
+#pragma unroll
+		for (int step = 0; step < 8; ++step) {
+			const int mid = (lo + hi) >> 1;
+			if (lo < hi && __ldg(gamma_thr + mid) <= c) lo = mid + 1;
+			else hi = lo < hi ? mid : hi;
+		}
+		out[i] = (uint8_t)lo;
 	}
 }
-void launch_tonemap(const float *accum, int W, int H, double inv_spp, int encoder, uint8_t *out, cudaStream_t s) {
+void launch_tonemap(const float *accum, int W, int H, double inv_spp, int encoder, const float *gamma_thr, uint8_t *out, cudaStream_t s) {
 	long n = (long)W * H * 3;
-	if (n > 0) k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(accum, n, inv_spp, encoder, out);
+	if (n > 0) k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(accum, n, inv_spp, encoder, gamma_thr, out);
 }
 
 // =========================================================================================================

@@ -182,7 +182,7 @@ def test_rt_ao_integrator_matches_cpu_restatement(ctx, oracle):
 @pytest.mark.parametrize("encoder", [0, 1, 2])
 def test_tonemap_encoders(ctx, oracle, encoder):
     rng = np.random.RandomState(encoder)
-    W, H, spp = 64, 48, 4
+    W, H, spp = 640, 480, 4
     vals = np.concatenate([rng.uniform(-0.5, 6.0, W * H * 3 - 6), [0.0, 1.0 * spp, 255.0 / 255.0 * spp, 1e-9, 1e9, 0.5 * spp]]).astype(np.float32)
     import torch  # device memory only
     t = torch.from_numpy(vals).cuda()
@@ -190,15 +190,13 @@ def test_tonemap_encoders(ctx, oracle, encoder):
     c = vals.astype(np.float32) * np.float32(1.0 / spp)
     if encoder == 0:
         exp = oracle.encode_gamma22(c)
-        diff = np.abs(out.ravel().astype(int) - exp.astype(int))
-        assert diff.max() <= 1 and (diff > 0).mean() < 5e-3  # device powf vs libm powf may differ by one ulp at a byte boundary
+        assert np.array_equal(out.ravel(), exp)  # thresholds bisected with libm powf on the host: byte-identical to rt.cpp's encode
     elif encoder == 1:
         exp = oracle.encode_linear(vals.astype(np.float64) * (1.0 / spp))
         assert np.array_equal(out.ravel(), exp)
     else:
         exp = oracle.encode_sqrt(c)
-        diff = np.abs(out.ravel().astype(int) - exp.astype(int))
-        assert diff.max() <= 1 and (diff > 0).mean() < 5e-3
+        assert np.array_equal(out.ravel(), exp)  # IEEE sqrt on both sides
 
 
 def test_ppm_writer_round_trip(ctx, oracle, tmp_path):
