@@ -36,10 +36,14 @@ class RenderParams(C.Structure):
 class RenderStats(C.Structure):
     """are_render_stats"""
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("tri_tests", C.c_uint64), ("quad_tests", C.c_uint64),
-                ("sphere_tests", C.c_uint64), ("node_visits", C.c_uint64), ("box_tests", C.c_uint64), ("kernel_ms", C.c_double), ("launches", C.c_uint64)]
+                ("sphere_tests", C.c_uint64), ("node_visits", C.c_uint64), ("box_tests", C.c_uint64), ("kernel_ms", C.c_double), ("launches", C.c_uint64),
+                ("kernel_variant", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+KERNEL_NONE, KERNEL_BRUTE, KERNEL_BRUTE_LEAN, KERNEL_BVH2, KERNEL_BVH2_BIG, KERNEL_WIDE, KERNEL_RT_AO = range(7)
 
 
 def make_camera(pos, target, up=(0, 1, 0), vfov_deg=40.0, focus_dist=1.0, defocus_angle_deg=0.0, jitter=1) -> Camera:

@@ -346,7 +346,10 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	if (cs.wide_depth <= 32) { UP(wnodes, wnodes) UP(wide_prims, wide_prims) UP(wide_ids, wide_ids) UP(wide_kinds, wide_kinds) }  // 32 = ARE_WIDE_STACK
 	UP(info, info) UP(prim_plane, prim_plane) UP(tri_uv, tri_uv) UP(tri64, tri64) UP(quad64, quad64) UP(sph64, sph64)
 	UP(tri_uv64, tri_uv64) UP(mats, mats) UP(texs, texs) UP(tex_data, tex_data) UP(rt_tris, rt_tris) UP(box_faces, box_faces) UP(shade, shade)
+	UP(lean_shade, lean_shade) UP(lean_sbase, lean_sbase)
 #undef UP
+	d.lean_ok = cs.lean_ok ? 1 : 0;
+	d.n_lean_shade = (int)cs.lean_shade.size();
 	d.brute_range = cs.brute_range;
 	d.n_nodes = (int)cs.nodes.size();
 	d.n_wnodes = d.wnodes ? (int)cs.wnodes.size() : 0;
@@ -590,6 +593,12 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 	a.ao_samples = p->ao_samples > 0 ? p->ao_samples : 32;
 	a.tmin = (float)p->t_min;
 	for (int k = 0; k < 3; ++k) { a.bg_bottom[k] = (float)p->background_bottom[k]; a.bg_top[k] = (float)p->background_top[k]; }
+	a.bg_black = 1;
+	for (int k = 0; k < 3; ++k) a.bg_black &= (a.bg_bottom[k] == 0.0f && a.bg_top[k] == 0.0f) ? 1 : 0;
+	{
+		const char *e = getenv("ARE_CUDA_NO_LEAN");  // A/B switch: generic brute-force kernel for a scene that has a lean form
+		a.lean = (e && e[0] == '1') ? 0 : 1;
+	}
 	a.accum = accum;
 	a.counters = ctx->d_counters;
 	int mode = 0;
@@ -631,6 +640,10 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 		}
 		stats->kernel_ms = ms;
 		stats->launches = (uint64_t)launched;
+		stats->kernel_variant = launched <= 0 ? ARE_KERNEL_NONE
+			: p->integrator == ARE_INTEGRATOR_RT_AO ? ARE_KERNEL_RT_AO
+			: mode == 0 ? (render_path_is_lean(a) ? ARE_KERNEL_BRUTE_LEAN : ARE_KERNEL_BRUTE)
+			: mode == 2 ? ARE_KERNEL_WIDE : (render_path_is_big(a) ? ARE_KERNEL_BVH2_BIG : ARE_KERNEL_BVH2);
 	}
 	return ARE_OK;
 }

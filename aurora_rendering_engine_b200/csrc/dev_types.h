@@ -100,6 +100,8 @@ struct WideNode {
 // tests, nt triangle tests, ns sphere tests.  The brute-force list is one big range; every BVH leaf is a small one.
 struct HotRange { int first, nq, nt, ns, nb; };
 
+enum { LEAN_MAX = 4 };  // boxes, quad tests and triangle tests (each) that the lean render kernel unrolls
+
 struct DevScene {
 	// --- fp32 render data ---
 	const HotPrim *brute;      // type-sorted hot primitives (nullptr when the scene is too big for the brute path)
@@ -117,6 +119,12 @@ struct DevScene {
 	int n_wnodes;
 	int n_hot;                 // slots in the hot arrays (a box takes two)
 	const HotIds *box_faces;   // 6 per box: the fused pair / quad behind each face, {-1,-1} when the face is absent
+	// "lean" tables of a small flat-shaded scene (scene.h: CompiledScene::lean_ok): the shading record of every brute
+	// slot — six per box, one per face — so the render loop goes hit -> record without any id / owner resolution
+	const ShadeRec *lean_shade;
+	const int *lean_sbase;     // per brute slot: index of its first record in lean_shade
+	int n_lean_shade;
+	int lean_ok;
 	// --- per device primitive ---
 	const PrimInfo *info;
 	const ShadeRec *shade;     // per device primitive

@@ -146,6 +146,23 @@ __device__ __forceinline__ void intersect_range(const HotPrim *prims, int first,
 	for (; i < end; ++i) test_sphere(LD(&prims[i].r0), LD(&prims[i].r1), o, d, tmin, i, h);
 }
 
+// The lean form (scene.h): at most LEAN_MAX boxes, quad tests and triangle tests, no spheres, boxes from slot 0.
+// A guarded full unroll — the counts are kernel parameters, so every guard is a uniform branch and every shared-memory
+// offset a compile-time constant (boxes) or one uniform base + constant (quads, triangles).
+__device__ __forceinline__ void intersect_lean(const HotPrim *prims, int nb, int nq, int nt, V3<float> o, V3<float> d, float tmin, Hit &h) {
+#pragma unroll
+	for (int i = 0; i < LEAN_MAX; ++i)
+		if (i < nb) test_box(lds4(&prims[2 * i].r0), lds4(&prims[2 * i].r1), lds4(&prims[2 * i].r2), lds4(&prims[2 * i + 1].r0), o, d, tmin, 2 * i, h);
+	const HotPrim *pq = prims + 2 * nb;
+#pragma unroll
+	for (int j = 0; j < LEAN_MAX; ++j)
+		if (j < nq) test_plane<true>(lds4(&pq[j].r0), lds4(&pq[j].r1), lds4(&pq[j].r2), o, d, tmin, 2 * nb + j, h);
+	const HotPrim *pt = pq + nq;
+#pragma unroll
+	for (int j = 0; j < LEAN_MAX; ++j)
+		if (j < nt) test_plane<false>(lds4(&pt[j].r0), lds4(&pt[j].r1), lds4(&pt[j].r2), o, d, tmin, 2 * nb + nq + j, h);
+}
+
 // ---- BVH2 traversal, per-thread stack -----------------------------------------------------------------
 #define ARE_BVH_STACK 48
 

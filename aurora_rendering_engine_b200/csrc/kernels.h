@@ -20,6 +20,8 @@ struct RenderArgs {
 	int ao_samples;
 	float tmin;
 	float bg_bottom[3], bg_top[3];
+	int bg_black;                    // both background colours are zero: a miss adds nothing
+	int lean;                        // use the lean brute-force kernel when the compiled scene has a lean form
 	float *accum;                    // W*H*3 floats, sample SUMS are added
 	unsigned long long *counters;    // [0] rays [1] node visits [2] quad tests [3] tri tests [4] sphere tests [5] box tests
 };
@@ -60,6 +62,8 @@ void launch_camera32(const CamBasis &cb, int W, int H, int n, const int *px, con
 // render kernels. Returns the number of kernels launched, <0 on a launch-configuration error.
 // mode: 0 brute force (shared memory), 1 BVH2, 2 compressed 8-wide BVH
 int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStream_t s);
+bool render_path_is_lean(const RenderArgs &a);  // brute force: the lean kernel is the one launched
+bool render_path_is_big(const RenderArgs &a);   // BVH: the high-occupancy build is the one launched
 int launch_render_rtao(const RenderArgs &a, cudaStream_t s);
 // gamma_thr: 256 floats, [v-1] = smallest c with the rt.cpp gamma encode >= v (v = 1..255), [255] = +inf (encoder 0 only)
 void launch_tonemap(const float *accum, int W, int H, double inv_spp, int encoder, const float *gamma_thr, uint8_t *out, cudaStream_t s);

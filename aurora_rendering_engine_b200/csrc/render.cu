@@ -58,6 +58,9 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #ifndef RENDER_MIN_BLOCKS
 #define RENDER_MIN_BLOCKS 6
 #endif
+#ifndef RENDER_MIN_BLOCKS_LEAN
+#define RENDER_MIN_BLOCKS_LEAN 6
+#endif
 #ifndef RENDER_MIN_BLOCKS_BIG
 #define RENDER_MIN_BLOCKS_BIG 12  // hierarchies that live in L2 (not L1) are latency-bound: 48 resident warps/SM at 40 registers (with spills)
 #endif                            // beat 24 at 80 — measured on the 1 M-primitive scene: 467 -> 577 Msamples/s; RTIOW (L1-resident) loses 5 %
@@ -74,18 +77,32 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #define LEAF_MIN_LANES 1   // leaf tests run once this many lanes hold one (measured: 1 is best on RTIOW and on the 1 M-primitive stress scene)
 #endif
 // MODE: 0 = brute force from shared memory, 1 = BVH2, 2 = compressed 8-wide BVH
-template <int MODE, bool COUNT, bool BIG = false>
-__global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : RENDER_MIN_BLOCKS) k_render_path(const __grid_constant__ RenderArgs A) {
+// LEAN (brute force only): the scene compiler's lean form (scene.h: at most LEAN_MAX boxes / quad tests / triangle
+// tests, no spheres, every surface shaded from its ShadeRec alone).  The tests are a guarded full unroll with
+// compile-time shared-memory offsets instead of four counted loops, and a hit goes straight to its shading record
+// (six per box, one per face) held in shared memory: no id chain, no owner resolution, no general material path.
+template <int MODE, bool COUNT, bool BIG = false, bool LEAN = false>
+__global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : (LEAN ? RENDER_MIN_BLOCKS_LEAN : RENDER_MIN_BLOCKS)) k_render_path(const __grid_constant__ RenderArgs A) {
 	constexpr bool BVH = MODE != 0, WIDE = MODE == 2;
+	static_assert(!LEAN || MODE == 0, "the lean form is a brute-force list");
 	extern __shared__ float4 s_raw[];
 	__shared__ float s_acc[RENDER_THREADS / 32][96];
 	const HotPrim *s_prims = reinterpret_cast<const HotPrim *>(s_raw);
+	const float4 *s_shade = s_raw + 3 * A.sc.n_hot;                                              // LEAN: 2 x float4 per record
+	const int *s_sbase = reinterpret_cast<const int *>(s_raw + 3 * A.sc.n_hot + 2 * A.sc.n_lean_shade);  // LEAN: per brute slot
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	for (int i = lane; i < 96; i += 32) s_acc[warp][i] = 0.0f;
 	if (!BVH) {
 		const float4 *src = reinterpret_cast<const float4 *>(A.sc.brute);
 		const int n4 = A.sc.n_hot * 3;
 		for (int i = threadIdx.x; i < n4; i += RENDER_THREADS) s_raw[i] = __ldg(src + i);
+		if (LEAN) {
+			const float4 *ssrc = reinterpret_cast<const float4 *>(A.sc.lean_shade);
+			float4 *sdst = s_raw + n4;
+			for (int i = threadIdx.x; i < 2 * A.sc.n_lean_shade; i += RENDER_THREADS) sdst[i] = __ldg(ssrc + i);
+			int *bdst = reinterpret_cast<int *>(sdst + 2 * A.sc.n_lean_shade);
+			for (int i = threadIdx.x; i < A.sc.n_hot; i += RENDER_THREADS) bdst[i] = __ldg(A.sc.lean_sbase + i);
+		}
 	}
 	__syncthreads();
 	int x0, y0;
@@ -98,6 +115,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 	const unsigned full = 0xffffffffu;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const int total = (x0 < A.W && y0 < A.H) ? 32 * A.s_count : 0;
+	const bool tile_inside = x0 + 8 <= A.W && y0 + 4 <= A.H;  // warp-uniform: no per-task border test
 
 	int next = 0;          // next unissued task (warp-uniform)
 	int task = -1;         // this lane's task, -1 = needs one
@@ -187,15 +205,32 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 			finished = ray_ok && !trav;
 		} else if (ray_ok) {
 			h.t = INFINITY; h.idx = -1; h.orig = orig;
-			intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, br.nb, o, d, A.tmin, h);
+			if (LEAN) intersect_lean(s_prims, br.nb, br.nq, br.nt, o, d, A.tmin, h);
+			else intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, br.nb, o, d, A.tmin, h);
 			++rays;
 		}
 		if (finished) {
 			F3 contrib = mk<float>(0.f, 0.f, 0.f);
 			bool done;
 			if (h.idx < 0) {
-				contrib = thr * background(A, d);
+				if (!A.bg_black) contrib = thr * background(A, d);
 				done = true;
+			} else if (LEAN) {
+				sP = o + h.t * d;
+				int rec = s_sbase[h.idx];
+				if (h.idx < 2 * br.nb) rec += box_hit_face(lds4(&s_prims[h.idx].r0), lds4(&s_prims[h.idx].r1), lds4(&s_prims[h.idx].r2), lds4(&s_prims[h.idx + 1].r1), sP);
+				const float4 s0 = s_shade[2 * rec], s1 = s_shade[2 * rec + 1];
+				sbits = __float_as_int(s0.w);
+				sN = mk<float>(s0.x, s0.y, s0.z);
+				sp0 = s1.w;
+				const F3 scol = mk<float>(s1.x, s1.y, s1.z);
+				if ((sbits & 255) == MK_LIGHT) {
+					contrib = thr * scol;
+					done = true;
+				} else {
+					done = bounce >= A.max_depth;
+					thr = thr * scol;
+				}
 			} else {
 				sP = o + h.t * d;
 				orig = h.idx;
@@ -246,7 +281,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 			if (need) {
 				const int k = next + __popc(m & lt_mask);
 				if (k < total) {
-					if (x0 + (k & 7) < A.W && y0 + ((k >> 3) & 3) < A.H) {  // tiles on the image border own pixels outside it
+					if (tile_inside || (x0 + (k & 7) < A.W && y0 + ((k >> 3) & 3) < A.H)) {  // tiles on the image border own pixels outside it
 						task = k;
 						bounce = 0;
 					}
@@ -271,7 +306,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 			} else {
 				F3 wo;
 				bool alive;
-				if (sbits >> 8) alive = scatter_dir<float>(sbits & 255, sp0, d, sN, r, wo);  // SHADE_FAST: solid colour, simple lobe
+				if (LEAN || (sbits >> 8)) alive = scatter_dir<float>(sbits & 255, sp0, d, sN, r, wo);  // SHADE_FAST: solid colour, simple lobe
 				else {  // general path: textures, Reflective's lobe choice
 					const Resolved rs = resolve_exact(A.sc, HotIds{ sdev, -1 }, sP);
 					const PrimInfo pi = A.sc.info[rs.dev_prim];
@@ -314,13 +349,16 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 	}
 }
 
+bool render_path_is_lean(const RenderArgs &a) { return a.sc.lean_ok && a.lean; }
+bool render_path_is_big(const RenderArgs &a) { return a.sc.n_nodes > BVH_BIG_NODES; }
+
 int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStream_t s) {
 	const bool use_bvh = mode != 0;
 	const int warps = ((a.W + 15) / 16) * ((a.H + 7) / 8) * 4;  // one warp per 8x4 tile
 	const int tiles = (warps + RENDER_THREADS / 32 - 1) / (RENDER_THREADS / 32);
 	if (tiles <= 0) return -1;
 	if (use_bvh) {
-		const bool big = a.sc.n_nodes > BVH_BIG_NODES;
+		const bool big = render_path_is_big(a);
 		if (mode == 2) {
 			if (!a.sc.wnodes) return -1;
 			if (count_tests) {
@@ -340,7 +378,10 @@ int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStre
 	} else {
 		if (!a.sc.brute || a.sc.n_hot > BRUTE_MAX_PRIMS) return -1;
 		size_t smem = (size_t)a.sc.n_hot * sizeof(HotPrim);
-		k_render_path<0, false><<<tiles, RENDER_THREADS, smem, s>>>(a);
+		if (render_path_is_lean(a)) {
+			smem += (size_t)a.sc.n_lean_shade * sizeof(ShadeRec) + (size_t)a.sc.n_hot * sizeof(int);
+			k_render_path<0, false, false, true><<<tiles, RENDER_THREADS, smem, s>>>(a);
+		} else k_render_path<0, false><<<tiles, RENDER_THREADS, smem, s>>>(a);
 	}
 	return 1;
 }

@@ -897,6 +897,36 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 				if (it.kind == kind) { emit_item(it, out.brute, out.brute_ids); cnt[kind]++; }
 		out.brute_range = { 0, cnt[HK_QUAD], cnt[HK_TRI], cnt[HK_SPHERE], cnt[HK_BOX] };
 	}
+	// ---- lean tables (small flat-shaded scenes: hit -> shading record with no owner resolution) ----
+	out.lean_ok = false;
+	out.lean_shade.clear();
+	out.lean_sbase.clear();
+	if (!out.brute.empty() && out.n_sph == 0 && out.brute_range.ns == 0 && out.brute_range.nb <= LEAN_MAX && out.brute_range.nq <= LEAN_MAX &&
+		out.brute_range.nt <= LEAN_MAX) {
+		bool ok = true;
+		const ShadeRec none = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
+		auto add = [&](HotIds id) {
+			if (id.a < 0) { out.lean_shade.push_back(none); return; }  // absent box face: never hit
+			const ShadeRec &sr = out.shade[id.a];
+			unsigned bits;
+			std::memcpy(&bits, &sr.r0.w, 4);
+			if (id.b >= 0 || !(bits >> 8)) ok = false;  // halves shade differently, or shading needs textures / a lobe choice
+			out.lean_shade.push_back(sr);
+		};
+		out.lean_sbase.assign(out.brute.size(), 0);
+		size_t slot = 0;
+		for (int b = 0; b < out.brute_range.nb; ++b, slot += 2) {
+			out.lean_sbase[slot] = out.lean_sbase[slot + 1] = (int)out.lean_shade.size();
+			const int box = -1 - out.brute_ids[slot].a;
+			for (int f = 0; f < 6; ++f) add(out.box_faces[6 * (size_t)box + f]);
+		}
+		for (; slot < out.brute.size(); ++slot) {
+			out.lean_sbase[slot] = (int)out.lean_shade.size();
+			add(out.brute_ids[slot]);
+		}
+		out.lean_ok = ok;
+		if (!ok) { out.lean_shade.clear(); out.lean_sbase.clear(); }
+	}
 	// ---- BVH ----
 	if (!hot.empty()) {
 		Builder b(hot, out);  // one hot primitive per leaf (the traversal kernel relies on it)

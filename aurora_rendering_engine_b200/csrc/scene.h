@@ -46,6 +46,12 @@ struct CompiledScene {
 	HotRange brute_range = { 0, 0, 0, 0, 0 };
 	std::vector<HotIds> box_faces;  // 6 per box
 	int n_boxes = 0;
+	// Lean form of the brute list: valid (lean_ok) when the scene has no spheres, at most LEAN_MAX boxes / quad tests /
+	// triangle tests, and every surface shades from its ShadeRec alone (solid colour + simple lobe, both halves of every
+	// fused pair alike).  lean_shade holds one record per brute slot, six per box (one per face, zeros for an absent face).
+	bool lean_ok = false;
+	std::vector<ShadeRec> lean_shade;
+	std::vector<int> lean_sbase;
 	std::vector<HotPrim> bvh_prims;
 	std::vector<HotIds> bvh_ids;
 	std::vector<BvhNode> nodes;

@@ -121,7 +121,17 @@ typedef struct are_render_stats {
 	uint64_t box_tests; /* parallelepiped (three slab pairs) tests: boxes detected among the scene's parallelograms */
 	double kernel_ms; /* device time of the render kernel(s), CUDA events on the launch stream */
 	uint64_t launches; /* kernels launched by this call */
+	uint64_t kernel_variant; /* which render kernel ran: ARE_KERNEL_* */
 } are_render_stats;
+enum {
+	ARE_KERNEL_NONE = 0,
+	ARE_KERNEL_BRUTE = 1, /* generic brute-force list from shared memory */
+	ARE_KERNEL_BRUTE_LEAN = 2, /* small flat-shaded scene: unrolled tests, per-face shading records in shared memory */
+	ARE_KERNEL_BVH2 = 3,
+	ARE_KERNEL_BVH2_BIG = 4, /* high-occupancy build for hierarchies that live in L2 */
+	ARE_KERNEL_WIDE = 5,
+	ARE_KERNEL_RT_AO = 6
+};
 
 /* ---- context ------------------------------------------------------------------------------------------- */
 int are_cuda_abi_version(void);

@@ -62,6 +62,12 @@ def main():
         byfile[cur[0] if cur else None] += n
         w = txt.split()
         byop[w[1] if w[0].startswith("@") else w[0]] += n
+    dump = os.environ.get("NCU_LINES_DUMP")  # full listing in address order: count, threads / instruction, source line, SASS
+    if dump:
+        with open(dump, "w") as f:
+            for (txt, cur), r in zip(seq, data):
+                n, t = int(r[ie]), int(r[te])
+                f.write(f"{n:12d} {t / max(1, n):5.1f}  {str(cur[0]) + ':' + str(cur[1]) if cur else '-':24s} {txt}\n")
     print(f"warp instructions {tot}  avg active threads {tott / max(1, tot):.2f}")
     for k, v in byfile.most_common():
         print(f"  {str(k):34s} {100 * v / tot:5.1f}%")
