@@ -59,7 +59,7 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #define RENDER_MIN_BLOCKS 6
 #endif
 #ifndef RENDER_MIN_BLOCKS_LEAN
-#define RENDER_MIN_BLOCKS_LEAN 6
+#define RENDER_MIN_BLOCKS_LEAN 8
 #endif
 #ifndef RENDER_MIN_BLOCKS_BIG
 #define RENDER_MIN_BLOCKS_BIG 12  // hierarchies that live in L2 (not L1) are latency-bound: 48 resident warps/SM at 40 registers (with spills)
@@ -88,8 +88,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 	extern __shared__ float4 s_raw[];
 	__shared__ float s_acc[RENDER_THREADS / 32][96];
 	const HotPrim *s_prims = reinterpret_cast<const HotPrim *>(s_raw);
-	const float4 *s_shade = s_raw + 3 * A.sc.n_hot;                                              // LEAN: 2 x float4 per record
-	const int *s_sbase = reinterpret_cast<const int *>(s_raw + 3 * A.sc.n_hot + 2 * A.sc.n_lean_shade);  // LEAN: per brute slot
+	// LEAN shared-memory layout behind the hot slots: [ShadeRec per record][frame per record: (tangent,0) (bitangent,0)][record base per slot]
+	const uint32_t sb_prims = (uint32_t)__cvta_generic_to_shared(s_raw);
+	const uint32_t sb_shade = sb_prims + 48u * A.sc.n_hot, sb_frame = sb_shade + 32u * A.sc.n_lean_shade, sb_sbase = sb_frame + 32u * A.sc.n_lean_shade;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	for (int i = lane; i < 96; i += 32) s_acc[warp][i] = 0.0f;
 	if (!BVH) {
@@ -98,9 +99,16 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 		for (int i = threadIdx.x; i < n4; i += RENDER_THREADS) s_raw[i] = __ldg(src + i);
 		if (LEAN) {
 			const float4 *ssrc = reinterpret_cast<const float4 *>(A.sc.lean_shade);
-			float4 *sdst = s_raw + n4;
+			float4 *sdst = s_raw + n4, *fdst = sdst + 2 * A.sc.n_lean_shade;
 			for (int i = threadIdx.x; i < 2 * A.sc.n_lean_shade; i += RENDER_THREADS) sdst[i] = __ldg(ssrc + i);
-			int *bdst = reinterpret_cast<int *>(sdst + 2 * A.sc.n_lean_shade);
+			for (int i = threadIdx.x; i < A.sc.n_lean_shade; i += RENDER_THREADS) {  // the cosine lobe's frame, once per record instead of once per bounce
+				const float4 n = __ldg(ssrc + 2 * i);
+				F3 tg, bt;
+				tangent_frame(mk<float>(n.x, n.y, n.z), tg, bt);
+				fdst[2 * i] = make_float4(tg.x, tg.y, tg.z, 0.f);
+				fdst[2 * i + 1] = make_float4(bt.x, bt.y, bt.z, 0.f);
+			}
+			int *bdst = reinterpret_cast<int *>(fdst + 2 * A.sc.n_lean_shade);
 			for (int i = threadIdx.x; i < A.sc.n_hot; i += RENDER_THREADS) bdst[i] = __ldg(A.sc.lean_sbase + i);
 		}
 	}
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 			finished = ray_ok && !trav;
 		} else if (ray_ok) {
 			h.t = INFINITY; h.idx = -1; h.orig = orig;
-			if (LEAN) intersect_lean(s_prims, br.nb, br.nq, br.nt, o, d, A.tmin, h);
+			if (LEAN) intersect_lean(sb_prims, br.nb, br.nq, br.nt, o, d, A.tmin, h);
 			else intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, br.nb, o, d, A.tmin, h);
 			++rays;
 		}
@@ -217,9 +225,13 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 				done = true;
 			} else if (LEAN) {
 				sP = o + h.t * d;
-				int rec = s_sbase[h.idx];
-				if (h.idx < 2 * br.nb) rec += box_hit_face(lds4(&s_prims[h.idx].r0), lds4(&s_prims[h.idx].r1), lds4(&s_prims[h.idx].r2), lds4(&s_prims[h.idx + 1].r1), sP);
-				const float4 s0 = s_shade[2 * rec], s1 = s_shade[2 * rec + 1];
+				int rec = lds1a(sb_sbase + 4u * h.idx);
+				if (h.idx < 2 * br.nb) {
+					const uint32_t pb = sb_prims + 48u * h.idx;
+					rec += box_hit_face(lds4a(pb), lds4a(pb + 16u), lds4a(pb + 32u), lds4a(pb + 64u), sP);
+				}
+				const float4 s0 = lds4a(sb_shade + 32u * rec), s1 = lds4a(sb_shade + 32u * rec + 16u);
+				sdev = rec;
 				sbits = __float_as_int(s0.w);
 				sN = mk<float>(s0.x, s0.y, s0.z);
 				sp0 = s1.w;
@@ -306,7 +318,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 			} else {
 				F3 wo;
 				bool alive;
-				if (LEAN || (sbits >> 8)) alive = scatter_dir<float>(sbits & 255, sp0, d, sN, r, wo);  // SHADE_FAST: solid colour, simple lobe
+				if (LEAN) alive = scatter_dir<float>(sbits & 255, sp0, d, sN, r, wo, sb_frame + 32u * sdev);
+				else if (sbits >> 8) alive = scatter_dir<float>(sbits & 255, sp0, d, sN, r, wo);  // SHADE_FAST: solid colour, simple lobe
 				else {  // general path: textures, Reflective's lobe choice
 					const Resolved rs = resolve_exact(A.sc, HotIds{ sdev, -1 }, sP);
 					const PrimInfo pi = A.sc.info[rs.dev_prim];
@@ -379,7 +392,7 @@ int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStre
 		if (!a.sc.brute || a.sc.n_hot > BRUTE_MAX_PRIMS) return -1;
 		size_t smem = (size_t)a.sc.n_hot * sizeof(HotPrim);
 		if (render_path_is_lean(a)) {
-			smem += (size_t)a.sc.n_lean_shade * sizeof(ShadeRec) + (size_t)a.sc.n_hot * sizeof(int);
+			smem += (size_t)a.sc.n_lean_shade * (sizeof(ShadeRec) + 2 * sizeof(float4)) + (size_t)a.sc.n_hot * sizeof(int);
 			k_render_path<0, false, false, true><<<tiles, RENDER_THREADS, smem, s>>>(a);
 		} else k_render_path<0, false><<<tiles, RENDER_THREADS, smem, s>>>(a);
 	}

@@ -120,25 +120,49 @@ __device__ V3<T> tex_eval(const DevScene &sc, int id, T u, T v, V3<T> P) {
 }
 
 // ---- sampling -----------------------------------------------------------------------------------------
+// rotateToHemisphere's frame (rt.cpp:50-53).  frame(-n) = (-tangent, bitangent): `up` depends on |n.z| only, the cross
+// products are odd / even in n and every operation commutes exactly with negation.
 template <typename T>
-__device__ __forceinline__ V3<T> cosine_dir(V3<T> n, T r1, T r2) {
+__device__ __forceinline__ void tangent_frame(V3<T> n, V3<T> &tangent, V3<T> &bitangent) {
+	V3<T> up = abs_t(n.z) < T(0.999) ? mk<T>(T(0), T(0), T(1)) : mk<T>(T(1), T(0), T(0));
+	tangent = nrm(cross(n, up));
+	bitangent = cross(n, tangent);
+}
+template <typename T>
+__device__ __forceinline__ V3<T> cosine_dir_in_frame(V3<T> n, V3<T> tangent, V3<T> bitangent, T r1, T r2) {
 	T sn, cs;
 	sincos2pi_t(r1, &sn, &cs);
 	T r2s = sqrt_t(r2);
 	T lx = r2s * cs, ly = r2s * sn;
-	V3<T> up = abs_t(n.z) < T(0.999) ? mk<T>(T(0), T(0), T(1)) : mk<T>(T(1), T(0), T(0));
-	V3<T> tangent = nrm(cross(n, up));
-	V3<T> bitangent = cross(n, tangent);
 	// rt.cpp:54 rebuilds lz from lx, ly; lx^2 + ly^2 = r2 exactly, so sqrt(1 - r2) is the same quantity without
 	// the sin/cos rounding amplified at grazing directions
 	T lz = sqrt_t(max_t(T(0), T(1) - r2));
 	return lx * tangent + ly * bitangent + lz * n;
 }
 template <typename T>
+__device__ __forceinline__ V3<T> cosine_dir(V3<T> n, T r1, T r2) {
+	V3<T> tangent, bitangent;
+	tangent_frame(n, tangent, bitangent);
+	return cosine_dir_in_frame(n, tangent, bitangent, r1, r2);
+}
+template <typename T>
 __device__ __forceinline__ V3<T> sphere_dir(T r0, T r1) {
 	T z = T(1) - T(2) * r0, rxy = sqrt_t(max_t(T(0), T(1) - z * z)), sn, cs;
 	sincos2pi_t(r1, &sn, &cs);
 	return mk<T>(rxy * cs, rxy * sn, z);
+}
+
+template <typename T>
+__device__ __forceinline__ V3<T> cosine_dir_framed(V3<T> nf, bool front, unsigned frame_addr, T r1, T r2);
+template <>
+__device__ __forceinline__ V3<double> cosine_dir_framed<double>(V3<double> nf, bool, unsigned, double r1, double r2) { return cosine_dir<double>(nf, r1, r2); }
+template <>
+__device__ __forceinline__ V3<float> cosine_dir_framed<float>(V3<float> nf, bool front, unsigned frame_addr, float r1, float r2) {
+	float4 t, b;
+	asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(frame_addr));
+	asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(frame_addr + 16u));
+	const V3<float> tg = front ? mk<float>(t.x, t.y, t.z) : mk<float>(-t.x, -t.y, -t.z);
+	return cosine_dir_in_frame<float>(nf, tg, mk<float>(b.x, b.y, b.z), r1, r2);
 }
 
 __device__ __forceinline__ int mat_texture(const MaterialRec &m, int prim_tex) {
@@ -151,8 +175,10 @@ __device__ __forceinline__ int mat_texture(const MaterialRec &m, int prim_tex) {
 // Direction sampling shared by the general path and the SHADE_FAST path of the render loop.
 // lobe: MK_DIELECTRIC (p0 = ior), MK_METAL (p0 = fuzz), MK_REFLECTIVE = perfect mirror, anything else = cosine lobe.
 // wi unit incoming, Ng geometric unit normal (either side). Returns alive; wo is unit length.
+// FRAME_ADDR != 0 (fp32 lean kernel): shared-memory address of the frame of +Ng, precomputed once per shading record
+// by the very routine above — (tangent, 0) (bitangent, 0) as two float4.
 template <typename T>
-__device__ __forceinline__ bool scatter_dir(int lobe, T p0, V3<T> wi, V3<T> Ng, Rnd4<T> r, V3<T> &wo) {
+__device__ __forceinline__ bool scatter_dir(int lobe, T p0, V3<T> wi, V3<T> Ng, Rnd4<T> r, V3<T> &wo, unsigned frame_addr = 0u) {
 	const bool front = dot(wi, Ng) < T(0);
 	const V3<T> nf = front ? Ng : -Ng;
 	if (lobe == MK_DIELECTRIC) {
@@ -176,7 +202,8 @@ __device__ __forceinline__ bool scatter_dir(int lobe, T p0, V3<T> wi, V3<T> Ng, 
 		wo = nrm(reflect(wi, nf));
 		return true;
 	}
-	wo = renorm(cosine_dir<T>(nf, r.x, r.y));
+	if (frame_addr != 0u) wo = renorm(cosine_dir_framed<T>(nf, front, frame_addr, r.x, r.y));
+	else wo = renorm(cosine_dir<T>(nf, r.x, r.y));
 	return true;
 }
 

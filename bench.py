@@ -312,16 +312,19 @@ def run_b200(a):
         ref_flops = st.rays * (F_TRI * len(sc.tris) + F_QUAD * len(sc.quads) + F_SPH * len(sc.spheres)) + F_SCATTER * max(0, st.rays - st.samples) + F_PRIMARY * st.samples
         traffic, ncu = None, None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this launch size, from the committed ncu capture
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_render_path_full.json")))
+            prof_name = "r01_render_lean_full.json" if st.kernel_variant == capi.KERNEL_BRUTE_LEAN else "r01_render_path_full.json"
+            prof = json.load(open(os.path.join(ROOT, "profiles", prof_name)))
             if prof.get("width") == W and prof.get("height") == H and prof.get("spp_per_step") == S:
                 traffic = prof.get("dram_bytes")
                 # the resource that actually binds this kernel (not measured live: copied from the committed capture)
                 ncu = {"issue_slot_utilisation_pct": prof.get("issue_slot_utilisation_pct"),
                        "active_threads_per_instruction": prof.get("active_threads_per_instruction"),
-                       "source": "profiles/r01_render_path_full.json (ncu --set full, same launch size)"}
+                       "source": "profiles/%s (ncu --set full, same launch size)" % prof_name}
         except Exception:
             pass
-        kernel_name = "k_render_rtao" if sc.integrator == 1 else "k_render_path<%s>" % ("bvh" if use_bvh else "brute/smem")
+        kernel_name = {capi.KERNEL_RT_AO: "k_render_rtao", capi.KERNEL_BRUTE: "k_render_path<brute/smem>",
+                       capi.KERNEL_BRUTE_LEAN: "k_render_path<brute/smem, lean>", capi.KERNEL_BVH2: "k_render_path<bvh2>",
+                       capi.KERNEL_BVH2_BIG: "k_render_path<bvh2, 12 CTAs/SM>", capi.KERNEL_WIDE: "k_render_path<wide bvh>"}.get(st.kernel_variant, "?")
         # the same kernel against the HBM roofline (MEASURED_PEAKS.json, driver-written): algorithmic bytes per launch = one
         # read-modify-write of the W*H*3 fp32 accumulator; the working set of the loop lives in shared memory / registers
         try:
