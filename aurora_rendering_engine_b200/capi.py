@@ -43,6 +43,16 @@ class RenderStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class CommitInfo(C.Structure):
+    """are_commit_info"""
+    _fields_ = [("builder", C.c_int), ("bvh_nodes", C.c_int), ("bvh_height", C.c_int), ("hot_slots", C.c_int), ("host_compile_ms", C.c_double),
+                ("host_bvh_ms", C.c_double), ("device_bvh_ms", C.c_double), ("device_bvh_launches", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+BVH_BUILDER_HOST_SAH, BVH_BUILDER_DEVICE_LBVH = 0, 1
 KERNEL_NONE, KERNEL_BRUTE, KERNEL_BRUTE_LEAN, KERNEL_BVH2, KERNEL_BVH2_BIG, KERNEL_WIDE, KERNEL_RT_AO = range(7)
 
 
@@ -126,6 +136,8 @@ SIGNATURES = {
     "are_cuda_destroy": (None, [_vp]),
     "are_cuda_last_error": (C.c_char_p, [_vp]),
     "are_cuda_set_stream": (C.c_int, [_vp, _vp]),
+    "are_cuda_set_bvh_builder": (C.c_int, [_vp, C.c_int]),
+    "are_cuda_get_commit_info": (C.c_int, [_vp, C.POINTER(CommitInfo)]),
     "are_cuda_add_texture": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int, C.c_int]),
     "are_cuda_add_material": (C.c_int, [_vp, C.c_int, _dp]),
     "are_cuda_add_triangle": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
@@ -262,6 +274,14 @@ class Context:
         self._ck(self.lib.are_cuda_set_stream(self.h, _vp(cuda_stream_handle)))
 
     # -- scene ----------------------------------------------------------------------------------------
+    def set_bvh_builder(self, builder: int):
+        self._ck(self.lib.are_cuda_set_bvh_builder(self.h, int(builder)))
+
+    def commit_info(self) -> CommitInfo:
+        info = CommitInfo()
+        self._ck(self.lib.are_cuda_get_commit_info(self.h, C.byref(info)))
+        return info
+
     def add_texture(self, kind, params, rgb=None):
         p = _d(params, (8,))
         if rgb is not None:

@@ -44,6 +44,11 @@ struct are_cuda_ctx {
 	CompileOptions opt;
 	PatchWorkspace patch_ws;
 	float *d_gamma_thr = nullptr;  // thresholds of the rt.cpp gamma-2.2 encode (built on first use)
+	int bvh_builder = ARE_BVH_BUILDER_HOST_SAH;
+	cudaMemPool_t pool = nullptr;  // scene arrays come from a private stream-ordered pool that keeps freed blocks: a re-commit reuses them
+	void *lbvh_ws = nullptr;  // scratch of the device BVH builder, grown on demand and kept between commits
+	size_t lbvh_ws_bytes = 0;
+	are_commit_info commit_info = {};
 	int wide_min_nodes = 0x7fffffff;  // AUTO never picks the compressed 8-wide BVH (measured slower); ARE_CUDA_WIDE_MIN_NODES overrides
 };
 
@@ -83,8 +88,10 @@ struct Bind {  // make the context's device current for the duration of a call
 	}
 };
 
+cudaError_t scene_malloc(are_cuda_ctx *ctx, void **p, size_t bytes) { return cudaMallocFromPoolAsync(p, bytes ? bytes : 1, ctx->pool, ctx->stream); }
+
 void free_scene_allocs(are_cuda_ctx *ctx) {
-	for (void *p : ctx->scene_allocs) cudaFree(p);
+	for (void *p : ctx->scene_allocs) cudaFreeAsync(p, ctx->stream);
 	ctx->scene_allocs.clear();
 	std::memset(&ctx->dev, 0, sizeof ctx->dev);
 	ctx->committed = false;
@@ -95,7 +102,7 @@ int upload(are_cuda_ctx *ctx, const std::vector<T> &v, const T **out, uint64_t &
 	*out = nullptr;
 	if (v.empty()) return ARE_OK;
 	void *d = nullptr;
-	CK(cudaMalloc(&d, v.size() * sizeof(T)));
+	CK(scene_malloc(ctx, &d, v.size() * sizeof(T)));
 	ctx->scene_allocs.push_back(d);
 	CK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
 	bytes += v.size() * sizeof(T);
@@ -194,6 +201,18 @@ int are_cuda_create(are_cuda_ctx **out, int device) {
 	Bind b(ctx);
 	cudaError_t e1 = cudaMalloc((void **)&ctx->d_counters, CNT_N * sizeof(unsigned long long));
 	cudaError_t e2 = cudaEventCreate(&ctx->ev0), e3 = cudaEventCreate(&ctx->ev1);
+	if (e1 == cudaSuccess) {
+		cudaMemPoolProps props = {};
+		props.allocType = cudaMemAllocationTypePinned;
+		props.handleTypes = cudaMemHandleTypeNone;
+		props.location.type = cudaMemLocationTypeDevice;
+		props.location.id = device;
+		e1 = cudaMemPoolCreate(&ctx->pool, &props);
+		if (e1 == cudaSuccess) {
+			uint64_t keep = ~0ull;  // never hand freed blocks back to the driver while the context lives
+			e1 = cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+	}
 	if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
 		std::string m = std::string("context set-up failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
 		delete ctx;
@@ -208,7 +227,10 @@ void are_cuda_destroy(are_cuda_ctx *ctx) {
 	Bind b(ctx);
 	cudaStreamSynchronize(ctx->stream);
 	free_scene_allocs(ctx);
+	cudaStreamSynchronize(ctx->stream);
+	if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
 	ctx->patch_ws.release();
+	if (ctx->lbvh_ws) cudaFree(ctx->lbvh_ws);
 	if (ctx->d_gamma_thr) cudaFree(ctx->d_gamma_thr);
 	if (ctx->own_accum) cudaFree(ctx->own_accum);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
@@ -222,6 +244,20 @@ const char *are_cuda_last_error(are_cuda_ctx *ctx) { return ctx ? ctx->err.c_str
 int are_cuda_set_stream(are_cuda_ctx *ctx, void *cuda_stream) {
 	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
 	ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+	return ARE_OK;
+}
+
+int are_cuda_set_bvh_builder(are_cuda_ctx *ctx, int builder) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	if (builder != ARE_BVH_BUILDER_HOST_SAH && builder != ARE_BVH_BUILDER_DEVICE_LBVH) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown BVH builder");
+	ctx->bvh_builder = builder;
+	return ARE_OK;
+}
+int are_cuda_get_commit_info(are_cuda_ctx *ctx, are_commit_info *out) {
+	int st = need_commit(ctx);
+	if (st) return st;
+	if (!out) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	*out = ctx->commit_info;
 	return ARE_OK;
 }
 
@@ -334,11 +370,76 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	if (const char *e = getenv("ARE_CUDA_NO_FUSE")) ctx->opt.fuse_parallelograms = !(e[0] == '1');
 	if (const char *e = getenv("ARE_CUDA_NO_BOXES")) ctx->opt.fuse_boxes = !(e[0] == '1');
 	if (const char *e = getenv("ARE_CUDA_WIDE")) ctx->opt.build_wide = e[0] == '1';
-	if (!compile_scene(ctx->scene, ctx->opt, ctx->cs, err)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, err);
-	const CompiledScene &cs = ctx->cs;
+	int builder = ctx->bvh_builder;
+	if (const char *e = getenv("ARE_CUDA_DEVICE_BVH")) builder = e[0] == '1' ? ARE_BVH_BUILDER_DEVICE_LBVH : ARE_BVH_BUILDER_HOST_SAH;
+	are_commit_info info = {};
 	DevScene d;
-	std::memset(&d, 0, sizeof d);
 	uint64_t bytes = 0;
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		ctx->opt.device_bvh = builder == ARE_BVH_BUILDER_DEVICE_LBVH;
+		const auto t0 = std::chrono::steady_clock::now();
+		if (!compile_scene(ctx->scene, ctx->opt, ctx->cs, err)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, err);
+		info.host_compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		info.host_bvh_ms = ctx->cs.host_bvh_ms;
+		if (!ctx->opt.device_bvh || ctx->cs.lb_lo.empty()) break;
+		// ---- device BVH build: inputs are temporaries, outputs belong to the scene ----
+		const CompiledScene &c = ctx->cs;
+		std::memset(&d, 0, sizeof d);
+		bytes = 0;
+		int st;
+		LbvhInput in;
+		LbvhOutput out;
+		std::memset(&in, 0, sizeof in);
+		std::memset(&out, 0, sizeof out);
+#define UPT(vec, field)                                                       \
+	if ((st = upload(ctx, c.vec, &in.field, bytes)) != ARE_OK) return st;
+		UPT(lb_lo, item_lo) UPT(lb_hi, item_hi) UPT(lb_prims, item_prims) UPT(lb_ids, item_ids) UPT(lb_slot, item_slot)
+#undef UPT
+		const size_t n_temp = ctx->scene_allocs.size();
+		in.n_items = (int)c.lb_lo.size();
+		in.n_slots = (int)c.lb_prims.size();
+		for (int k = 0; k < 3; ++k) { in.cmin[k] = c.lb_cmin[k]; in.cmax[k] = c.lb_cmax[k]; }
+		void *p = nullptr;
+		CK(scene_malloc(ctx, &p, (size_t)(in.n_items > 1 ? in.n_items - 1 : 0) * sizeof(BvhNode))); ctx->scene_allocs.push_back(p); out.nodes = static_cast<BvhNode *>(p);
+		CK(scene_malloc(ctx, &p, (size_t)in.n_slots * sizeof(HotPrim))); ctx->scene_allocs.push_back(p); out.prims = static_cast<HotPrim *>(p);
+		CK(scene_malloc(ctx, &p, (size_t)in.n_slots * sizeof(HotIds))); ctx->scene_allocs.push_back(p); out.ids = static_cast<HotIds *>(p);
+		const size_t ws_need = lbvh_workspace_bytes(in.n_items);
+		if (ctx->lbvh_ws_bytes < ws_need) {
+			if (ctx->lbvh_ws) { CK(cudaFree(ctx->lbvh_ws)); ctx->lbvh_ws = nullptr; ctx->lbvh_ws_bytes = 0; }
+			CK(cudaMalloc(&ctx->lbvh_ws, ws_need + ws_need / 4));
+			ctx->lbvh_ws_bytes = ws_need + ws_need / 4;
+		}
+		CK(cudaEventRecord(ctx->ev0, ctx->stream));
+		std::string berr;
+		const int launched = lbvh_build(in, out, ctx->lbvh_ws, ctx->lbvh_ws_bytes, ctx->stream, berr);
+		if (launched < 0) return fail(ctx, ARE_ERR_CUDA, "device BVH build: " + berr);
+		CK(cudaEventRecord(ctx->ev1, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		float ms = 0.f;
+		CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		// the five input temporaries go; the three outputs stay
+		for (size_t i = 0; i < n_temp; ++i) cudaFreeAsync(ctx->scene_allocs[i], ctx->stream);
+		ctx->scene_allocs.erase(ctx->scene_allocs.begin(), ctx->scene_allocs.begin() + n_temp);
+		if (out.height > ARE_BVH_STACK) {  // deeper than the traversal stack (many coincident centres): the SAH builder bounds its depth
+			free_scene_allocs(ctx);
+			builder = ARE_BVH_BUILDER_HOST_SAH;
+			continue;
+		}
+		d.nodes = out.nodes; d.bvh_prims = out.prims; d.bvh_ids = out.ids;
+		d.n_nodes = out.n_nodes;
+		d.root_leaf_meta = out.root_leaf_ref;
+		info.device_bvh_ms = ms;
+		info.device_bvh_launches = (uint64_t)launched;
+		info.bvh_height = out.height;
+		break;
+	}
+	const CompiledScene &cs = ctx->cs;
+	const bool device_built = ctx->opt.device_bvh && !cs.lb_lo.empty();
+	if (!device_built) std::memset(&d, 0, sizeof d);
+	const BvhNode *dev_nodes = d.nodes;
+	const HotPrim *dev_bvh_prims = d.bvh_prims;
+	const HotIds *dev_bvh_ids = d.bvh_ids;
+	const int dev_n_nodes = d.n_nodes, dev_root_leaf = d.root_leaf_meta;
 	int st;
 #define UP(vec, field)                                                     \
 	if ((st = upload(ctx, cs.vec, &d.field, bytes)) != ARE_OK) return st;
@@ -352,15 +453,21 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	d.n_lean_shade = (int)cs.lean_shade.size();
 	d.brute_range = cs.brute_range;
 	d.n_nodes = (int)cs.nodes.size();
+	d.root_leaf_meta = cs.root_leaf_meta;
+	if (device_built) { d.nodes = dev_nodes; d.bvh_prims = dev_bvh_prims; d.bvh_ids = dev_bvh_ids; d.n_nodes = dev_n_nodes; d.root_leaf_meta = dev_root_leaf; }
 	d.n_wnodes = d.wnodes ? (int)cs.wnodes.size() : 0;
 	if (const char *e = getenv("ARE_CUDA_WIDE_MIN_NODES")) ctx->wide_min_nodes = atoi(e);
-	d.root_leaf_meta = cs.root_leaf_meta;
 	d.n_hot = cs.n_hot;
 	d.n_tri = cs.n_tri; d.n_quad = cs.n_quad; d.n_sph = cs.n_sph;
 	d.n_mat = (int)cs.mats.size(); d.n_tex = (int)cs.texs.size();
 	CK(cudaStreamSynchronize(ctx->stream));
 	ctx->dev = d;
 	ctx->committed = true;
+	info.builder = device_built ? ARE_BVH_BUILDER_DEVICE_LBVH : ARE_BVH_BUILDER_HOST_SAH;
+	info.bvh_nodes = d.n_nodes;
+	if (!device_built) info.bvh_height = cs.bvh_depth;
+	info.hot_slots = cs.n_hot;
+	ctx->commit_info = info;
 	if (h2d_bytes) *h2d_bytes = bytes;
 	return ARE_OK;
 }

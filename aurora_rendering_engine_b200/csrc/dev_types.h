@@ -100,6 +100,8 @@ struct WideNode {
 // tests, nt triangle tests, ns sphere tests.  The brute-force list is one big range; every BVH leaf is a small one.
 struct HotRange { int first, nq, nt, ns, nb; };
 
+#define ARE_BVH_STACK 48  // entries of the per-thread BVH2 traversal stack = the deepest hierarchy the kernels accept
+
 enum { LEAN_MAX = 4 };  // boxes, quad tests and triangle tests (each) that the lean render kernel unrolls
 
 struct DevScene {

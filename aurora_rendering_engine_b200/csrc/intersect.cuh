@@ -182,7 +182,6 @@ __device__ __forceinline__ void intersect_lean(uint32_t sb, int nb, int nq, int 
 }
 
 // ---- BVH2 traversal, per-thread stack -----------------------------------------------------------------
-#define ARE_BVH_STACK 48
 
 struct TravCounters {
 	unsigned long long nodes, quads, tris, spheres, boxes;

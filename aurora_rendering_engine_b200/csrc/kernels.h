@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+
 #include "dev_types.h"
 #include "philox.cuh"
 
@@ -71,5 +73,25 @@ void launch_tonemap(const float *accum, int W, int H, double inv_spp, int encode
 double launch_fp32_peak(float *sink, int sm_count, int iters, cudaStream_t s);
 
 size_t brute_smem_limit_prims();
+
+// BVH2 construction on the device (lbvh.cu).  All pointers are device memory; the outputs are allocated by the caller:
+// nodes[n_items - 1], prims[n_slots], ids[n_slots].  Returns the number of kernels launched, < 0 on a CUDA error (err).
+struct LbvhInput {
+	const f4 *item_lo, *item_hi;    // per hot item: conservative fp32 bounds; lo.w = the item's test kind as int bits (0 box, 1 quad, 2 triangle, 3 sphere)
+	const HotPrim *item_prims;      // records in item order (a box takes two slots)
+	const HotIds *item_ids;
+	const int *item_slot;           // first slot of each item in item_prims / item_ids
+	int n_items, n_slots;
+	float cmin[3], cmax[3];         // bounds of the item box centres
+};
+struct LbvhOutput {
+	BvhNode *nodes;
+	HotPrim *prims;
+	HotIds *ids;
+	int n_nodes, height, root_leaf_ref;
+};
+// `workspace`: at least lbvh_workspace_bytes(n_items) bytes of device memory (scratch; reusable across builds)
+size_t lbvh_workspace_bytes(int n_items);
+int lbvh_build(const LbvhInput &in, LbvhOutput &out, void *workspace, size_t workspace_bytes, cudaStream_t s, std::string &err);
 
 }  // namespace areb

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -928,7 +929,41 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 		if (!ok) { out.lean_shade.clear(); out.lean_sbase.clear(); }
 	}
 	// ---- BVH ----
-	if (!hot.empty()) {
+	const auto bvh_t0 = std::chrono::steady_clock::now();
+	if (!hot.empty() && opt.device_bvh) {
+		// input of the device builder: conservative fp32 bounds (rounded outwards) + the records in item order
+		const size_t n = hot.size();
+		out.lb_lo.resize(n); out.lb_hi.resize(n); out.lb_slot.resize(n);
+		const float inf = std::numeric_limits<float>::infinity();
+		int slots = 0;
+		for (size_t i = 0; i < n; ++i) { out.lb_slot[i] = slots; slots += hot[i].kind == HK_BOX ? 2 : 1; }
+		out.lb_prims.resize(slots); out.lb_ids.resize(slots);
+		const unsigned T = host_threads();
+		std::vector<float> tmin(3 * (size_t)T, inf), tmax(3 * (size_t)T, -inf);
+		std::atomic<unsigned> next_slot{ 0 };
+		parallel_chunks(n, 8192, [&](size_t i0, size_t i1) {
+			const unsigned me = next_slot.fetch_add(1);  // private min / max slot of this chunk
+			auto down = [&](double x) { float f = (float)x; return (double)f > x ? std::nextafter(f, -inf) : f; };
+			auto up = [&](double x) { float f = (float)x; return (double)f < x ? std::nextafter(f, inf) : f; };
+			for (size_t i = i0; i < i1; ++i) {
+				const HotItem &it = hot[i];
+				float kindf;
+				const int kind = it.kind;
+				std::memcpy(&kindf, &kind, 4);
+				out.lb_lo[i] = { down(it.box.lo[0]), down(it.box.lo[1]), down(it.box.lo[2]), kindf };
+				out.lb_hi[i] = { up(it.box.hi[0]), up(it.box.hi[1]), up(it.box.hi[2]), 0.f };
+				const float c[3] = { 0.5f * (out.lb_lo[i].x + out.lb_hi[i].x), 0.5f * (out.lb_lo[i].y + out.lb_hi[i].y), 0.5f * (out.lb_lo[i].z + out.lb_hi[i].z) };
+				for (int k = 0; k < 3; ++k) { tmin[3 * me + k] = std::min(tmin[3 * me + k], c[k]); tmax[3 * me + k] = std::max(tmax[3 * me + k], c[k]); }
+				const int sl = out.lb_slot[i];
+				out.lb_prims[sl] = it.rec; out.lb_ids[sl] = it.ids;
+				if (it.kind == HK_BOX) { out.lb_prims[sl + 1] = it.rec2; out.lb_ids[sl + 1] = it.ids; }
+			}
+		});
+		for (int k = 0; k < 3; ++k) { out.lb_cmin[k] = inf; out.lb_cmax[k] = -inf; }
+		for (unsigned t = 0; t < T; ++t)
+			for (int k = 0; k < 3; ++k) { out.lb_cmin[k] = std::min(out.lb_cmin[k], tmin[3 * t + k]); out.lb_cmax[k] = std::max(out.lb_cmax[k], tmax[3 * t + k]); }
+		phase("device BVH input");
+	} else if (!hot.empty()) {
 		Builder b(hot, out);  // one hot primitive per leaf (the traversal kernel relies on it)
 		ChildRef root = b.build(0, (int)hot.size(), 0, 0, 0);
 		if (root.ref < 0) out.root_leaf_meta = root.ref;  // a one-primitive scene: the root IS the leaf reference
@@ -938,6 +973,7 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 		// BVH2 on B200 for this kernel: built for small scenes (cheap) and on request for large ones.
 		if (opt.build_wide || out.nodes.size() <= 65536) WideBuilder(out, out).build();
 	}
+	out.host_bvh_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - bvh_t0).count();
 	phase("wide BVH collapse");
 	if (verbose) fprintf(stderr, "[are_cuda compile] %zu hot items, BVH2 %zu nodes depth %d, wide %zu nodes depth %d\n", hot.size(), out.nodes.size(), out.bvh_depth, out.wnodes.size(), out.wide_depth);
 	return true;

@@ -73,6 +73,14 @@ struct CompiledScene {
 	std::vector<TextureRec> texs;
 	std::vector<float> tex_data;
 	int bvh_depth = 0;
+	// Input of the device BVH builder (CompileOptions::device_bvh; lbvh.cu) instead of nodes / bvh_prims / bvh_ids:
+	// per hot item conservative fp32 bounds (lo.w = test kind as int bits), records in item order, first slot per item.
+	std::vector<f4> lb_lo, lb_hi;
+	std::vector<HotPrim> lb_prims;
+	std::vector<HotIds> lb_ids;
+	std::vector<int> lb_slot;
+	float lb_cmin[3] = { 0, 0, 0 }, lb_cmax[3] = { 0, 0, 0 };  // bounds of the item box centres
+	double host_bvh_ms = 0.0;  // time spent in the host BVH builders (0 under device_bvh)
 };
 
 struct CompileOptions {
@@ -80,6 +88,7 @@ struct CompileOptions {
 	bool fuse_boxes = true;
 	int brute_max = 1024;
 	bool build_wide = false;  // also build the compressed 8-wide BVH for scenes beyond 65536 BVH2 nodes
+	bool device_bvh = false;  // leave the hierarchy to the device builder (lbvh.cu): emit its input instead of nodes
 };
 
 // Validation mirroring are::Triangle's ctor (src/object/triangle.cpp:22-36): returns nullptr when fine, else the

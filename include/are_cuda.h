@@ -142,6 +142,24 @@ const char *are_cuda_last_error(are_cuda_ctx *ctx); /* ctx may be NULL: last err
 /* Use an existing CUDA stream (cudaStream_t passed as void*; NULL = the legacy default stream) for all work. */
 int are_cuda_set_stream(are_cuda_ctx *ctx, void *cuda_stream);
 
+/* Who builds the BVH at the next commit.  The reference has no hierarchy (its ObjectSet is scanned linearly,
+ * include/object/object_set.h:10-12); both builders are NEW.
+ *   HOST_SAH     binned surface-area heuristic on all host threads (default): best trees, ~0.75 s per million primitives
+ *   DEVICE_LBVH  Morton codes + radix sort + Karras' radix tree + bottom-up boxes on the GPU: milliseconds per million
+ *                primitives, somewhat slower traversal — for scenes that change every frame.  Falls back to HOST_SAH when
+ *                the tree would be deeper than the traversal stack (are_commit_info.builder tells). */
+enum { ARE_BVH_BUILDER_HOST_SAH = 0, ARE_BVH_BUILDER_DEVICE_LBVH = 1 };
+int are_cuda_set_bvh_builder(are_cuda_ctx *ctx, int builder);
+typedef struct are_commit_info {
+	int builder; /* ARE_BVH_BUILDER_* actually used by the last commit */
+	int bvh_nodes, bvh_height, hot_slots;
+	double host_compile_ms; /* flattening, fusion, box detection (+ the host BVH build under HOST_SAH) */
+	double host_bvh_ms; /* of which: host BVH builders */
+	double device_bvh_ms; /* DEVICE_LBVH: CUDA-event time of the build kernels */
+	uint64_t device_bvh_launches;
+} are_commit_info;
+int are_cuda_get_commit_info(are_cuda_ctx *ctx, are_commit_info *out);
+
 /* ---- scene description (host side, cheap; nothing touches the GPU until commit) ---------------------- */
 /* Each add_* returns the new non-negative id, or a negative are_status. */
 int are_cuda_add_texture(are_cuda_ctx *ctx, int kind, const double params[8], const double *rgb, int w, int h);

@@ -1,0 +1,122 @@
+"""Device BVH builder (csrc/lbvh.cu) through the C ABI.
+
+A BVH only prunes: whichever builder made it, a ray must meet the same primitive at the same distance, because the
+leaves run the same per-primitive arithmetic.  So the device-built hierarchy (Morton codes + radix sort + Karras tree)
+is checked against the host binned-SAH hierarchy and against brute force for IDENTICAL closest hits, and its images
+against the host-built ones and the CPU twin.
+"""
+import numpy as np
+import pytest
+
+from aurora_rendering_engine_b200 import capi, scenes
+from oracle_binding import psnr
+
+pytestmark = pytest.mark.gpu
+
+
+def _commit(ctx, sc, builder):
+    ctx.clear()
+    ctx.set_bvh_builder(builder)
+    sc.feed(ctx)
+    ctx.commit()
+    return ctx.commit_info()
+
+
+def test_lbvh_closest_hits_equal_host_sah_and_brute(ctx):
+    sc = scenes.stress(n_prims=20_000, width=8, height=8)
+    rng = np.random.RandomState(5)
+    n = 300_000
+    Q = rng.uniform(-12, 12, (n, 3))
+    D = rng.normal(size=(n, 3))
+    D[:1000, 0] = 0.0
+    D[1000:2000, 1] = 0.0
+    info_h = _commit(ctx, sc, capi.BVH_BUILDER_HOST_SAH)
+    ph, th, Ph, Nh, uvh = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=2)
+    info_d = _commit(ctx, sc, capi.BVH_BUILDER_DEVICE_LBVH)
+    pd, td, Pd, Nd, uvd = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=2)
+    assert info_h.builder == capi.BVH_BUILDER_HOST_SAH and info_d.builder == capi.BVH_BUILDER_DEVICE_LBVH
+    assert info_d.bvh_nodes == info_h.bvh_nodes == info_d.hot_slots - 1  # one primitive per leaf, no boxes in this scene
+    assert 0 < info_d.bvh_height <= 48 and info_d.device_bvh_ms > 0 and info_d.device_bvh_launches >= 5
+    print(f"[lbvh 20k] host SAH {info_h.host_bvh_ms:.2f} ms (height {info_h.bvh_height}), device LBVH {info_d.device_bvh_ms:.3f} ms (height {info_d.bvh_height})")
+    assert 0.01 < (ph >= 0).mean() < 0.99
+    assert np.array_equal(ph, pd)
+    hit = ph >= 0
+    assert np.array_equal(th[hit], td[hit]) and np.array_equal(Ph[hit], Pd[hit]) and np.array_equal(uvh[hit], uvd[hit])
+
+
+def test_lbvh_small_scene_equals_brute_force(ctx):
+    """500 primitives: the brute-force list is the third witness."""
+    sc = scenes.stress(n_prims=500, width=8, height=8)
+    rng = np.random.RandomState(6)
+    n = 100_000
+    Q = rng.uniform(-4, 4, (n, 3))
+    D = rng.normal(size=(n, 3))
+    _commit(ctx, sc, capi.BVH_BUILDER_DEVICE_LBVH)
+    pb, tb, *_ = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=1)
+    pd, td, *_ = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=2)
+    assert (pb >= 0).mean() > 0.01
+    assert np.array_equal(pb, pd) and np.array_equal(tb[pb >= 0], td[pd >= 0])
+
+
+@pytest.mark.parametrize("name,kw,spp", [
+    ("cornell_box", dict(width=72, height=64), 8),     # boxes: two slots per leaf
+    ("rtiow_final", dict(width=96, height=54), 4),     # one huge sphere among hundreds of small ones
+    ("textured", dict(width=96, height=54), 8),
+])
+def test_lbvh_images_equal_host_sah_images(ctx, oracle, name, kw, spp):
+    sc = scenes.by_name(name, **kw)
+    cam = capi.make_camera(**sc.camera_args())
+    par = capi.make_params(**sc.params_args(sample_count=spp, traversal=2, max_depth=12))
+    _commit(ctx, sc, capi.BVH_BUILDER_HOST_SAH)
+    ih, sh = ctx.render(cam, par)
+    info = _commit(ctx, sc, capi.BVH_BUILDER_DEVICE_LBVH)
+    idv, sd = ctx.render(cam, par)
+    assert info.builder == capi.BVH_BUILDER_DEVICE_LBVH
+    assert sh.rays == sd.rays, (sh.rays, sd.rays)
+    # same paths; sliced traversals finish in a different order, so only the float summation order may differ
+    assert np.allclose(ih, idv, rtol=1e-5, atol=1e-6), float(np.abs(ih - idv).max())
+    osc = sc.feed(oracle.scene())
+    oimg, ost = osc.render(cam, par)
+    p = psnr(np.clip(idv / spp, 0, 1), np.clip(oimg / spp, 0, 1))
+    assert p >= 40.0 and abs(int(sd.rays) - int(ost.rays)) < 1e-2 * ost.rays, (p, sd.rays, ost.rays)
+
+
+def test_lbvh_edge_cases(ctx):
+    """One primitive (the root is the leaf), two primitives, many primitives with one and the same centre (equal
+    Morton codes are split on the index bits), an empty scene."""
+    def scene(spheres):
+        s = scenes.SceneDesc("edge", width=32, height=24, spp=4, max_depth=4)
+        t = s.solid(0.7, 0.6, 0.5)
+        m = s.mat(scenes.MAT_LAMBERTIAN, -1)
+        for c, r in spheres:
+            s.sphere(c, r, m, t)
+        s.camera = dict(pos=(0, 0, 5), target=(0, 0, 0), up=(0, 1, 0), vfov_deg=40.0, focus_dist=5.0, jitter=1)
+        return s
+
+    rng = np.random.RandomState(7)
+    n = 20_000
+    Q = np.tile(np.array([0.0, 0.0, 5.0]), (n, 1))
+    D = np.concatenate([rng.uniform(-0.5, 0.5, (n, 2)), -np.ones((n, 1))], axis=1)
+    cases = {
+        "one": [((0, 0, 0), 1.0)],
+        "two": [((-0.6, 0, 0), 0.5), ((0.6, 0, 0), 0.5)],
+        "concentric": [((0, 0, 0), 0.2 + 0.01 * k) for k in range(100)],
+        "coincident": [((0.3, 0.1, 0), 0.4)] * 64 + [((-0.8, 0, 0), 0.3)],
+    }
+    for label, sph in cases.items():
+        sc = scene(sph)
+        info_h = _commit(ctx, sc, capi.BVH_BUILDER_HOST_SAH)
+        ph, th, *_ = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=2)
+        info_d = _commit(ctx, sc, capi.BVH_BUILDER_DEVICE_LBVH)
+        pd, td, *_ = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=2)
+        assert info_d.builder == capi.BVH_BUILDER_DEVICE_LBVH and info_d.bvh_nodes == len(sph) - 1, (label, info_d.as_dict())
+        hit = ph >= 0
+        assert hit.any() and np.array_equal(hit, pd >= 0), label
+        assert np.array_equal(th[hit], td[hit]), label
+        if label != "coincident":  # identical spheres: which of them reports the (identical) hit depends on the visiting order
+            assert np.array_equal(ph, pd), label
+    ctx.clear()
+    ctx.set_bvh_builder(capi.BVH_BUILDER_DEVICE_LBVH)
+    ctx.commit()
+    p0, *_ = ctx.hit_batch(Q[:16], D[:16], t_min=1e-3, precision=32, traversal=2)
+    assert (p0 < 0).all()
