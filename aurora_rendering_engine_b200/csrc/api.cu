@@ -451,6 +451,7 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 #undef UP
 	d.lean_ok = cs.lean_ok ? 1 : 0;
 	d.n_lean_shade = (int)cs.lean_shade.size();
+	d.lean_n_open = cs.lean_n_open;
 	d.brute_range = cs.brute_range;
 	d.n_nodes = (int)cs.nodes.size();
 	d.root_leaf_meta = cs.root_leaf_meta;

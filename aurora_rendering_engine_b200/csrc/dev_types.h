@@ -127,6 +127,7 @@ struct DevScene {
 	const int *lean_sbase;     // per brute slot: index of its first record in lean_shade
 	int n_lean_shade;
 	int lean_ok;
+	int lean_n_open;           // brute list: the first lean_n_open boxes are open (one face absent), the others closed
 	// --- per device primitive ---
 	const PrimInfo *info;
 	const ShadeRec *shade;     // per device primitive

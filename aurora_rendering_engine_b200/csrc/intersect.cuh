@@ -95,6 +95,8 @@ __device__ __forceinline__ void test_sphere(float4 r0, float4 r1, V3<float> o, V
 // An open box is stored with its one absent face on axis 2, "-" side (scene compiler): a ray enters through that
 // hole iff the entry is decided by axis 2 while moving along +n2, and leaves through it iff the exit is decided by
 // axis 2 while moving along -n2.
+// OPEN: 0 = the record says (r3.w), 1 = known closed (the open-face logic is compiled out), 2 = known open
+template <int OPEN = 0>
 __device__ __forceinline__ void test_box(float4 r0, float4 r1, float4 r2, float4 r3, V3<float> o, V3<float> d, float tmin, int idx, Hit &h) {
 	const float s0 = fmaf(r0.x, d.x, fmaf(r0.y, d.y, fmaf(r0.z, d.z, 1e-30f)));
 	const float s1 = fmaf(r1.x, d.x, fmaf(r1.y, d.y, fmaf(r1.z, d.z, 1e-30f)));
@@ -108,7 +110,7 @@ __device__ __forceinline__ void test_box(float4 r0, float4 r1, float4 r2, float4
 	const float n2 = m2 - k2, f2 = m2 + k2;
 	const float t_in = fmaxf(fmaxf(m0 - k0, m1 - k1), n2), t_out = fminf(fminf(m0 + k0, m1 + k1), f2);
 	bool in_ok = t_in > tmin, out_ok = t_out > tmin;
-	if (r3.w != 0.0f) {  // warp-uniform: all lanes test the same primitive
+	if (OPEN == 2 || (OPEN == 0 && r3.w != 0.0f)) {  // warp-uniform: all lanes test the same primitive
 		in_ok = in_ok & !((n2 == t_in) & (s2 > 0.0f));
 		out_ok = out_ok & !((f2 == t_out) & (s2 < 0.0f));
 	}
@@ -167,10 +169,14 @@ __device__ __forceinline__ int lds1a(uint32_t addr) {
 	asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
 	return v;
 }
-__device__ __forceinline__ void intersect_lean(uint32_t sb, int nb, int nq, int nt, V3<float> o, V3<float> d, float tmin, Hit &h) {
+__device__ __forceinline__ void intersect_lean(uint32_t sb, int nb, int n_open, int nq, int nt, V3<float> o, V3<float> d, float tmin, Hit &h) {
 #pragma unroll
 	for (int i = 0; i < LEAN_MAX; ++i)
-		if (i < nb) test_box(lds4a(sb + 96 * i), lds4a(sb + 96 * i + 16), lds4a(sb + 96 * i + 32), lds4a(sb + 96 * i + 48), o, d, tmin, 2 * i, h);
+		if (i < nb) {
+			const float4 r0 = lds4a(sb + 96 * i), r1 = lds4a(sb + 96 * i + 16), r2 = lds4a(sb + 96 * i + 32), r3 = lds4a(sb + 96 * i + 48);
+			if (i < n_open) test_box<2>(r0, r1, r2, r3, o, d, tmin, 2 * i, h);  // open boxes come first in the list
+			else test_box<1>(r0, r1, r2, r3, o, d, tmin, 2 * i, h);
+		}
 	const uint32_t qb = sb + 96 * nb;
 #pragma unroll
 	for (int j = 0; j < LEAN_MAX; ++j)

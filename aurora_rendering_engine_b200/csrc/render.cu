@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 			finished = ray_ok && !trav;
 		} else if (ray_ok) {
 			h.t = INFINITY; h.idx = -1; h.orig = orig;
-			if (LEAN) intersect_lean(sb_prims, br.nb, br.nq, br.nt, o, d, A.tmin, h);
+			if (LEAN) intersect_lean(sb_prims, br.nb, A.sc.lean_n_open, br.nq, br.nt, o, d, A.tmin, h);
 			else intersect_range<lds4>(s_prims, br.first, br.nq, br.nt, br.ns, br.nb, o, d, A.tmin, h);
 			++rays;
 		}

@@ -893,7 +893,13 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 	// ---- brute list (type-sorted) ----
 	if (out.n_hot <= opt.brute_max) {
 		int cnt[HK_KINDS] = { 0, 0, 0, 0 };
-		for (int kind = 0; kind < HK_KINDS; ++kind)
+		// boxes first, open ones (a face absent: the Cornell room) before closed ones — the lean kernel compiles the
+		// open-face logic out of the closed-box tests (DevScene::lean_n_open)
+		out.lean_n_open = 0;
+		for (int open = 1; open >= 0; --open)
+			for (const HotItem &it : hot)
+				if (it.kind == HK_BOX && (it.rec2.r0.w != 0.0f) == (open == 1)) { emit_item(it, out.brute, out.brute_ids); cnt[HK_BOX]++; out.lean_n_open += open; }
+		for (int kind = HK_BOX + 1; kind < HK_KINDS; ++kind)
 			for (const HotItem &it : hot)
 				if (it.kind == kind) { emit_item(it, out.brute, out.brute_ids); cnt[kind]++; }
 		out.brute_range = { 0, cnt[HK_QUAD], cnt[HK_TRI], cnt[HK_SPHERE], cnt[HK_BOX] };

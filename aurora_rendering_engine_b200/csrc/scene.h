@@ -50,6 +50,7 @@ struct CompiledScene {
 	// triangle tests, and every surface shades from its ShadeRec alone (solid colour + simple lobe, both halves of every
 	// fused pair alike).  lean_shade holds one record per brute slot, six per box (one per face, zeros for an absent face).
 	bool lean_ok = false;
+	int lean_n_open = 0;  // the first lean_n_open boxes of the brute list have an absent face
 	std::vector<ShadeRec> lean_shade;
 	std::vector<int> lean_sbase;
 	std::vector<HotPrim> bvh_prims;
