@@ -174,8 +174,12 @@ __device__ __forceinline__ void intersect_lean(uint32_t sb, int nb, int n_open, 
 	for (int i = 0; i < LEAN_MAX; ++i)
 		if (i < nb) {
 			const float4 r0 = lds4a(sb + 96 * i), r1 = lds4a(sb + 96 * i + 16), r2 = lds4a(sb + 96 * i + 32), r3 = lds4a(sb + 96 * i + 48);
+#ifdef LEAN_NO_OPEN_SPLIT  // A/B: the record's own flag, predicated open-face logic in every box test
+			test_box<0>(r0, r1, r2, r3, o, d, tmin, 2 * i, h);
+#else
 			if (i < n_open) test_box<2>(r0, r1, r2, r3, o, d, tmin, 2 * i, h);  // open boxes come first in the list
 			else test_box<1>(r0, r1, r2, r3, o, d, tmin, 2 * i, h);
+#endif
 		}
 	const uint32_t qb = sb + 96 * nb;
 #pragma unroll
