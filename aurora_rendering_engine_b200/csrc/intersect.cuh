@@ -305,6 +305,42 @@ __device__ __forceinline__ bool bvh_visit(const DevScene &sc, float tmin, const 
 	return alive;
 }
 
+// ---- single-cursor formulation -------------------------------------------------------------------------
+// The continuation logic is what a BVH2 step spends most of its (half-rate) ALU-pipe instructions on, so it is kept
+// to the minimum: ONE cursor word (>= 0 inner node, < 0 leaf reference, TRAV_DONE finished), a stack POINTER instead of
+// an index (no address arithmetic per push / pop), a TRAV_DONE sentinel at the bottom of the stack (a pop never checks
+// for emptiness) and no overflow test (are_cuda_commit refuses hierarchies deeper than the stack).  A child that is
+// missed gets distance +inf, so "nearer child" also covers the one-hit case:
+//   near / far by two selects, push far if both were hit, pop if neither was.
+#define TRAV_DONE ((int)0x80000000)  // not a leaf reference: ~(slot | kind << 29) with slot < 2^29 never has all low bits clear... kind 3, slot 2^29-1 only
+template <bool COUNT>
+__device__ __forceinline__ void bvh_step(const DevScene &sc, float tmin, const RaySlopes &rs, int &cur, int *&top, const Hit &h, TravCounters *cnt) {
+	const BvhNode *n = sc.nodes + cur;
+	const float4 b0 = ldg4(&n->b0), b1 = ldg4(&n->b1), b2 = ldg4(&n->b2);
+	const int2 ch = __ldg(reinterpret_cast<const int2 *>(&n->child[0]));
+	if (COUNT) cnt->nodes++;
+	const float c0x = fmaf(b0.x, rs.idx, -rs.oxi), c0y = fmaf(b0.z, rs.idy, -rs.oyi), c0z = fmaf(b2.x, rs.idz, -rs.ozi);
+	const float c1x = fmaf(b1.x, rs.idx, -rs.oxi), c1y = fmaf(b1.z, rs.idy, -rs.oyi), c1z = fmaf(b2.z, rs.idz, -rs.ozi);
+	const float t0n = fmaxf(fmaxf(fmaf(-b0.y, rs.ax, c0x), fmaf(-b0.w, rs.ay, c0y)), fmaxf(fmaf(-b2.y, rs.az, c0z), tmin));
+	const float t0f = fminf(fminf(fmaf(b0.y, rs.ax, c0x), fmaf(b0.w, rs.ay, c0y)), fminf(fmaf(b2.y, rs.az, c0z), h.t));
+	const float t1n = fmaxf(fmaxf(fmaf(-b1.y, rs.ax, c1x), fmaf(-b1.w, rs.ay, c1y)), fmaxf(fmaf(-b2.w, rs.az, c1z), tmin));
+	const float t1f = fminf(fminf(fmaf(b1.y, rs.ax, c1x), fmaf(b1.w, rs.ay, c1y)), fminf(fmaf(b2.w, rs.az, c1z), h.t));
+	const bool hit0 = t0n <= t0f, hit1 = t1n <= t1f;
+	const float d0 = hit0 ? t0n : INFINITY, d1 = hit1 ? t1n : INFINITY;
+	const bool near0 = d0 <= d1;
+	int next = near0 ? ch.x : ch.y;
+	const int farc = near0 ? ch.y : ch.x;
+	if (hit0 & hit1) *top++ = farc;
+	if (!(hit0 | hit1)) next = *--top;
+	cur = next;
+}
+// leaf phase of the single-cursor form: test the leaf under the cursor, then pop
+template <bool COUNT>
+__device__ __forceinline__ void bvh_leaf(const DevScene &sc, V3<float> o, V3<float> d, float tmin, int &cur, int *&top, Hit &h, TravCounters *cnt) {
+	test_leaf<COUNT>(sc, cur, o, d, tmin, h, cnt);
+	cur = *--top;
+}
+
 // Whole traversal in one go (per-ray harness).
 template <bool COUNT>
 __device__ __forceinline__ void intersect_bvh(const DevScene &sc, V3<float> o, V3<float> d, float tmin, Hit &h, TravCounters *cnt) {
@@ -314,6 +350,7 @@ __device__ __forceinline__ void intersect_bvh(const DevScene &sc, V3<float> o, V
 	}
 	const RaySlopes rs = ray_slopes(o, d);
 	int stack[ARE_BVH_STACK];
+#ifdef ARE_TRAV_TWO_WORD  // A/B: the (node, pending leaf, stack index) formulation
 	int sp = 0, node = 0, pend = 0;
 	bool more = true;
 	while (more) {
@@ -323,6 +360,15 @@ __device__ __forceinline__ void intersect_bvh(const DevScene &sc, V3<float> o, V
 			more = trav_pop(sp, stack, node, pend);
 		} else more = bvh_visit<COUNT>(sc, tmin, rs, node, pend, sp, stack, h, cnt);
 	}
+#else
+	stack[0] = TRAV_DONE;
+	int *top = stack + 1;
+	int cur = 0;
+	while (cur != TRAV_DONE) {
+		if (cur >= 0) bvh_step<COUNT>(sc, tmin, rs, cur, top, h, cnt);
+		else bvh_leaf<COUNT>(sc, o, d, tmin, cur, top, h, cnt);
+	}
+#endif
 }
 
 // ---- map a hot hit back to the user primitive ---------------------------------------------------------

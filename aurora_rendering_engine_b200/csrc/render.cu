@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 	bool trav = false;  // BVH: traversal in progress
 	int node = 0, pend = 0, sp = 0;
 	int stack[MODE == 1 ? ARE_BVH_STACK : 1];
+	int *top = stack;  // single-cursor BVH2 traversal: stack pointer
 	uint2 ng = make_uint2(0u, 0u), tg = ng;  // wide-BVH cursor
 	uint2 wstack[WIDE ? ARE_WIDE_STACK : 1];
 	unsigned int rays = 0;
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 			}
 			finished = ray_ok && !trav;
 		} else if (BVH) {
+#ifdef ARE_TRAV_TWO_WORD
 			if (ray_ok && !trav) {  // a fresh ray
 				h.t = INFINITY; h.idx = -1; h.orig = orig;
 				++rays;
@@ -211,6 +213,32 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 				}
 			}
 			finished = ray_ok && !trav;
+#else
+			// single-cursor form (intersect.cuh): `node` is the cursor, `top` the stack pointer, trav <=> cursor != TRAV_DONE
+			if (ray_ok && !trav) {  // a fresh ray
+				h.t = INFINITY; h.idx = -1; h.orig = orig;
+				++rays;
+				if (A.sc.n_nodes == 0) {  // zero or one primitive
+					if (A.sc.root_leaf_meta != 0) test_leaf<COUNT>(A.sc, A.sc.root_leaf_meta, o, d, A.tmin, h, &tc);
+				} else { node = 0; stack[0] = TRAV_DONE; top = stack + 1; trav = true; }
+			}
+			const int n_rays = __popc(__ballot_sync(full, ray_ok));
+			if (__any_sync(full, trav)) {
+				const RaySlopes rs = ray_slopes(o, d);
+				if (!trav) node = TRAV_DONE;
+				while (true) {
+#pragma unroll 1
+					for (int rep = 0; rep < TRAV_STEPS_PER_VOTE; ++rep) {  // several steps between the warp votes that decide the end of the slice
+						if (node >= 0) bvh_step<COUNT>(A.sc, A.tmin, rs, node, top, h, &tc);                    // node phase
+						if (node < 0 && node != TRAV_DONE) bvh_leaf<COUNT>(A.sc, o, d, A.tmin, node, top, h, &tc);  // leaf phase
+					}
+					const int n_trav = __popc(__ballot_sync(full, node != TRAV_DONE));
+					if (n_trav == 0 || (n_trav < TRAV_MIN_LANES && n_trav < n_rays)) break;
+				}
+				trav = node != TRAV_DONE;
+			}
+			finished = ray_ok && !trav;
+#endif
 		} else if (ray_ok) {
 			h.t = INFINITY; h.idx = -1; h.orig = orig;
 			if (LEAN) intersect_lean(sb_prims, br.nb, A.sc.lean_n_open, br.nq, br.nt, o, d, A.tmin, h);
