@@ -435,6 +435,8 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	}
 	const CompiledScene &cs = ctx->cs;
 	const bool device_built = ctx->opt.device_bvh && !cs.lb_lo.empty();
+	// the traversal kernels push at most height - 1 far children above the sentinel and do not test for overflow
+	if (!device_built && cs.bvh_depth > ARE_BVH_STACK) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "BVH deeper than the traversal stack");
 	if (!device_built) std::memset(&d, 0, sizeof d);
 	const BvhNode *dev_nodes = d.nodes;
 	const HotPrim *dev_bvh_prims = d.bvh_prims;

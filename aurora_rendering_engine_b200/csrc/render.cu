@@ -58,6 +58,9 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #ifndef RENDER_MIN_BLOCKS
 #define RENDER_MIN_BLOCKS 6
 #endif
+#ifndef RENDER_MIN_BLOCKS_BVH2
+#define RENDER_MIN_BLOCKS_BVH2 7  // single-cursor BVH2 traversal, L1-resident hierarchies: 72 registers; measured 6 / 7 / 8 CTAs/SM on RTIOW: 4207 / 4359 / 4211 Msamples/s
+#endif
 #ifndef RENDER_MIN_BLOCKS_LEAN
 #define RENDER_MIN_BLOCKS_LEAN 8
 #endif
@@ -82,7 +85,7 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 // compile-time shared-memory offsets instead of four counted loops, and a hit goes straight to its shading record
 // (six per box, one per face) held in shared memory: no id chain, no owner resolution, no general material path.
 template <int MODE, bool COUNT, bool BIG = false, bool LEAN = false>
-__global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : (LEAN ? RENDER_MIN_BLOCKS_LEAN : RENDER_MIN_BLOCKS)) k_render_path(const __grid_constant__ RenderArgs A) {
+__global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : (LEAN ? RENDER_MIN_BLOCKS_LEAN : (MODE == 1 ? RENDER_MIN_BLOCKS_BVH2 : RENDER_MIN_BLOCKS))) k_render_path(const __grid_constant__ RenderArgs A) {
 	constexpr bool BVH = MODE != 0, WIDE = MODE == 2;
 	static_assert(!LEAN || MODE == 0, "the lean form is a brute-force list");
 	extern __shared__ float4 s_raw[];
