@@ -309,6 +309,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 			}
 			if (done) {
 				const float csum = contrib.x + contrib.y + contrib.z;  // radiance is non-negative: 0 adds nothing, NaN / inf are dropped
+				// (measured: dropping the finiteness half of this test in the lean kernel — its contributions are finite by
+				// construction — removes six instructions and LOSES 1.8 %: the compiler schedules the loop differently)
 				if (csum > 0.0f && csum < INFINITY) {
 					float *acc = &s_acc[warp][(task & 31) * 3];
 					atomicAdd(acc, contrib.x); atomicAdd(acc + 1, contrib.y); atomicAdd(acc + 2, contrib.z);
