@@ -91,6 +91,15 @@ public:
 		check(are_cuda_render(ctx_, &c, &p, sums, &stats_));
 	}
 
+	/// Who builds the hierarchy at the next upload(): ARE_BVH_BUILDER_HOST_SAH (default) or ARE_BVH_BUILDER_DEVICE_LBVH
+	/// (milliseconds per million primitives; for scenes that change every frame).
+	void set_bvh_builder(int builder) { check(are_cuda_set_bvh_builder(ctx_, builder)); }
+	are_commit_info commit_info() {
+		are_commit_info info;
+		check(are_cuda_get_commit_info(ctx_, &info));
+		return info;
+	}
+
 	const are_render_stats &stats() const { return stats_; }
 	std::uint64_t uploaded_bytes() const { return uploaded_bytes_; }
 	are_cuda_ctx *context() { return ctx_; }
