@@ -708,10 +708,29 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 			for (size_t t = t0; t < t1; ++t)
 				for (int k = 0; k < 3; ++k) edges[3 * t + k] = { EHash()(ekey(vert((int)t, (k + 1) % 3), vert((int)t, (k + 2) % 3))), (int)t, k };
 		});
+		// runs of equal hash = candidate shared edges; every (triangle, edge) remembers its run, lone edges get none
+		struct Range { int first, second; };
+		std::vector<Range> run_of((size_t)nt * 3, Range{ 0, 0 });
+		std::atomic<int> any_run{ 0 };
+		auto mark_runs = [&](size_t lo, size_t hi) {  // edges[lo, hi) sorted; runs never cross a bucket (bucket = top hash byte)
+			bool found = false;
+			for (size_t i = lo; i < hi;) {
+				size_t j = i + 1;
+				while (j < hi && edges[j].h == edges[i].h) ++j;
+				if (j - i >= 2) {
+					found = true;
+					for (size_t m = i; m < j; ++m) run_of[3 * (size_t)edges[m].tri + edges[m].opp] = Range{ (int)i, (int)j };
+				}
+				i = j;
+			}
+			if (found) any_run.store(1);
+		};
 		{  // sort by (hash, triangle, edge): scatter into 256 buckets on the top hash byte, then sort the buckets in parallel
 			const auto less = [](const EdgeUse &a, const EdgeUse &b) { return a.h != b.h ? a.h < b.h : (a.tri != b.tri ? a.tri < b.tri : a.opp < b.opp); };
-			if (edges.size() < 65536) std::sort(edges.begin(), edges.end(), less);
-			else {
+			if (edges.size() < 65536) {
+				std::sort(edges.begin(), edges.end(), less);
+				mark_runs(0, edges.size());
+			} else {
 				size_t start[257] = { 0 };
 				for (const EdgeUse &e : edges) ++start[(e.h >> 56) + 1];
 				for (int b = 0; b < 256; ++b) start[b + 1] += start[b];
@@ -721,26 +740,20 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 				for (const EdgeUse &e : edges) tmp[fill[e.h >> 56]++] = e;
 				edges.swap(tmp);
 				parallel_chunks(256, 1, [&](size_t b0, size_t b1) {
-					for (size_t b = b0; b < b1; ++b) std::sort(edges.begin() + start[b], edges.begin() + start[b + 1], less);
+					for (size_t b = b0; b < b1; ++b) {
+						std::sort(edges.begin() + start[b], edges.begin() + start[b + 1], less);
+						mark_runs(start[b], start[b + 1]);
+					}
 				});
 			}
 		}
-		// runs of equal hash = candidate shared edges; every (triangle, edge) remembers its run, lone edges get none
-		struct Range { int first, second; };
-		std::vector<Range> run_of((size_t)nt * 3, Range{ 0, 0 });
-		for (size_t i = 0; i < edges.size();) {
-			size_t j = i + 1;
-			while (j < edges.size() && edges[j].h == edges[i].h) ++j;
-			if (j - i >= 2)
-				for (size_t m = i; m < j; ++m) run_of[3 * (size_t)edges[m].tri + edges[m].opp] = Range{ (int)i, (int)j };
-			i = j;
-		}
+		if (any_run.load())  // no shared edge anywhere (a cloud of loose triangles): nothing to fuse
 		for (int t = 0; t < nt; ++t) {
 			if (fused[t]) continue;
 			for (int k = 0; k < 3 && !fused[t]; ++k) {
-				D3 d0 = vert(t, (k + 1) % 3), d1 = vert(t, (k + 2) % 3), a = vert(t, k);
 				const Range range = run_of[3 * (size_t)t + k];
 				if (range.second - range.first < 2) continue;  // nobody else uses this edge
+				D3 d0 = vert(t, (k + 1) % 3), d1 = vert(t, (k + 2) % 3), a = vert(t, k);
 				const EKey key = ekey(d0, d1);
 				for (const EdgeUse *it = edges.data() + range.first; it != edges.data() + range.second; ++it) {
 					int j = it->tri;
