@@ -151,6 +151,7 @@ SIGNATURES = {
     "are_cuda_commit": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "are_cuda_compile_probe": (C.c_int, [C.c_int, _dp, _dp, _dp, _ip]),
     "are_cuda_compile_probe_digest": (C.c_int, [C.c_int, _dp, _dp, _dp, _ip, C.POINTER(C.c_uint64)]),
+    "are_cuda_compile_probe_forms": (C.c_int, [C.c_int, _dp, _dp, _dp, _ip]),
     "are_cuda_hit_batch": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_double, C.c_int, C.c_int, _ip, _dp, _dp, _dp, _dp]),
     "are_cuda_scatter_batch": (C.c_int, [_vp, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _ip]),
     "are_cuda_texture_batch": (C.c_int, [_vp, C.c_int, _ip, _dp, _dp, C.c_int, _dp]),
@@ -221,6 +222,18 @@ def compile_probe(Q, u, v) -> dict:
     d = dict(zip(keys, (int(x) for x in out)))
     d["digest"] = int(digest.value)
     return d
+
+
+def compile_probe_forms(Q, u, v) -> dict:
+    """Host-only probe of the lean form and the device-builder input (are_cuda_compile_probe_forms): no GPU involved."""
+    lib = load_library()
+    Q, u, v = (np.ascontiguousarray(x, dtype=np.float64) for x in (Q, u, v))
+    out = np.zeros(8, np.int32)
+    st = lib.are_cuda_compile_probe_forms(len(Q), Q.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp), out.ctypes.data_as(_ip))
+    if st != ARE_OK:
+        raise AreCudaError(st, "compile probe rejected the triangles")
+    keys = ("lean_ok", "lean_records", "lean_open_boxes", "lbvh_items", "lbvh_slots", "lbvh_conservative", "host_bvh_nodes", "brute_boxes")
+    return dict(zip(keys, (int(x) for x in out)))
 
 
 def _d(a, shape=None):

@@ -516,6 +516,49 @@ int are_cuda_compile_probe_digest(int n_tri, const double *Q, const double *u, c
 	return ARE_OK;
 }
 
+int are_cuda_compile_probe_forms(int n_tri, const double *Q, const double *u, const double *v, int out[8]) {
+	if (n_tri < 0 || !out || (n_tri && (!Q || !u || !v))) return ARE_ERR_INVALID_ARGUMENT;
+	HostScene hs;
+	hs.textures.emplace_back();
+	hs.materials.emplace_back();
+	for (int i = 0; i < n_tri; ++i) {
+		if (validate_edges(u + 3 * (size_t)i, v + 3 * (size_t)i)) return ARE_ERR_INVALID_ARGUMENT;
+		HostPrim p;
+		p.type = PT_TRIANGLE;
+		std::memcpy(p.Q, Q + 3 * (size_t)i, sizeof p.Q);
+		std::memcpy(p.u, u + 3 * (size_t)i, sizeof p.u);
+		std::memcpy(p.v, v + 3 * (size_t)i, sizeof p.v);
+		hs.prims.push_back(p);
+	}
+	CompileOptions opt;
+	opt.brute_max = (int)brute_smem_limit_prims();
+	opt.device_bvh = true;
+	CompiledScene cs;
+	std::string err;
+	if (!compile_scene(hs, opt, cs, err)) return ARE_ERR_INVALID_ARGUMENT;
+	// every item's fp32 box must contain the fp64 vertices of the triangles behind it
+	int conservative = 0;
+	for (size_t i = 0; i < cs.lb_lo.size(); ++i) {
+		const HotIds id = cs.lb_ids[(size_t)cs.lb_slot[i]];
+		bool ok = true;
+		const int tris[2] = { id.a, id.b >= 0 ? id.b : (id.b <= -2 ? -2 - id.b : -1) };
+		for (int t : tris) {
+			if (t < 0 || t >= cs.n_tri) continue;  // box items (a < 0) are covered through their faces' own tests elsewhere
+			const double *q = &cs.tri64[9 * (size_t)t];
+			for (int k = 0; k < 3; ++k) {
+				const double p[3] = { q[0] + (k == 1 ? q[3] : (k == 2 ? q[6] : 0.0)), q[1] + (k == 1 ? q[4] : (k == 2 ? q[7] : 0.0)), q[2] + (k == 1 ? q[5] : (k == 2 ? q[8] : 0.0)) };
+				const float lo[3] = { cs.lb_lo[i].x, cs.lb_lo[i].y, cs.lb_lo[i].z }, hi[3] = { cs.lb_hi[i].x, cs.lb_hi[i].y, cs.lb_hi[i].z };
+				for (int a = 0; a < 3; ++a) ok = ok && (double)lo[a] <= p[a] && p[a] <= (double)hi[a];
+			}
+		}
+		conservative += ok ? 1 : 0;
+	}
+	const int r[8] = { cs.lean_ok ? 1 : 0, (int)cs.lean_shade.size(), cs.lean_n_open, (int)cs.lb_lo.size(), (int)cs.lb_prims.size(), conservative,
+		(int)cs.nodes.size(), cs.brute_range.nb };
+	std::memcpy(out, r, sizeof r);
+	return ARE_OK;
+}
+
 // ---- per-ray harness -------------------------------------------------------------------------------------
 int are_cuda_hit_batch(are_cuda_ctx *ctx, int n, const double *ray_Q, const double *ray_D, double t_min, int precision, int traversal,
 	int *prim, double *t, double *P, double *N, double *uv) {

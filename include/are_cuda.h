@@ -185,6 +185,11 @@ int are_cuda_compile_probe(int n_tri, const double *Q, const double *u, const do
 /* Same, plus an FNV-1a digest of the compiled hierarchy (nodes, leaf-ordered primitives, ids): the BVH is built by
  * several host threads (ARE_CUDA_BUILD_THREADS overrides the count) and must not depend on how many. */
 int are_cuda_compile_probe_digest(int n_tri, const double *Q, const double *u, const double *v, int out[8], uint64_t *digest);
+/* Host-only probe of the two derived forms: compiles with the device BVH builder selected and reports out[8] =
+ * { lean form valid, lean shading records, open boxes leading the brute list, device-builder items, their slots,
+ *   items whose fp32 box contains the fp64 vertices behind it (must equal the item count), host BVH nodes (0: the
+ *   hierarchy is left to the device), brute boxes }. */
+int are_cuda_compile_probe_forms(int n_tri, const double *Q, const double *u, const double *v, int out[8]);
 
 /* ---- per-ray harness ----------------------------------------------------------------------------------- */
 /* Closest hit of n rays against the committed scene.  D is normalised first, as are::Ray's ctor does

@@ -112,6 +112,35 @@ def test_scene_compiler_fuses_parallelograms_and_boxes(lib):
     assert r["fused_pairs"] == 2 and r["boxes"] == 0 and r["brute_quads"] == 2
 
 
+def test_lean_form_and_device_builder_input(lib):
+    """Host-only probe of the two derived forms of the compiled scene: the lean brute-force form (what the lean render
+    kernel reads) and the input of the device BVH builder (conservative fp32 boxes, records in item order)."""
+    import numpy as np
+    from aurora_rendering_engine_b200 import capi
+
+    def tris(sc):
+        return (np.stack([t[0] for t in sc.tris]), np.stack([t[1] for t in sc.tris]), np.stack([t[2] for t in sc.tris]))
+
+    # Cornell box: 3 boxes (the room first: it is the open one) + the light quad -> 3 * 6 + 1 shading records
+    r = capi.compile_probe_forms(*tris(scenes.cornell_box()))
+    assert (r["lean_ok"], r["lean_records"], r["lean_open_boxes"], r["brute_boxes"]) == (1, 19, 1, 3)
+    assert r["lbvh_items"] == 4 and r["lbvh_slots"] == 7 and r["host_bvh_nodes"] == 0 and r["lbvh_conservative"] == r["lbvh_items"]
+    # more than four loose triangles: no lean form; every item box contains its fp64 vertices after rounding to fp32
+    sc = scenes.stress(n_prims=4000)
+    r = capi.compile_probe_forms(*tris(sc))
+    assert r["lean_ok"] == 0 and r["lean_records"] == 0
+    assert r["lbvh_items"] == r["lbvh_slots"] == len(sc.tris) and r["lbvh_conservative"] == r["lbvh_items"]
+    # vertices far from the origin with awkward fractions: rounding to fp32 must go outwards
+    rng = np.random.RandomState(11)
+    Q = rng.uniform(-1, 1, (500, 3)) * 1e4 + 1.0 / 3.0
+    u, v = rng.uniform(-1, 1, (500, 3)) / 7.0, rng.uniform(-1, 1, (500, 3)) / 7.0
+    r = capi.compile_probe_forms(Q, u, v)
+    assert r["lbvh_conservative"] == r["lbvh_items"] == 500
+    # four loose triangles still fit the lean form
+    r = capi.compile_probe_forms(Q[:4] * 1e-4, u[:4], v[:4])
+    assert (r["lean_ok"], r["lean_records"], r["lean_open_boxes"]) == (1, 4, 0)
+
+
 def test_parallel_bvh_build_is_independent_of_thread_count(lib, monkeypatch):
     """The host BVH builder hands subtrees to threads that write straight into their (pre-computable) place of the
     depth-first arrays: the compiled hierarchy must be byte-identical for 1 thread and for many."""
