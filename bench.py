@@ -5,6 +5,9 @@ Workload (config.workload): BASELINE config 3 — Cornell box (5 walls + light +
 dimensions), 2048x2048, max depth 50.  The job's 16384 spp are rendered in chunks; ONE STEP = one chunk of
 ``--spp-per-step`` samples per pixel over the whole frame on every rank (weak scaling: rank r, step k renders
 global samples [(k*N + r)*S, +S)), and the timed region ends with the job's NCCL sum-reduce of the accumulators.
+The default chunk is 256 spp (64 launches make the job): a warp's pool is its 8x4 tile x the chunk's samples and its last
+trips run on its few longest paths, so the chunk size shows — 64 / 128 / 256 / 512 spp per launch: 8175 / 8359 / 8456 / 8511
+Msamples/s.
 
   value      Msamples/s, whole job, scene + accumulator resident in HBM, CUDA events on the launch stream,
              max over ranks.  (Mrays/s is reported beside it.)
@@ -49,7 +52,7 @@ def parse():
     ap.add_argument("--scene", default="cornell_box")
     ap.add_argument("--width", type=int, default=2048)
     ap.add_argument("--height", type=int, default=2048)
-    ap.add_argument("--spp-per-step", type=int, default=64)
+    ap.add_argument("--spp-per-step", type=int, default=256)
     ap.add_argument("--traversal", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
