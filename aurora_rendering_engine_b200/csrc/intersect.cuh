@@ -330,7 +330,7 @@ __device__ __forceinline__ void bvh_step(const DevScene &sc, float tmin, const R
 	const bool near0 = d0 <= d1;
 	int next = near0 ? ch.x : ch.y;
 	const int farc = near0 ? ch.y : ch.x;
-	if (hit0 & hit1) *top++ = farc;
+	if (hit0 & hit1) *top++ = farc;  // (measured: prefetch.global.L1 of the postponed child's node here: -1.3 % / -3.5 %)
 	if (!(hit0 | hit1)) next = *--top;
 	cur = next;
 }
