@@ -235,84 +235,15 @@ __device__ __forceinline__ void test_leaf(const DevScene &sc, int ref, V3<float>
 	}
 }
 
-// Traversal cursor kept by the caller (so a traversal can be suspended and resumed): `node` >= 0 is the inner node to
-// visit next, `pend` != 0 a leaf waiting to be tested (leaf tests are postponed so that many lanes run them together),
-// the stack holds inner nodes and leaves alike.
-__device__ __forceinline__ void trav_set(int x, int &node, int &pend) {
-	if (x < 0) { pend = x; node = -1; }
-	else node = x;
-}
-// BRANCHY selects the formulation of the continuation logic (measured, profiles/r01_scenes.md): plain branches win in
-// the high-occupancy 40-register build used for hierarchies that live in L2 (latency-bound, and the select-heavy
-// form spills), the branch-free form wins in the 80-register build used for L1-resident hierarchies (issue-bound).
-template <bool BRANCHY = false>
-__device__ __forceinline__ bool trav_pop(int &sp, const int *stack, int &node, int &pend) {
-	if (BRANCHY) {
-		if (sp == 0) { node = -1; return false; }
-		trav_set(stack[--sp], node, pend);
-		return true;
-	}
-	const bool has = sp > 0;
-	int x = 0;
-	if (has) x = stack[--sp];
-	pend = (has & (x < 0)) ? x : 0;
-	node = (has & (x >= 0)) ? x : -1;
-	return has;
-}
-// Visit inner node `node`: slab-test both children, continue with the nearer one that is hit, push the farther.
-// Returns false when nothing is left to do.
-template <bool COUNT, bool BRANCHY = false>
-__device__ __forceinline__ bool bvh_visit(const DevScene &sc, float tmin, const RaySlopes &rs, int &node, int &pend, int &sp, int *stack, const Hit &h, TravCounters *cnt) {
-	const BvhNode *n = sc.nodes + node;
-	const float4 b0 = ldg4(&n->b0), b1 = ldg4(&n->b1), b2 = ldg4(&n->b2);
-	const int2 ch = __ldg(reinterpret_cast<const int2 *>(&n->child[0]));
-	if (COUNT) cnt->nodes++;
-	// per axis: distance to the slab centre, then -/+ the half-width scaled by |1/d|: near and far are ordered by construction
-	const float c0x = fmaf(b0.x, rs.idx, -rs.oxi), c0y = fmaf(b0.z, rs.idy, -rs.oyi), c0z = fmaf(b2.x, rs.idz, -rs.ozi);
-	const float c1x = fmaf(b1.x, rs.idx, -rs.oxi), c1y = fmaf(b1.z, rs.idy, -rs.oyi), c1z = fmaf(b2.z, rs.idz, -rs.ozi);
-	const float t0n = fmaxf(fmaxf(fmaf(-b0.y, rs.ax, c0x), fmaf(-b0.w, rs.ay, c0y)), fmaxf(fmaf(-b2.y, rs.az, c0z), tmin));
-	const float t0f = fminf(fminf(fmaf(b0.y, rs.ax, c0x), fmaf(b0.w, rs.ay, c0y)), fminf(fmaf(b2.y, rs.az, c0z), h.t));
-	const float t1n = fmaxf(fmaxf(fmaf(-b1.y, rs.ax, c1x), fmaf(-b1.w, rs.ay, c1y)), fmaxf(fmaf(-b2.w, rs.az, c1z), tmin));
-	const float t1f = fminf(fminf(fmaf(b1.y, rs.ax, c1x), fmaf(b1.w, rs.ay, c1y)), fminf(fmaf(b2.w, rs.az, c1z), h.t));
-	const bool hit0 = t0n <= t0f, hit1 = t1n <= t1f;
-	// Branch-free continuation (the three outcomes — both / one / none — are otherwise three divergent paths run by 4-6
-	// lanes each, ~30 % of the warp instructions of a traversal-bound launch): push the farther child when both are
-	// hit, continue with the nearer hit child, else pop.  Short predicated bodies, one local store / load at most.
-	if (BRANCHY) {
-		if (hit0 && hit1) {
-			const bool near0 = t0n <= t1n;
-			if (sp < ARE_BVH_STACK) stack[sp++] = near0 ? ch.y : ch.x;
-			trav_set(near0 ? ch.x : ch.y, node, pend);
-			return true;
-		}
-		if (hit0 || hit1) {
-			trav_set(hit0 ? ch.x : ch.y, node, pend);
-			return true;
-		}
-		return trav_pop<true>(sp, stack, node, pend);
-	}
-	const bool both = hit0 & hit1, any = hit0 | hit1;
-	const bool near0 = t0n <= t1n;
-	const int farc = near0 ? ch.y : ch.x;
-	const int first = (hit0 & (near0 | !hit1)) ? ch.x : ch.y;
-	if (both & (sp < ARE_BVH_STACK)) stack[sp++] = farc;
-	const bool pop = !any & (sp > 0);
-	int x = first;
-	if (pop) x = stack[--sp];
-	const bool alive = any | pop;
-	pend = (alive & (x < 0)) ? x : 0;  // a leaf reference waits in `pend` for the leaf phase
-	node = (alive & (x >= 0)) ? x : -1;
-	return alive;
-}
-
-// ---- single-cursor formulation -------------------------------------------------------------------------
-// The continuation logic is what a BVH2 step spends most of its (half-rate) ALU-pipe instructions on, so it is kept
-// to the minimum: ONE cursor word (>= 0 inner node, < 0 leaf reference, TRAV_DONE finished), a stack POINTER instead of
+// ---- traversal step -------------------------------------------------------------------------------------
+// The continuation logic is what a BVH2 step spends most of its (half-rate) ALU-pipe instructions on (~30 of them in the
+// first formulation of this round: separate "node" and "pending leaf" words, a stack index with overflow and emptiness
+// tests; RTIOW +18 % without them, profiles/r01_scenes.md), so it is kept to the minimum: ONE cursor word (>= 0 inner node, < 0 leaf reference, TRAV_DONE finished), a stack POINTER instead of
 // an index (no address arithmetic per push / pop), a TRAV_DONE sentinel at the bottom of the stack (a pop never checks
 // for emptiness) and no overflow test (are_cuda_commit refuses hierarchies deeper than the stack).  A child that is
 // missed gets distance +inf, so "nearer child" also covers the one-hit case:
 //   near / far by two selects, push far if both were hit, pop if neither was.
-#define TRAV_DONE ((int)0x80000000)  // not a leaf reference: ~(slot | kind << 29) with slot < 2^29 never has all low bits clear... kind 3, slot 2^29-1 only
+#define TRAV_DONE ((int)0x80000000)  // = ~(slot 2^29 - 1 | kind 3 << 29): the one leaf reference that cannot occur (hot arrays are far smaller)
 template <bool COUNT>
 __device__ __forceinline__ void bvh_step(const DevScene &sc, float tmin, const RaySlopes &rs, int &cur, int *&top, const Hit &h, TravCounters *cnt) {
 	const BvhNode *n = sc.nodes + cur;
@@ -350,17 +281,6 @@ __device__ __forceinline__ void intersect_bvh(const DevScene &sc, V3<float> o, V
 	}
 	const RaySlopes rs = ray_slopes(o, d);
 	int stack[ARE_BVH_STACK];
-#ifdef ARE_TRAV_TWO_WORD  // A/B: the (node, pending leaf, stack index) formulation
-	int sp = 0, node = 0, pend = 0;
-	bool more = true;
-	while (more) {
-		if (pend != 0) {
-			test_leaf<COUNT>(sc, pend, o, d, tmin, h, cnt);
-			pend = 0;
-			more = trav_pop(sp, stack, node, pend);
-		} else more = bvh_visit<COUNT>(sc, tmin, rs, node, pend, sp, stack, h, cnt);
-	}
-#else
 	stack[0] = TRAV_DONE;
 	int *top = stack + 1;
 	int cur = 0;
@@ -368,7 +288,6 @@ __device__ __forceinline__ void intersect_bvh(const DevScene &sc, V3<float> o, V
 		if (cur >= 0) bvh_step<COUNT>(sc, tmin, rs, cur, top, h, cnt);
 		else bvh_leaf<COUNT>(sc, o, d, tmin, cur, top, h, cnt);
 	}
-#endif
 }
 
 // ---- map a hot hit back to the user primitive ---------------------------------------------------------

@@ -76,9 +76,8 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #ifndef TRAV_STEPS_PER_VOTE
 #define TRAV_STEPS_PER_VOTE 4  // measured 1 / 2 / 4 / 8: RTIOW 3498 / 3582 / 3596 / 3417, 1 M primitives 584 / 591 / 602 / 607 Msamples/s
 #endif
-#ifndef LEAF_MIN_LANES
-#define LEAF_MIN_LANES 1   // leaf tests run once this many lanes hold one (measured: 1 is best on RTIOW and on the 1 M-primitive stress scene)
-#endif
+// (Postponing leaf tests until several lanes hold one was measured in the first formulation of the traversal: testing a
+// leaf as soon as a lane has it was best on RTIOW and on the 1 M-primitive scene, and needs no votes.)
 // MODE: 0 = brute force from shared memory, 1 = BVH2, 2 = compressed 8-wide BVH
 // LEAN (brute force only): the scene compiler's lean form (scene.h: at most LEAN_MAX boxes / quad tests / triangle
 // tests, no spheres, every surface shaded from its ShadeRec alone).  The tests are a guarded full unroll with
@@ -142,9 +141,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 	Hit h;          // best hit of the ray in flight (BVH: survives across trips while its traversal is suspended)
 	h.t = INFINITY; h.idx = -1; h.orig = -1;
 	bool trav = false;  // BVH: traversal in progress
-	int node = 0, pend = 0, sp = 0;
+	int node = 0, sp = 0;  // BVH2: `node` is the traversal cursor (intersect.cuh: bvh_step); 8-wide: sp indexes wstack
 	int stack[MODE == 1 ? ARE_BVH_STACK : 1];
-	int *top = stack;  // single-cursor BVH2 traversal: stack pointer
+	int *top = stack;  // BVH2 stack pointer
 	uint2 ng = make_uint2(0u, 0u), tg = ng;  // wide-BVH cursor
 	uint2 wstack[WIDE ? ARE_WIDE_STACK : 1];
 	unsigned int rays = 0;
@@ -181,42 +180,6 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 			}
 			finished = ray_ok && !trav;
 		} else if (BVH) {
-#ifdef ARE_TRAV_TWO_WORD
-			if (ray_ok && !trav) {  // a fresh ray
-				h.t = INFINITY; h.idx = -1; h.orig = orig;
-				++rays;
-				if (A.sc.n_nodes == 0) {  // zero or one primitive
-					if (A.sc.root_leaf_meta != 0) test_leaf<COUNT>(A.sc, A.sc.root_leaf_meta, o, d, A.tmin, h, &tc);
-				} else { node = 0; pend = 0; sp = 0; trav = true; }
-			}
-			const int n_rays = __popc(__ballot_sync(full, ray_ok));
-			if (__any_sync(full, trav)) {
-				const RaySlopes rs = ray_slopes(o, d);
-				while (true) {
-#pragma unroll 1
-					for (int rep = 0; rep < TRAV_STEPS_PER_VOTE; ++rep) {  // several steps between the warp votes that decide the end of the slice
-						// node phase: every traversing lane that has no leaf waiting visits one inner node
-						if (trav && pend == 0) trav = bvh_visit<COUNT, BIG>(A.sc, A.tmin, rs, node, pend, sp, stack, h, &tc);
-						// leaf phase.  LEAF_MIN_LANES > 1 postpones it until that many lanes hold a leaf (or nobody can do anything
-						// else) so the primitive tests run with more lanes; measured best is 1, which needs no votes at all.
-						bool leaf_now = true;
-						if (LEAF_MIN_LANES > 1) {
-							const unsigned m_leaf = __ballot_sync(full, trav && pend != 0);
-							const unsigned m_node = __ballot_sync(full, trav && pend == 0);
-							leaf_now = m_leaf != 0u && (__popc(m_leaf) >= LEAF_MIN_LANES || m_node == 0u);
-						}
-						if (leaf_now && trav && pend != 0) {
-							test_leaf<COUNT>(A.sc, pend, o, d, A.tmin, h, &tc);
-							pend = 0;
-							trav = trav_pop<BIG>(sp, stack, node, pend);
-						}
-					}
-					const int n_trav = __popc(__ballot_sync(full, trav));
-					if (n_trav == 0 || (n_trav < TRAV_MIN_LANES && n_trav < n_rays)) break;
-				}
-			}
-			finished = ray_ok && !trav;
-#else
 			// single-cursor form (intersect.cuh): `node` is the cursor, `top` the stack pointer, trav <=> cursor != TRAV_DONE
 			if (ray_ok && !trav) {  // a fresh ray
 				h.t = INFINITY; h.idx = -1; h.orig = orig;
@@ -241,7 +204,6 @@ __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : 
 				trav = node != TRAV_DONE;
 			}
 			finished = ray_ok && !trav;
-#endif
 		} else if (ray_ok) {
 			h.t = INFINITY; h.idx = -1; h.orig = orig;
 			if (LEAN) intersect_lean(sb_prims, br.nb, A.sc.lean_n_open, br.nq, br.nt, o, d, A.tmin, h);
