@@ -420,7 +420,9 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 		// the five input temporaries go; the three outputs stay
 		for (size_t i = 0; i < n_temp; ++i) cudaFreeAsync(ctx->scene_allocs[i], ctx->stream);
 		ctx->scene_allocs.erase(ctx->scene_allocs.begin(), ctx->scene_allocs.begin() + n_temp);
-		if (out.height > ARE_BVH_STACK) {  // deeper than the traversal stack (many coincident centres): the SAH builder bounds its depth
+		int max_height = ARE_BVH_STACK;
+		if (const char *e = getenv("ARE_CUDA_LBVH_MAX_HEIGHT")) max_height = std::min(max_height, atoi(e));  // test hook for the fall-back below
+		if (out.height > max_height) {  // deeper than the traversal stack (many coincident centres): the SAH builder bounds its depth
 			free_scene_allocs(ctx);
 			builder = ARE_BVH_BUILDER_HOST_SAH;
 			continue;

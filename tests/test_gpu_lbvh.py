@@ -120,3 +120,21 @@ def test_lbvh_edge_cases(ctx):
     ctx.commit()
     p0, *_ = ctx.hit_batch(Q[:16], D[:16], t_min=1e-3, precision=32, traversal=2)
     assert (p0 < 0).all()
+
+
+def test_lbvh_falls_back_to_host_builder_when_too_deep(ctx, monkeypatch):
+    """A device-built tree deeper than the traversal stack is discarded and the host SAH builder takes over (the limit is
+    lowered through the test hook ARE_CUDA_LBVH_MAX_HEIGHT to provoke it); the scene renders as usual."""
+    sc = scenes.stress(n_prims=2000, width=48, height=32)
+    cam = capi.make_camera(**sc.camera_args())
+    par = capi.make_params(**sc.params_args(sample_count=4, traversal=2))
+    info = _commit(ctx, sc, capi.BVH_BUILDER_HOST_SAH)
+    ref, sr = ctx.render(cam, par)
+    monkeypatch.setenv("ARE_CUDA_LBVH_MAX_HEIGHT", "5")
+    info = _commit(ctx, sc, capi.BVH_BUILDER_DEVICE_LBVH)
+    monkeypatch.delenv("ARE_CUDA_LBVH_MAX_HEIGHT")
+    assert info.builder == capi.BVH_BUILDER_HOST_SAH and info.device_bvh_ms == 0 and info.bvh_nodes == 1999
+    img, st = ctx.render(cam, par)
+    assert st.rays == sr.rays and np.array_equal(img, ref)
+    info = _commit(ctx, sc, capi.BVH_BUILDER_DEVICE_LBVH)
+    assert info.builder == capi.BVH_BUILDER_DEVICE_LBVH and info.bvh_height > 5
