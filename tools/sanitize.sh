@@ -1,6 +1,6 @@
 #!/bin/bash
 # tools/sanitize.sh — compute-sanitizer (memcheck, racecheck, initcheck) over one small invocation of every kernel family:
-# smoke() (megakernel brute force + fp64 harness), a BVH2 / wide-BVH render, the RT_AO integrator, Texture::paste and
+# the megakernel (lean and generic brute force) + fp64 harness, a BVH2 / wide-BVH render, the device BVH builder, the RT_AO integrator, Texture::paste and
 # the patch renderer.  Writes gpurun_out/sanitizer_<tool>.log; exit status 0 only if every tool reports 0 errors.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -18,6 +18,21 @@ with capi.Context(0) as ctx:
         assert np.isfinite(img).all()
         Q = np.random.RandomState(0).uniform(-1, 1, (2000, 3)); D = np.random.RandomState(1).normal(size=(2000, 3))
         ctx.hit_batch(Q, D, precision=64); ctx.hit_batch(Q, D, precision=32, traversal=trav)
+    # the generic brute-force kernel on a scene that has a lean form, and the device BVH builder (lbvh.cu) + a render of its tree
+    os.environ["ARE_CUDA_NO_LEAN"] = "1"
+    sc = scenes.by_name("cornell_box", width=48, height=48)
+    ctx.clear(); sc.feed(ctx); ctx.commit()
+    img, st = ctx.render(capi.make_camera(**sc.camera_args()), capi.make_params(**sc.params_args(sample_count=2, traversal=1, max_depth=8)))
+    assert st.kernel_variant == capi.KERNEL_BRUTE
+    del os.environ["ARE_CUDA_NO_LEAN"]
+    ctx.set_bvh_builder(capi.BVH_BUILDER_DEVICE_LBVH)
+    for name, kw in (("cornell_box", dict(width=48, height=48)), ("stress", dict(n_prims=30000, width=48, height=27))):
+        sc = scenes.by_name(name, **kw)
+        ctx.clear(); sc.feed(ctx); ctx.commit()
+        assert ctx.commit_info().builder == capi.BVH_BUILDER_DEVICE_LBVH
+        img, st = ctx.render(capi.make_camera(**sc.camera_args()), capi.make_params(**sc.params_args(sample_count=2, traversal=2, max_depth=8)))
+        assert np.isfinite(img).all()
+    ctx.set_bvh_builder(capi.BVH_BUILDER_HOST_SAH)
     ps = scenes.patch_random(1, width=64, height=48, mirror_walls=True)
     ctx.patch_render(ps); ctx.patch_trace_texture(ps, ps.origin, 12, 40, 40)
     dst = np.zeros((40, 50, 3)); src = np.random.RandomState(2).uniform(size=(20, 30, 3))
