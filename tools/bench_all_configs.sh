@@ -6,9 +6,9 @@
 cd "$(dirname "$0")/.."
 P="python bench.py --steps 4 --warmup 3 --cpu-seconds 8"
 $P --scene rt_cornell --width 512 --height 512 --spp-per-step 1 2>/dev/null
-$P --scene rtiow_final --width 1200 --height 675 --spp-per-step 20 2>/dev/null
-$P --scene textured --width 1920 --height 1080 --spp-per-step 16 2>/dev/null
-$P --scene cornell_box --width 2048 --height 2048 --spp-per-step 64 2>/dev/null
+$P --scene rtiow_final --width 1200 --height 675 --spp-per-step 250 2>/dev/null
+$P --scene textured --width 1920 --height 1080 --spp-per-step 256 2>/dev/null
+$P --scene cornell_box --width 2048 --height 2048 --spp-per-step 256 2>/dev/null
 ARE_CUDA_VERBOSE=1 $P --scene stress --width 3840 --height 2160 --spp-per-step 2 2>gpurun_out/stress_commit.err
 if [ -x oracle/_ref/rt_ref ]; then
   d=$(mktemp -d); ( cd $d; s=$(date +%s.%N); $OLDPWD/oracle/_ref/rt_ref > rt_ref.log 2>&1; e=$(date +%s.%N); ARE_RT_SEED=1 $OLDPWD/oracle/_ref/rt_ref_counted > cnt.log 2>&1
