@@ -61,7 +61,7 @@ struct MaterialRec {
 
 struct TextureRec {
 	int kind, w, h, pad_;
-	long long data_off;  // IMAGE: float offset into tex_data (rgb per texel). NOISE: float offset of 256x3 gradients, followed by 768 ints
+	long long data_off;  // IMAGE: float offset into tex_data (rgb per texel). NOISE: float offset of 256 float4 gradients, followed by 768 ints and 768 doubles
 	double p[8];
 	float pf[8];
 };

@@ -579,10 +579,14 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 			int perm[768];
 			make_noise_tables((uint64_t)t.p[1], grad, perm);
 			size_t base = out.tex_data.size();
-			out.tex_data.resize(base + 768 + 768 + 1536);
-			for (int i = 0; i < 768; ++i) out.tex_data[base + i] = (float)grad[i];
-			std::memcpy(&out.tex_data[base + 768], perm, sizeof perm);
-			std::memcpy(&out.tex_data[base + 1536], grad, sizeof grad);
+			// [256 x (gx, gy, gz, 0) fp32: one LDG.128 per lattice corner][3 x 256 int permutations][768 fp64 gradients (harness)]
+			out.tex_data.resize(base + 1024 + 768 + 1536);
+			for (int i = 0; i < 256; ++i) {
+				for (int k = 0; k < 3; ++k) out.tex_data[base + 4 * i + k] = (float)grad[3 * i + k];
+				out.tex_data[base + 4 * i + 3] = 0.f;
+			}
+			std::memcpy(&out.tex_data[base + 1024], perm, sizeof perm);
+			std::memcpy(&out.tex_data[base + 1792], grad, sizeof grad);
 		}
 		out.texs.push_back(r);
 	}

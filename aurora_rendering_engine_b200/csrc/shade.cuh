@@ -34,9 +34,11 @@ __device__ __forceinline__ V3<float> renorm(V3<float> a) { return a; }
 template <typename T> struct Pi { static constexpr T value = T(3.14159265358979323846); };
 
 // ---- textures -----------------------------------------------------------------------------------------
+// table layout (scene.cpp): [256 x float4 gradients][3 x 256 int permutations][768 double gradients]
 template <typename T>
 __device__ T perlin_noise(const float *tab, V3<T> p) {
-	const int *perm = reinterpret_cast<const int *>(tab + 768);
+	const int *perm = reinterpret_cast<const int *>(tab + 1024);
+	const float4 *grad = reinterpret_cast<const float4 *>(tab);
 	T fx = floor_t(p.x), fy = floor_t(p.y), fz = floor_t(p.z);
 	T u = p.x - fx, v = p.y - fy, w = p.z - fz;
 	int i = (int)fx, j = (int)fy, k = (int)fz;
@@ -48,7 +50,8 @@ __device__ T perlin_noise(const float *tab, V3<T> p) {
 #pragma unroll
 			for (int dk = 0; dk < 2; ++dk) {
 				int g = perm[(i + di) & 255] ^ perm[256 + ((j + dj) & 255)] ^ perm[512 + ((k + dk) & 255)];
-				V3<T> gv = mk<T>(T(tab[3 * g]), T(tab[3 * g + 1]), T(tab[3 * g + 2]));
+				const float4 gq = __ldg(grad + g);  // one 16-byte load per lattice corner
+				V3<T> gv = mk<T>(T(gq.x), T(gq.y), T(gq.z));
 				V3<T> wv = mk<T>(u - T(di), v - T(dj), w - T(dk));
 				acc += (di ? uu : T(1) - uu) * (dj ? vv : T(1) - vv) * (dk ? ww : T(1) - ww) * dot(gv, wv);
 			}
@@ -63,10 +66,9 @@ __device__ __forceinline__ float perlin_noise_tab<float>(const DevScene &sc, con
 }
 template <>
 __device__ inline double perlin_noise_tab<double>(const DevScene &sc, const TextureRec &t, V3<double> p) {
-	// layout: [768 float gradients][768 int perm][768 double gradients]
 	const float *tab = sc.tex_data + t.data_off;
-	const int *perm = reinterpret_cast<const int *>(tab + 768);
-	const double *gd = reinterpret_cast<const double *>(tab + 1536);
+	const int *perm = reinterpret_cast<const int *>(tab + 1024);
+	const double *gd = reinterpret_cast<const double *>(tab + 1792);
 	double fx = floor(p.x), fy = floor(p.y), fz = floor(p.z);
 	double u = p.x - fx, v = p.y - fy, w = p.z - fz;
 	int i = (int)fx, j = (int)fy, k = (int)fz;
