@@ -9,7 +9,10 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <thread>
+#include <type_traits>
+#include <utility>
 #include <unordered_map>
 
 #include "philox.cuh"
@@ -96,8 +99,17 @@ struct HotItem {
 	Box box;
 	double c[3];  // centroid
 	D3 gQ, gu, gv;  // parallelogram geometry (quads / fused pairs), for box detection
-	bool dead = false;  // absorbed into a box
+	bool dead;  // absorbed into a box (no default member initialiser: the struct stays trivial, see HotVec)
 };
+// std::vector whose resize() default-initialises, i.e. leaves trivial elements untouched: the 260-byte hot items of a
+// million-primitive scene are then first touched by the threads that fill them, not zero-filled by one thread first.
+template <typename T>
+struct DefaultInitAlloc : std::allocator<T> {
+	template <typename U> struct rebind { using other = DefaultInitAlloc<U>; };
+	template <typename U> void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void *>(p)) U; }
+	template <typename U, typename... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+typedef std::vector<HotItem, DefaultInitAlloc<HotItem>> HotVec;
 inline void emit_item(const HotItem &it, std::vector<HotPrim> &prims, std::vector<HotIds> &ids) {
 	prims.push_back(it.rec);
 	ids.push_back(it.ids);
@@ -154,12 +166,12 @@ struct Builder {
 		double c[3];  // centroid
 		int item;
 	};
-	const std::vector<HotItem> &items;
+	const HotVec &items;
 	std::vector<Ref> refs;
 	CompiledScene &out;
 	bool any_box = false;
 	int spawn_depth = 0;  // subtrees above this depth (and big enough) hand their left half to a new thread
-	Builder(const std::vector<HotItem> &it, CompiledScene &o) : items(it), out(o) {
+	Builder(const HotVec &it, CompiledScene &o) : items(it), out(o) {
 		refs.resize(items.size());
 		size_t slots = 0;
 		for (size_t i = 0; i < refs.size(); ++i) {
@@ -687,7 +699,7 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 	};
 	phase("flatten primitives");
 	// ---- hot list with parallelogram fusion ----
-	std::vector<HotItem> hot;
+	HotVec hot;
 	hot.reserve(order.size());
 	const int nt = out.n_tri;
 	std::vector<char> fused(nt, 0);
@@ -695,6 +707,7 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 		HotItem it;
 		it.kind = kind; it.rec = rec; it.rec2 = rec; it.ids = ids; it.box = b;
 		it.gQ = gQ; it.gu = gu; it.gv = gv;
+		it.dead = false;
 		for (int k = 0; k < 3; ++k) it.c[k] = 0.5 * (b.lo[k] + b.hi[k]);
 		hot.push_back(it);
 	};
@@ -707,7 +720,8 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 			D3 Q = d3(q);
 			return k == 0 ? Q : (k == 1 ? Q + d3(q + 3) : Q + d3(q + 6));
 		};
-		std::vector<EdgeUse> edges((size_t)nt * 3);
+		typedef std::vector<EdgeUse, DefaultInitAlloc<EdgeUse>> EdgeVec;  // filled by all threads: no serial zero-fill first
+		EdgeVec edges((size_t)nt * 3);
 		parallel_chunks((size_t)nt, 4096, [&](size_t t0, size_t t1) {
 			for (size_t t = t0; t < t1; ++t)
 				for (int k = 0; k < 3; ++k) edges[3 * t + k] = { EHash()(ekey(vert((int)t, (k + 1) % 3), vert((int)t, (k + 2) % 3))), (int)t, k };
@@ -729,19 +743,43 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 			}
 			if (found) any_run.store(1);
 		};
+		phase("  fusion: edge hashes");
 		{  // sort by (hash, triangle, edge): scatter into 256 buckets on the top hash byte, then sort the buckets in parallel
 			const auto less = [](const EdgeUse &a, const EdgeUse &b) { return a.h != b.h ? a.h < b.h : (a.tri != b.tri ? a.tri < b.tri : a.opp < b.opp); };
 			if (edges.size() < 65536) {
 				std::sort(edges.begin(), edges.end(), less);
 				mark_runs(0, edges.size());
 			} else {
+				// counting sort on the top hash byte with one histogram per thread: thread t's edges of bucket b go to
+				// start[b] + (what threads < t hold of b), so the scatter is stable and needs no atomics
+				const unsigned T = std::max(1u, std::min(host_threads(), 64u));
+				std::vector<size_t> hist((size_t)T * 256, 0);
+				const size_t ne = edges.size();
+				{
+					std::vector<std::thread> th;
+					for (unsigned t = 0; t < T; ++t)
+						th.emplace_back([&, t] {
+							size_t *h = &hist[(size_t)t * 256];
+							for (size_t i = ne * t / T; i < ne * (t + 1) / T; ++i) ++h[edges[i].h >> 56];
+						});
+					for (auto &x : th) x.join();
+				}
 				size_t start[257] = { 0 };
-				for (const EdgeUse &e : edges) ++start[(e.h >> 56) + 1];
-				for (int b = 0; b < 256; ++b) start[b + 1] += start[b];
-				std::vector<EdgeUse> tmp(edges.size());
-				size_t fill[256];
-				std::memcpy(fill, start, sizeof fill);
-				for (const EdgeUse &e : edges) tmp[fill[e.h >> 56]++] = e;
+				for (int b = 0; b < 256; ++b) {
+					size_t at = start[b];
+					for (unsigned t = 0; t < T; ++t) { const size_t c = hist[(size_t)t * 256 + b]; hist[(size_t)t * 256 + b] = at; at += c; }
+					start[b + 1] = at;
+				}
+				EdgeVec tmp(ne);
+				{
+					std::vector<std::thread> th;
+					for (unsigned t = 0; t < T; ++t)
+						th.emplace_back([&, t] {
+							size_t *fill = &hist[(size_t)t * 256];
+							for (size_t i = ne * t / T; i < ne * (t + 1) / T; ++i) tmp[fill[edges[i].h >> 56]++] = edges[i];
+						});
+					for (auto &x : th) x.join();
+				}
 				edges.swap(tmp);
 				parallel_chunks(256, 1, [&](size_t b0, size_t b1) {
 					for (size_t b = b0; b < b1; ++b) {
@@ -751,6 +789,7 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 				});
 			}
 		}
+		phase("  fusion: edge sort + runs");
 		if (any_run.load())  // no shared edge anywhere (a cloud of loose triangles): nothing to fuse
 		for (int t = 0; t < nt; ++t) {
 			if (fused[t]) continue;
@@ -782,6 +821,7 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 			}
 		}
 	}
+	phase("  fusion: pair search");
 	{  // every primitive that was not fused becomes a hot item of its own, in device order: positions by a prefix count,
 		// then all host threads fill them
 		std::vector<int> pos(order.size() + 1);
@@ -882,6 +922,7 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 						const D3 edges[3] = { a, b, c };
 						const D3 centre = B + 0.5 * (a + b + c);
 						HotItem bx;
+						bx.dead = false;
 						bx.kind = HK_BOX;
 						bx.ids = { -1 - out.n_boxes, -1 };
 						bx.box.reset();
@@ -987,6 +1028,9 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 	}
 	// ---- BVH ----
 	const auto bvh_t0 = std::chrono::steady_clock::now();
+	if (hot.empty() || !opt.device_bvh) {  // no device-builder input this time (reset() leaves these arrays alone)
+		out.lb_lo.clear(); out.lb_hi.clear(); out.lb_prims.clear(); out.lb_ids.clear(); out.lb_slot.clear();
+	}
 	if (!hot.empty() && opt.device_bvh) {
 		// input of the device builder: conservative fp32 bounds (rounded outwards) + the records in item order
 		const size_t n = hot.size();

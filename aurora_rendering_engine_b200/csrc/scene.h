@@ -87,9 +87,11 @@ struct CompiledScene {
 	// already mapped instead of page-faulting ~150 MB per million primitives in again.
 	void reset() {
 		brute.clear(); brute_ids.clear(); box_faces.clear(); bvh_prims.clear(); bvh_ids.clear(); nodes.clear(); wnodes.clear();
-		wide_prims.clear(); wide_ids.clear(); wide_kinds.clear(); info.clear(); prim_plane.clear(); shade.clear(); tri_uv.clear();
-		rt_tris.clear(); tri64.clear(); quad64.clear(); sph64.clear(); tri_uv64.clear(); mats.clear(); texs.clear(); tex_data.clear();
-		lean_shade.clear(); lean_sbase.clear(); lb_lo.clear(); lb_hi.clear(); lb_prims.clear(); lb_ids.clear(); lb_slot.clear();
+		wide_prims.clear(); wide_ids.clear(); wide_kinds.clear(); mats.clear(); texs.clear(); tex_data.clear();
+		lean_shade.clear(); lean_sbase.clear();
+		// NOT cleared: the per-primitive arrays (info, prim_plane, shade, tri_uv, rt_tris, tri64, quad64, sph64, tri_uv64) and
+		// the device-builder input (lb_*).  compile_scene resizes them to the new counts and overwrites every element, so a
+		// re-commit of a scene of the same size does not zero-fill ~250 bytes per primitive on one thread first.
 		brute_range = { 0, 0, 0, 0, 0 };
 		n_boxes = 0; lean_ok = false; lean_n_open = 0; wide_depth = 0; root_leaf_meta = 0; n_hot = 0; n_fused_pairs = 0;
 		n_tri = n_quad = n_sph = 0; bvh_depth = 0; host_bvh_ms = 0.0;
