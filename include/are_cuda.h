@@ -154,7 +154,7 @@ typedef struct are_commit_info {
 	int builder; /* ARE_BVH_BUILDER_* actually used by the last commit */
 	int bvh_nodes, bvh_height, hot_slots;
 	double host_compile_ms; /* flattening, fusion, box detection (+ the host BVH build under HOST_SAH) */
-	double host_bvh_ms; /* of which: host BVH builders */
+	double host_bvh_ms; /* of which: the host BVH builders (HOST_SAH) / preparing the device builder's input (DEVICE_LBVH) */
 	double device_bvh_ms; /* DEVICE_LBVH: CUDA-event time of the build kernels */
 	uint64_t device_bvh_launches;
 } are_commit_info;
