@@ -148,13 +148,19 @@ class SceneDesc:
 # ---------------------------------------------------------------------------------------------------------
 # config 0 — rt.cpp's scene (experiments/rt.cpp:153-185)
 # ---------------------------------------------------------------------------------------------------------
-def rt_cornell(width=512, height=512):
-    s = SceneDesc("rt_cornell", width=width, height=height, spp=1, max_depth=2, integrator=INTEGRATOR_RT_AO,
+def rt_cornell(width=512, height=512, diffuse_walls=False):
+    """diffuse_walls=True: the five room walls are MAT_DIFFUSE instead of MAT_METAL 0.90 (the boxes stay mirrors), which is
+    what makes rt.cpp's cosine gather + Russian roulette (rt.cpp:278-329) run at all — in the scene as shipped it is dead
+    code.  oracle/_ref/rt_ref_diffuse_counted is the reference program with exactly that edit."""
+    s = SceneDesc("rt_cornell_diffuse" if diffuse_walls else "rt_cornell", width=width, height=height, spp=1, max_depth=2, integrator=INTEGRATOR_RT_AO,
                   ao_samples=32, t_min=1e-5, background_bottom=(0.06, 0.09, 0.14), background_top=(0.06, 0.09, 0.14))
     red, green, white = s.solid(0.8, 0.15, 0.15), s.solid(0.15, 0.8, 0.15), s.solid(0.8, 0.8, 0.8)
     checker = s.tex(TEX_CHECKER_UV, 8, 0.9, 0.9, 0.9, 0.1, 0.1, 0.1)
     meta = s.solid(0.93, 0.95, 1.0)
-    wall = s.mat(MAT_REFLECTIVE, 0.90, 0.0, 0.0, 0.0)        # MAT_METAL 0.90 with the default (black) tint, rt.cpp:160-164
+    if diffuse_walls:
+        wall = s.mat(MAT_DIFFUSE)
+    else:
+        wall = s.mat(MAT_REFLECTIVE, 0.90, 0.0, 0.0, 0.0)    # MAT_METAL 0.90 with the default (black) tint, rt.cpp:160-164
     box = s.mat(MAT_REFLECTIVE, 0.90, 0.92, 0.94, 1.0)       # rt.cpp:165-166
     f = np.float32  # the original holds fp32 coordinates
     s.quad_as_tris((-1, -1, -1), (-1, 1, -1), (-1, 1, 1), (-1, -1, 1), wall, red)
@@ -332,6 +338,8 @@ def stress(n_prims=1_000_000, width=3840, height=2160, spp=256, seed=4, extent=5
 
 
 def by_name(name, **kw):
+    if name == "rt_cornell_diffuse":
+        return rt_cornell(diffuse_walls=True, **kw)
     return {"rt_cornell": rt_cornell, "cornell_box": cornell_box, "rtiow_final": rtiow_final, "textured": textured,
             "stress": stress}[name](**kw)
 

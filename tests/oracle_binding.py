@@ -414,3 +414,28 @@ class PatchReference(_PatchLib):
     @classmethod
     def available(cls):
         return os.path.exists(cls.PATH)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# experiments/rt.cpp with diffuse walls (oracle/_ref/rt_ref_diffuse_counted): the reference's cosine gather + RR
+# ---------------------------------------------------------------------------------------------------------
+RT_REF_DIFFUSE_COUNTED = os.path.join(ORACLE_DIR, "_ref", "rt_ref_diffuse_counted")
+
+
+def run_rt_reference(binary, workdir, seed=1, timeout=600):
+    """Run one of the compiled rt.cpp programs in `workdir` -> (image (512,512,3) float64 in [0,1] = bytes/255 of its
+    out_diffuse.ppm, rays cast or None when the build does not count)."""
+    import re
+    env = dict(os.environ, ARE_RT_SEED=str(seed))
+    r = subprocess.run([binary], cwd=str(workdir), check=True, capture_output=True, timeout=timeout, env=env)
+    raw = open(os.path.join(str(workdir), "out_diffuse.ppm"), "rb").read()
+    hdr = b"P6\n512 512\n255\n"
+    assert raw.startswith(hdr)
+    img = np.frombuffer(raw[len(hdr):], np.uint8).reshape(512, 512, 3).astype(np.float64) / 255.0
+    m = re.search(rb"ARE_COUNT rays=(\d+)", r.stdout)
+    return img, (int(m.group(1)) if m else None)
+
+
+def block_mean(img, b):
+    h, w, c = img.shape
+    return img.reshape(h // b, b, w // b, b, c).mean(axis=(1, 3))

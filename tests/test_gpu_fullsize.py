@@ -117,3 +117,46 @@ def test_config4_stress_1M_3840x2160_builders_agree(ctx):
     assert out["sah"][1].rays == out["lbvh"][1].rays
     assert np.allclose(out["sah"][0], out["lbvh"][0], rtol=1e-5, atol=1e-5)
     assert np.isfinite(out["lbvh"][0]).all() and out["lbvh"][0].mean() > 0
+
+
+def test_config4_stress_1M_matches_cpu_twin(ctx, oracle):
+    """The full 1 M-primitive scene against the fp64 CPU twin (which prunes with its own AABB tree, proven equal to its
+    linear scan in tests/test_oracle_vs_reference.py): two 256x16 windows of the 3840x2160 frame on the same Philox
+    samples, and 100 000 closest-hit queries through the cloud — for both builders."""
+    sc = scenes.stress()
+    assert sc.num_prims == 1_000_000 and (sc.width, sc.height) == (3840, 2160)
+    cam = capi.make_camera(**sc.camera_args())
+    osc = sc.feed(oracle.scene())
+    spp = 4
+    windows = ((1800, 1000, 2056, 1016), (900, 600, 1156, 616))
+    par = capi.make_params(**sc.params_args(sample_count=spp, traversal=2))
+    want = []
+    for w in windows:
+        oimg, ost = osc.render(cam, par, window=w)
+        want.append((oimg, ost))
+    rng = np.random.RandomState(11)
+    n = 100_000
+    Q = rng.uniform(-40, 40, (n, 3))
+    D = rng.normal(size=(n, 3))
+    oprim, ot, *_ = osc.hit_batch(Q, D, 1e-3)
+    assert (oprim >= 0).mean() > 0.1
+    for builder in (capi.BVH_BUILDER_HOST_SAH, capi.BVH_BUILDER_DEVICE_LBVH):
+        ctx.clear()
+        ctx.set_bvh_builder(builder)
+        sc.feed(ctx)
+        ctx.commit()
+        img, st = ctx.render(cam, par)
+        assert st.kernel_variant == capi.KERNEL_BVH2_BIG
+        for (x0, y0, x1, y1), (oimg, ost) in zip(windows, want):
+            a = np.clip(img[y0:y1, x0:x1].astype(np.float64) / spp, 0, 1)
+            b = np.clip(oimg[y0:y1, x0:x1] / spp, 0, 1)
+            p = psnr(a, b)
+            print(f"[stress 1M builder {builder} window {x0},{y0}] PSNR {p:.1f} dB, twin rays/sample {ost.rays / ost.samples:.3f}")
+            assert p >= 40.0, (builder, (x0, y0), p)
+        prim, t, *_ = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=2)
+        mism = float((prim != oprim).mean())
+        hit = (oprim >= 0) & (prim == oprim)
+        rel = np.abs(t[hit] - ot[hit]) / np.maximum(np.abs(ot[hit]), np.abs(Q[hit]).max(axis=1))
+        print(f"[stress 1M builder {builder}] closest-hit mismatches {mism:.2e}, 99.9 % of |dt| <= {np.percentile(rel, 99.9):.2e}")
+        assert mism < 5e-4, (builder, mism)   # grazing rays only
+        assert hit.sum() > 10_000 and np.percentile(rel, 99.9) < 1e-5

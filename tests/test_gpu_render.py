@@ -179,6 +179,52 @@ def test_rt_ao_integrator_matches_cpu_restatement(ctx, oracle):
     assert p >= PSNR_MIN, f"PSNR {p:.1f} dB"
 
 
+def test_rt_ao_gather_matches_cpu_restatement(ctx, oracle):
+    """SURVEY §8a row a14 — rt.cpp's cosine gather + Russian roulette (rt.cpp:278-329) and rotateToHemisphere (:50-55):
+    dead code in the all-mirror scene the reference ships, reached here by making the five walls MAT_DIFFUSE (the boxes
+    stay mirrors, so the gather's own mirror branch runs too).  Same Philox streams on both sides."""
+    sc = scenes.rt_cornell(width=128, height=128, diffuse_walls=True)
+    img, st, oimg, ost = _render_both(sc, ctx, oracle, spp=2)
+    p = psnr(img, oimg)
+    print(f"[rt_ao gather] PSNR {p:.1f} dB, rays gpu/cpu {st.rays}/{ost.rays}, mean {img.mean():.5f}/{oimg.mean():.5f}")
+    assert st.kernel_variant == capi.KERNEL_RT_AO
+    assert abs(int(st.rays) - int(ost.rays)) < 2e-3 * ost.rays
+    assert st.rays / st.samples > 40   # 43.5 rays per pixel with the gather against 34.2 without
+    assert abs(img.mean() - oimg.mean()) < 2e-3 * oimg.mean()
+    assert p >= PSNR_MIN, f"PSNR {p:.1f} dB"
+
+
+def test_rt_ao_gather_matches_the_real_reference_program(ctx, tmp_path):
+    """The same path against the REAL reference: experiments/rt.cpp with the five walls' material argument changed to
+    MAT_DIFFUSE by sed (oracle/_ref/rt_ref_diffuse_counted).  The program encodes ONE noisy estimate per pixel from
+    mt19937, so the GPU renders K single-sample images, encodes each with the same formula and averages; compared over
+    16x16 blocks (noise falls with the block size, a systematic difference would not) plus the true ray count."""
+    import os
+    from oracle_binding import RT_REF_DIFFUSE_COUNTED, block_mean, run_rt_reference
+    if not os.path.exists(RT_REF_DIFFUSE_COUNTED):
+        pytest.skip("oracle/_ref/rt_ref_diffuse_counted not present")
+    ref, ref_rays = run_rt_reference(RT_REF_DIFFUSE_COUNTED, tmp_path, seed=5)
+    sc = scenes.rt_cornell(diffuse_walls=True)
+    cam = capi.make_camera(**sc.camera_args())
+    sc.feed(ctx)
+    ctx.commit()
+    K, G, rays = 32, np.zeros((512, 512, 3)), 0
+    acc = ctx.alloc_accum(512, 512)
+    for k in range(K):
+        ctx.zero_accum(acc, 512, 512)
+        st = ctx.render_device(cam, capi.make_params(**sc.params_args(sample_begin=k, sample_count=1)), acc, want_stats=True)
+        G += ctx.tonemap(acc, 512, 512, 1.0, encoder=0).astype(np.float64) / 255.0
+        rays += int(st.rays)
+    ctx.free_accum(acc)
+    G /= K
+    p16 = psnr(block_mean(G, 16), block_mean(ref, 16))
+    print(f"[rt_ao gather vs rt_ref_diffuse] 16x16-block PSNR {p16:.1f} dB, rays/pixel {rays / K / 262144:.3f} vs {ref_rays / 262144:.3f}, "
+          f"mean {G.mean():.5f} vs {ref.mean():.5f}")
+    assert abs(rays / K - ref_rays) < 2e-3 * ref_rays, (rays / K, ref_rays)
+    assert abs(G.mean() - ref.mean()) < 3e-3 * ref.mean()
+    assert p16 >= 50.0, p16
+
+
 @pytest.mark.parametrize("encoder", [0, 1, 2])
 def test_tonemap_encoders(ctx, oracle, encoder):
     rng = np.random.RandomState(encoder)

@@ -215,3 +215,30 @@ def test_cpu_twin_tree_equals_linear_scan(oracle):
     assert (prim >= 0).sum() > 300
     assert np.array_equal(best_p, prim)
     assert np.array_equal(best_t[prim >= 0], t[prim >= 0])
+
+
+def test_rt_gather_restatement_vs_the_real_program_with_diffuse_walls(oracle, tmp_path):
+    """rt.cpp's cosine gather + Russian roulette (rt.cpp:278-329, :50-55) is dead code in the scene
+    the reference ships (all surfaces MAT_METAL).  oracle/_ref/rt_ref_diffuse_counted is the same program with the five
+    walls made MAT_DIFFUSE by sed; it draws from mt19937, the restatement from Philox, so the pin is statistical: the
+    true ray count per pixel, and the mean of ENCODED single-sample images (the program encodes one noisy estimate per
+    pixel) over 16x16 blocks — noise falls with the block size, a systematic difference would not."""
+    from aurora_rendering_engine_b200 import capi
+    from oracle_binding import RT_REF_DIFFUSE_COUNTED, block_mean, psnr, run_rt_reference
+    if not os.path.exists(RT_REF_DIFFUSE_COUNTED):
+        pytest.skip("oracle/_ref/rt_ref_diffuse_counted not present")
+    ref, ref_rays = run_rt_reference(RT_REF_DIFFUSE_COUNTED, tmp_path, seed=3)
+    sc = scenes.rt_cornell(diffuse_walls=True)
+    osc = sc.feed(oracle.scene())
+    cam = capi.make_camera(**sc.camera_args())
+    K, G, rays = 4, np.zeros((512, 512, 3)), 0
+    for k in range(K):
+        one, st = osc.render(cam, capi.make_params(**sc.params_args(sample_count=1, sample_begin=k)))
+        G += oracle.encode_gamma22(one.astype(np.float32)).reshape(512, 512, 3) / 255.0
+        rays += int(st.rays)
+    G /= K
+    assert abs(rays / K - ref_rays) < 2e-3 * ref_rays, (rays / K, ref_rays)   # 43.5 rays per pixel (34.2 in the all-mirror scene)
+    assert ref_rays / 262144 > 40
+    assert abs(G.mean() - ref.mean()) < 3e-3 * ref.mean(), (G.mean(), ref.mean())
+    p16 = psnr(block_mean(G, 16), block_mean(ref, 16))
+    assert p16 >= 48.0, p16   # measured 52-54 dB; per pixel it is 30 dB (the reference's own run-to-run noise: 28 dB)
