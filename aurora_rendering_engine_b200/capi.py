@@ -46,14 +46,17 @@ class RenderStats(C.Structure):
 class CommitInfo(C.Structure):
     """are_commit_info"""
     _fields_ = [("builder", C.c_int), ("bvh_nodes", C.c_int), ("bvh_height", C.c_int), ("hot_slots", C.c_int), ("host_compile_ms", C.c_double),
-                ("host_bvh_ms", C.c_double), ("device_bvh_ms", C.c_double), ("device_bvh_launches", C.c_uint64)]
+                ("host_bvh_ms", C.c_double), ("device_bvh_ms", C.c_double), ("device_bvh_launches", C.c_uint64), ("baked", C.c_int32), ("pad_", C.c_int32),
+                ("bake_compile_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 BVH_BUILDER_HOST_SAH, BVH_BUILDER_DEVICE_LBVH = 0, 1
-KERNEL_NONE, KERNEL_BRUTE, KERNEL_BRUTE_LEAN, KERNEL_BVH2, KERNEL_BVH2_BIG, KERNEL_WIDE, KERNEL_RT_AO = range(7)
+KERNEL_NONE, KERNEL_BRUTE, KERNEL_BRUTE_LEAN, KERNEL_BVH2, KERNEL_BVH2_BIG, KERNEL_WIDE, KERNEL_RT_AO, KERNEL_BRUTE_BAKED = range(8)
+(OPT_LEAN_KERNEL, OPT_BAKED_KERNEL, OPT_BAKED_PACKED, OPT_FUSE_PARALLELOGRAMS, OPT_FUSE_BOXES, OPT_BUILD_WIDE, OPT_WIDE_MIN_NODES,
+ OPT_LBVH_MAX_HEIGHT) = range(1, 9)
 
 
 def make_camera(pos, target, up=(0, 1, 0), vfov_deg=40.0, focus_dist=1.0, defocus_angle_deg=0.0, jitter=1) -> Camera:
@@ -138,6 +141,8 @@ SIGNATURES = {
     "are_cuda_set_stream": (C.c_int, [_vp, _vp]),
     "are_cuda_set_bvh_builder": (C.c_int, [_vp, C.c_int]),
     "are_cuda_get_commit_info": (C.c_int, [_vp, C.POINTER(CommitInfo)]),
+    "are_cuda_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "are_cuda_set_build_threads": (None, [C.c_int]),
     "are_cuda_add_texture": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int, C.c_int]),
     "are_cuda_add_material": (C.c_int, [_vp, C.c_int, _dp]),
     "are_cuda_add_triangle": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
@@ -152,6 +157,7 @@ SIGNATURES = {
     "are_cuda_compile_probe": (C.c_int, [C.c_int, _dp, _dp, _dp, _ip]),
     "are_cuda_compile_probe_digest": (C.c_int, [C.c_int, _dp, _dp, _dp, _ip, C.POINTER(C.c_uint64)]),
     "are_cuda_compile_probe_forms": (C.c_int, [C.c_int, _dp, _dp, _dp, _ip]),
+    "are_cuda_bake_probe": (C.c_int, [C.c_int, _dp, _dp, _dp, C.c_int, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_char_p]),
     "are_cuda_hit_batch": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_double, C.c_int, C.c_int, _ip, _dp, _dp, _dp, _dp]),
     "are_cuda_scatter_batch": (C.c_int, [_vp, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, _ip]),
     "are_cuda_texture_batch": (C.c_int, [_vp, C.c_int, _ip, _dp, _dp, C.c_int, _dp]),
@@ -208,6 +214,11 @@ def patch_plan_probe(ps) -> dict:
     return dict(zip(("nodes", "node_texels", "ops", "levels", "ops_a", "ops_b"), [int(x) for x in out]))
 
 
+def set_build_threads(n: int):
+    """Host threads of the scene compiler, process-wide (0 = all hardware threads)."""
+    load_library().are_cuda_set_build_threads(int(n))
+
+
 def compile_probe(Q, u, v) -> dict:
     """Host-only scene-compiler probe (are_cuda_compile_probe): no GPU involved."""
     lib = load_library()
@@ -234,6 +245,20 @@ def compile_probe_forms(Q, u, v) -> dict:
         raise AreCudaError(st, "compile probe rejected the triangles")
     keys = ("lean_ok", "lean_records", "lean_open_boxes", "lbvh_items", "lbvh_slots", "lbvh_conservative", "host_bvh_nodes", "brute_boxes")
     return dict(zip(keys, (int(x) for x in out)))
+
+
+def bake_probe(Q, u, v, packed=False, cubin_path=None) -> str:
+    """Host-only: the CUDA source generated for the lean form of a triangle scene (are_cuda_bake_probe); with cubin_path
+    also the NVRTC-compiled sm_100a CUBIN.  No GPU involved."""
+    lib = load_library()
+    Q, u, v = (np.ascontiguousarray(x, dtype=np.float64) for x in (Q, u, v))
+    n = C.c_uint64(0)
+    buf = C.create_string_buffer(1 << 18)
+    st = lib.are_cuda_bake_probe(len(Q), Q.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp), int(bool(packed)), buf, len(buf),
+                                 C.byref(n), os.fsencode(cubin_path) if cubin_path else None)
+    if st != ARE_OK:
+        raise AreCudaError(st, (lib.are_cuda_last_error(None) or b"").decode())
+    return buf.value.decode()
 
 
 def _d(a, shape=None):
@@ -289,6 +314,9 @@ class Context:
     # -- scene ----------------------------------------------------------------------------------------
     def set_bvh_builder(self, builder: int):
         self._ck(self.lib.are_cuda_set_bvh_builder(self.h, int(builder)))
+
+    def set_option(self, option: int, value: int):
+        self._ck(self.lib.are_cuda_set_option(self.h, int(option), int(value)))
 
     def commit_info(self) -> CommitInfo:
         info = CommitInfo()

@@ -20,6 +20,7 @@
 #endif
 
 #include "../../include/are_cuda.h"
+#include "bake.h"
 #include "dev_types.h"
 #include "kernels.h"
 #include "patch.h"
@@ -49,7 +50,15 @@ struct are_cuda_ctx {
 	void *lbvh_ws = nullptr;  // scratch of the device BVH builder, grown on demand and kept between commits
 	size_t lbvh_ws_bytes = 0;
 	are_commit_info commit_info = {};
-	int wide_min_nodes = 0x7fffffff;  // AUTO never picks the compressed 8-wide BVH (measured slower); ARE_CUDA_WIDE_MIN_NODES overrides
+	int wide_min_nodes = 0x7fffffff;  // AUTO never picks the compressed 8-wide BVH (measured slower); ARE_OPT_WIDE_MIN_NODES overrides
+	// options (are_cuda_set_option)
+	bool opt_lean = true;            // lean brute-force kernel for scenes that have a lean form
+	bool opt_bake = true;            // scene-specialised kernel (NVRTC at commit) for the same scenes
+	bool opt_bake_packed = false;    // its slab products as fma.rn.f32x2 pairs
+	int opt_builder_override = -1;   // -1: are_cuda_set_bvh_builder decides
+	int opt_lbvh_max_height = ARE_BVH_STACK;
+	const BakedKernel *baked = nullptr;  // owned by the process-wide cache in bake.cpp
+	std::string bake_note;
 };
 
 static std::string g_create_error;
@@ -253,6 +262,22 @@ int are_cuda_set_bvh_builder(are_cuda_ctx *ctx, int builder) {
 	ctx->bvh_builder = builder;
 	return ARE_OK;
 }
+void are_cuda_set_build_threads(int n) { set_build_threads(n); }
+
+int are_cuda_set_option(are_cuda_ctx *ctx, int option, int value) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	switch (option) {
+	case ARE_OPT_LEAN_KERNEL: ctx->opt_lean = value != 0; return ARE_OK;  // takes effect at the next render
+	case ARE_OPT_BAKED_KERNEL: ctx->opt_bake = value != 0; return ARE_OK;  // off: at once; on: from the next commit
+	case ARE_OPT_BAKED_PACKED: ctx->opt_bake_packed = value != 0; ctx->committed = false; return ARE_OK;
+	case ARE_OPT_FUSE_PARALLELOGRAMS: ctx->opt.fuse_parallelograms = value != 0; ctx->committed = false; return ARE_OK;
+	case ARE_OPT_FUSE_BOXES: ctx->opt.fuse_boxes = value != 0; ctx->committed = false; return ARE_OK;
+	case ARE_OPT_BUILD_WIDE: ctx->opt.build_wide = value != 0; ctx->committed = false; return ARE_OK;
+	case ARE_OPT_WIDE_MIN_NODES: ctx->wide_min_nodes = value; return ARE_OK;
+	case ARE_OPT_LBVH_MAX_HEIGHT: ctx->opt_lbvh_max_height = value > 0 ? value : ARE_BVH_STACK; ctx->committed = false; return ARE_OK;
+	default: return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown option");
+	}
+}
 int are_cuda_get_commit_info(are_cuda_ctx *ctx, are_commit_info *out) {
 	int st = need_commit(ctx);
 	if (st) return st;
@@ -367,11 +392,7 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	free_scene_allocs(ctx);
 	std::string err;
 	ctx->opt.brute_max = (int)brute_smem_limit_prims();
-	if (const char *e = getenv("ARE_CUDA_NO_FUSE")) ctx->opt.fuse_parallelograms = !(e[0] == '1');
-	if (const char *e = getenv("ARE_CUDA_NO_BOXES")) ctx->opt.fuse_boxes = !(e[0] == '1');
-	if (const char *e = getenv("ARE_CUDA_WIDE")) ctx->opt.build_wide = e[0] == '1';
 	int builder = ctx->bvh_builder;
-	if (const char *e = getenv("ARE_CUDA_DEVICE_BVH")) builder = e[0] == '1' ? ARE_BVH_BUILDER_DEVICE_LBVH : ARE_BVH_BUILDER_HOST_SAH;
 	are_commit_info info = {};
 	DevScene d;
 	uint64_t bytes = 0;
@@ -420,8 +441,7 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 		// the five input temporaries go; the three outputs stay
 		for (size_t i = 0; i < n_temp; ++i) cudaFreeAsync(ctx->scene_allocs[i], ctx->stream);
 		ctx->scene_allocs.erase(ctx->scene_allocs.begin(), ctx->scene_allocs.begin() + n_temp);
-		int max_height = ARE_BVH_STACK;
-		if (const char *e = getenv("ARE_CUDA_LBVH_MAX_HEIGHT")) max_height = std::min(max_height, atoi(e));  // test hook for the fall-back below
+		const int max_height = std::min((int)ARE_BVH_STACK, ctx->opt_lbvh_max_height);  // ARE_OPT_LBVH_MAX_HEIGHT: test hook for the fall-back below
 		if (out.height > max_height) {  // deeper than the traversal stack (many coincident centres): the SAH builder bounds its depth
 			free_scene_allocs(ctx);
 			builder = ARE_BVH_BUILDER_HOST_SAH;
@@ -461,13 +481,19 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	d.root_leaf_meta = cs.root_leaf_meta;
 	if (device_built) { d.nodes = dev_nodes; d.bvh_prims = dev_bvh_prims; d.bvh_ids = dev_bvh_ids; d.n_nodes = dev_n_nodes; d.root_leaf_meta = dev_root_leaf; }
 	d.n_wnodes = d.wnodes ? (int)cs.wnodes.size() : 0;
-	if (const char *e = getenv("ARE_CUDA_WIDE_MIN_NODES")) ctx->wide_min_nodes = atoi(e);
 	d.n_hot = cs.n_hot;
 	d.n_tri = cs.n_tri; d.n_quad = cs.n_quad; d.n_sph = cs.n_sph;
 	d.n_mat = (int)cs.mats.size(); d.n_tex = (int)cs.texs.size();
 	CK(cudaStreamSynchronize(ctx->stream));
 	ctx->dev = d;
 	ctx->committed = true;
+	// scene-specialised kernel for scenes that have a lean form: generated + NVRTC-compiled once per distinct scene
+	ctx->baked = nullptr;
+	ctx->bake_note.clear();
+	if (cs.lean_ok && ctx->opt_lean && ctx->opt_bake) {
+		ctx->baked = bake_get(cs, ctx->opt_bake_packed, ctx->device, ctx->bake_note, &info.bake_compile_ms);
+		info.baked = ctx->baked ? 1 : 0;
+	}
 	info.builder = device_built ? ARE_BVH_BUILDER_DEVICE_LBVH : ARE_BVH_BUILDER_HOST_SAH;
 	info.bvh_nodes = d.n_nodes;
 	if (!device_built) info.bvh_height = cs.bvh_depth;
@@ -558,6 +584,46 @@ int are_cuda_compile_probe_forms(int n_tri, const double *Q, const double *u, co
 	const int r[8] = { cs.lean_ok ? 1 : 0, (int)cs.lean_shade.size(), cs.lean_n_open, (int)cs.lb_lo.size(), (int)cs.lb_prims.size(), conservative,
 		(int)cs.nodes.size(), cs.brute_range.nb };
 	std::memcpy(out, r, sizeof r);
+	return ARE_OK;
+}
+
+int are_cuda_bake_probe(int n_tri, const double *Q, const double *u, const double *v, int packed, char *source_out, uint64_t source_cap,
+	uint64_t *source_len, const char *cubin_path) {
+	if (n_tri < 0 || (n_tri && (!Q || !u || !v))) return ARE_ERR_INVALID_ARGUMENT;
+	HostScene hs;
+	hs.textures.emplace_back();
+	hs.materials.emplace_back();
+	for (int i = 0; i < n_tri; ++i) {
+		if (validate_edges(u + 3 * (size_t)i, v + 3 * (size_t)i)) return ARE_ERR_INVALID_ARGUMENT;
+		HostPrim p;
+		p.type = PT_TRIANGLE;
+		std::memcpy(p.Q, Q + 3 * (size_t)i, sizeof p.Q);
+		std::memcpy(p.u, u + 3 * (size_t)i, sizeof p.u);
+		std::memcpy(p.v, v + 3 * (size_t)i, sizeof p.v);
+		hs.prims.push_back(p);
+	}
+	CompileOptions opt;
+	opt.brute_max = (int)brute_smem_limit_prims();
+	CompiledScene cs;
+	std::string err;
+	if (!compile_scene(hs, opt, cs, err)) return ARE_ERR_INVALID_ARGUMENT;
+	const std::string src = bake_source(cs, packed != 0);
+	if (source_len) *source_len = src.size();
+	if (src.empty()) return ARE_ERR_RUNTIME;  // no lean form
+	if (source_out && source_cap) {
+		const size_t n = std::min<size_t>(src.size(), (size_t)source_cap - 1);
+		std::memcpy(source_out, src.data(), n);
+		source_out[n] = 0;
+	}
+	if (cubin_path) {
+		std::string cubin, log;
+		if (!bake_compile_cubin(src, cubin, log)) { g_create_error = log; return ARE_ERR_RUNTIME; }
+		FILE *f = fopen(cubin_path, "wb");
+		if (!f) return ARE_ERR_IO;
+		const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+		fclose(f);
+		if (!ok) return ARE_ERR_IO;
+	}
 	return ARE_OK;
 }
 
@@ -750,10 +816,7 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 	for (int k = 0; k < 3; ++k) { a.bg_bottom[k] = (float)p->background_bottom[k]; a.bg_top[k] = (float)p->background_top[k]; }
 	a.bg_black = 1;
 	for (int k = 0; k < 3; ++k) a.bg_black &= (a.bg_bottom[k] == 0.0f && a.bg_top[k] == 0.0f) ? 1 : 0;
-	{
-		const char *e = getenv("ARE_CUDA_NO_LEAN");  // A/B switch: generic brute-force kernel for a scene that has a lean form
-		a.lean = (e && e[0] == '1') ? 0 : 1;
-	}
+	a.lean = ctx->opt_lean ? 1 : 0;
 	a.accum = accum;
 	a.counters = ctx->d_counters;
 	int mode = 0;
@@ -767,8 +830,19 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 	CK(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * sizeof(unsigned long long), ctx->stream));
 	if (stats) CK(cudaEventRecord(ctx->ev0, ctx->stream));
 	int launched = 0;
+	bool baked = false;
 	if (p->sample_count > 0) {
-		launched = p->integrator == ARE_INTEGRATOR_RT_AO ? launch_render_rtao(a, ctx->stream) : launch_render_path(a, mode, count_tests != 0, ctx->stream);
+		if (p->integrator == ARE_INTEGRATOR_RT_AO) launched = launch_render_rtao(a, ctx->stream);
+		else {
+			int blocks, threads;
+			size_t smem;
+			baked = mode == 0 && ctx->baked && ctx->opt_bake && render_path_is_lean(a) && render_path_lean_dims(a, blocks, threads, smem);
+			if (baked) {
+				std::string err;
+				launched = bake_launch(ctx->baked, a, blocks, threads, smem, ctx->stream, err);
+				if (launched < 0) return fail(ctx, ARE_ERR_CUDA, err);
+			} else launched = launch_render_path(a, mode, count_tests != 0, ctx->stream);
+		}
 		if (launched < 0) return fail(ctx, ARE_ERR_CUDA, "render launch configuration rejected");
 		CK(cudaGetLastError());
 	}
@@ -797,7 +871,7 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 		stats->launches = (uint64_t)launched;
 		stats->kernel_variant = launched <= 0 ? ARE_KERNEL_NONE
 			: p->integrator == ARE_INTEGRATOR_RT_AO ? ARE_KERNEL_RT_AO
-			: mode == 0 ? (render_path_is_lean(a) ? ARE_KERNEL_BRUTE_LEAN : ARE_KERNEL_BRUTE)
+			: mode == 0 ? (baked ? ARE_KERNEL_BRUTE_BAKED : render_path_is_lean(a) ? ARE_KERNEL_BRUTE_LEAN : ARE_KERNEL_BRUTE)
 			: mode == 2 ? ARE_KERNEL_WIDE : (render_path_is_big(a) ? ARE_KERNEL_BVH2_BIG : ARE_KERNEL_BVH2);
 	}
 	return ARE_OK;

@@ -17,7 +17,7 @@
 //
 // The fp64 copies (Q,u,v as the host gave them) feed only the decision-exact harness kernels.
 #pragma once
-#include <stdint.h>
+#include "rtc_compat.h"
 
 #if defined(__CUDACC__)
 #define ARE_HD __host__ __device__

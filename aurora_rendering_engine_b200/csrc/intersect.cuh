@@ -45,14 +45,10 @@ __device__ __forceinline__ void plane_coords(float4 r1, float4 r2, V3<float> p, 
 // One plane-form test. QUAD: accept alpha,beta in [0,1]; else triangle: alpha,beta >= 0, alpha+beta <= 1.
 // Range checks run on the float bit patterns: x in [0,1]  <=>  bits(x) <= 0x3f800000 as unsigned (negative
 // values have the sign bit set, NaN is above 0x7f800000), so two coordinates cost one UMAX + one ISETP.
+// Acceptance of a plane-form candidate (distance t, planar coordinates a, b): shared with the scene-specialised
+// ("baked") kernel, which computes t, a and b with the zero components of its constant vectors left out.
 template <bool QUAD>
-__device__ __forceinline__ void test_plane(float4 r0, float4 r1, float4 r2, V3<float> o, V3<float> d, float tmin, int idx, Hit &h) {
-	float denom = fmaf(r0.x, d.x, fmaf(r0.y, d.y, r0.z * d.z));
-	float num = fmaf(-r0.x, o.x, fmaf(-r0.y, o.y, fmaf(-r0.z, o.z, r0.w)));
-	float t = num * rcp_fast(denom);
-	V3<float> p = mk<float>(fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z));
-	float a, b;
-	plane_coords(r1, r2, p, a, b);
+__device__ __forceinline__ void plane_accept(float t, float a, float b, float tmin, int idx, Hit &h) {
 	bool ok = (t > tmin) & (t < h.t);
 	if (QUAD) {
 		ok = ok & (max(__float_as_uint(a), __float_as_uint(b)) <= 0x3f800000u);
@@ -61,6 +57,16 @@ __device__ __forceinline__ void test_plane(float4 r0, float4 r1, float4 r2, V3<f
 		ok = ok & ((int)(__float_as_uint(a) | __float_as_uint(b) | __float_as_uint(c)) >= 0);
 	}
 	if (ok) { h.t = t; h.idx = idx; }
+}
+template <bool QUAD>
+__device__ __forceinline__ void test_plane(float4 r0, float4 r1, float4 r2, V3<float> o, V3<float> d, float tmin, int idx, Hit &h) {
+	float denom = fmaf(r0.x, d.x, fmaf(r0.y, d.y, r0.z * d.z));
+	float num = fmaf(-r0.x, o.x, fmaf(-r0.y, o.y, fmaf(-r0.z, o.z, r0.w)));
+	float t = num * rcp_fast(denom);
+	V3<float> p = mk<float>(fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z));
+	float a, b;
+	plane_coords(r1, r2, p, a, b);
+	plane_accept<QUAD>(t, a, b, tmin, idx, h);
 }
 
 // Sphere: r0 = (c, r), r1.x = r*r.  Discriminant from the perpendicular offset l = oc - (oc·d)d, i.e.
@@ -96,6 +102,24 @@ __device__ __forceinline__ void test_sphere(float4 r0, float4 r1, V3<float> o, V
 // hole iff the entry is decided by axis 2 while moving along +n2, and leaves through it iff the exit is decided by
 // axis 2 while moving along -n2.
 // OPEN: 0 = the record says (r3.w), 1 = known closed (the open-face logic is compiled out), 2 = known open
+// The part of the test after the six dot products (s_i = n_i·d + 1e-30, e_i = c_i - n_i·o), shared with the baked kernel.
+template <int OPEN>
+__device__ __forceinline__ void test_box_se(float s0, float s1, float s2, float e0, float e1, float e2, float h0, float h1, float h2, bool open_flag,
+	float tmin, int idx, Hit &h) {
+	const float i0 = rcp_fast(s0), i1 = rcp_fast(s1), i2 = rcp_fast(s2);
+	const float m0 = e0 * i0, m1 = e1 * i1, m2 = e2 * i2;
+	const float k0 = h0 * fabsf(i0), k1 = h1 * fabsf(i1), k2 = h2 * fabsf(i2);
+	const float n2 = m2 - k2, f2 = m2 + k2;
+	const float t_in = fmaxf(fmaxf(m0 - k0, m1 - k1), n2), t_out = fminf(fminf(m0 + k0, m1 + k1), f2);
+	bool in_ok = t_in > tmin, out_ok = t_out > tmin;
+	if (OPEN == 2 || (OPEN == 0 && open_flag)) {  // warp-uniform: all lanes test the same primitive
+		in_ok = in_ok & !((n2 == t_in) & (s2 > 0.0f));
+		out_ok = out_ok & !((f2 == t_out) & (s2 < 0.0f));
+	}
+	const float t = in_ok ? t_in : t_out;
+	const bool ok = (t_in <= t_out) & (in_ok | out_ok) & (t < h.t);
+	if (ok) { h.t = t; h.idx = idx; }
+}
 template <int OPEN = 0>
 __device__ __forceinline__ void test_box(float4 r0, float4 r1, float4 r2, float4 r3, V3<float> o, V3<float> d, float tmin, int idx, Hit &h) {
 	const float s0 = fmaf(r0.x, d.x, fmaf(r0.y, d.y, fmaf(r0.z, d.z, 1e-30f)));
@@ -104,19 +128,7 @@ __device__ __forceinline__ void test_box(float4 r0, float4 r1, float4 r2, float4
 	const float e0 = fmaf(-r0.x, o.x, fmaf(-r0.y, o.y, fmaf(-r0.z, o.z, r0.w)));
 	const float e1 = fmaf(-r1.x, o.x, fmaf(-r1.y, o.y, fmaf(-r1.z, o.z, r1.w)));
 	const float e2 = fmaf(-r2.x, o.x, fmaf(-r2.y, o.y, fmaf(-r2.z, o.z, r2.w)));
-	const float i0 = rcp_fast(s0), i1 = rcp_fast(s1), i2 = rcp_fast(s2);
-	const float m0 = e0 * i0, m1 = e1 * i1, m2 = e2 * i2;
-	const float k0 = r3.x * fabsf(i0), k1 = r3.y * fabsf(i1), k2 = r3.z * fabsf(i2);
-	const float n2 = m2 - k2, f2 = m2 + k2;
-	const float t_in = fmaxf(fmaxf(m0 - k0, m1 - k1), n2), t_out = fminf(fminf(m0 + k0, m1 + k1), f2);
-	bool in_ok = t_in > tmin, out_ok = t_out > tmin;
-	if (OPEN == 2 || (OPEN == 0 && r3.w != 0.0f)) {  // warp-uniform: all lanes test the same primitive
-		in_ok = in_ok & !((n2 == t_in) & (s2 > 0.0f));
-		out_ok = out_ok & !((f2 == t_out) & (s2 < 0.0f));
-	}
-	const float t = in_ok ? t_in : t_out;
-	const bool ok = (t_in <= t_out) & (in_ok | out_ok) & (t < h.t);
-	if (ok) { h.t = t; h.idx = idx; }
+	test_box_se<OPEN>(s0, s1, s2, e0, e1, e2, r3.x, r3.y, r3.z, r3.w != 0.0f, tmin, idx, h);
 }
 // Which face (2*axis + side) of a box the hit point P lies on: the axis whose normalised slab coordinate
 // q_i = (n_i·P - c_i)/h_i is closest to +-1, i.e. largest in magnitude; rih = (1/h_0, 1/h_1, 1/h_2).

@@ -7,28 +7,10 @@
 
 #include "dev_types.h"
 #include "philox.cuh"
+#include "render_args.h"
 
 namespace areb {
 
-struct RenderArgs {
-	DevScene sc;
-	CamBasis cam;
-	CamF camf;       // cam rounded to fp32 (path integrator)
-	RtCam rtcam;     // RT_AO integrator only
-	PhiloxKey key;   // the ten round keys of the render seed (constant-bank operands in the kernel)
-	int W, H;
-	int s_begin, s_count;
-	int max_depth;
-	int ao_samples;
-	float tmin;
-	float bg_bottom[3], bg_top[3];
-	int bg_black;                    // both background colours are zero: a miss adds nothing
-	int lean;                        // use the lean brute-force kernel when the compiled scene has a lean form
-	float *accum;                    // W*H*3 floats, sample SUMS are added
-	unsigned long long *counters;    // [0] rays [1] node visits [2] quad tests [3] tri tests [4] sphere tests [5] box tests
-};
-
-enum { CNT_RAYS = 0, CNT_NODES = 1, CNT_QUADS = 2, CNT_TRIS = 3, CNT_SPHERES = 4, CNT_BOXES = 5, CNT_N = 8 };
 
 // fp64 harness (harness64.cu, -fmad=false)
 void launch_hit64(const DevScene &sc, int n, const double *Q, const double *D, double tmin, int *prim, double *t, double *P, double *N, double *uv, cudaStream_t s);
@@ -65,6 +47,7 @@ void launch_camera32(const CamBasis &cb, int W, int H, int n, const int *px, con
 // mode: 0 brute force (shared memory), 1 BVH2, 2 compressed 8-wide BVH
 int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStream_t s);
 bool render_path_is_lean(const RenderArgs &a);  // brute force: the lean kernel is the one launched
+bool render_path_lean_dims(const RenderArgs &a, int &blocks, int &threads, size_t &smem);  // launch shape of the lean (and baked) kernel
 bool render_path_is_big(const RenderArgs &a);   // BVH: the high-occupancy build is the one launched
 int launch_render_rtao(const RenderArgs &a, cudaStream_t s);
 // gamma_thr: 256 floats, [v-1] = smallest c with the rt.cpp gamma encode >= v (v = 1..255), [255] = +inf (encoder 0 only)

@@ -3,7 +3,7 @@
 // job is addressable, so any GPU can render any sample range and the 1-GPU and N-GPU estimators draw the very
 // same samples.  The ten round keys depend only on the seed; they are computed once per thread.
 #pragma once
-#include <stdint.h>
+#include "rtc_compat.h"
 
 namespace areb {
 

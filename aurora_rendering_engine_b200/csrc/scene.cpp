@@ -36,12 +36,13 @@ inline bool near_zero(D3 a) {  // are::Vec3::near_zero, src/basic/vec3.cpp:143-1
 	return std::fabs(a.x) < s && std::fabs(a.y) < s && std::fabs(a.z) < s;
 }
 
-// Host threads for the data-parallel phases of the scene compiler (ARE_CUDA_BUILD_THREADS overrides the count).
-inline unsigned host_threads() {
-	unsigned hw = std::thread::hardware_concurrency();
-	if (const char *e = getenv("ARE_CUDA_BUILD_THREADS")) hw = (unsigned)std::max(1, atoi(e));
-	return std::max(1u, std::min(hw, 64u));
+// Host threads for the data-parallel phases of the scene compiler (set_build_threads overrides the hardware count).
+std::atomic<int> g_build_threads{ 0 };
+inline unsigned hw_threads() {
+	const int forced = g_build_threads.load(std::memory_order_relaxed);
+	return forced > 0 ? (unsigned)forced : std::thread::hardware_concurrency();
 }
+inline unsigned host_threads() { return std::max(1u, std::min(hw_threads(), 64u)); }
 // fn(begin, end) over [0,n) in contiguous chunks, one per thread; results must not depend on the chunking
 template <typename F>
 void parallel_chunks(size_t n, size_t min_chunk, F fn) {
@@ -184,8 +185,7 @@ struct Builder {
 		out.nodes.assign(items.empty() ? 0 : items.size() - 1, BvhNode());
 		out.bvh_prims.assign(slots, HotPrim());
 		out.bvh_ids.assign(slots, HotIds{ -1, -1 });
-		unsigned hw = std::thread::hardware_concurrency();
-		if (const char *e = getenv("ARE_CUDA_BUILD_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+		const unsigned hw = std::max(1u, hw_threads());
 		while ((1u << spawn_depth) < hw && spawn_depth < 8) ++spawn_depth;
 		if (hw > 1) spawn_depth += 2;  // 4 tasks per core: SAH splits are uneven
 		else spawn_depth = 0;
@@ -551,6 +551,8 @@ void make_rt_cam(const double pos[3], const double target[3], const double up[3]
 	out.aspect = (float)W / (float)H;
 	out.scale = (float)std::tan((float)vfov_deg * 0.5f * 3.14159265358979323846 / 180.f);
 }
+
+void set_build_threads(int n) { g_build_threads.store(n > 0 ? n : 0); }
 
 bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene &out, std::string &err) {
 	out.reset();

@@ -111,6 +111,9 @@ struct CompileOptions {
 // reference's exception message.
 const char *validate_edges(const double u[3], const double v[3]);
 
+// Host threads used by the scene compiler (0 = all hardware threads).  The compiled scene does not depend on the count.
+void set_build_threads(int n);
+
 // Returns false and fills err on inconsistent ids etc.
 bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene &out, std::string &err);
 

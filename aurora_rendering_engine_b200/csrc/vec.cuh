@@ -3,8 +3,11 @@
 // (the render kernels).  Semantics follow the reference: x/0 and normalize(0) give a NaN vector
 // (vec3.cpp:90-99,112-129,174-179), division multiplies by the reciprocal (vec3.cpp:178).
 #pragma once
+#include "rtc_compat.h"
+#if !defined(__CUDACC_RTC__)
 #include <cuda_runtime.h>
 #include <math.h>
+#endif
 
 namespace areb {
 

@@ -103,7 +103,7 @@ class JobResult:
 class RenderJob:
     """A scene committed on this rank's GPU plus a device accumulator; ``render_range`` adds samples into it."""
 
-    def __init__(self, scene_desc, device_index: int = 0, traversal: int = 0):
+    def __init__(self, scene_desc, device_index: int = 0, traversal: int = 0, options: dict | None = None):
         import torch
         self.torch = torch
         self.sc = scene_desc
@@ -111,6 +111,8 @@ class RenderJob:
         torch.cuda.set_device(device_index)
         self.ctx = capi.Context(device_index)
         self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        for opt, val in (options or {}).items():   # capi.OPT_* -> value (are_cuda_set_option)
+            self.ctx.set_option(opt, val)
         scene_desc.feed(self.ctx)
         self.h2d_bytes = self.ctx.commit()
         self.cam = capi.make_camera(**scene_desc.camera_args())

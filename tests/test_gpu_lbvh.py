@@ -124,15 +124,15 @@ def test_lbvh_edge_cases(ctx):
 
 def test_lbvh_falls_back_to_host_builder_when_too_deep(ctx, monkeypatch):
     """A device-built tree deeper than the traversal stack is discarded and the host SAH builder takes over (the limit is
-    lowered through the test hook ARE_CUDA_LBVH_MAX_HEIGHT to provoke it); the scene renders as usual."""
+    lowered through the test hook ARE_OPT_LBVH_MAX_HEIGHT to provoke it); the scene renders as usual."""
     sc = scenes.stress(n_prims=2000, width=48, height=32)
     cam = capi.make_camera(**sc.camera_args())
     par = capi.make_params(**sc.params_args(sample_count=4, traversal=2))
     info = _commit(ctx, sc, capi.BVH_BUILDER_HOST_SAH)
     ref, sr = ctx.render(cam, par)
-    monkeypatch.setenv("ARE_CUDA_LBVH_MAX_HEIGHT", "5")
+    ctx.set_option(capi.OPT_LBVH_MAX_HEIGHT, 5)
     info = _commit(ctx, sc, capi.BVH_BUILDER_DEVICE_LBVH)
-    monkeypatch.delenv("ARE_CUDA_LBVH_MAX_HEIGHT")
+    ctx.set_option(capi.OPT_LBVH_MAX_HEIGHT, 0)
     assert info.builder == capi.BVH_BUILDER_HOST_SAH and info.device_bvh_ms == 0 and info.bvh_nodes == 1999
     img, st = ctx.render(cam, par)
     assert st.rays == sr.rays and np.array_equal(img, ref)

@@ -451,7 +451,7 @@ def _mixed_small_scene(width=96, height=64):
 
 
 @pytest.mark.parametrize("which", ["cornell", "mixed"])
-def test_lean_kernel_equals_generic_brute_kernel(ctx, oracle, monkeypatch, which):
+def test_lean_kernel_equals_generic_brute_kernel(ctx, oracle, which):
     """The lean brute-force kernel (guarded full unroll + per-face shading records in shared memory) is a
     re-arrangement of the generic brute-force kernel: same tests, same shading values, same Philox draws."""
     sc = scenes.cornell_box(width=80, height=72) if which == "cornell" else _mixed_small_scene()
@@ -460,14 +460,25 @@ def test_lean_kernel_equals_generic_brute_kernel(ctx, oracle, monkeypatch, which
     ctx.clear()
     sc.feed(ctx)
     ctx.commit()
-    monkeypatch.delenv("ARE_CUDA_NO_LEAN", raising=False)
+    baked, st_baked = ctx.render(cam, par)
+    ctx.set_option(capi.OPT_BAKED_KERNEL, 0)
     lean, st_lean = ctx.render(cam, par)
-    monkeypatch.setenv("ARE_CUDA_NO_LEAN", "1")
+    ctx.set_option(capi.OPT_LEAN_KERNEL, 0)
     gen, st_gen = ctx.render(cam, par)
-    monkeypatch.delenv("ARE_CUDA_NO_LEAN", raising=False)
+    ctx.set_option(capi.OPT_LEAN_KERNEL, 1)
+    ctx.set_option(capi.OPT_BAKED_KERNEL, 1)
     assert st_lean.kernel_variant == capi.KERNEL_BRUTE_LEAN and st_gen.kernel_variant == capi.KERNEL_BRUTE
     assert st_lean.rays == st_gen.rays, (st_lean.rays, st_gen.rays)
     assert np.array_equal(lean, gen), f"max |lean - generic| = {np.abs(lean - gen).max()}"
+    # the scene-specialised kernel (NVRTC at commit): same tests with the scene's constants as immediates
+    assert ctx.commit_info().baked == 1 and st_baked.kernel_variant == capi.KERNEL_BRUTE_BAKED
+    assert st_baked.rays == st_lean.rays and np.array_equal(baked, lean), f"max |baked - lean| = {np.abs(baked - lean).max()}"
+    # ... and with its slab products as fma.rn.f32x2 pairs
+    ctx.set_option(capi.OPT_BAKED_PACKED, 1)
+    ctx.commit()
+    packed, st_packed = ctx.render(cam, par)
+    ctx.set_option(capi.OPT_BAKED_PACKED, 0)
+    assert st_packed.kernel_variant == capi.KERNEL_BRUTE_BAKED and st_packed.rays == st_lean.rays and np.array_equal(packed, lean)
     osc = sc.feed(oracle.scene())
     oimg, ost = osc.render(cam, par)
     p = psnr(np.clip(lean / 8.0, 0, 1), np.clip(oimg / 8.0, 0, 1))

@@ -19,12 +19,13 @@ with capi.Context(0) as ctx:
         Q = np.random.RandomState(0).uniform(-1, 1, (2000, 3)); D = np.random.RandomState(1).normal(size=(2000, 3))
         ctx.hit_batch(Q, D, precision=64); ctx.hit_batch(Q, D, precision=32, traversal=trav)
     # the generic brute-force kernel on a scene that has a lean form, and the device BVH builder (lbvh.cu) + a render of its tree
-    os.environ["ARE_CUDA_NO_LEAN"] = "1"
     sc = scenes.by_name("cornell_box", width=48, height=48)
     ctx.clear(); sc.feed(ctx); ctx.commit()
-    img, st = ctx.render(capi.make_camera(**sc.camera_args()), capi.make_params(**sc.params_args(sample_count=2, traversal=1, max_depth=8)))
-    assert st.kernel_variant == capi.KERNEL_BRUTE
-    del os.environ["ARE_CUDA_NO_LEAN"]
+    for opts, want in (((1, 1), capi.KERNEL_BRUTE_BAKED), ((1, 0), capi.KERNEL_BRUTE_LEAN), ((0, 0), capi.KERNEL_BRUTE)):
+        ctx.set_option(capi.OPT_LEAN_KERNEL, opts[0]); ctx.set_option(capi.OPT_BAKED_KERNEL, opts[1])
+        img, st = ctx.render(capi.make_camera(**sc.camera_args()), capi.make_params(**sc.params_args(sample_count=2, traversal=1, max_depth=8)))
+        assert st.kernel_variant == want, (st.kernel_variant, want)
+    ctx.set_option(capi.OPT_LEAN_KERNEL, 1); ctx.set_option(capi.OPT_BAKED_KERNEL, 1)
     ctx.set_bvh_builder(capi.BVH_BUILDER_DEVICE_LBVH)
     for name, kw in (("cornell_box", dict(width=48, height=48)), ("stress", dict(n_prims=30000, width=48, height=27))):
         sc = scenes.by_name(name, **kw)
