@@ -143,6 +143,7 @@ SIGNATURES = {
     "are_cuda_get_commit_info": (C.c_int, [_vp, C.POINTER(CommitInfo)]),
     "are_cuda_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "are_cuda_set_build_threads": (None, [C.c_int]),
+    "are_cuda_get_baked_cubin": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint64)]),
     "are_cuda_add_texture": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int, C.c_int]),
     "are_cuda_add_material": (C.c_int, [_vp, C.c_int, _dp]),
     "are_cuda_add_triangle": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_int]),
@@ -317,6 +318,14 @@ class Context:
 
     def set_option(self, option: int, value: int):
         self._ck(self.lib.are_cuda_set_option(self.h, int(option), int(value)))
+
+    def baked_cubin(self) -> bytes:
+        """The CUBIN of the committed scene's scene-specialised kernel (raises when the scene has none)."""
+        n = C.c_uint64(0)
+        self._ck(self.lib.are_cuda_get_baked_cubin(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self._ck(self.lib.are_cuda_get_baked_cubin(self.h, buf, n.value, C.byref(n)))
+        return buf.raw
 
     def commit_info(self) -> CommitInfo:
         info = CommitInfo()

@@ -264,17 +264,27 @@ int are_cuda_set_bvh_builder(are_cuda_ctx *ctx, int builder) {
 }
 void are_cuda_set_build_threads(int n) { set_build_threads(n); }
 
+int are_cuda_get_baked_cubin(are_cuda_ctx *ctx, void *out, uint64_t cap, uint64_t *size) {
+	int st = need_commit(ctx);
+	if (st) return st;
+	const std::string *img = bake_cubin(ctx->baked);
+	if (size) *size = img ? img->size() : 0;
+	if (!img) return fail(ctx, ARE_ERR_RUNTIME, ctx->bake_note.empty() ? "the committed scene has no baked kernel" : ctx->bake_note);
+	if (out && cap >= img->size()) std::memcpy(out, img->data(), img->size());
+	return ARE_OK;
+}
+
 int are_cuda_set_option(are_cuda_ctx *ctx, int option, int value) {
 	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
 	switch (option) {
 	case ARE_OPT_LEAN_KERNEL: ctx->opt_lean = value != 0; return ARE_OK;  // takes effect at the next render
 	case ARE_OPT_BAKED_KERNEL: ctx->opt_bake = value != 0; return ARE_OK;  // off: at once; on: from the next commit
-	case ARE_OPT_BAKED_PACKED: ctx->opt_bake_packed = value != 0; ctx->committed = false; return ARE_OK;
-	case ARE_OPT_FUSE_PARALLELOGRAMS: ctx->opt.fuse_parallelograms = value != 0; ctx->committed = false; return ARE_OK;
-	case ARE_OPT_FUSE_BOXES: ctx->opt.fuse_boxes = value != 0; ctx->committed = false; return ARE_OK;
-	case ARE_OPT_BUILD_WIDE: ctx->opt.build_wide = value != 0; ctx->committed = false; return ARE_OK;
+	case ARE_OPT_BAKED_PACKED: ctx->opt_bake_packed = value != 0; return ARE_OK;
+	case ARE_OPT_FUSE_PARALLELOGRAMS: ctx->opt.fuse_parallelograms = value != 0; return ARE_OK;
+	case ARE_OPT_FUSE_BOXES: ctx->opt.fuse_boxes = value != 0; return ARE_OK;
+	case ARE_OPT_BUILD_WIDE: ctx->opt.build_wide = value != 0; return ARE_OK;
 	case ARE_OPT_WIDE_MIN_NODES: ctx->wide_min_nodes = value; return ARE_OK;
-	case ARE_OPT_LBVH_MAX_HEIGHT: ctx->opt_lbvh_max_height = value > 0 ? value : ARE_BVH_STACK; ctx->committed = false; return ARE_OK;
+	case ARE_OPT_LBVH_MAX_HEIGHT: ctx->opt_lbvh_max_height = value > 0 ? value : ARE_BVH_STACK; return ARE_OK;
 	default: return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown option");
 	}
 }

@@ -170,7 +170,9 @@ Rtc &rtc() {
 	static Rtc r;
 	static std::once_flag once;
 	std::call_once(once, [] {
-		const char *names[] = { "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12" };
+		// the toolkit's own NVRTC first: a bare soname would resolve to whatever libnvrtc.so.12 the process has already
+		// loaded (PyTorch bundles one of a different minor version), and the CUBIN should not depend on import order
+		const char *names[] = { "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.12", "libnvrtc.so" };
 		for (const char *n : names)
 			if ((r.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
 		if (!r.lib) { r.why = "libnvrtc.so.12 not found"; return; }
@@ -245,6 +247,7 @@ bool bake_compile_cubin(const std::string &src, std::string &cubin, std::string 
 struct BakedKernel {
 	CUmodule mod = nullptr;
 	CUfunction fn = nullptr;
+	const std::string *cubin = nullptr;  // the image it was loaded from (owned by g_cubins)
 };
 
 namespace {
@@ -280,12 +283,15 @@ const BakedKernel *bake_get(const CompiledScene &cs, bool packed, int device, st
 		cb = g_cubins.emplace(key, std::move(cubin)).first;
 	}
 	BakedKernel k;
+	k.cubin = &cb->second;
 	CUresult e = d.ModuleLoadData(&k.mod, cb->second.data());
 	if (e == CUDA_SUCCESS) e = d.ModuleGetFunction(&k.fn, k.mod, "k_render_baked");
 	if (e != CUDA_SUCCESS) { err = "loading the baked kernel: " + cu_err(d, e); return nullptr; }
 	if (compile_ms) *compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	return &g_cache.emplace(std::make_pair(key, device), k).first->second;
 }
+
+const std::string *bake_cubin(const BakedKernel *k) { return k ? k->cubin : nullptr; }
 
 int bake_launch(const BakedKernel *k, const RenderArgs &a, int blocks, int threads, size_t smem, cudaStream_t s, std::string &err) {
 	Drv &d = drv();

@@ -30,6 +30,9 @@ struct BakedKernel;  // one loaded module + function (per device), owned by the 
 // (no NVRTC, compile error, ...).  compile_ms: time spent in NVRTC + module load, 0 on a cache hit.
 const BakedKernel *bake_get(const CompiledScene &cs, bool packed, int device, std::string &err, double *compile_ms);
 
+// The CUBIN image a baked kernel was loaded from (for cuobjdump / nvdisasm next to an ncu capture).
+const std::string *bake_cubin(const BakedKernel *k);
+
 // Launch on stream s.  Returns 1 (kernels launched) or -1 with err.
 int bake_launch(const BakedKernel *k, const RenderArgs &a, int blocks, int threads, size_t smem, cudaStream_t s, std::string &err);
 

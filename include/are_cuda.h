@@ -164,8 +164,8 @@ typedef struct are_commit_info {
 } are_commit_info;
 int are_cuda_get_commit_info(are_cuda_ctx *ctx, are_commit_info *out);
 
-/* Context options (what used to be ARE_CUDA_* environment switches).  Scene-compiler options take effect at the next
- * are_cuda_commit (setting one marks the scene as not committed); kernel-choice options at the next render. */
+/* Context options (what used to be ARE_CUDA_* environment switches).  Scene-compiler options (3-6, 8) take effect at the
+ * next are_cuda_commit; kernel-choice options (1, 2, 7) at the next render. */
 typedef enum are_option {
 	ARE_OPT_LEAN_KERNEL = 1, /* 1 (default): small flat-shaded scenes use the lean brute-force kernel; 0: the generic one */
 	ARE_OPT_BAKED_KERNEL = 2, /* 1 (default): ... and its scene-specialised form, generated and compiled with NVRTC at commit:
@@ -179,6 +179,9 @@ typedef enum are_option {
 	ARE_OPT_LBVH_MAX_HEIGHT = 8 /* test hook: device-built trees taller than this fall back to the host builder */
 } are_option;
 int are_cuda_set_option(are_cuda_ctx *ctx, int option, int value);
+/* The sm_100a CUBIN of the committed scene's baked kernel (what cuobjdump -sass / nvdisasm -g read next to an ncu capture).
+ * *size = its length; copied to out when cap suffices.  ARE_ERR_RUNTIME when the scene has none (last_error says why). */
+int are_cuda_get_baked_cubin(are_cuda_ctx *ctx, void *out, uint64_t cap, uint64_t *size);
 /* Host threads of the scene compiler, process-wide (0 = all hardware threads).  The compiled scene never depends on it. */
 void are_cuda_set_build_threads(int n);
 

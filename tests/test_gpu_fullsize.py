@@ -131,7 +131,10 @@ def test_config4_stress_1M_matches_cpu_twin(ctx, oracle):
     assert sc.num_prims == 1_000_000 and (sc.width, sc.height) == (3840, 2160)
     cam = capi.make_camera(**sc.camera_args())
     osc = sc.feed(oracle.scene())
-    spp = 4
+    # Rays travel 80-180 units to primitives of radius 0.02-0.05: fp32 places a hit to ~1e-5, so ~5e-4 of the grazing
+    # decisions differ from the fp64 twin — per SAMPLE.  The image difference those flips leave falls with the sample
+    # count (measured: 37.8 dB at 4 spp), hence 16.
+    spp = 16
     windows = ((1800, 1000, 2056, 1016), (900, 600, 1156, 616))
     par = capi.make_params(**sc.params_args(sample_count=spp, traversal=2))
     want = []
