@@ -136,6 +136,8 @@ SIGNATURES = {
     "are_cuda_abi_version": (C.c_int, []),
     "are_cuda_device_count": (C.c_int, []),
     "are_cuda_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "are_cuda_create_multi": (C.c_int, [C.POINTER(_vp), _ip, C.c_int]),
+    "are_cuda_group_info": (C.c_int, [_vp, _ip, _ip]),
     "are_cuda_destroy": (None, [_vp]),
     "are_cuda_last_error": (C.c_char_p, [_vp]),
     "are_cuda_set_stream": (C.c_int, [_vp, _vp]),
@@ -183,6 +185,7 @@ SIGNATURES = {
     "are_cuda_free_accum": (C.c_int, [_vp, _vp]),
     "are_cuda_synchronize": (C.c_int, [_vp]),
     "are_cuda_measure_fp32_peak": (C.c_int, [_vp, _dp, _ip, _ip]),
+    "are_cuda_measure_l2_peak": (C.c_int, [_vp, _dp, C.POINTER(C.c_uint64)]),
 }
 
 
@@ -276,10 +279,17 @@ def _ptr(a, t=_dp):
 class Context:
     """One are_cuda_ctx (one GPU).  Mirrors the header one-to-one; numpy arrays in, numpy arrays out."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: an index (one GPU), or a sequence of indices (a multi-device group, are_cuda_create_multi: renders are
+        sharded by sample range over the devices and summed on the first)."""
         self.lib = load_library()
         h = _vp()
-        st = self.lib.are_cuda_create(C.byref(h), int(device))
+        if isinstance(device, (list, tuple)):
+            devs = np.ascontiguousarray(device, np.int32)
+            st = self.lib.are_cuda_create_multi(C.byref(h), _ptr(devs, _ip), len(devs))
+            device = int(devs[0])
+        else:
+            st = self.lib.are_cuda_create(C.byref(h), int(device))
         if st != ARE_OK:
             msg = self.lib.are_cuda_last_error(None)
             raise AreCudaError(st, (msg or b"").decode())
@@ -308,6 +318,11 @@ class Context:
         if st < 0:
             raise AreCudaError(st, (self.lib.are_cuda_last_error(self.h) or b"").decode())
         return st
+
+    def group_info(self):
+        n, p = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.are_cuda_group_info(self.h, C.byref(n), C.byref(p)))
+        return n.value, bool(p.value)
 
     def set_stream(self, cuda_stream_handle: int):
         self._ck(self.lib.are_cuda_set_stream(self.h, _vp(cuda_stream_handle)))
@@ -523,6 +538,11 @@ class Context:
 
     def synchronize(self):
         self._ck(self.lib.are_cuda_synchronize(self.h))
+
+    def measure_l2_peak(self):
+        g, n = C.c_double(0), C.c_uint64(0)
+        self._ck(self.lib.are_cuda_measure_l2_peak(self.h, C.byref(g), C.byref(n)))
+        return dict(gb_per_s=g.value, buffer_bytes=n.value)
 
     def measure_fp32_peak(self):
         t, sm, clk = C.c_double(0), C.c_int(0), C.c_int(0)

@@ -59,6 +59,17 @@ struct are_cuda_ctx {
 	int opt_lbvh_max_height = ARE_BVH_STACK;
 	const BakedKernel *baked = nullptr;  // owned by the process-wide cache in bake.cpp
 	std::string bake_note;
+	// multi-device context (are_cuda_create_multi): this context drives devices[0]; `peers` are full single-device contexts
+	// on the other devices, owned here.  They share this context's compiled scene (csp) and render sample shards.
+	const CompiledScene *csp = nullptr;   // the compiled scene the committed device arrays were made from (&cs, or the parent's)
+	std::vector<are_cuda_ctx *> peers;
+	are_cuda_ctx *parent = nullptr;
+	cudaEvent_t ev_done = nullptr;        // multi-device: this device's render of the current round is on its stream up to here
+	cudaEvent_t ev_red = nullptr;         // ... and its reduce kernel
+	float *stage = nullptr;               // first device, groups without full peer mapping: one frame of staging
+	size_t stage_elems = 0;
+	cudaStream_t own_stream = nullptr;    // peers run on their own non-blocking stream
+	bool p2p_all = false;                 // every device of the group can map every other device's memory
 };
 
 static std::string g_create_error;
@@ -149,8 +160,8 @@ bool resolve_traversal(are_cuda_ctx *ctx, int traversal, int &mode) {
 	} else if (traversal == ARE_TRAVERSAL_BVH) mode = 1;
 	else if (traversal == ARE_TRAVERSAL_WIDE) mode = wide_ok ? 2 : 1;  // a single-primitive scene has no wide hierarchy
 	else if (traversal == ARE_TRAVERSAL_AUTO) {
-		if (brute_ok && ctx->cs.n_hot <= 32) mode = 0;
-		else mode = (wide_ok && (int)ctx->cs.nodes.size() > ctx->wide_min_nodes) ? 2 : 1;
+		if (brute_ok && ctx->csp->n_hot <= 32) mode = 0;
+		else mode = (wide_ok && (int)ctx->csp->nodes.size() > ctx->wide_min_nodes) ? 2 : 1;
 	} else return false;
 	return true;
 }
@@ -231,8 +242,65 @@ int are_cuda_create(are_cuda_ctx **out, int device) {
 	return ARE_OK;
 }
 
+int are_cuda_create_multi(are_cuda_ctx **out, const int *devices, int n_devices) {
+	if (!out) return fail(nullptr, ARE_ERR_INVALID_ARGUMENT, "out is null");
+	*out = nullptr;
+	if (!devices || n_devices < 1 || n_devices > ARE_MAX_GROUP_DEVICES) return fail(nullptr, ARE_ERR_INVALID_ARGUMENT, "1 to 16 devices expected");
+	for (int i = 0; i < n_devices; ++i)
+		for (int j = 0; j < i; ++j)
+			if (devices[i] == devices[j]) return fail(nullptr, ARE_ERR_INVALID_ARGUMENT, "a device is listed twice");
+	are_cuda_ctx *root = nullptr;
+	int st = are_cuda_create(&root, devices[0]);
+	if (st != ARE_OK) return st;
+	std::vector<are_cuda_ctx *> all(1, root);
+	for (int i = 1; i < n_devices && st == ARE_OK; ++i) {
+		are_cuda_ctx *c = nullptr;
+		st = are_cuda_create(&c, devices[i]);
+		if (st != ARE_OK) break;
+		c->parent = root;
+		root->peers.push_back(c);
+		all.push_back(c);
+		Bind b(c);
+		if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { st = fail(nullptr, ARE_ERR_CUDA, "peer stream creation failed"); break; }
+		c->stream = c->own_stream;
+	}
+	bool p2p = true;
+	for (size_t i = 0; st == ARE_OK && i < all.size(); ++i) {
+		Bind b(all[i]);
+		if (cudaEventCreateWithFlags(&all[i]->ev_done, cudaEventDisableTiming) != cudaSuccess ||
+			cudaEventCreateWithFlags(&all[i]->ev_red, cudaEventDisableTiming) != cudaSuccess) { st = fail(nullptr, ARE_ERR_CUDA, "event creation failed"); break; }
+		for (size_t j = 0; j < all.size(); ++j) {
+			if (i == j) continue;
+			int can = 0;
+			cudaDeviceCanAccessPeer(&can, all[i]->device, all[j]->device);
+			if (can) {
+				cudaError_t e = cudaDeviceEnablePeerAccess(all[j]->device, 0);
+				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+				cudaGetLastError();
+			}
+			p2p = p2p && can;
+		}
+	}
+	if (st != ARE_OK) { are_cuda_destroy(root); return st; }
+	root->p2p_all = p2p && all.size() > 1;
+	*out = root;
+	return ARE_OK;
+}
+
+int are_cuda_group_info(are_cuda_ctx *ctx, int *n_devices, int *peer_mapped) {
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	if (n_devices) *n_devices = 1 + (int)ctx->peers.size();
+	if (peer_mapped) *peer_mapped = ctx->p2p_all ? 1 : 0;
+	return ARE_OK;
+}
+
 void are_cuda_destroy(are_cuda_ctx *ctx) {
 	if (!ctx) return;
+	for (are_cuda_ctx *p : ctx->peers) {  // a group owns its peer contexts
+		p->parent = nullptr;
+		are_cuda_destroy(p);
+	}
+	ctx->peers.clear();
 	Bind b(ctx);
 	cudaStreamSynchronize(ctx->stream);
 	free_scene_allocs(ctx);
@@ -245,6 +313,10 @@ void are_cuda_destroy(are_cuda_ctx *ctx) {
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+	if (ctx->ev_red) cudaEventDestroy(ctx->ev_red);
+	if (ctx->stage) cudaFree(ctx->stage);
+	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
 
@@ -322,8 +394,22 @@ int are_cuda_add_material(are_cuda_ctx *ctx, int kind, const double params[8]) {
 	HostMaterial m;
 	m.kind = kind;
 	if (params) std::memcpy(m.p, params, sizeof m.p);
+	else {  // documented defaults: no texture override, unit radiance scale, untinted mirror, glass
+		if (kind == ARE_MAT_LAMBERTIAN || kind == ARE_MAT_DIFFUSE_LIGHT) m.p[0] = -1.0;
+		if (kind == ARE_MAT_METAL) m.p[1] = -1.0;
+		if (kind == ARE_MAT_DIFFUSE_LIGHT) m.p[1] = 1.0;
+		if (kind == ARE_MAT_REFLECTIVE) { m.p[1] = m.p[2] = m.p[3] = 1.0; }
+		if (kind == ARE_MAT_DIELECTRIC) m.p[0] = 1.5;
+	}
 	if (kind == ARE_MAT_DIELECTRIC && !(m.p[0] > 0.0)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "index of refraction must be positive");
-	if (kind == ARE_MAT_REFLECTIVE && !params) { m.p[1] = m.p[2] = m.p[3] = 1.0; }
+	{  // a texture override is -1 or the id of a texture that exists already
+		const int slot = (kind == ARE_MAT_LAMBERTIAN || kind == ARE_MAT_DIFFUSE_LIGHT) ? 0 : (kind == ARE_MAT_METAL ? 1 : -1);
+		if (slot >= 0) {
+			const double o = m.p[slot];
+			if (!(o == std::floor(o)) || o < -1.0 || o >= (double)ctx->scene.textures.size())
+				return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "texture override must be -1 or the id of an existing texture");
+		}
+	}
 	ctx->scene.materials.push_back(m);
 	ctx->committed = false;
 	return (int)ctx->scene.materials.size() - 1;
@@ -394,42 +480,33 @@ int are_cuda_clear(are_cuda_ctx *ctx) {
 
 int are_cuda_num_primitives(are_cuda_ctx *ctx) { return ctx ? (int)ctx->scene.prims.size() : ARE_ERR_INVALID_ARGUMENT; }
 
-int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
-	Range nvtx_range("are_cuda_commit (scene compile + upload)");
-	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+// Device half of a commit: upload the compiled scene `cs` to ctx's GPU (building the hierarchy there when the device
+// builder was selected).  Returns ARE_OK, a negative status, or 1 when the device-built tree is taller than the traversal
+// stack (the caller recompiles with the host builder).  `cs` may belong to another context (multi-device groups).
+static int commit_device(are_cuda_ctx *ctx, const CompiledScene &cs, bool want_device_bvh, int max_height, bool lean, bool bake, bool bake_packed,
+	are_commit_info &info, uint64_t &bytes) {
 	Bind b(ctx);
 	CK(cudaStreamSynchronize(ctx->stream));
 	free_scene_allocs(ctx);
-	std::string err;
-	ctx->opt.brute_max = (int)brute_smem_limit_prims();
-	int builder = ctx->bvh_builder;
-	are_commit_info info = {};
 	DevScene d;
-	uint64_t bytes = 0;
-	for (int attempt = 0; attempt < 2; ++attempt) {
-		ctx->opt.device_bvh = builder == ARE_BVH_BUILDER_DEVICE_LBVH;
-		const auto t0 = std::chrono::steady_clock::now();
-		if (!compile_scene(ctx->scene, ctx->opt, ctx->cs, err)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, err);
-		info.host_compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-		info.host_bvh_ms = ctx->cs.host_bvh_ms;
-		if (!ctx->opt.device_bvh || ctx->cs.lb_lo.empty()) break;
+	std::memset(&d, 0, sizeof d);
+	bytes = 0;
+	const bool device_built = want_device_bvh && !cs.lb_lo.empty();
+	if (device_built) {
 		// ---- device BVH build: inputs are temporaries, outputs belong to the scene ----
-		const CompiledScene &c = ctx->cs;
-		std::memset(&d, 0, sizeof d);
-		bytes = 0;
 		int st;
 		LbvhInput in;
 		LbvhOutput out;
 		std::memset(&in, 0, sizeof in);
 		std::memset(&out, 0, sizeof out);
 #define UPT(vec, field)                                                       \
-	if ((st = upload(ctx, c.vec, &in.field, bytes)) != ARE_OK) return st;
+	if ((st = upload(ctx, cs.vec, &in.field, bytes)) != ARE_OK) return st;
 		UPT(lb_lo, item_lo) UPT(lb_hi, item_hi) UPT(lb_prims, item_prims) UPT(lb_ids, item_ids) UPT(lb_slot, item_slot)
 #undef UPT
 		const size_t n_temp = ctx->scene_allocs.size();
-		in.n_items = (int)c.lb_lo.size();
-		in.n_slots = (int)c.lb_prims.size();
-		for (int k = 0; k < 3; ++k) { in.cmin[k] = c.lb_cmin[k]; in.cmax[k] = c.lb_cmax[k]; }
+		in.n_items = (int)cs.lb_lo.size();
+		in.n_slots = (int)cs.lb_prims.size();
+		for (int k = 0; k < 3; ++k) { in.cmin[k] = cs.lb_cmin[k]; in.cmax[k] = cs.lb_cmax[k]; }
 		void *p = nullptr;
 		CK(scene_malloc(ctx, &p, (size_t)(in.n_items > 1 ? in.n_items - 1 : 0) * sizeof(BvhNode))); ctx->scene_allocs.push_back(p); out.nodes = static_cast<BvhNode *>(p);
 		CK(scene_malloc(ctx, &p, (size_t)in.n_slots * sizeof(HotPrim))); ctx->scene_allocs.push_back(p); out.prims = static_cast<HotPrim *>(p);
@@ -451,11 +528,9 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 		// the five input temporaries go; the three outputs stay
 		for (size_t i = 0; i < n_temp; ++i) cudaFreeAsync(ctx->scene_allocs[i], ctx->stream);
 		ctx->scene_allocs.erase(ctx->scene_allocs.begin(), ctx->scene_allocs.begin() + n_temp);
-		const int max_height = std::min((int)ARE_BVH_STACK, ctx->opt_lbvh_max_height);  // ARE_OPT_LBVH_MAX_HEIGHT: test hook for the fall-back below
 		if (out.height > max_height) {  // deeper than the traversal stack (many coincident centres): the SAH builder bounds its depth
 			free_scene_allocs(ctx);
-			builder = ARE_BVH_BUILDER_HOST_SAH;
-			continue;
+			return 1;
 		}
 		d.nodes = out.nodes; d.bvh_prims = out.prims; d.bvh_ids = out.ids;
 		d.n_nodes = out.n_nodes;
@@ -463,13 +538,9 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 		info.device_bvh_ms = ms;
 		info.device_bvh_launches = (uint64_t)launched;
 		info.bvh_height = out.height;
-		break;
 	}
-	const CompiledScene &cs = ctx->cs;
-	const bool device_built = ctx->opt.device_bvh && !cs.lb_lo.empty();
 	// the traversal kernels push at most height - 1 far children above the sentinel and do not test for overflow
 	if (!device_built && cs.bvh_depth > ARE_BVH_STACK) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "BVH deeper than the traversal stack");
-	if (!device_built) std::memset(&d, 0, sizeof d);
 	const BvhNode *dev_nodes = d.nodes;
 	const HotPrim *dev_bvh_prims = d.bvh_prims;
 	const HotIds *dev_bvh_ids = d.bvh_ids;
@@ -496,18 +567,57 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 	d.n_mat = (int)cs.mats.size(); d.n_tex = (int)cs.texs.size();
 	CK(cudaStreamSynchronize(ctx->stream));
 	ctx->dev = d;
+	ctx->csp = &cs;
 	ctx->committed = true;
 	// scene-specialised kernel for scenes that have a lean form: generated + NVRTC-compiled once per distinct scene
 	ctx->baked = nullptr;
 	ctx->bake_note.clear();
-	if (cs.lean_ok && ctx->opt_lean && ctx->opt_bake) {
-		ctx->baked = bake_get(cs, ctx->opt_bake_packed, ctx->device, ctx->bake_note, &info.bake_compile_ms);
+	ctx->opt_lean = lean; ctx->opt_bake = bake; ctx->opt_bake_packed = bake_packed;
+	if (cs.lean_ok && lean && bake) {
+		ctx->baked = bake_get(cs, bake_packed, ctx->device, ctx->bake_note, &info.bake_compile_ms);
 		info.baked = ctx->baked ? 1 : 0;
 	}
 	info.builder = device_built ? ARE_BVH_BUILDER_DEVICE_LBVH : ARE_BVH_BUILDER_HOST_SAH;
 	info.bvh_nodes = d.n_nodes;
 	if (!device_built) info.bvh_height = cs.bvh_depth;
 	info.hot_slots = cs.n_hot;
+	return ARE_OK;
+}
+
+int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
+	Range nvtx_range("are_cuda_commit (scene compile + upload)");
+	if (!ctx) return ARE_ERR_INVALID_ARGUMENT;
+	if (ctx->parent) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "commit the group's first context");
+	std::string err;
+	ctx->opt.brute_max = (int)brute_smem_limit_prims();
+	int builder = ctx->bvh_builder;
+	const int max_height = std::min((int)ARE_BVH_STACK, ctx->opt_lbvh_max_height);  // ARE_OPT_LBVH_MAX_HEIGHT: test hook for the fall-back below
+	are_commit_info info = {};
+	uint64_t bytes = 0;
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		ctx->committed = false;
+		for (are_cuda_ctx *p : ctx->peers) p->committed = false;
+		ctx->opt.device_bvh = builder == ARE_BVH_BUILDER_DEVICE_LBVH;
+		const auto t0 = std::chrono::steady_clock::now();
+		if (!compile_scene(ctx->scene, ctx->opt, ctx->cs, err)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, err);  // host half, once per group
+		const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		info = are_commit_info();
+		int st = commit_device(ctx, ctx->cs, ctx->opt.device_bvh, max_height, ctx->opt_lean, ctx->opt_bake, ctx->opt_bake_packed, info, bytes);
+		for (size_t i = 0; st == ARE_OK && i < ctx->peers.size(); ++i) {
+			are_commit_info pinfo = {};
+			uint64_t pbytes = 0;
+			st = commit_device(ctx->peers[i], ctx->cs, ctx->opt.device_bvh, max_height, ctx->opt_lean, ctx->opt_bake, ctx->opt_bake_packed, pinfo, pbytes);
+			if (st < 0) fail(ctx, st, std::string("device ") + std::to_string(ctx->peers[i]->device) + ": " + ctx->peers[i]->err);
+			bytes += pbytes;
+			info.device_bvh_ms = std::max(info.device_bvh_ms, pinfo.device_bvh_ms);
+			info.bake_compile_ms += pinfo.bake_compile_ms;
+		}
+		info.host_compile_ms = host_ms;
+		info.host_bvh_ms = ctx->cs.host_bvh_ms;
+		if (st == 1 && attempt == 0) { builder = ARE_BVH_BUILDER_HOST_SAH; continue; }
+		if (st != ARE_OK) return st < 0 ? st : fail(ctx, ARE_ERR_RUNTIME, "device-built BVH rejected twice");
+		break;
+	}
 	ctx->commit_info = info;
 	if (h2d_bytes) *h2d_bytes = bytes;
 	return ARE_OK;
@@ -798,8 +908,10 @@ int are_cuda_philox_batch(are_cuda_ctx *ctx, int n, uint64_t seed, const uint32_
 }
 
 // ---- rendering -------------------------------------------------------------------------------------------
-int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_render_params *p, float *accum, are_render_stats *stats, int count_tests) {
-	Range nvtx_range("are_cuda_render_device");
+}  // extern "C"
+
+// One device: add the sample sums of [sample_begin, sample_begin + sample_count) into accum (on ctx's GPU).
+static int render_single(are_cuda_ctx *ctx, const are_camera *cam, const are_render_params *p, float *accum, are_render_stats *stats, int count_tests) {
 	int st = need_commit(ctx);
 	if (st) return st;
 	if (!cam || !p || !accum) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
@@ -832,7 +944,7 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 	int mode = 0;
 	if (p->integrator == ARE_INTEGRATOR_RT_AO) {
 		// experiments/rt.cpp knows triangles only, tested by linear scan from shared memory
-		if (ctx->cs.n_tri == 0 || ctx->cs.n_quad != 0 || ctx->cs.n_sph != 0 || ctx->cs.n_tri > 1000)
+		if (ctx->csp->n_tri == 0 || ctx->csp->n_quad != 0 || ctx->csp->n_sph != 0 || ctx->csp->n_tri > 1000)
 			return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "RT_AO integrator renders triangle-only scenes of at most 1000 triangles");
 		make_rt_cam(cam->pos, cam->target, cam->up, cam->vfov_deg, p->width, p->height, a.rtcam);
 	} else if (p->integrator != ARE_INTEGRATOR_PATH) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown integrator");
@@ -867,15 +979,15 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 		stats->samples = (uint64_t)p->width * p->height * p->sample_count;
 		stats->rays = c[CNT_RAYS];
 		if (p->integrator == ARE_INTEGRATOR_RT_AO) {  // rt.cpp's linear scan: every ray tests every triangle (rt.cpp:209-218)
-			stats->tri_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.n_tri;
+			stats->tri_tests = c[CNT_RAYS] * (uint64_t)ctx->csp->n_tri;
 		} else if (mode != 0) {
 			stats->node_visits = c[CNT_NODES]; stats->quad_tests = c[CNT_QUADS]; stats->tri_tests = c[CNT_TRIS]; stats->sphere_tests = c[CNT_SPHERES];
 			stats->box_tests = c[CNT_BOXES];
 		} else {  // brute force: every ray tests every hot primitive — exact by construction
-			stats->quad_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.brute_range.nq;
-			stats->tri_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.brute_range.nt;
-			stats->sphere_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.brute_range.ns;
-			stats->box_tests = c[CNT_RAYS] * (uint64_t)ctx->cs.brute_range.nb;
+			stats->quad_tests = c[CNT_RAYS] * (uint64_t)ctx->csp->brute_range.nq;
+			stats->tri_tests = c[CNT_RAYS] * (uint64_t)ctx->csp->brute_range.nt;
+			stats->sphere_tests = c[CNT_RAYS] * (uint64_t)ctx->csp->brute_range.ns;
+			stats->box_tests = c[CNT_RAYS] * (uint64_t)ctx->csp->brute_range.nb;
 		}
 		stats->kernel_ms = ms;
 		stats->launches = (uint64_t)launched;
@@ -885,6 +997,124 @@ int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_r
 			: mode == 2 ? ARE_KERNEL_WIDE : (render_path_is_big(a) ? ARE_KERNEL_BVH2_BIG : ARE_KERNEL_BVH2);
 	}
 	return ARE_OK;
+}
+
+static int ensure_own_accum(are_cuda_ctx *ctx, size_t elems) {
+	if (ctx->own_accum_elems >= elems) return ARE_OK;
+	if (ctx->own_accum) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(ctx->own_accum)); ctx->own_accum = nullptr; ctx->own_accum_elems = 0; }
+	CK(cudaMalloc((void **)&ctx->own_accum, elems * sizeof(float)));
+	ctx->own_accum_elems = elems;
+	return ARE_OK;
+}
+
+// A multi-device group (are_cuda_create_multi): device i renders the i-th share of the sample range — the Philox counter
+// carries the GLOBAL sample index, so the group draws exactly the samples one device would — the first
+// device straight into `accum`, the others into their own zeroed scratch accumulators.  The sum is then formed by ONE
+// kernel per device over NVLink peer memory (render.cu: k_peer_reduce): device d adds slice d of every scratch buffer
+// into slice d of `accum`, so all N NVSwitch ports carry 1/N of the traffic each (a reduce-scatter whose outputs land
+// directly in the root's buffer) instead of the root pulling N-1 whole frames.  Everything is ordered by events between
+// the devices' streams; the host does not wait unless stats are requested.
+static int render_multi(are_cuda_ctx *ctx, const are_camera *cam, const are_render_params *p, float *accum, are_render_stats *stats, int count_tests) {
+	int st = need_commit(ctx);
+	if (st) return st;
+	if (!cam || !p || !accum) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	if (p->width <= 0 || p->height <= 0 || p->sample_count < 0) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "bad render parameters");
+	std::vector<are_cuda_ctx *> all;
+	all.push_back(ctx);
+	for (are_cuda_ctx *c : ctx->peers) all.push_back(c);
+	const int N = (int)all.size();
+	const size_t elems = (size_t)p->width * p->height * 3;
+	const int base = p->sample_count / N, rem = p->sample_count % N;
+	for (int i = 1; i < N; ++i) {  // the previous round's reduce kernels (on every device) must be done with this scratch buffer
+		are_cuda_ctx *c = all[i];
+		Bind b(c);
+		c->opt_lean = ctx->opt_lean; c->opt_bake = ctx->opt_bake;
+		for (are_cuda_ctx *o : all) CK(cudaStreamWaitEvent(c->stream, o->ev_red, 0));
+		if ((st = ensure_own_accum(c, elems)) != ARE_OK) return fail(ctx, st, c->err);
+		CK(cudaMemsetAsync(c->own_accum, 0, elems * sizeof(float), c->stream));
+	}
+	for (int i = 0; i < N; ++i) {
+		are_cuda_ctx *c = all[i];
+		are_render_params pi = *p;
+		pi.sample_begin = p->sample_begin + i * base + std::min(i, rem);
+		pi.sample_count = base + (i < rem ? 1 : 0);
+		Bind b(c);
+		CK(cudaEventRecord(c->ev0, c->stream));
+		st = render_single(c, cam, &pi, i == 0 ? accum : c->own_accum, nullptr, count_tests);
+		if (st != ARE_OK) return i == 0 ? st : fail(ctx, st, "device " + std::to_string(c->device) + ": " + c->err);
+		CK(cudaEventRecord(c->ev1, c->stream));
+		CK(cudaEventRecord(c->ev_done, c->stream));
+	}
+	if (N > 1) {
+		PeerReduceArgs ra;
+		std::memset(&ra, 0, sizeof ra);
+		ra.dst = accum;
+		ra.n_src = N - 1;
+		for (int i = 1; i < N; ++i) ra.src[i - 1] = all[i]->own_accum;
+		const size_t n4 = (reinterpret_cast<uintptr_t>(accum) & 15) == 0 ? elems / 4 : 0;
+		if (ctx->p2p_all) {
+			for (int i = 0; i < N; ++i) {
+				are_cuda_ctx *c = all[i];
+				Bind b(c);
+				for (are_cuda_ctx *o : all)
+					if (o != c) CK(cudaStreamWaitEvent(c->stream, o->ev_done, 0));
+				ra.begin4 = n4 * i / N; ra.end4 = n4 * (i + 1) / N;
+				ra.tail_begin = i == N - 1 ? 4 * n4 : elems; ra.tail_end = elems;
+				launch_peer_reduce(ra, c->sm_count, c->stream);
+				CK(cudaGetLastError());
+				CK(cudaEventRecord(c->ev_red, c->stream));
+			}
+			Bind b(ctx);
+			for (int i = 1; i < N; ++i) CK(cudaStreamWaitEvent(ctx->stream, all[i]->ev_red, 0));
+		} else {  // no peer mapping between some pair: stage every scratch frame through the first device
+			Bind b(ctx);
+			if (!ctx->stage || ctx->stage_elems < elems) {
+				if (ctx->stage) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(ctx->stage)); ctx->stage = nullptr; }
+				CK(cudaMalloc((void **)&ctx->stage, elems * sizeof(float)));
+				ctx->stage_elems = elems;
+			}
+			for (int i = 1; i < N; ++i) {
+				CK(cudaStreamWaitEvent(ctx->stream, all[i]->ev_done, 0));
+				CK(cudaMemcpyPeerAsync(ctx->stage, ctx->device, all[i]->own_accum, all[i]->device, elems * sizeof(float), ctx->stream));
+				PeerReduceArgs one = ra;
+				one.n_src = 1; one.src[0] = ctx->stage;
+				one.begin4 = 0; one.end4 = n4; one.tail_begin = 4 * n4; one.tail_end = elems;
+				launch_peer_reduce(one, ctx->sm_count, ctx->stream);
+				CK(cudaGetLastError());
+			}
+			CK(cudaEventRecord(ctx->ev_red, ctx->stream));
+		}
+	}
+	if (stats) {
+		std::memset(stats, 0, sizeof *stats);
+		for (int i = 0; i < N; ++i) {
+			are_cuda_ctx *c = all[i];
+			Bind b(c);
+			unsigned long long cn[CNT_N];
+			CK(cudaMemcpyAsync(cn, c->d_counters, sizeof cn, cudaMemcpyDeviceToHost, c->stream));
+			CK(cudaStreamSynchronize(c->stream));
+			float ms = 0.f;
+			CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+			stats->kernel_ms = std::max(stats->kernel_ms, (double)ms);
+			stats->rays += cn[CNT_RAYS];
+			stats->node_visits += cn[CNT_NODES]; stats->quad_tests += cn[CNT_QUADS]; stats->tri_tests += cn[CNT_TRIS];
+			stats->sphere_tests += cn[CNT_SPHERES]; stats->box_tests += cn[CNT_BOXES];
+			stats->launches += (base + (i < rem ? 1 : 0)) > 0 ? 1 : 0;
+		}
+		stats->launches += N > 1 ? (uint64_t)N : 0;  // the reduce kernels
+		stats->samples = (uint64_t)p->width * p->height * p->sample_count;
+		stats->kernel_variant = ARE_KERNEL_NONE;  // per-device variants may differ; query a single-device context for it
+		CK(cudaStreamSynchronize(ctx->stream));
+	}
+	return ARE_OK;
+}
+
+extern "C" {
+
+int are_cuda_render_device(are_cuda_ctx *ctx, const are_camera *cam, const are_render_params *p, float *accum, are_render_stats *stats, int count_tests) {
+	Range nvtx_range("are_cuda_render_device");
+	if (ctx && !ctx->peers.empty()) return render_multi(ctx, cam, p, accum, stats, count_tests);
+	return render_single(ctx, cam, p, accum, stats, count_tests);
 }
 
 int are_cuda_alloc_accum(are_cuda_ctx *ctx, int width, int height, float **out) {
@@ -930,11 +1160,7 @@ int are_cuda_render(are_cuda_ctx *ctx, const are_camera *cam, const are_render_p
 	if (p->width <= 0 || p->height <= 0) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "bad render parameters");
 	Bind b(ctx);
 	const size_t elems = (size_t)p->width * p->height * 3;
-	if (ctx->own_accum_elems < elems) {
-		if (ctx->own_accum) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(ctx->own_accum)); ctx->own_accum = nullptr; ctx->own_accum_elems = 0; }
-		CK(cudaMalloc((void **)&ctx->own_accum, elems * sizeof(float)));
-		ctx->own_accum_elems = elems;
-	}
+	if ((st = ensure_own_accum(ctx, elems)) != ARE_OK) return st;
 	CK(cudaMemsetAsync(ctx->own_accum, 0, elems * sizeof(float), ctx->stream));
 	are_render_stats local;
 	st = are_cuda_render_device(ctx, cam, p, ctx->own_accum, stats ? stats : &local, 0);
@@ -1155,6 +1381,33 @@ int are_cuda_write_ppm(const char *path, int width, int height, const uint8_t *r
 	bool ok = fwrite(rgb8, 1, n, f) == n;
 	fclose(f);
 	return ok ? ARE_OK : ARE_ERR_IO;
+}
+
+int are_cuda_measure_l2_peak(are_cuda_ctx *ctx, double *gb_per_s, uint64_t *buffer_bytes) {
+	if (!ctx || !gb_per_s) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	Bind b(ctx);
+	int l2 = 0;
+	cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx->device);
+	// a quarter of the L2 (B200: 126 MB in two partitions): resident whichever partition a line lands in
+	const size_t bytes = std::max<size_t>((size_t)8 << 20, ((size_t)l2 / 4) & ~(size_t)0xfffff);
+	Tmp buf, sink;
+	TMP_OUT(buf, bytes);
+	TMP_OUT(sink, 16);
+	CK(cudaMemsetAsync(buf.p, 0, bytes, ctx->stream));
+	double best = 0.0;
+	for (int rep = 0; rep < 5; ++rep) {
+		CK(cudaEventRecord(ctx->ev0, ctx->stream));
+		const double moved = launch_l2_peak(buf.as<float>(), bytes, ctx->sm_count, 24, sink.as<float>(), ctx->stream);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(ctx->ev1, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		float ms = 0.f;
+		CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+		if (rep >= 1 && ms > 0.f) best = std::max(best, moved / (ms * 1e-3) / 1e9);
+	}
+	*gb_per_s = best;
+	if (buffer_bytes) *buffer_bytes = bytes;
+	return ARE_OK;
 }
 
 int are_cuda_measure_fp32_peak(are_cuda_ctx *ctx, double *tflops, int *sm_count, int *sm_clock_khz) {

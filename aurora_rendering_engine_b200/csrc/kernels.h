@@ -52,8 +52,20 @@ bool render_path_is_big(const RenderArgs &a);   // BVH: the high-occupancy build
 int launch_render_rtao(const RenderArgs &a, cudaStream_t s);
 // gamma_thr: 256 floats, [v-1] = smallest c with the rt.cpp gamma encode >= v (v = 1..255), [255] = +inf (encoder 0 only)
 void launch_tonemap(const float *accum, int W, int H, double inv_spp, int encoder, const float *gamma_thr, uint8_t *out, cudaStream_t s);
+// dst[i] += sum_s src[s][i] over float4 indices [begin4, end4) and floats [tail_begin, tail_end): the per-device slice of
+// the multi-device accumulator sum.  dst / src may live on other GPUs (peer-mapped memory over NVLink).
+struct PeerReduceArgs {
+	float *dst;
+	const float *src[15];
+	int n_src;
+	size_t begin4, end4, tail_begin, tail_end;
+};
+void launch_peer_reduce(const PeerReduceArgs &a, int sm_count, cudaStream_t s);
 // register-resident FFMA loop; returns FLOPs executed per launch
 double launch_fp32_peak(float *sink, int sm_count, int iters, cudaStream_t s);
+
+// streams an L2-resident buffer `passes` times with ld.global.cg.v4; returns bytes read per launch
+double launch_l2_peak(const float *buf, size_t bytes, int sm_count, int passes, float *sink, cudaStream_t s);
 
 size_t brute_smem_limit_prims();
 

@@ -12,6 +12,8 @@
 //   k_fp32_peak     FFMA issue-rate micro-kernel (roofline denominator).
 #include <stdio.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 #include "render_path.cuh"
 
@@ -181,6 +183,34 @@ void launch_tonemap(const float *accum, int W, int H, double inv_spp, int encode
 }
 
 // =========================================================================================================
+// multi-device accumulator sum over peer memory
+// =========================================================================================================
+__global__ void __launch_bounds__(256) k_peer_reduce(const __grid_constant__ PeerReduceArgs a) {
+	const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	float4 *d4 = reinterpret_cast<float4 *>(a.dst);
+	for (size_t i = a.begin4 + t0; i < a.end4; i += stride) {
+		float4 acc = d4[i];
+#pragma unroll 4
+		for (int s = 0; s < a.n_src; ++s) {
+			const float4 v = __ldg(reinterpret_cast<const float4 *>(a.src[s]) + i);
+			acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+		}
+		d4[i] = acc;
+	}
+	for (size_t i = a.tail_begin + t0; i < a.tail_end; i += stride) {
+		float acc = a.dst[i];
+		for (int s = 0; s < a.n_src; ++s) acc += a.src[s][i];
+		a.dst[i] = acc;
+	}
+}
+void launch_peer_reduce(const PeerReduceArgs &a, int sm_count, cudaStream_t s) {
+	const size_t work = (a.end4 - a.begin4) + (a.tail_end - a.tail_begin);
+	if (work == 0 || a.n_src <= 0) return;
+	const int grid = (int)std::min<size_t>((work + 255) / 256, (size_t)std::max(1, sm_count) * 8);
+	k_peer_reduce<<<grid, 256, 0, s>>>(a);
+}
+
+// =========================================================================================================
 // FP32 FMA issue peak
 // =========================================================================================================
 __global__ void __launch_bounds__(256) k_fp32_peak(float *sink, int iters) {
@@ -195,6 +225,29 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float *sink, int iters) {
 	}
 	float r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 	if (r == 123.456f) sink[0] = r;
+}
+// L2 read bandwidth: every CTA streams the whole (L2-resident) buffer with 16-byte loads, starting at its own offset
+__global__ void __launch_bounds__(256) k_l2_peak(const float4 *__restrict__ buf, size_t n4, int passes, float *sink) {
+	float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (int p = 0; p < passes; ++p) {
+		size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x + (size_t)p * 977) % n4;
+#pragma unroll 4
+		for (size_t k = 0; k < n4 / stride; ++k) {
+			const float4 v = __ldcg(buf + i);  // cache at L2 only: every load is an L2 access, none is served by L1
+			acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+			i += stride;
+			if (i >= n4) i -= n4;
+		}
+	}
+	if (acc.x + acc.y + acc.z + acc.w == 123.456f) sink[0] = acc.x;
+}
+double launch_l2_peak(const float *buf, size_t bytes, int sm_count, int passes, float *sink, cudaStream_t s) {
+	const size_t n4 = bytes / 16;
+	const int grid = sm_count * 8;
+	const size_t stride = (size_t)grid * 256;
+	k_l2_peak<<<grid, 256, 0, s>>>(reinterpret_cast<const float4 *>(buf), n4, passes, sink);
+	return (double)(n4 / stride) * (double)stride * 16.0 * (double)passes;
 }
 double launch_fp32_peak(float *sink, int sm_count, int iters, cudaStream_t s) {
 	const int grid = sm_count * 8;

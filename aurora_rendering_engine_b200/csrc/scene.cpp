@@ -232,7 +232,12 @@ struct Builder {
 		cb.reset();
 		for (int i = lo; i < hi; ++i) cb.grow(D3{ refs[i].c[0], refs[i].c[1], refs[i].c[2] });
 		int mid = -1;
-		if (depth < 40) {
+		// SAH splits can be arbitrarily uneven; median splits halve.  SAH is used only while a median-split subtree under the
+		// worse child (n - 1 items, height ceil(log2(n - 1))) would still fit the traversal stack, so the finished tree never
+		// exceeds ARE_BVH_STACK levels whatever the scene (skewed scenes used to fail the commit instead).
+		int lg = 0;
+		while ((1 << lg) < n) ++lg;
+		if (depth + lg + 2 <= ARE_BVH_STACK) {
 			const int NB = 16;
 			double best_cost = std::numeric_limits<double>::infinity();
 			int best_axis = -1, best_split = -1;

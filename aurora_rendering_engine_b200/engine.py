@@ -10,6 +10,7 @@ PyTorch is used here for device memory, streams and the process group only; ever
 """
 from __future__ import annotations
 
+import hashlib
 import os
 from dataclasses import dataclass
 
@@ -103,7 +104,7 @@ class JobResult:
 class RenderJob:
     """A scene committed on this rank's GPU plus a device accumulator; ``render_range`` adds samples into it."""
 
-    def __init__(self, scene_desc, device_index: int = 0, traversal: int = 0, options: dict | None = None):
+    def __init__(self, scene_desc, device_index: int = 0, traversal: int = 0, options: dict | None = None, builder: int | None = None):
         import torch
         self.torch = torch
         self.sc = scene_desc
@@ -113,6 +114,8 @@ class RenderJob:
         self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         for opt, val in (options or {}).items():   # capi.OPT_* -> value (are_cuda_set_option)
             self.ctx.set_option(opt, val)
+        if builder is not None:
+            self.ctx.set_bvh_builder(builder)
         scene_desc.feed(self.ctx)
         self.h2d_bytes = self.ctx.commit()
         self.cam = capi.make_camera(**scene_desc.camera_args())
@@ -120,6 +123,8 @@ class RenderJob:
         self.accum = torch.zeros((scene_desc.height, scene_desc.width, 3), dtype=torch.float32, device=f"cuda:{device_index}")
         self.result = JobResult(self.accum)
         self.done = []  # (begin, count) sample ranges already in the accumulator
+        self.shard = None  # (begin, count) this job is responsible for (render_job sets it); None = unrestricted
+        self.rank, self.world = 0, 1
 
     def params(self, begin, count, **over):
         return capi.make_params(**self.sc.params_args(sample_begin=begin, sample_count=count, traversal=self.traversal, **over))
@@ -149,23 +154,43 @@ class RenderJob:
     # -- checkpoint / resume: the accumulator holds plain sample sums and the RNG is counter-based, so a job is fully
     #    described by (accumulator, which global sample ranges are in it)
     def signature(self) -> str:
+        """Everything that decides WHICH estimator the accumulator holds: scene, frame, depth, integrator, traversal, and a
+        digest of the camera and of every render parameter except the sample range (seed, t_min, background, ...).  A
+        checkpoint written under another signature holds samples of another picture."""
         sc = self.sc
-        return f"{sc.name}|{sc.width}x{sc.height}|{sc.num_prims}|depth{sc.max_depth}|integrator{sc.integrator}"
+        par = {k: v for k, v in sc.params_args(traversal=self.traversal).items() if k not in ("sample_begin", "sample_count")}
+        blob = repr((sorted((k, repr(v)) for k, v in sc.camera_args().items()), sorted((k, repr(v)) for k, v in par.items())))
+        return (f"{sc.name}|{sc.width}x{sc.height}|{sc.num_prims}|depth{sc.max_depth}|integrator{sc.integrator}|"
+                f"{hashlib.sha256(blob.encode()).hexdigest()[:16]}")
 
     def save_checkpoint(self, path: str):
         self.torch.cuda.current_stream().synchronize()
         tmp = path + ".tmp.npz"
+        shard = self.shard if self.shard is not None else (-1, -1)
         np.savez(tmp, accum=self.accum.cpu().numpy(), done=np.array(merge_ranges(self.done), dtype=np.int64).reshape(-1, 2),
-                 signature=np.array(self.signature()))
+                 signature=np.array(self.signature()), shard=np.array(shard, dtype=np.int64), rank_world=np.array([self.rank, self.world], dtype=np.int64))
         os.replace(tmp, path)
 
     def load_checkpoint(self, path: str):
-        """Restore accumulator + progress; raises ValueError for a checkpoint of another job."""
+        """Restore accumulator + progress.  Raises ValueError for a checkpoint of another job (scene, camera, seed, ...), of
+        another rank / world size / shard, or one whose recorded sample ranges overlap or leave this job's shard — loading
+        any of those would put samples into the sum twice or samples of another estimator beside this one's."""
         ck = np.load(path)
         if str(ck["signature"]) != self.signature():
             raise ValueError(f"checkpoint belongs to {ck['signature']}, this job is {self.signature()}")
+        done = [(int(b), int(c)) for b, c in ck["done"]]
+        if overlapping(done):
+            raise ValueError("checkpoint lists overlapping sample ranges")
+        if self.shard is not None:
+            if "shard" in ck.files and tuple(int(x) for x in ck["shard"]) not in ((-1, -1), tuple(self.shard)):
+                raise ValueError(f"checkpoint was written for shard {tuple(int(x) for x in ck['shard'])} "
+                                 f"(rank/world {tuple(int(x) for x in ck['rank_world'])}), this rank renders {tuple(self.shard)}")
+            lo, hi = self.shard[0], self.shard[0] + self.shard[1]
+            for b, c in done:
+                if b < lo or b + c > hi:
+                    raise ValueError(f"checkpoint holds samples [{b}, {b + c}) outside this rank's shard [{lo}, {hi})")
         self.accum.copy_(self.torch.from_numpy(ck["accum"]))
-        self.done = [(int(b), int(c)) for b, c in ck["done"]]
+        self.done = done
         return self.done
 
     def close(self):
@@ -183,8 +208,11 @@ def render_job(scene_desc, spp: int, chunk: int = 64, traversal: int = 0, want_s
         import torch.distributed as dist
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    if checkpoint and world > 1 and "{rank}" not in checkpoint:
+        raise ValueError("a multi-rank job needs one checkpoint file per rank: put {rank} in the path")
     job = RenderJob(scene_desc, local_rank, traversal)
     begin, count = shard_samples(spp, world, rank)
+    job.shard, job.rank, job.world = (begin, count), rank, world
     ck = checkpoint.format(rank=rank) if checkpoint else None
     if ck and os.path.exists(ck):
         job.load_checkpoint(ck)

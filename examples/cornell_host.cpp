@@ -7,7 +7,7 @@
 //
 //   g++ -std=c++17 -O2 -Iinclude examples/cornell_host.cpp -Laurora_rendering_engine_b200/lib -lare_b200 [continued]
 //       -Wl,-rpath,$PWD/aurora_rendering_engine_b200/lib -o cornell_host
-//   ./cornell_host out.ppm [width height spp [raw_float_dump]]
+//   ./cornell_host out.ppm [width height spp [raw_float_dump [n_gpus]]]      n_gpus: 0 = every visible GPU (default 1)
 #include <are_cuda.hpp>
 #include <camera.h>
 #include <material/diffuse_light.h>
@@ -77,7 +77,10 @@ int main(int argc, char **argv) {
 	cam.focus_dist = 10.0;
 
 	try {
-		cuda::Renderer gpu(0);
+		const int want = argc > 6 ? std::atoi(argv[6]) : 1;
+		std::vector<int> devices = cuda::Renderer::all_devices();
+		if (want > 0 && static_cast<size_t>(want) < devices.size()) devices.resize(static_cast<size_t>(want));
+		cuda::Renderer gpu(devices);  // one renderer over all of them: samples sharded, sums reduced over NVLink peer memory
 		gpu.upload(sc.set);
 		cuda::Settings s;
 		s.spp = spp;
@@ -92,8 +95,8 @@ int main(int argc, char **argv) {
 		Texture image = gpu.render(cam, W, H, s);
 		if (!image.save_texture(out_path)) { std::fprintf(stderr, "cannot write %s\n", out_path); return 2; }
 		const are_render_stats &st = gpu.stats();
-		std::printf("%d triangles, %dx%d, %d spp: %llu rays in %.2f ms (%.1f Mrays/s), wrote %s\n", (int)sc.set.triangles.size(), W, H, spp,
-			(unsigned long long)st.rays, st.kernel_ms, st.rays / (st.kernel_ms * 1e3), out_path);
+		std::printf("%d triangles, %dx%d, %d spp on %d GPU(s): %llu rays in %.2f ms (%.1f Mrays/s), wrote %s\n", (int)sc.set.triangles.size(), W, H, spp,
+			gpu.device_count(), (unsigned long long)st.rays, st.kernel_ms, st.rays / (st.kernel_ms * 1e3), out_path);
 	} catch (const std::exception &e) {
 		std::fprintf(stderr, "error: %s\n", e.what());
 		return 1;

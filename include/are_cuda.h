@@ -20,8 +20,8 @@
  * Conventions: all functions return ARE_OK (0) or a negative are_status; no exception crosses this boundary
  * (the C++ shim in include/are_cuda.hpp re-throws std::runtime_error / std::invalid_argument to match the
  * reference's error behaviour).  Vectors are 3 consecutive doubles, exactly the layout of are::Vec3
- * (double e_[3], include/basic/vec3.h:11).  One context drives one GPU; contexts are not thread-safe (the
- * reference is single-threaded).  There is no CPU fallback: without a CUDA device are_cuda_create fails.
+ * (double e_[3], include/basic/vec3.h:11).  A context drives one GPU (are_cuda_create) or several GPUs of one box
+ * (are_cuda_create_multi); contexts are not thread-safe (the reference is single-threaded).  There is no CPU fallback: without a CUDA device are_cuda_create fails.
  */
 #ifndef ARE_CUDA_H
 #define ARE_CUDA_H
@@ -138,6 +138,17 @@ enum {
 int are_cuda_abi_version(void);
 int are_cuda_device_count(void); /* number of visible CUDA devices, 0 if none / no driver */
 int are_cuda_create(are_cuda_ctx **out, int device);
+/* One context driving SEVERAL GPUs of one box in this process: the scene is compiled once and
+ * committed to every device; are_cuda_render / are_cuda_render_device split the sample range over the devices (device i
+ * renders the i-th share of [sample_begin, sample_begin + sample_count); the Philox counter carries the global sample
+ * index, so the group draws exactly the samples one device would) and return the SUM — in a buffer on devices[0], which
+ * is also the device every other entry point (per-ray batches, tonemap, patch renderer) runs on.  The sum is formed by
+ * one kernel per device over NVLink peer memory (each device adds one slice of all frames into the root's buffer); where
+ * two devices cannot map each other the frames are staged through the first.  No MPI, NCCL or host threads involved. */
+#define ARE_MAX_GROUP_DEVICES 16
+int are_cuda_create_multi(are_cuda_ctx **out, const int *devices, int n_devices);
+/* n_devices of the group (1 for are_cuda_create), peer_mapped = 1 when the peer-memory reduce is in use. */
+int are_cuda_group_info(are_cuda_ctx *ctx, int *n_devices, int *peer_mapped);
 void are_cuda_destroy(are_cuda_ctx *ctx);
 const char *are_cuda_last_error(are_cuda_ctx *ctx); /* ctx may be NULL: last error of a failed create */
 /* Use an existing CUDA stream (cudaStream_t passed as void*; NULL = the legacy default stream) for all work. */
@@ -351,6 +362,9 @@ int are_cuda_synchronize(are_cuda_ctx *ctx);
 /* Measured FP32 FMA issue peak of this device (TFLOP/s): a register-resident FFMA micro-kernel, used as the
  * roofline denominator next to the nominal SMs x 128 lanes x 2 x clock figure. */
 int are_cuda_measure_fp32_peak(are_cuda_ctx *ctx, double *tflops, int *sm_count, int *sm_clock_khz);
+/* Measured L2 read bandwidth (GB/s): every CTA streams a buffer of a quarter of the L2 with ld.global.cg.v4 — the
+ * roofline denominator of the traversal kernels whose hierarchy lives in L2.  buffer_bytes may be NULL. */
+int are_cuda_measure_l2_peak(are_cuda_ctx *ctx, double *gb_per_s, uint64_t *buffer_bytes);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,23 @@ public:
 	explicit Renderer(int device = 0) {
 		if (are_cuda_create(&ctx_, device) != ARE_OK) throw std::runtime_error(std::string("are_cuda_create: ") + are_cuda_last_error(nullptr));
 	}
+	/// Several GPUs of one box behind one renderer: every render() / render_sums() is sharded by sample range over the
+	/// devices and summed on devices[0] over NVLink peer memory (are_cuda_create_multi).
+	explicit Renderer(const std::vector<int> &devices) {
+		if (are_cuda_create_multi(&ctx_, devices.data(), static_cast<int>(devices.size())) != ARE_OK)
+			throw std::runtime_error(std::string("are_cuda_create_multi: ") + are_cuda_last_error(nullptr));
+	}
+	/// All visible GPUs.
+	static std::vector<int> all_devices() {
+		std::vector<int> d(static_cast<size_t>(are_cuda_device_count() > 0 ? are_cuda_device_count() : 0));
+		for (size_t i = 0; i < d.size(); ++i) d[i] = static_cast<int>(i);
+		return d;
+	}
+	int device_count() const {
+		int n = 1;
+		are_cuda_group_info(ctx_, &n, nullptr);
+		return n;
+	}
 	~Renderer() { are_cuda_destroy(ctx_); }
 	Renderer(const Renderer &) = delete;
 	Renderer &operator=(const Renderer &) = delete;
@@ -222,7 +239,7 @@ public:
 				type_.push_back(mirror ? 1 : 0);
 				metal_.push_back(mirror ? mirror->reflectivity_ : 0.0);
 				const Texture *tex = t->texture();
-				const Color3 c = tex->data() ? const_cast<Texture *>(tex)->pixel(0, 0) : Color3(tex->params()[0], tex->params()[1], tex->params()[2]);
+				const Color3 c = tex->data() ? static_cast<const Texture &>(*tex).pixel(0, 0) : Color3(tex->params()[0], tex->params()[1], tex->params()[2]);
 				for (int k = 0; k < 3; ++k) albedo_.push_back(c[k]);
 			}
 			material_.push_back(it->second);

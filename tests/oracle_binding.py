@@ -201,10 +201,11 @@ class Reference(_VecLib):
 class Oracle(_VecLib):
     """oracle/are_oracle.c."""
 
-    def __init__(self):
-        if not os.path.exists(ORACLE_SO):
+    def __init__(self, path=None):
+        """path: another build of the same source (bench.py times oracle/liboracle_fast.so, -O3 -march=native)."""
+        if path is None and not os.path.exists(ORACLE_SO):
             build_oracle()
-        super().__init__(C.CDLL(ORACLE_SO), "lib_")
+        super().__init__(C.CDLL(path or ORACLE_SO), "lib_")
         L = self.lib
         L.lib_triset_closest_hit.restype = C.c_long
         L.orc_scene_create.restype = _vp

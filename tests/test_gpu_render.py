@@ -423,6 +423,25 @@ def test_checkpoint_resume_is_bit_identical(lib, tmp_path):
     with pytest.raises(ValueError):
         other.load_checkpoint(ck.format(rank=0))
     other.close()
+    # same scene and frame but another camera / background = another estimator: refused
+    for change in (dict(camera=dict(sc.camera, vfov_deg=41.0)), dict(background_top=(0.1, 0.1, 0.1)), dict(t_min=2e-3)):
+        sc2 = scenes.cornell_box(width=48, height=48)
+        for k, v in change.items():
+            setattr(sc2, k, v)
+        j = engine.RenderJob(sc2, 0)
+        with pytest.raises(ValueError, match="belongs to"):
+            j.load_checkpoint(ck.format(rank=0))
+        j.close()
+    # another rank's shard: the file's samples [0, 12) lie outside [12, 24)
+    j = engine.RenderJob(sc, 0)
+    j.shard, j.rank, j.world = (12, 12), 1, 2
+    with pytest.raises(ValueError, match="outside this rank's shard"):
+        j.load_checkpoint(ck.format(rank=0))
+    j.save_checkpoint(str(tmp_path / "r1.npz"))
+    j.shard = (0, 12)
+    with pytest.raises(ValueError, match="written for shard"):
+        j.load_checkpoint(str(tmp_path / "r1.npz"))
+    j.close()
 
 
 def _mixed_small_scene(width=96, height=64):
