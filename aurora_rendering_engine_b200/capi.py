@@ -287,7 +287,7 @@ class Context:
         if isinstance(device, (list, tuple)):
             devs = np.ascontiguousarray(device, np.int32)
             st = self.lib.are_cuda_create_multi(C.byref(h), _ptr(devs, _ip), len(devs))
-            device = int(devs[0])
+            device = int(devs[0]) if len(devs) else -1
         else:
             st = self.lib.are_cuda_create(C.byref(h), int(device))
         if st != ARE_OK:
@@ -476,8 +476,11 @@ class Context:
         self._ck(self.lib.are_cuda_render(self.h, C.byref(cam), C.byref(params), _ptr(out, _fp), C.byref(st)))
         return out, st
 
-    def tonemap(self, accum_ptr: int, width, height, inv_spp, encoder=0):
-        out = np.empty((height, width, 3), np.uint8)
+    def tonemap(self, accum_ptr: int, width, height, inv_spp, encoder=0, out: np.ndarray | None = None):
+        """8-bit encode on the device -> (H, W, 3) uint8.  `out`: write into this array (e.g. a view of a P6 file image)."""
+        if out is None:
+            out = np.empty((height, width, 3), np.uint8)
+        assert out.dtype == np.uint8 and out.size == height * width * 3 and out.flags.c_contiguous
         self._ck(self.lib.are_cuda_tonemap(self.h, _vp(accum_ptr), int(width), int(height), float(inv_spp), int(encoder),
                                            _ptr(out, C.POINTER(C.c_uint8))))
         return out

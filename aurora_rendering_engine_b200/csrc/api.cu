@@ -45,6 +45,8 @@ struct are_cuda_ctx {
 	CompileOptions opt;
 	PatchWorkspace patch_ws;
 	float *d_gamma_thr = nullptr;  // thresholds of the rt.cpp gamma-2.2 encode (built on first use)
+	uint8_t *d_rgb8 = nullptr;     // tone-mapped frame, kept between calls (a cudaMalloc / cudaFree pair per call costs more than the encode)
+	size_t d_rgb8_bytes = 0;
 	int bvh_builder = ARE_BVH_BUILDER_HOST_SAH;
 	cudaMemPool_t pool = nullptr;  // scene arrays come from a private stream-ordered pool that keeps freed blocks: a re-commit reuses them
 	void *lbvh_ws = nullptr;  // scratch of the device BVH builder, grown on demand and kept between commits
@@ -309,6 +311,7 @@ void are_cuda_destroy(are_cuda_ctx *ctx) {
 	ctx->patch_ws.release();
 	if (ctx->lbvh_ws) cudaFree(ctx->lbvh_ws);
 	if (ctx->d_gamma_thr) cudaFree(ctx->d_gamma_thr);
+	if (ctx->d_rgb8) cudaFree(ctx->d_rgb8);
 	if (ctx->own_accum) cudaFree(ctx->own_accum);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1202,11 +1205,14 @@ int are_cuda_tonemap(are_cuda_ctx *ctx, const float *accum, int width, int heigh
 		CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_gamma_thr), sizeof thr));
 		CK(cudaMemcpy(ctx->d_gamma_thr, thr, sizeof thr, cudaMemcpyHostToDevice));
 	}
-	Tmp d;
-	TMP_OUT(d, n);
-	launch_tonemap(accum, width, height, inv_spp, encoder, ctx->d_gamma_thr, d.as<uint8_t>(), ctx->stream);
+	if (ctx->d_rgb8_bytes < n) {
+		if (ctx->d_rgb8) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(ctx->d_rgb8)); ctx->d_rgb8 = nullptr; ctx->d_rgb8_bytes = 0; }
+		CK(cudaMalloc(reinterpret_cast<void **>(&ctx->d_rgb8), n));
+		ctx->d_rgb8_bytes = n;
+	}
+	launch_tonemap(accum, width, height, inv_spp, encoder, ctx->d_gamma_thr, ctx->d_rgb8, ctx->stream);
 	CK(cudaGetLastError());
-	CK(cudaMemcpyAsync(out_host, d.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(out_host, ctx->d_rgb8, n, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	return ARE_OK;
 }

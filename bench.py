@@ -415,6 +415,12 @@ def strong_job(b, spp_total, chunk=256):
     torch, job, ctx, sc = b.torch, b.job, b.ctx, b.sc
     begin, count = b.engine.shard_samples(spp_total, b.world, b.rank)
     chunks = b.engine.chunk_ranges(begin, count, chunk)
+    import numpy as np
+    header = b"P6\n%d %d\n255\n" % (sc.width, sc.height)
+    ppm = bytearray(len(header) + sc.width * sc.height * 3) if b.rank == 0 else None  # the file image: header + payload
+    if ppm is not None:
+        ppm[:len(header)] = header
+        payload = np.frombuffer(ppm, np.uint8, offset=len(header)).reshape(sc.height, sc.width, 3)
     out = {}
     for rep in range(3):  # the first repetition warms up
         job.accum.zero_()
@@ -427,10 +433,8 @@ def strong_job(b, spp_total, chunk=256):
         e[1].record()
         b.engine.reduce_sum_to_root(job.accum, b.world)
         e[2].record()
-        ppm = None
-        if b.rank == 0:
-            rgb8 = ctx.tonemap(job.accum.data_ptr(), sc.width, sc.height, 1.0 / spp_total, 0)  # k_tonemap + D2H, synchronises
-            ppm = b"P6\n%d %d\n255\n" % (sc.width, sc.height) + rgb8.tobytes()
+        if b.rank == 0:  # k_tonemap + D2H straight into the payload of the P6 image (synchronises)
+            ctx.tonemap(job.accum.data_ptr(), sc.width, sc.height, 1.0 / spp_total, 0, out=payload)
         else:
             torch.cuda.synchronize()
         wall_rank = (time.perf_counter() - t0) * 1e3
