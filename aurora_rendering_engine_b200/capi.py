@@ -56,7 +56,7 @@ class CommitInfo(C.Structure):
 BVH_BUILDER_HOST_SAH, BVH_BUILDER_DEVICE_LBVH = 0, 1
 KERNEL_NONE, KERNEL_BRUTE, KERNEL_BRUTE_LEAN, KERNEL_BVH2, KERNEL_BVH2_BIG, KERNEL_WIDE, KERNEL_RT_AO, KERNEL_BRUTE_BAKED = range(8)
 (OPT_LEAN_KERNEL, OPT_BAKED_KERNEL, OPT_BAKED_PACKED, OPT_FUSE_PARALLELOGRAMS, OPT_FUSE_BOXES, OPT_BUILD_WIDE, OPT_WIDE_MIN_NODES,
- OPT_LBVH_MAX_HEIGHT) = range(1, 9)
+ OPT_LBVH_MAX_HEIGHT, OPT_L2_PERSIST_NODES) = range(1, 10)
 
 
 def make_camera(pos, target, up=(0, 1, 0), vfov_deg=40.0, focus_dist=1.0, defocus_angle_deg=0.0, jitter=1) -> Camera:
@@ -157,6 +157,9 @@ SIGNATURES = {
     "are_cuda_clear": (C.c_int, [_vp]),
     "are_cuda_num_primitives": (C.c_int, [_vp]),
     "are_cuda_commit": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "are_cuda_update_triangles": (C.c_int, [_vp, C.c_int, _ip, _dp, _dp, _dp]),
+    "are_cuda_update_spheres": (C.c_int, [_vp, C.c_int, _ip, _dp, _dp]),
+    "are_cuda_refit": (C.c_int, [_vp, _dp]),
     "are_cuda_compile_probe": (C.c_int, [C.c_int, _dp, _dp, _dp, _ip]),
     "are_cuda_compile_probe_digest": (C.c_int, [C.c_int, _dp, _dp, _dp, _ip, C.POINTER(C.c_uint64)]),
     "are_cuda_compile_probe_forms": (C.c_int, [C.c_int, _dp, _dp, _dp, _ip]),
@@ -395,6 +398,22 @@ class Context:
         n = C.c_uint64(0)
         self._ck(self.lib.are_cuda_commit(self.h, C.byref(n)))
         return n.value
+
+    def update_triangles(self, ids, Q, u, v):
+        ids = np.ascontiguousarray(ids, np.int32)
+        Q, u, v = _d(Q), _d(u), _d(v)
+        self._ck(self.lib.are_cuda_update_triangles(self.h, len(ids), _ptr(ids, _ip), _ptr(Q), _ptr(u), _ptr(v)))
+
+    def update_spheres(self, ids, c, r):
+        ids = np.ascontiguousarray(ids, np.int32)
+        c, r = _d(c), _d(r)
+        self._ck(self.lib.are_cuda_update_spheres(self.h, len(ids), _ptr(ids, _ip), _ptr(c), _ptr(r)))
+
+    def refit(self) -> float:
+        """Refit the device-built hierarchy to the primitives moved by update_*; returns the device time in ms."""
+        ms = C.c_double(0)
+        self._ck(self.lib.are_cuda_refit(self.h, C.byref(ms)))
+        return ms.value
 
     # -- per-ray harness ------------------------------------------------------------------------------
     def hit_batch(self, Q, D, t_min=0.0, precision=64, traversal=0):

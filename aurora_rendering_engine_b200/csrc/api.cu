@@ -49,8 +49,11 @@ struct are_cuda_ctx {
 	size_t d_rgb8_bytes = 0;
 	int bvh_builder = ARE_BVH_BUILDER_HOST_SAH;
 	cudaMemPool_t pool = nullptr;  // scene arrays come from a private stream-ordered pool that keeps freed blocks: a re-commit reuses them
-	void *lbvh_ws = nullptr;  // scratch of the device BVH builder, grown on demand and kept between commits
+	void *lbvh_ws = nullptr;  // scratch of the device BVH builder, grown on demand and kept between commits (a refit reads it)
 	size_t lbvh_ws_bytes = 0;
+	int lbvh_items = 0;       // items of the device-built hierarchy the workspace describes (0: none — no refit possible)
+	std::vector<int> dirty;   // user ids of primitives moved by are_cuda_update_* since the last commit / refit
+	std::vector<char> dirty_flag;
 	are_commit_info commit_info = {};
 	int wide_min_nodes = 0x7fffffff;  // AUTO never picks the compressed 8-wide BVH (measured slower); ARE_OPT_WIDE_MIN_NODES overrides
 	// options (are_cuda_set_option)
@@ -59,6 +62,8 @@ struct are_cuda_ctx {
 	bool opt_bake_packed = false;    // its slab products as fma.rn.f32x2 pairs
 	int opt_builder_override = -1;   // -1: are_cuda_set_bvh_builder decides
 	int opt_lbvh_max_height = ARE_BVH_STACK;
+	int opt_l2_persist = 0;          // BVH renders: mark the node array as L2-persisting (cudaAccessPolicyWindow) for the launch
+	size_t l2_persist_max = 0, l2_window_max = 0;
 	const BakedKernel *baked = nullptr;  // owned by the process-wide cache in bake.cpp
 	std::string bake_note;
 	// multi-device context (are_cuda_create_multi): this context drives devices[0]; `peers` are full single-device contexts
@@ -219,8 +224,11 @@ int are_cuda_create(are_cuda_ctx **out, int device) {
 	ctx = new are_cuda_ctx();
 	ctx->device = device;
 	ctx->sm_count = prop.multiProcessorCount;
+	ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+	ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
 	std::memset(&ctx->dev, 0, sizeof ctx->dev);
 	Bind b(ctx);
+	if (ctx->l2_persist_max > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max) != cudaSuccess) { cudaGetLastError(); ctx->l2_persist_max = 0; }
 	cudaError_t e1 = cudaMalloc((void **)&ctx->d_counters, CNT_N * sizeof(unsigned long long));
 	cudaError_t e2 = cudaEventCreate(&ctx->ev0), e3 = cudaEventCreate(&ctx->ev1);
 	if (e1 == cudaSuccess) {
@@ -360,6 +368,7 @@ int are_cuda_set_option(are_cuda_ctx *ctx, int option, int value) {
 	case ARE_OPT_BUILD_WIDE: ctx->opt.build_wide = value != 0; return ARE_OK;
 	case ARE_OPT_WIDE_MIN_NODES: ctx->wide_min_nodes = value; return ARE_OK;
 	case ARE_OPT_LBVH_MAX_HEIGHT: ctx->opt_lbvh_max_height = value > 0 ? value : ARE_BVH_STACK; return ARE_OK;
+	case ARE_OPT_L2_PERSIST_NODES: ctx->opt_l2_persist = value; return ARE_OK;
 	default: return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown option");
 	}
 }
@@ -494,6 +503,7 @@ static int commit_device(are_cuda_ctx *ctx, const CompiledScene &cs, bool want_d
 	DevScene d;
 	std::memset(&d, 0, sizeof d);
 	bytes = 0;
+	ctx->lbvh_items = 0;
 	const bool device_built = want_device_bvh && !cs.lb_lo.empty();
 	if (device_built) {
 		// ---- device BVH build: inputs are temporaries, outputs belong to the scene ----
@@ -541,6 +551,7 @@ static int commit_device(are_cuda_ctx *ctx, const CompiledScene &cs, bool want_d
 		info.device_bvh_ms = ms;
 		info.device_bvh_launches = (uint64_t)launched;
 		info.bvh_height = out.height;
+		ctx->lbvh_items = in.n_items;
 	}
 	// the traversal kernels push at most height - 1 far children above the sentinel and do not test for overflow
 	if (!device_built && cs.bvh_depth > ARE_BVH_STACK) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "BVH deeper than the traversal stack");
@@ -568,6 +579,8 @@ static int commit_device(are_cuda_ctx *ctx, const CompiledScene &cs, bool want_d
 	d.n_hot = cs.n_hot;
 	d.n_tri = cs.n_tri; d.n_quad = cs.n_quad; d.n_sph = cs.n_sph;
 	d.n_mat = (int)cs.mats.size(); d.n_tex = (int)cs.texs.size();
+	d.has_noise = 0;
+	for (const TextureRec &t : cs.texs) d.has_noise |= t.kind == TK_NOISE ? 1 : 0;
 	CK(cudaStreamSynchronize(ctx->stream));
 	ctx->dev = d;
 	ctx->csp = &cs;
@@ -622,7 +635,132 @@ int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes) {
 		break;
 	}
 	ctx->commit_info = info;
+	ctx->dirty.clear();
+	ctx->dirty_flag.clear();
 	if (h2d_bytes) *h2d_bytes = bytes;
+	return ARE_OK;
+}
+
+// ---- moving primitives: update + refit ---------------------------------------------------------------------
+static int mark_dirty(are_cuda_ctx *ctx, int id, int type) {
+	if (id < 0 || id >= (int)ctx->scene.prims.size() || ctx->scene.prims[id].type != type)
+		return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "prim_id out of range or of another primitive type");
+	if (ctx->dirty_flag.size() != ctx->scene.prims.size()) ctx->dirty_flag.assign(ctx->scene.prims.size(), 0);
+	if (!ctx->dirty_flag[id]) { ctx->dirty_flag[id] = 1; ctx->dirty.push_back(id); }
+	return ARE_OK;
+}
+
+int are_cuda_update_triangles(are_cuda_ctx *ctx, int n, const int *prim_ids, const double *Q, const double *u, const double *v) {
+	if (!ctx || n < 0 || (n && (!prim_ids || !Q || !u || !v))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	for (int k = 0; k < n; ++k) {
+		if (const char *why = validate_edges(u + 3 * (size_t)k, v + 3 * (size_t)k)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, why);
+		int st = mark_dirty(ctx, prim_ids[k], PT_TRIANGLE);
+		if (st) return st;
+		HostPrim &p = ctx->scene.prims[prim_ids[k]];
+		std::memcpy(p.Q, Q + 3 * (size_t)k, 24); std::memcpy(p.u, u + 3 * (size_t)k, 24); std::memcpy(p.v, v + 3 * (size_t)k, 24);
+	}
+	return ARE_OK;
+}
+
+int are_cuda_update_spheres(are_cuda_ctx *ctx, int n, const int *prim_ids, const double *center, const double *radius) {
+	if (!ctx || n < 0 || (n && (!prim_ids || !center || !radius))) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "null argument");
+	for (int k = 0; k < n; ++k) {
+		if (!(radius[k] > 0.0) || !std::isfinite(radius[k])) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "sphere radius must be positive");
+		int st = mark_dirty(ctx, prim_ids[k], PT_SPHERE);
+		if (st) return st;
+		HostPrim &p = ctx->scene.prims[prim_ids[k]];
+		std::memcpy(p.Q, center + 3 * (size_t)k, 24);
+		p.u[0] = radius[k];
+	}
+	return ARE_OK;
+}
+
+// Device half of a refit on one context of the group.
+static int refit_device(are_cuda_ctx *ctx, const CompiledScene &cs, const std::vector<int> &item, const std::vector<int> &dp, const std::vector<HotPrim> &rec,
+	const std::vector<f4> &lo, const std::vector<f4> &hi, const std::vector<double> &geo, const std::vector<f4> &rt, float &ms) {
+	Bind b(ctx);
+	const int m = (int)item.size();
+	if (ctx->lbvh_items != (int)cs.lb_lo.size() || !ctx->lbvh_ws) return fail(ctx, ARE_ERR_RUNTIME, "no device-built hierarchy to refit");
+	Tmp d_item, d_dp, d_rec, d_lo, d_hi, d_geo, d_rt;
+	TMP_IN(d_item, item.data(), (size_t)m * sizeof(int));
+	TMP_IN(d_dp, dp.data(), (size_t)m * sizeof(int));
+	TMP_IN(d_rec, rec.data(), (size_t)m * sizeof(HotPrim));
+	TMP_IN(d_lo, lo.data(), (size_t)m * sizeof(f4));
+	TMP_IN(d_hi, hi.data(), (size_t)m * sizeof(f4));
+	TMP_IN(d_geo, geo.data(), (size_t)m * 9 * sizeof(double));
+	TMP_IN(d_rt, rt.data(), (size_t)m * 3 * sizeof(f4));
+	CK(cudaEventRecord(ctx->ev0, ctx->stream));
+	PrimScatterArgs ps;
+	ps.m = m; ps.dp = d_dp.as<int>(); ps.rec = d_rec.as<HotPrim>(); ps.geo64 = d_geo.as<double>(); ps.rt = d_rt.as<f4>();
+	ps.prim_plane = const_cast<HotPrim *>(ctx->dev.prim_plane); ps.shade = const_cast<ShadeRec *>(ctx->dev.shade);
+	ps.tri64 = const_cast<double *>(ctx->dev.tri64); ps.quad64 = const_cast<double *>(ctx->dev.quad64); ps.sph64 = const_cast<double *>(ctx->dev.sph64);
+	ps.rt_tris = const_cast<f4 *>(ctx->dev.rt_tris);
+	ps.n_tri = ctx->dev.n_tri; ps.n_quad = ctx->dev.n_quad;
+	launch_prim_scatter(ps, ctx->stream);
+	CK(cudaGetLastError());
+	std::string err;
+	const int launched = lbvh_refit(ctx->lbvh_ws, ctx->lbvh_ws_bytes, ctx->lbvh_items, m, d_item.as<int>(), d_rec.as<HotPrim>(), d_lo.as<f4>(), d_hi.as<f4>(),
+		const_cast<HotPrim *>(ctx->dev.bvh_prims), const_cast<BvhNode *>(ctx->dev.nodes), ctx->stream, err);
+	if (launched < 0) return fail(ctx, ARE_ERR_CUDA, "refit: " + err);
+	CK(cudaEventRecord(ctx->ev1, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+	return ARE_OK;
+}
+
+int are_cuda_refit(are_cuda_ctx *ctx, double *device_ms) {
+	Range nvtx_range("are_cuda_refit");
+	int st = need_commit(ctx);
+	if (st) return st;
+	if (ctx->parent) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "refit the group's first context");
+	if (device_ms) *device_ms = 0.0;
+	CompiledScene &cs = ctx->cs;
+	const size_t np = ctx->scene.prims.size();
+	// eligible: hierarchy built on the device over items that are the primitives themselves (nothing fused, no boxes)
+	if (ctx->lbvh_items <= 1 || cs.lb_lo.size() != np || cs.info.size() != np)
+		return fail(ctx, ARE_ERR_RUNTIME, "refit needs a device-built hierarchy (ARE_BVH_BUILDER_DEVICE_LBVH) over unfused primitives: commit instead");
+	if (ctx->dirty.empty()) return ARE_OK;
+	std::vector<int> dp_of_user(np), item_of_dp(np);
+	for (size_t dp = 0; dp < np; ++dp) dp_of_user[(size_t)cs.info[dp].user_id] = (int)dp;
+	for (size_t i = 0; i < np; ++i) {
+		const HotIds id = cs.lb_ids[(size_t)cs.lb_slot[i]];
+		if (id.a < 0 || id.b != -1) return fail(ctx, ARE_ERR_RUNTIME, "refit needs unfused primitives: commit instead");
+		item_of_dp[(size_t)id.a] = (int)i;
+	}
+	const int m = (int)ctx->dirty.size();
+	std::vector<int> item(m), dpv(m);
+	std::vector<HotPrim> rec(m);
+	std::vector<f4> lo(m), hi(m), rt(3 * (size_t)m);
+	std::vector<double> geo(9 * (size_t)m, 0.0);
+	for (int k = 0; k < m; ++k) {
+		const HostPrim &p = ctx->scene.prims[(size_t)ctx->dirty[k]];
+		PrimUpdate u;
+		if (!prim_update_records(p, u)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "updated primitive is degenerate");
+		const int dp = dp_of_user[(size_t)ctx->dirty[k]];
+		dpv[k] = dp; item[k] = item_of_dp[(size_t)dp];
+		rec[k] = u.rec; lo[k] = u.lo; hi[k] = u.hi;
+		for (int i = 0; i < 3; ++i) rt[3 * (size_t)k + i] = u.rt[i];
+		double *g = &geo[9 * (size_t)k];
+		if (p.type == PT_SPHERE) { g[0] = p.Q[0]; g[1] = p.Q[1]; g[2] = p.Q[2]; g[3] = p.u[0]; }
+		else { std::memcpy(g, p.Q, 24); std::memcpy(g + 3, p.u, 24); std::memcpy(g + 6, p.v, 24); }
+		// keep the host copies in step (multi-device peers and later refits read them)
+		cs.prim_plane[(size_t)dp] = u.rec;
+		if (p.type != PT_SPHERE) { cs.shade[(size_t)dp].r0.x = u.rec.r0.x; cs.shade[(size_t)dp].r0.y = u.rec.r0.y; cs.shade[(size_t)dp].r0.z = u.rec.r0.z; }
+		cs.lb_prims[(size_t)cs.lb_slot[(size_t)item[k]]] = u.rec;
+		cs.lb_lo[(size_t)item[k]] = u.lo; cs.lb_hi[(size_t)item[k]] = u.hi;
+	}
+	float ms = 0.f, worst = 0.f;
+	st = refit_device(ctx, cs, item, dpv, rec, lo, hi, geo, rt, ms);
+	worst = ms;
+	for (size_t i = 0; st == ARE_OK && i < ctx->peers.size(); ++i) {
+		st = refit_device(ctx->peers[i], cs, item, dpv, rec, lo, hi, geo, rt, ms);
+		if (st != ARE_OK) fail(ctx, st, ctx->peers[i]->err);
+		worst = std::max(worst, ms);
+	}
+	if (st != ARE_OK) return st;
+	for (int id : ctx->dirty) ctx->dirty_flag[(size_t)id] = 0;
+	ctx->dirty.clear();
+	if (device_ms) *device_ms = worst;
 	return ARE_OK;
 }
 
@@ -966,7 +1104,29 @@ static int render_single(are_cuda_ctx *ctx, const are_camera *cam, const are_ren
 				std::string err;
 				launched = bake_launch(ctx->baked, a, blocks, threads, smem, ctx->stream, err);
 				if (launched < 0) return fail(ctx, ARE_ERR_CUDA, err);
-			} else launched = launch_render_path(a, mode, count_tests != 0, ctx->stream);
+			} else {
+				// the hierarchy of a large scene lives in L2; optionally pin (a share of) the node array there
+				// for the duration of the launch so that primitive records and accumulator traffic cannot evict it
+				const bool persist = mode != 0 && ctx->opt_l2_persist > 0 && ctx->dev.n_nodes > 0 && ctx->l2_persist_max > 0;
+				if (persist) {
+					cudaStreamAttrValue av;
+					std::memset(&av, 0, sizeof av);
+					const size_t bytes = std::min((size_t)ctx->dev.n_nodes * sizeof(BvhNode), ctx->l2_window_max);
+					av.accessPolicyWindow.base_ptr = const_cast<BvhNode *>(ctx->dev.nodes);
+					av.accessPolicyWindow.num_bytes = bytes;
+					// value = per cent of the persisting carve-out the window may claim (100: all of it)
+					av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)ctx->l2_persist_max * (ctx->opt_l2_persist / 100.0) / (double)bytes);
+					av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+					av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+					CK(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+				}
+				launched = launch_render_path(a, mode, count_tests != 0, ctx->stream);
+				if (persist) {
+					cudaStreamAttrValue av;
+					std::memset(&av, 0, sizeof av);
+					CK(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+				}
+			}
 		}
 		if (launched < 0) return fail(ctx, ARE_ERR_CUDA, "render launch configuration rejected");
 		CK(cudaGetLastError());

@@ -147,6 +147,7 @@ struct DevScene {
 	const TextureRec *texs;
 	const float *tex_data;
 	int n_mat, n_tex;
+	int has_noise;             // some texture is TK_NOISE: the render loop runs its cooperative turbulence stage
 };
 
 // camera basis precomputed on the host in fp64 (mirrors oracle cam_setup; experiments/rt.cpp:339-343)

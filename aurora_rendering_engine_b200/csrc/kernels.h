@@ -89,4 +89,27 @@ struct LbvhOutput {
 size_t lbvh_workspace_bytes(int n_items);
 int lbvh_build(const LbvhInput &in, LbvhOutput &out, void *workspace, size_t workspace_bytes, cudaStream_t s, std::string &err);
 
+// Refit of the hierarchy lbvh_build left in `workspace` (same n_items; nothing else may have used the workspace since):
+// m primitives moved — item index item[k] (= device primitive index in a scene without fused items), new record rec[k]
+// and conservative bounds lo[k] / hi[k] — their leaf records and boxes are replaced and every node box is recomputed
+// bottom-up over the unchanged topology.  Returns kernels launched, < 0 on a CUDA error.
+// ... and of the per-primitive device arrays the shading stage and the fp64 harness read (device primitive index dp[k]):
+// plane form / sphere record, the geometric normal inside the shading record, the fp64 (Q,u,v) / (c,r) copy (geo64: 9
+// doubles per update, spheres use 4), the rt.cpp-style triangle record.
+struct PrimScatterArgs {
+	int m;
+	const int *dp;
+	const HotPrim *rec;
+	const double *geo64;
+	const f4 *rt;  // 3 per update
+	HotPrim *prim_plane;
+	ShadeRec *shade;
+	double *tri64, *quad64, *sph64;
+	f4 *rt_tris;
+	int n_tri, n_quad;
+};
+void launch_prim_scatter(const PrimScatterArgs &a, cudaStream_t s);
+int lbvh_refit(void *workspace, size_t workspace_bytes, int n_items, int m, const int *item, const HotPrim *rec, const f4 *lo, const f4 *hi,
+	HotPrim *prims, BvhNode *nodes, cudaStream_t s, std::string &err);
+
 }  // namespace areb

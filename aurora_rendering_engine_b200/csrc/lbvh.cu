@@ -160,6 +160,42 @@ __global__ void k_lbvh_boxes(int n, const int2 *__restrict__ child, const int *_
 	}
 }
 
+// refit: leaf of every item (inverse of the sort permutation), then the moved items' records and boxes into their leaves
+__global__ void k_lbvh_leaf_of_item(int n, const int *__restrict__ item_sorted, int *__restrict__ leaf_of_item) {
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j < n) leaf_of_item[item_sorted[j]] = j;
+}
+__global__ void k_lbvh_refit_leaves(int m, const int *__restrict__ item, const HotPrim *__restrict__ rec, const f4 *__restrict__ lo, const f4 *__restrict__ hi,
+	const int *__restrict__ leaf_of_item, const int *__restrict__ slot, HotPrim *__restrict__ prims, f4 *__restrict__ leaf_lo, f4 *__restrict__ leaf_hi) {
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= m) return;
+	const int j = leaf_of_item[item[k]];
+	prims[slot[j]] = rec[k];
+	leaf_lo[j] = lo[k];
+	leaf_hi[j] = hi[k];
+}
+
+__global__ void k_prim_scatter(const PrimScatterArgs a) {
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= a.m) return;
+	const int dp = a.dp[k];
+	const HotPrim r = a.rec[k];
+	a.prim_plane[dp] = r;
+	const double *g = a.geo64 + 9 * (size_t)k;
+	if (dp < a.n_tri + a.n_quad) {
+		ShadeRec sr = a.shade[dp];
+		sr.r0.x = r.r0.x; sr.r0.y = r.r0.y; sr.r0.z = r.r0.z;  // the geometric normal; material bits and colour stay
+		a.shade[dp] = sr;
+		double *dst = dp < a.n_tri ? a.tri64 + 9 * (size_t)dp : a.quad64 + 9 * (size_t)(dp - a.n_tri);
+		for (int i = 0; i < 9; ++i) dst[i] = g[i];
+		if (dp < a.n_tri)
+			for (int i = 0; i < 3; ++i) a.rt_tris[3 * (size_t)dp + i] = a.rt[3 * (size_t)k + i];
+	} else {
+		double *dst = a.sph64 + 4 * (size_t)(dp - a.n_tri - a.n_quad);
+		for (int i = 0; i < 4; ++i) dst[i] = g[i];
+	}
+}
+
 // carves 256-byte aligned arrays out of the caller's workspace
 struct Carver {
 	unsigned char *base;
@@ -183,12 +219,6 @@ cudaError_t cub_temp_bytes(int n, size_t &bytes) {
 
 }  // namespace
 
-#define LB(call)                                                          \
-	do {                                                                  \
-		cudaError_t e_ = (call);                                          \
-		if (e_ != cudaSuccess) { err = cudaGetErrorString(e_); return -1; } \
-	} while (0)
-
 size_t lbvh_workspace_bytes(int n_items) {
 	const size_t n = n_items > 0 ? (size_t)n_items : 1;
 	size_t cub_bytes = 0;
@@ -198,6 +228,51 @@ size_t lbvh_workspace_bytes(int n_items) {
 	return 2 * al(n * 4) + 9 * al(n * 4) + al(n * 8) + 4 * al(n * 16) + al(cub_bytes) + 256;
 }
 
+#define LB(call)                                                          \
+	do {                                                                  \
+		cudaError_t e_ = (call);                                          \
+		if (e_ != cudaSuccess) { err = cudaGetErrorString(e_); return -1; } \
+	} while (0)
+
+// The workspace layout, shared by build and refit (the refit reads what the build left behind).
+struct LbvhArrays {
+	unsigned *code, *code_sorted;
+	int *item, *item_sorted, *size, *slot, *leaf_ref, *parent_inner, *parent_leaf, *node_height, *arrivals;
+	int2 *child;
+	f4 *leaf_lo, *leaf_hi, *node_lo, *node_hi;
+	explicit LbvhArrays(void *workspace, int n) {
+		Carver sc{ static_cast<unsigned char *>(workspace) };
+		code = sc.get<unsigned>(n); code_sorted = sc.get<unsigned>(n);
+		item = sc.get<int>(n); item_sorted = sc.get<int>(n); size = sc.get<int>(n); slot = sc.get<int>(n); leaf_ref = sc.get<int>(n);
+		parent_inner = sc.get<int>(n); parent_leaf = sc.get<int>(n); node_height = sc.get<int>(n); arrivals = sc.get<int>(n);
+		child = sc.get<int2>(n);
+		leaf_lo = sc.get<f4>(n); leaf_hi = sc.get<f4>(n); node_lo = sc.get<f4>(n); node_hi = sc.get<f4>(n);
+	}
+};
+
+void launch_prim_scatter(const PrimScatterArgs &a, cudaStream_t s) {
+	if (a.m > 0) k_prim_scatter<<<(a.m + 255) / 256, 256, 0, s>>>(a);
+}
+
+int lbvh_refit(void *workspace, size_t workspace_bytes, int n_items, int m, const int *item, const HotPrim *rec, const f4 *lo, const f4 *hi,
+	HotPrim *prims, BvhNode *nodes, cudaStream_t s, std::string &err) {
+	const int n = n_items;
+	if (n <= 1 || m <= 0) return 0;
+	if (!workspace || workspace_bytes < lbvh_workspace_bytes(n)) { err = "device BVH refit: workspace too small"; return -1; }
+	LbvhArrays w(workspace, n);
+	const int B = 256;
+	// `item` (unsorted ids, dead after the sort) is reused as the leaf-of-item map; `code` is free as well
+	int *leaf_of_item = w.item;
+	k_lbvh_leaf_of_item<<<(n + B - 1) / B, B, 0, s>>>(n, w.item_sorted, leaf_of_item);
+	LB(cudaGetLastError());
+	k_lbvh_refit_leaves<<<(m + B - 1) / B, B, 0, s>>>(m, item, rec, lo, hi, leaf_of_item, w.slot, prims, w.leaf_lo, w.leaf_hi);
+	LB(cudaGetLastError());
+	LB(cudaMemsetAsync(w.arrivals, 0, (size_t)n * sizeof(int), s));
+	k_lbvh_boxes<<<(n + B - 1) / B, B, 0, s>>>(n, w.child, w.parent_inner, w.parent_leaf, w.leaf_ref, w.leaf_lo, w.leaf_hi, w.node_lo, w.node_hi, w.node_height, w.arrivals, nodes);
+	LB(cudaGetLastError());
+	return 3;
+}
+
 int lbvh_build(const LbvhInput &in, LbvhOutput &out, void *workspace, size_t workspace_bytes, cudaStream_t s, std::string &err) {
 	const int n = in.n_items;
 	out.height = 0;
@@ -205,15 +280,16 @@ int lbvh_build(const LbvhInput &in, LbvhOutput &out, void *workspace, size_t wor
 	out.n_nodes = 0;
 	if (n <= 0) return 0;
 	if (!workspace || workspace_bytes < lbvh_workspace_bytes(n)) { err = "device BVH build: workspace too small"; return -1; }
-	Carver sc{ static_cast<unsigned char *>(workspace) };
-	unsigned *code = sc.get<unsigned>(n), *code_sorted = sc.get<unsigned>(n);
-	int *item = sc.get<int>(n), *item_sorted = sc.get<int>(n), *size = sc.get<int>(n), *slot = sc.get<int>(n), *leaf_ref = sc.get<int>(n);
-	int *parent_inner = sc.get<int>(n), *parent_leaf = sc.get<int>(n), *node_height = sc.get<int>(n), *arrivals = sc.get<int>(n);
-	int2 *child = sc.get<int2>(n);
-	f4 *leaf_lo = sc.get<f4>(n), *leaf_hi = sc.get<f4>(n), *node_lo = sc.get<f4>(n), *node_hi = sc.get<f4>(n);
+	LbvhArrays w(workspace, n);
+	unsigned *code = w.code, *code_sorted = w.code_sorted;
+	int *item = w.item, *item_sorted = w.item_sorted, *size = w.size, *slot = w.slot, *leaf_ref = w.leaf_ref;
+	int *parent_inner = w.parent_inner, *parent_leaf = w.parent_leaf, *node_height = w.node_height, *arrivals = w.arrivals;
+	int2 *child = w.child;
+	f4 *leaf_lo = w.leaf_lo, *leaf_hi = w.leaf_hi, *node_lo = w.node_lo, *node_hi = w.node_hi;
 	size_t cub_bytes = 0;
 	LB(cub_temp_bytes(n, cub_bytes));
-	unsigned char *tmp = sc.get<unsigned char>(cub_bytes);
+	// cub's temporary storage sits behind the arrays
+	unsigned char *tmp = reinterpret_cast<unsigned char *>(w.node_hi) + (((size_t)n * sizeof(f4) + 255) & ~(size_t)255);
 	const int B = 256, G = (n + B - 1) / B;
 	float3 cmin = make_float3(in.cmin[0], in.cmin[1], in.cmin[2]), scale;
 	const float ext[3] = { in.cmax[0] - in.cmin[0], in.cmax[1] - in.cmin[1], in.cmax[2] - in.cmin[2] };

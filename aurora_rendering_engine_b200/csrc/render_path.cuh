@@ -293,6 +293,28 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 		}
 		// ---- C. one Philox draw per lane: camera ray for a new path, scatter for a continuing one -------
 		if (!trav) ray_ok = false;  // a suspended traversal keeps its ray
+		// C0. Noise-textured surfaces: the lanes about to scatter on one hand their turbulence sums to the whole warp
+		// (shade.cuh: turbulence_coop) instead of each walking seven octaves alone in a nearly empty warp.
+		float turb = 0.0f;
+		bool have_turb = false;
+		if (!LEAN && A.sc.has_noise) {
+			const bool general = task >= 0 && !trav && bounce > 0 && !(sbits >> 8);
+			if (__any_sync(full, general)) {
+				int noise_tex = -1;
+				if (general) {
+					const PrimInfo pi = A.sc.info[resolve_exact(A.sc, HotIds{ sdev, -1 }, sP).dev_prim];
+					const MaterialRec &m = A.sc.mats[pi.mat];
+					if (m.kind != MK_DIELECTRIC && m.kind != MK_LIGHT) {
+						const int t = mat_texture(m, pi.tex);
+						if (A.sc.texs[t].kind == TK_NOISE) noise_tex = t;
+					}
+				}
+				if (__any_sync(full, noise_tex >= 0)) {
+					turb = turbulence_coop(A.sc, noise_tex >= 0, noise_tex, sP);
+					have_turb = noise_tex >= 0;
+				}
+			}
+		}
 		if (task >= 0 && !trav) {
 			// task -> (pixel of the tile, sample): recomputed here instead of living in four registers across the trip
 			const int px = x0 + (task & 7), py = y0 + ((task >> 3) & 3);
@@ -316,7 +338,7 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 					float u, v;
 					F3 att, emit;
 					surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, u, v);
-					alive = scatter<float>(A.sc, pi.mat, pi.tex, d, sN, sP, u, v, r, wo, att, emit);
+					alive = scatter<float>(A.sc, pi.mat, pi.tex, d, sN, sP, u, v, r, wo, att, emit, have_turb ? &turb : nullptr);
 					thr = thr * att;
 				}
 				if (alive) {

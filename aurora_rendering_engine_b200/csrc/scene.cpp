@@ -557,6 +557,46 @@ void make_rt_cam(const double pos[3], const double target[3], const double up[3]
 	out.scale = (float)std::tan((float)vfov_deg * 0.5f * 3.14159265358979323846 / 180.f);
 }
 
+bool prim_update_records(const HostPrim &p, PrimUpdate &o) {
+	const float inf = std::numeric_limits<float>::infinity();
+	auto down = [&](double x) { float f = (float)x; return (double)f > x ? std::nextafter(f, -inf) : f; };
+	auto up = [&](double x) { float f = (float)x; return (double)f < x ? std::nextafter(f, inf) : f; };
+	Box b;
+	b.reset();
+	const D3 Q = d3(p.Q), u = d3(p.u), v = d3(p.v);
+	int kind;
+	std::memset(o.rt, 0, sizeof o.rt);
+	if (p.type == PT_SPHERE) {
+		const double r = p.u[0];
+		if (!(r > 0.0) || !std::isfinite(r)) return false;
+		o.rec = sphere_form(Q, r);
+		b.grow(Q - D3{ r, r, r });
+		b.grow(Q + D3{ r, r, r });
+		kind = HK_SPHERE;
+	} else {
+		if (validate_edges(p.u, p.v)) return false;
+		o.rec = plane_form(Q, u, v);
+		b.grow(Q); b.grow(Q + u); b.grow(Q + v);
+		if (p.type == PT_QUAD) { b.grow(Q + u + v); kind = HK_QUAD; }
+		else {
+			kind = HK_TRI;
+			const float v0[3] = { (float)p.Q[0], (float)p.Q[1], (float)p.Q[2] };
+			const float e1[3] = { (float)p.u[0], (float)p.u[1], (float)p.u[2] }, e2[3] = { (float)p.v[0], (float)p.v[1], (float)p.v[2] };
+			volatile float cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+			volatile float l2 = cx * cx + cy * cy + cz * cz;
+			const float il = 1.0f / std::sqrt((float)l2);
+			o.rt[0] = { v0[0], v0[1], v0[2], e1[0] };
+			o.rt[1] = { e1[1], e1[2], e2[0], e2[1] };
+			o.rt[2] = { e2[2], cx * il, cy * il, cz * il };
+		}
+	}
+	float kindf;
+	std::memcpy(&kindf, &kind, 4);
+	o.lo = { down(b.lo[0]), down(b.lo[1]), down(b.lo[2]), kindf };
+	o.hi = { up(b.hi[0]), up(b.hi[1]), up(b.hi[2]), 0.f };
+	return true;
+}
+
 void set_build_threads(int n) { g_build_threads.store(n > 0 ? n : 0); }
 
 bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene &out, std::string &err) {

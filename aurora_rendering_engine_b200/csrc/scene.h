@@ -117,6 +117,16 @@ void set_build_threads(int n);
 // Returns false and fills err on inconsistent ids etc.
 bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene &out, std::string &err);
 
+// Refit support (are_cuda_refit): the derived records of ONE primitive whose geometry changed, by the formulas
+// compile_scene uses — plane form / sphere record, conservative fp32 bounds (lo.w = the test kind as int bits, the
+// device builder's convention), rt.cpp-style record for triangles.  False for geometry the validation rejects.
+struct PrimUpdate {
+	HotPrim rec;
+	f4 lo, hi;
+	f4 rt[3];
+};
+bool prim_update_records(const HostPrim &p, PrimUpdate &out);
+
 // Perlin tables: 256 unit gradients (xyz doubles) + 3x256 permutations from Philox(seed); spec shared with the oracle.
 void make_noise_tables(uint64_t seed, double *grad768, int *perm768);
 

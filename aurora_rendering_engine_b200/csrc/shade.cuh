@@ -84,8 +84,44 @@ __device__ inline double perlin_noise_tab<double>(const DevScene &sc, const Text
 	return acc;
 }
 
+// ---- warp-cooperative turbulence --------------------------------------------------------------------------------
+// A surface hit needs sum_{o<7} 2^-o noise(2^o P) — seven octaves of eight lattice corners, ~770 instructions — and in
+// the render loop only the few lanes whose ray ended on a noise-textured surface need it (5.7 of 32 on BASELINE config
+// 2), so evaluated lane by lane it is the most expensive and the emptiest code of the kernel.  Here the warp shares it:
+// the requesting lanes are counted off four at a time, lane l works on requester l/8 and octave l%8 (the eighth lane of
+// a group idles), i.e. ONE octave per lane with all 32 lanes busy, and three shuffle-adds form each requester's sum.
+// Called by all 32 lanes in converged code.  Returns the sum to the lanes that set `need`; 0 elsewhere.
+__device__ __forceinline__ float turbulence_coop(const DevScene &sc, bool need, int tex_id, V3<float> P) {
+	const unsigned full = 0xffffffffu;
+	const int lane = threadIdx.x & 31, slot = lane >> 3, oct = lane & 7;
+	unsigned m = __ballot_sync(full, need);
+	const int my_rank = __popc(m & ((1u << lane) - 1u));  // this lane is the my_rank-th requester (if it is one)
+	float result = 0.0f;
+	int round = 0;
+	while (m) {  // warp-uniform
+		const unsigned src = __fns(m, 0, slot + 1);  // lane of this group's requester, 0xffffffff when the round has fewer than slot + 1
+		const int s = src == 0xffffffffu ? 0 : (int)src;
+		const float px = __shfl_sync(full, P.x, s), py = __shfl_sync(full, P.y, s), pz = __shfl_sync(full, P.z, s);
+		const int tid = __shfl_sync(full, tex_id, s);
+		float v = 0.0f;
+		if (src != 0xffffffffu && oct < 7) {
+			const float up = (float)(1 << oct), w = 1.0f / up;  // exact powers of two: the same points and weights as repeated doubling / halving
+			v = w * perlin_noise<float>(sc.tex_data + sc.texs[tid].data_off, mk<float>(px * up, py * up, pz * up));
+		}
+		v += __shfl_xor_sync(full, v, 1);
+		v += __shfl_xor_sync(full, v, 2);
+		v += __shfl_xor_sync(full, v, 4);
+		const float got = __shfl_sync(full, v, ((my_rank - 4 * round) & 3) * 8);
+		if (need && my_rank >= 4 * round && my_rank < 4 * round + 4) result = got;
+		m &= m - 1; m &= m - 1; m &= m - 1; m &= m - 1;  // the four lowest requesters are served
+		++round;
+	}
+	return result;
+}
+
+// turb: when non-null, the turbulence sum of a TK_NOISE texture at P already formed by turbulence_coop
 template <typename T>
-__device__ V3<T> tex_eval(const DevScene &sc, int id, T u, T v, V3<T> P) {
+__device__ V3<T> tex_eval(const DevScene &sc, int id, T u, T v, V3<T> P, const T *turb = nullptr) {
 	const TextureRec &t = sc.texs[id];
 	switch (t.kind) {
 	case TK_SOLID:
@@ -102,11 +138,13 @@ __device__ V3<T> tex_eval(const DevScene &sc, int id, T u, T v, V3<T> P) {
 	case TK_NOISE: {
 		T acc = T(0), weight = T(1);
 		V3<T> q = P;
-		for (int i = 0; i < 7; ++i) {
-			acc += weight * perlin_noise_tab<T>(sc, t, q);
-			weight *= T(0.5);
-			q = T(2) * q;
-		}
+		if (turb) acc = *turb;
+		else
+			for (int i = 0; i < 7; ++i) {
+				acc += weight * perlin_noise_tab<T>(sc, t, q);
+				weight *= T(0.5);
+				q = T(2) * q;
+			}
 		T g = T(0.5) * (T(1) + sin_t(tparam<T>(t, 0) * P.z + T(10) * abs_t(acc)));
 		return mk<T>(g, g, g);
 	}
@@ -212,7 +250,7 @@ __device__ __forceinline__ bool scatter_dir(int lobe, T p0, V3<T> wi, V3<T> Ng, 
 // Material response, general path (any texture kind). Returns alive.
 template <typename T>
 __device__ bool scatter(const DevScene &sc, int mat, int tex, V3<T> wi, V3<T> Ng, V3<T> P, T u, T v, Rnd4<T> r,
-	V3<T> &wo, V3<T> &att, V3<T> &emit) {
+	V3<T> &wo, V3<T> &att, V3<T> &emit, const T *turb = nullptr) {
 	const MaterialRec &m = sc.mats[mat];
 	emit = mk<T>(T(0), T(0), T(0));
 	att = emit;
@@ -230,7 +268,7 @@ __device__ bool scatter(const DevScene &sc, int mat, int tex, V3<T> wi, V3<T> Ng
 		att = mk<T>(mparam<T>(m, 1), mparam<T>(m, 2), mparam<T>(m, 3));
 		return scatter_dir<T>(MK_REFLECTIVE, T(0), wi, Ng, r, wo);
 	}
-	att = tex_eval<T>(sc, mat_texture(m, tex), u, v, P);
+	att = tex_eval<T>(sc, mat_texture(m, tex), u, v, P, turb);
 	return scatter_dir<T>(kind == MK_METAL ? MK_METAL : MK_LAMBERTIAN, kind == MK_METAL ? mparam<T>(m, 0) : T(0), wi, Ng, r, wo);
 }
 

@@ -69,6 +69,7 @@ def parse():
     ap.add_argument("--kernel", default="auto", choices=["auto", "lean", "generic", "baked-packed"],
                     help="A/B: auto = scene-specialised (baked) kernel where the scene has a lean form; lean = precompiled lean kernel; generic = generic brute-force kernel")
     ap.add_argument("--builder", type=int, default=-1, help="BVH builder: 0 host SAH, 1 device LBVH (default: host; device for the 1 M-primitive scene)")
+    ap.add_argument("--l2-persist", type=int, default=0, help="A/B: BVH renders mark the node array L2-persisting, per cent of the carve-out (ARE_OPT_L2_PERSIST_NODES)")
     ap.add_argument("--job-spp", type=int, default=1024, help="strong-scaling job: total samples per pixel sharded over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -517,8 +518,11 @@ def run_traffic_probe(a):
 
 def kernel_options(a):
     from aurora_rendering_engine_b200 import capi
-    return {"lean": {capi.OPT_BAKED_KERNEL: 0}, "generic": {capi.OPT_BAKED_KERNEL: 0, capi.OPT_LEAN_KERNEL: 0},
-            "baked-packed": {capi.OPT_BAKED_PACKED: 1}}.get(a.kernel, {})
+    o = dict({"lean": {capi.OPT_BAKED_KERNEL: 0}, "generic": {capi.OPT_BAKED_KERNEL: 0, capi.OPT_LEAN_KERNEL: 0},
+              "baked-packed": {capi.OPT_BAKED_PACKED: 1}}.get(a.kernel, {}))
+    if a.l2_persist:
+        o[capi.OPT_L2_PERSIST_NODES] = a.l2_persist
+    return o
 
 
 def measure_other_config(a, name, S, peaks, steps=3, warmup=3):

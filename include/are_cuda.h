@@ -187,7 +187,9 @@ typedef enum are_option {
 	ARE_OPT_FUSE_BOXES = 5, /* 1 (default): parallelograms forming a parallelepiped become one slab test */
 	ARE_OPT_BUILD_WIDE = 6, /* 0 (default) / 1: also build the compressed 8-wide BVH for scenes beyond 65536 nodes */
 	ARE_OPT_WIDE_MIN_NODES = 7, /* ARE_TRAVERSAL_AUTO picks the 8-wide BVH above this node count (default: never) */
-	ARE_OPT_LBVH_MAX_HEIGHT = 8 /* test hook: device-built trees taller than this fall back to the host builder */
+	ARE_OPT_LBVH_MAX_HEIGHT = 8, /* test hook: device-built trees taller than this fall back to the host builder */
+	ARE_OPT_L2_PERSIST_NODES = 9 /* 0 (default) / 1..100: BVH renders mark the node array as an L2-persisting access window
+	                                (cudaAccessPolicyWindow) claiming this per cent of the device's persisting carve-out */
 } are_option;
 int are_cuda_set_option(are_cuda_ctx *ctx, int option, int value);
 /* The sm_100a CUBIN of the committed scene's baked kernel (what cuobjdump -sass / nvdisasm -g read next to an ncu capture).
@@ -213,6 +215,17 @@ int are_cuda_clear(are_cuda_ctx *ctx);
 int are_cuda_num_primitives(are_cuda_ctx *ctx);
 /* Flatten to SoA, build the BVH (host, binned SAH) and upload. Returns bytes uploaded via *h2d_bytes (may be NULL). */
 int are_cuda_commit(are_cuda_ctx *ctx, uint64_t *h2d_bytes);
+
+/* Moving primitives of a committed scene without rebuilding its hierarchy (refit).  update_* replace the
+ * geometry of existing primitives (same ids, same types, same validation as the add_* calls); are_cuda_refit then writes
+ * the moved primitives' records into their leaves and recomputes every node box bottom-up over the UNCHANGED topology of
+ * the device-built tree: three kernels, well under a millisecond per million primitives, against a full commit.  The
+ * tree loses quality as primitives move far; commit again from time to time.  Requires ARE_BVH_BUILDER_DEVICE_LBVH and a
+ * scene whose hot items are its primitives (no fused parallelograms / boxes) — otherwise ARE_ERR_RUNTIME, and the caller
+ * commits instead (the updates are kept).  device_ms (may be NULL): CUDA-event time of the refit kernels. */
+int are_cuda_update_triangles(are_cuda_ctx *ctx, int n, const int *prim_ids, const double *Q, const double *u, const double *v);
+int are_cuda_update_spheres(are_cuda_ctx *ctx, int n, const int *prim_ids, const double *center, const double *radius);
+int are_cuda_refit(are_cuda_ctx *ctx, double *device_ms);
 
 /* Host-only probe of the scene compiler (no GPU needed): flattens n_tri triangles exactly as are_cuda_commit would
  * and reports out[8] = { hot slots, fused triangle pairs, boxes, BVH nodes, BVH depth, brute quads, brute triangles,

@@ -138,3 +138,77 @@ def test_lbvh_falls_back_to_host_builder_when_too_deep(ctx, monkeypatch):
     assert st.rays == sr.rays and np.array_equal(img, ref)
     info = _commit(ctx, sc, capi.BVH_BUILDER_DEVICE_LBVH)
     assert info.builder == capi.BVH_BUILDER_DEVICE_LBVH and info.bvh_height > 5
+
+
+def test_refit_after_moving_primitives(ctx):
+    """SURVEY §8f-2 refit: move a third of the primitives of a device-built scene, refit the hierarchy over its unchanged
+    topology, and get exactly what a fresh commit of the moved scene gives — closest hits (fp32 traversal AND the fp64
+    harness, i.e. the per-primitive arrays moved too), and the rendered image up to summation order."""
+    sc = scenes.stress(n_prims=20_000, width=96, height=54)
+    cam = capi.make_camera(**sc.camera_args())
+    par = capi.make_params(**sc.params_args(sample_count=4, traversal=2))
+    info = _commit(ctx, sc, capi.BVH_BUILDER_DEVICE_LBVH)
+    assert info.builder == capi.BVH_BUILDER_DEVICE_LBVH
+    before, _ = ctx.render(cam, par)
+    rng = np.random.RandomState(3)
+    ns, nt = len(sc.spheres), len(sc.tris)
+    ms = rng.choice(ns, ns // 3, replace=False)          # stress(): spheres are primitives 0..ns-1, triangles ns..ns+nt-1
+    mt = rng.choice(nt, nt // 3, replace=False)
+    for i in ms:
+        c, r, m, t = sc.spheres[i]
+        sc.spheres[i] = (c + rng.normal(scale=0.3, size=3), r * rng.uniform(0.7, 1.4), m, t)
+    for i in mt:
+        Q, u, v, m, t, uv = sc.tris[i]
+        sc.tris[i] = (Q + rng.normal(scale=0.3, size=3), u * rng.uniform(0.8, 1.3), v + 0.2 * u, m, t, uv)
+    ctx.update_spheres(ms, np.stack([sc.spheres[i][0] for i in ms]), np.array([sc.spheres[i][1] for i in ms]))
+    ctx.update_triangles(ns + mt, np.stack([sc.tris[i][0] for i in mt]), np.stack([sc.tris[i][1] for i in mt]), np.stack([sc.tris[i][2] for i in mt]))
+    dev_ms = ctx.refit()
+    assert 0 < dev_ms < 50
+    img, st = ctx.render(cam, par)
+    assert not np.array_equal(img, before)
+    Q = rng.uniform(-12, 12, (100_000, 3))
+    D = rng.normal(size=(100_000, 3))
+    got32 = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=2)
+    got64 = ctx.hit_batch(Q, D, t_min=1e-3, precision=64)
+    with capi.Context(0) as fresh:                        # the moved scene committed from scratch
+        fresh.set_bvh_builder(capi.BVH_BUILDER_DEVICE_LBVH)
+        sc.feed(fresh)
+        fresh.commit()
+        ref, sr = fresh.render(cam, par)
+        want32 = fresh.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=2)
+        want64 = fresh.hit_batch(Q, D, t_min=1e-3, precision=64)
+    for a, b in zip(got32, want32):
+        assert np.array_equal(a, b, equal_nan=True)
+    for a, b in zip(got64, want64):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert st.rays == sr.rays and np.allclose(img, ref, rtol=1e-5, atol=1e-5)
+    # a second refit on top of the first (dirty list re-armed), then moving things back gives the first image again
+    ctx.update_spheres(ms[:10], np.stack([sc.spheres[i][0] for i in ms[:10]]) + 1.0, np.array([sc.spheres[i][1] for i in ms[:10]]))
+    ctx.refit()
+    ctx.update_spheres(ms[:10], np.stack([sc.spheres[i][0] for i in ms[:10]]), np.array([sc.spheres[i][1] for i in ms[:10]]))
+    ctx.refit()
+    again, _ = ctx.render(cam, par)
+    assert np.allclose(again, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_refit_refuses_what_it_cannot_do(ctx):
+    """Host-built hierarchies and scenes with fused items (the Cornell box: parallelograms, boxes) are not refittable: the
+    call says so and the caller commits; wrong ids / types / degenerate geometry are rejected at update time."""
+    sc = scenes.stress(n_prims=2000, width=32, height=32)
+    _commit(ctx, sc, capi.BVH_BUILDER_HOST_SAH)
+    ctx.update_spheres([0], [[0.0, 0.0, 0.0]], [0.05])
+    with pytest.raises(capi.AreCudaError, match="commit instead"):
+        ctx.refit()
+    ctx.commit()   # the update is kept: a commit picks it up
+    with pytest.raises(capi.AreCudaError):
+        ctx.update_spheres([len(sc.spheres)], [[0.0, 0.0, 0.0]], [0.05])      # that id is a triangle
+    with pytest.raises(capi.AreCudaError):
+        ctx.update_spheres([0], [[0.0, 0.0, 0.0]], [-1.0])
+    with pytest.raises(capi.AreCudaError):
+        ctx.update_triangles([len(sc.spheres)], [[0.0, 0.0, 0.0]], [[1.0, 0.0, 0.0]], [[2.0, 0.0, 0.0]])  # collinear edges
+    box = scenes.cornell_box(width=32, height=32)
+    _commit(ctx, box, capi.BVH_BUILDER_DEVICE_LBVH)
+    Q, u, v, *_ = box.tris[0]
+    ctx.update_triangles([0], [Q + 1.0], [u], [v])
+    with pytest.raises(capi.AreCudaError, match="commit instead"):
+        ctx.refit()
