@@ -54,7 +54,7 @@ class CommitInfo(C.Structure):
 
 
 BVH_BUILDER_HOST_SAH, BVH_BUILDER_DEVICE_LBVH = 0, 1
-KERNEL_NONE, KERNEL_BRUTE, KERNEL_BRUTE_LEAN, KERNEL_BVH2, KERNEL_BVH2_BIG, KERNEL_WIDE, KERNEL_RT_AO, KERNEL_BRUTE_BAKED = range(8)
+KERNEL_NONE, KERNEL_BRUTE, KERNEL_BRUTE_LEAN, KERNEL_BVH2, KERNEL_BVH2_BIG, KERNEL_WIDE, KERNEL_RT_AO, KERNEL_BRUTE_BAKED, KERNEL_WAVEFRONT = range(9)
 (OPT_LEAN_KERNEL, OPT_BAKED_KERNEL, OPT_BAKED_PACKED, OPT_FUSE_PARALLELOGRAMS, OPT_FUSE_BOXES, OPT_BUILD_WIDE, OPT_WIDE_MIN_NODES,
  OPT_LBVH_MAX_HEIGHT, OPT_L2_PERSIST_NODES) = range(1, 10)
 

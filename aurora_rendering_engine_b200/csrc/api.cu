@@ -73,6 +73,8 @@ struct are_cuda_ctx {
 	are_cuda_ctx *parent = nullptr;
 	cudaEvent_t ev_done = nullptr;        // multi-device: this device's render of the current round is on its stream up to here
 	cudaEvent_t ev_red = nullptr;         // ... and its reduce kernel
+	void *wf_ws = nullptr;                // ray queues of the wavefront integrator, grown on demand
+	size_t wf_ws_bytes = 0;
 	float *stage = nullptr;               // first device, groups without full peer mapping: one frame of staging
 	size_t stage_elems = 0;
 	cudaStream_t own_stream = nullptr;    // peers run on their own non-blocking stream
@@ -327,6 +329,7 @@ void are_cuda_destroy(are_cuda_ctx *ctx) {
 	if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
 	if (ctx->ev_red) cudaEventDestroy(ctx->ev_red);
 	if (ctx->stage) cudaFree(ctx->stage);
+	if (ctx->wf_ws) cudaFree(ctx->wf_ws);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
@@ -1088,7 +1091,7 @@ static int render_single(are_cuda_ctx *ctx, const are_camera *cam, const are_ren
 		if (ctx->csp->n_tri == 0 || ctx->csp->n_quad != 0 || ctx->csp->n_sph != 0 || ctx->csp->n_tri > 1000)
 			return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "RT_AO integrator renders triangle-only scenes of at most 1000 triangles");
 		make_rt_cam(cam->pos, cam->target, cam->up, cam->vfov_deg, p->width, p->height, a.rtcam);
-	} else if (p->integrator != ARE_INTEGRATOR_PATH) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown integrator");
+	} else if (p->integrator != ARE_INTEGRATOR_PATH && p->integrator != ARE_INTEGRATOR_PATH_WAVEFRONT) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown integrator");
 	else if (!resolve_traversal(ctx, p->traversal, mode)) return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown traversal, or scene too large for brute-force traversal");
 	CK(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * sizeof(unsigned long long), ctx->stream));
 	if (stats) CK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -1096,7 +1099,19 @@ static int render_single(are_cuda_ctx *ctx, const are_camera *cam, const are_ren
 	bool baked = false;
 	if (p->sample_count > 0) {
 		if (p->integrator == ARE_INTEGRATOR_RT_AO) launched = launch_render_rtao(a, ctx->stream);
-		else {
+		else if (p->integrator == ARE_INTEGRATOR_PATH_WAVEFRONT) {
+			// ray queues: at most ~16 M rays in flight (1.7 GB), i.e. as many samples per pixel per batch as that allows
+			const size_t frame = (size_t)p->width * p->height;
+			const int batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)p->sample_count, ((size_t)16 << 20) / frame));
+			const size_t need = wavefront_workspace_bytes(p->width, p->height, batch);
+			if (ctx->wf_ws_bytes < need) {
+				if (ctx->wf_ws) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(ctx->wf_ws)); ctx->wf_ws = nullptr; ctx->wf_ws_bytes = 0; }
+				CK(cudaMalloc(&ctx->wf_ws, need));
+				ctx->wf_ws_bytes = need;
+			}
+			mode = 1;  // the wavefront extends through the BVH2
+			launched = launch_render_wavefront(a, count_tests != 0, batch, ctx->wf_ws, ctx->stream);
+		} else {
 			int blocks, threads;
 			size_t smem;
 			baked = mode == 0 && ctx->baked && ctx->opt_bake && render_path_is_lean(a) && render_path_lean_dims(a, blocks, threads, smem);
@@ -1156,6 +1171,7 @@ static int render_single(are_cuda_ctx *ctx, const are_camera *cam, const are_ren
 		stats->launches = (uint64_t)launched;
 		stats->kernel_variant = launched <= 0 ? ARE_KERNEL_NONE
 			: p->integrator == ARE_INTEGRATOR_RT_AO ? ARE_KERNEL_RT_AO
+			: p->integrator == ARE_INTEGRATOR_PATH_WAVEFRONT ? ARE_KERNEL_WAVEFRONT
 			: mode == 0 ? (baked ? ARE_KERNEL_BRUTE_BAKED : render_path_is_lean(a) ? ARE_KERNEL_BRUTE_LEAN : ARE_KERNEL_BRUTE)
 			: mode == 2 ? ARE_KERNEL_WIDE : (render_path_is_big(a) ? ARE_KERNEL_BVH2_BIG : ARE_KERNEL_BVH2);
 	}

@@ -256,8 +256,35 @@ __device__ __forceinline__ void test_leaf(const DevScene &sc, int ref, V3<float>
 // missed gets distance +inf, so "nearer child" also covers the one-hit case:
 //   near / far by two selects, push far if both were hit, pop if neither was.
 #define TRAV_DONE ((int)0x80000000)  // = ~(slot 2^29 - 1 | kind 3 << 29): the one leaf reference that cannot occur (hot arrays are far smaller)
-template <bool COUNT>
-__device__ __forceinline__ void bvh_step(const DevScene &sc, float tmin, const RaySlopes &rs, int &cur, int *&top, const Hit &h, TravCounters *cnt) {
+#define TRAV_DONE_V ((int)0x80000000)  // = TRAV_DONE (below)
+// Where the postponed children live.  PtrStack: a per-thread array in local memory walked by a pointer (the default).
+// ShortStack (north_star item 2, built with -DARE_SHORT_STACK=n): the first n entries of every thread sit in shared memory
+// (entry e of thread t at s[e][t]: conflict-free) and only a traversal that postpones more than n children at once
+// touches the local-memory overflow array.  Measured against PtrStack in profiles/r02_short_stack.md.
+struct PtrStack {
+	int *top;
+	__device__ __forceinline__ void reset(int *base) { base[0] = TRAV_DONE_V; top = base + 1; }
+	__device__ __forceinline__ void push(int v) { *top++ = v; }
+	__device__ __forceinline__ int pop() { return *--top; }
+};
+template <int N, int THREADS>
+struct ShortStack {
+	int *deep;      // local-memory overflow, entries N, N + 1, ...
+	int *sm;        // &s[0][thread]
+	int sp;
+	__device__ __forceinline__ void reset(int *base) { deep = base; sp = 1; sm[0] = TRAV_DONE_V; }
+	__device__ __forceinline__ void push(int v) {
+		if (sp < N) sm[sp * THREADS] = v;
+		else deep[sp - N] = v;
+		++sp;
+	}
+	__device__ __forceinline__ int pop() {
+		--sp;
+		return sp < N ? sm[sp * THREADS] : deep[sp - N];
+	}
+};
+template <bool COUNT, class STK>
+__device__ __forceinline__ void bvh_step(const DevScene &sc, float tmin, const RaySlopes &rs, int &cur, STK &stk, const Hit &h, TravCounters *cnt) {
 	const BvhNode *n = sc.nodes + cur;
 	const float4 b0 = ldg4(&n->b0), b1 = ldg4(&n->b1), b2 = ldg4(&n->b2);
 	const int2 ch = __ldg(reinterpret_cast<const int2 *>(&n->child[0]));
@@ -273,15 +300,15 @@ __device__ __forceinline__ void bvh_step(const DevScene &sc, float tmin, const R
 	const bool near0 = d0 <= d1;
 	int next = near0 ? ch.x : ch.y;
 	const int farc = near0 ? ch.y : ch.x;
-	if (hit0 & hit1) *top++ = farc;  // (measured: prefetch.global.L1 of the postponed child's node here: -1.3 % / -3.5 %)
-	if (!(hit0 | hit1)) next = *--top;
+	if (hit0 & hit1) stk.push(farc);  // (measured: prefetch.global.L1 of the postponed child's node here: -1.3 % / -3.5 %)
+	if (!(hit0 | hit1)) next = stk.pop();
 	cur = next;
 }
 // leaf phase of the single-cursor form: test the leaf under the cursor, then pop
-template <bool COUNT>
-__device__ __forceinline__ void bvh_leaf(const DevScene &sc, V3<float> o, V3<float> d, float tmin, int &cur, int *&top, Hit &h, TravCounters *cnt) {
+template <bool COUNT, class STK>
+__device__ __forceinline__ void bvh_leaf(const DevScene &sc, V3<float> o, V3<float> d, float tmin, int &cur, STK &stk, Hit &h, TravCounters *cnt) {
 	test_leaf<COUNT>(sc, cur, o, d, tmin, h, cnt);
-	cur = *--top;
+	cur = stk.pop();
 }
 
 // Whole traversal in one go (per-ray harness).
@@ -293,12 +320,12 @@ __device__ __forceinline__ void intersect_bvh(const DevScene &sc, V3<float> o, V
 	}
 	const RaySlopes rs = ray_slopes(o, d);
 	int stack[ARE_BVH_STACK];
-	stack[0] = TRAV_DONE;
-	int *top = stack + 1;
+	PtrStack stk;
+	stk.reset(stack);
 	int cur = 0;
 	while (cur != TRAV_DONE) {
-		if (cur >= 0) bvh_step<COUNT>(sc, tmin, rs, cur, top, h, cnt);
-		else bvh_leaf<COUNT>(sc, o, d, tmin, cur, top, h, cnt);
+		if (cur >= 0) bvh_step<COUNT>(sc, tmin, rs, cur, stk, h, cnt);
+		else bvh_leaf<COUNT>(sc, o, d, tmin, cur, stk, h, cnt);
 	}
 }
 

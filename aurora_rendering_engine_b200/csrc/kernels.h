@@ -50,6 +50,9 @@ bool render_path_is_lean(const RenderArgs &a);  // brute force: the lean kernel 
 bool render_path_lean_dims(const RenderArgs &a, int &blocks, int &threads, size_t &smem);  // launch shape of the lean (and baked) kernel
 bool render_path_is_big(const RenderArgs &a);   // BVH: the high-occupancy build is the one launched
 int launch_render_rtao(const RenderArgs &a, cudaStream_t s);
+// wavefront schedule of the same path integrator (wavefront.cu): generate / extend / shade + compact over ray queues in HBM
+size_t wavefront_workspace_bytes(int W, int H, int batch_spp);
+int launch_render_wavefront(const RenderArgs &a, bool count_tests, int batch_spp, void *workspace, cudaStream_t s);
 // gamma_thr: 256 floats, [v-1] = smallest c with the rt.cpp gamma encode >= v (v = 1..255), [255] = +inf (encoder 0 only)
 void launch_tonemap(const float *accum, int W, int H, double inv_spp, int encoder, const float *gamma_thr, uint8_t *out, cudaStream_t s);
 // dst[i] += sum_s src[s][i] over float4 indices [begin4, end4) and floats [tail_begin, tail_end): the per-device slice of

@@ -21,9 +21,9 @@ namespace areb {
 
 size_t brute_smem_limit_prims() { return BRUTE_MAX_PRIMS; }
 
-template <int MODE, bool COUNT, bool BIG = false, bool LEAN = false>
+template <int MODE, bool COUNT, bool BIG = false, bool LEAN = false, bool NOISE = true>
 __global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : (LEAN ? RENDER_MIN_BLOCKS_LEAN : (MODE == 1 ? RENDER_MIN_BLOCKS_BVH2 : RENDER_MIN_BLOCKS))) k_render_path(const __grid_constant__ RenderArgs A) {
-	render_path_body<MODE, COUNT, BIG, LEAN>(A);
+	render_path_body<MODE, COUNT, BIG, LEAN, false, NOISE>(A);
 }
 
 bool render_path_is_lean(const RenderArgs &a) { return a.sc.lean_ok && a.lean; }
@@ -42,32 +42,29 @@ int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStre
 	const int warps = ((a.W + 15) / 16) * ((a.H + 7) / 8) * 4;  // one warp per 8x4 tile
 	const int tiles = (warps + RENDER_THREADS / 32 - 1) / (RENDER_THREADS / 32);
 	if (tiles <= 0) return -1;
+	const bool noise = a.sc.has_noise != 0;  // scenes without noise textures run the builds without the cooperative turbulence stage
+#define LAUNCH(MODE, COUNT, BIG, smem)                                                                     \
+	do {                                                                                                   \
+		if (noise || COUNT) k_render_path<MODE, COUNT, BIG, false, true><<<tiles, RENDER_THREADS, smem, s>>>(a); \
+		else k_render_path<MODE, COUNT, BIG, false, false><<<tiles, RENDER_THREADS, smem, s>>>(a);           \
+	} while (0)
 	if (use_bvh) {
 		const bool big = render_path_is_big(a);
 		if (mode == 2) {
 			if (!a.sc.wnodes) return -1;
-			if (count_tests) {
-				if (big) k_render_path<2, true, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
-				else k_render_path<2, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
-			} else {
-				if (big) k_render_path<2, false, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
-				else k_render_path<2, false><<<tiles, RENDER_THREADS, 0, s>>>(a);
-			}
-		} else if (count_tests) {
-			if (big) k_render_path<1, true, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
-			else k_render_path<1, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
-		} else {
-			if (big) k_render_path<1, false, true><<<tiles, RENDER_THREADS, 0, s>>>(a);
-			else k_render_path<1, false><<<tiles, RENDER_THREADS, 0, s>>>(a);
-		}
+			if (count_tests) { if (big) LAUNCH(2, true, true, 0); else LAUNCH(2, true, false, 0); }
+			else { if (big) LAUNCH(2, false, true, 0); else LAUNCH(2, false, false, 0); }
+		} else if (count_tests) { if (big) LAUNCH(1, true, true, 0); else LAUNCH(1, true, false, 0); }
+		else { if (big) LAUNCH(1, false, true, 0); else LAUNCH(1, false, false, 0); }
 	} else {
 		if (!a.sc.brute || a.sc.n_hot > BRUTE_MAX_PRIMS) return -1;
 		size_t smem = (size_t)a.sc.n_hot * sizeof(HotPrim);
 		if (render_path_is_lean(a)) {
 			smem += (size_t)a.sc.n_lean_shade * (sizeof(ShadeRec) + 2 * sizeof(float4)) + (size_t)a.sc.n_hot * sizeof(int);
 			k_render_path<0, false, false, true><<<tiles, RENDER_THREADS, smem, s>>>(a);
-		} else k_render_path<0, false><<<tiles, RENDER_THREADS, smem, s>>>(a);
+		} else LAUNCH(0, false, false, smem);
 	}
+#undef LAUNCH
 	return 1;
 }
 

@@ -19,9 +19,8 @@ typedef V3<float> F3;
 #define BRUTE_MAX_PRIMS 512  // 24 KB of shared memory; larger scenes traverse the BVH
 
 __device__ __forceinline__ F3 background(const RenderArgs &A, F3 d) {
-	float a = 0.5f * (d.y + 1.0f);
-	return mk<float>((1.0f - a) * A.bg_bottom[0] + a * A.bg_top[0], (1.0f - a) * A.bg_bottom[1] + a * A.bg_top[1],
-		(1.0f - a) * A.bg_bottom[2] + a * A.bg_top[2]);
+	const float a = 0.5f * (d.y + 1.0f), b = 1.0f - a;
+	return mk<float>(fmaf(b, A.bg_bottom[0], a * A.bg_top[0]), fmaf(b, A.bg_bottom[1], a * A.bg_top[1]), fmaf(b, A.bg_bottom[2], a * A.bg_top[2]));
 }
 __device__ __forceinline__ bool finite3(F3 v) { return isfinite(v.x) && isfinite(v.y) && isfinite(v.z); }
 
@@ -73,7 +72,9 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 // BAKED (LEAN only): the closest-hit tests are not read from shared memory but are straight-line code generated from the
 // committed scene and compiled at commit time (bake.cpp): intersect_baked() with every primitive constant an immediate
 // and the zero components of its normals left out.  Everything else is the lean kernel.
-template <int MODE, bool COUNT, bool BIG = false, bool LEAN = false, bool BAKED = false>
+// NOISE = false: the scene has no noise texture, the cooperative turbulence stage is compiled out (its live values cost
+// the BVH kernels registers: RTIOW lost 4 % with the stage merely present).
+template <int MODE, bool COUNT, bool BIG = false, bool LEAN = false, bool BAKED = false, bool NOISE = true>
 __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 	constexpr bool BVH = MODE != 0, WIDE = MODE == 2;
 	static_assert(!LEAN || MODE == 0, "the lean form is a brute-force list");
@@ -134,7 +135,14 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 	bool trav = false;  // BVH: traversal in progress
 	int node = 0, sp = 0;  // BVH2: `node` is the traversal cursor (intersect.cuh: bvh_step); 8-wide: sp indexes wstack
 	int stack[MODE == 1 ? ARE_BVH_STACK : 1];
-	int *top = stack;  // BVH2 stack pointer
+#ifdef ARE_SHORT_STACK
+	__shared__ int s_short[MODE == 1 ? ARE_SHORT_STACK : 1][RENDER_THREADS];
+	ShortStack<ARE_SHORT_STACK, RENDER_THREADS> stk;
+	stk.sm = &s_short[0][threadIdx.x]; stk.deep = stack; stk.sp = 0;
+#else
+	PtrStack stk;  // BVH2 stack pointer
+	stk.top = stack;
+#endif
 	uint2 ng = make_uint2(0u, 0u), tg = ng;  // wide-BVH cursor
 	uint2 wstack[WIDE ? ARE_WIDE_STACK : 1];
 	unsigned int rays = 0;
@@ -177,7 +185,7 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 				++rays;
 				if (A.sc.n_nodes == 0) {  // zero or one primitive
 					if (A.sc.root_leaf_meta != 0) test_leaf<COUNT>(A.sc, A.sc.root_leaf_meta, o, d, A.tmin, h, &tc);
-				} else { node = 0; stack[0] = TRAV_DONE; top = stack + 1; trav = true; }
+				} else { node = 0; stk.reset(stack); trav = true; }
 			}
 			const int n_rays = __popc(__ballot_sync(full, ray_ok));
 			if (__any_sync(full, trav)) {
@@ -186,8 +194,8 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 				while (true) {
 #pragma unroll 1
 					for (int rep = 0; rep < TRAV_STEPS_PER_VOTE; ++rep) {  // several steps between the warp votes that decide the end of the slice
-						if (node >= 0) bvh_step<COUNT>(A.sc, A.tmin, rs, node, top, h, &tc);                    // node phase
-						if (node < 0 && node != TRAV_DONE) bvh_leaf<COUNT>(A.sc, o, d, A.tmin, node, top, h, &tc);  // leaf phase
+						if (node >= 0) bvh_step<COUNT>(A.sc, A.tmin, rs, node, stk, h, &tc);                    // node phase
+						if (node < 0 && node != TRAV_DONE) bvh_leaf<COUNT>(A.sc, o, d, A.tmin, node, stk, h, &tc);  // leaf phase
 					}
 					const int n_trav = __popc(__ballot_sync(full, node != TRAV_DONE));
 					if (n_trav == 0 || (n_trav < TRAV_MIN_LANES && n_trav < n_rays)) break;
@@ -297,7 +305,7 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 		// (shade.cuh: turbulence_coop) instead of each walking seven octaves alone in a nearly empty warp.
 		float turb = 0.0f;
 		bool have_turb = false;
-		if (!LEAN && A.sc.has_noise) {
+		if (!LEAN && NOISE && A.sc.has_noise) {
 			const bool general = task >= 0 && !trav && bounce > 0 && !(sbits >> 8);
 			if (__any_sync(full, general)) {
 				int noise_tex = -1;
@@ -337,7 +345,8 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 					const PrimInfo pi = A.sc.info[rs.dev_prim];
 					float u, v;
 					F3 att, emit;
-					surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, u, v);
+					const int tk = A.sc.texs[mat_texture(A.sc.mats[pi.mat], pi.tex)].kind;
+					surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, u, v, tk == TK_CHECKER_UV || tk == TK_IMAGE);
 					alive = scatter<float>(A.sc, pi.mat, pi.tex, d, sN, sP, u, v, r, wo, att, emit, have_turb ? &turb : nullptr);
 					thr = thr * att;
 				}

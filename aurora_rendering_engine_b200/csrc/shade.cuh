@@ -99,12 +99,18 @@ __device__ __forceinline__ float turbulence_coop(const DevScene &sc, bool need, 
 	float result = 0.0f;
 	int round = 0;
 	while (m) {  // warp-uniform
-		const unsigned src = __fns(m, 0, slot + 1);  // lane of this group's requester, 0xffffffff when the round has fewer than slot + 1
-		const int s = src == 0xffffffffu ? 0 : (int)src;
+		// lanes of this round's (up to) four requesters: warp-uniform bit tricks on the ballot (cheaper than four __fns)
+		unsigned mm = m;
+		const int l0 = __ffs(mm) - 1; mm &= mm - 1;
+		const int l1 = __ffs(mm) - 1; mm &= mm - 1;
+		const int l2 = __ffs(mm) - 1; mm &= mm - 1;
+		const int l3 = __ffs(mm) - 1;
+		const int src = slot == 0 ? l0 : (slot == 1 ? l1 : (slot == 2 ? l2 : l3));  // -1 when the round has fewer than slot + 1
+		const int s = src < 0 ? 0 : src;
 		const float px = __shfl_sync(full, P.x, s), py = __shfl_sync(full, P.y, s), pz = __shfl_sync(full, P.z, s);
 		const int tid = __shfl_sync(full, tex_id, s);
 		float v = 0.0f;
-		if (src != 0xffffffffu && oct < 7) {
+		if (src >= 0 && oct < 7) {
 			const float up = (float)(1 << oct), w = 1.0f / up;  // exact powers of two: the same points and weights as repeated doubling / halving
 			v = w * perlin_noise<float>(sc.tex_data + sc.texs[tid].data_off, mk<float>(px * up, py * up, pz * up));
 		}
@@ -177,7 +183,7 @@ __device__ __forceinline__ V3<T> cosine_dir_in_frame(V3<T> n, V3<T> tangent, V3<
 	// rt.cpp:54 rebuilds lz from lx, ly; lx^2 + ly^2 = r2 exactly, so sqrt(1 - r2) is the same quantity without
 	// the sin/cos rounding amplified at grazing directions
 	T lz = sqrt_t(max_t(T(0), T(1) - r2));
-	return lx * tangent + ly * bitangent + lz * n;
+	return mad(lz, n, mad2(lx, tangent, ly, bitangent));
 }
 template <typename T>
 __device__ __forceinline__ V3<T> cosine_dir(V3<T> n, T r1, T r2) {
@@ -275,11 +281,15 @@ __device__ bool scatter(const DevScene &sc, int mat, int tex, V3<T> wi, V3<T> Ng
 // ---- surface resolution -------------------------------------------------------------------------------
 // Geometric unit normal (not flipped) and (u,v) of device primitive `dp` at point P, fp32 render data.
 // (a,b) = planar coordinates of P in the primitive's own (u,v) frame (ignored for spheres).
-__device__ __forceinline__ void surface_at(const DevScene &sc, int dp, V3<float> P, float a, float b, V3<float> &N, float &u, float &v) {
+// need_uv = false: the caller's texture is position-only (solid, 3-D checker, noise) — a sphere's (u, v) costs an acosf and
+// an atan2f, ~100 instructions that such surfaces never look at.
+__device__ __forceinline__ void surface_at(const DevScene &sc, int dp, V3<float> P, float a, float b, V3<float> &N, float &u, float &v, bool need_uv = true) {
 	const HotPrim &h = sc.prim_plane[dp];
 	if (dp >= sc.n_tri + sc.n_quad) {
 		float inv_r = 1.0f / h.r0.w;
 		N = inv_r * (P - mk<float>(h.r0.x, h.r0.y, h.r0.z));
+		u = 0.0f; v = 0.0f;
+		if (!need_uv) return;
 		float theta = acosf(fmaxf(-1.0f, fminf(1.0f, -N.y))), phi = atan2f(-N.z, N.x) + Pi<float>::value;
 		u = phi * (0.5f / Pi<float>::value);
 		v = theta * (1.0f / Pi<float>::value);
@@ -288,8 +298,8 @@ __device__ __forceinline__ void surface_at(const DevScene &sc, int dp, V3<float>
 		if (dp < sc.n_tri) {
 			const float *t = sc.tri_uv + 6 * dp;
 			float b0 = 1.0f - a - b;
-			u = t[0] * b0 + t[2] * a + t[4] * b;
-			v = t[1] * b0 + t[3] * a + t[5] * b;
+			u = fmaf(t[4], b, fmaf(t[2], a, t[0] * b0));
+			v = fmaf(t[5], b, fmaf(t[3], a, t[1] * b0));
 		} else {
 			u = a;
 			v = b;
@@ -324,11 +334,11 @@ __device__ __forceinline__ CamT<float> cam_from_f32(const CamF &b) {
 template <typename T>
 __device__ __forceinline__ void cam_ray(const CamT<T> &c, T inv_w, T inv_h, int x, int y, Rnd4<T> r, V3<T> &o, V3<T> &d) {
 	T fx = (T(2) * (T(x) + r.x) * inv_w - T(1)) * c.sx, fy = (T(1) - T(2) * (T(y) + r.y) * inv_h) * c.sy;
-	V3<T> dir = c.fwd + (fx * c.right + fy * c.up);
+	V3<T> dir = c.fwd + mad2(fx, c.right, fy, c.up);
 	if (c.lens_r > T(0)) {
 		T rr = c.lens_r * sqrt_t(r.z), sn, cs;
 		sincos2pi_t(r.w, &sn, &cs);
-		V3<T> off = (rr * cs) * c.right + (rr * sn) * c.up;
+		V3<T> off = mad2(rr * cs, c.right, rr * sn, c.up);
 		o = c.pos + off;
 		d = nrm(c.focus * dir - off);
 	} else {

@@ -28,6 +28,26 @@ template <typename T> __host__ __device__ __forceinline__ V3<T> cross(V3<T> a, V
 	return mk<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 template <typename T> __host__ __device__ __forceinline__ T len2(V3<T> a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+#if defined(__CUDA_ARCH__)
+// fp32 on the device: sums of products are written out with explicit fused multiply-adds.  Left to the compiler, WHICH
+// product of a*b + c*d gets fused depends on the code around the expression, and the render kernels (generic, lean,
+// baked: three compilations of these routines) must round every path identically — their images are compared bit for
+// bit.  (The fp64 harness is built with -fmad=false and keeps the plain expressions: it mirrors the reference's x86 code.)
+__device__ __forceinline__ float dot(V3<float> a, V3<float> b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+__device__ __forceinline__ float len2(V3<float> a) { return fmaf(a.z, a.z, fmaf(a.y, a.y, a.x * a.x)); }
+__device__ __forceinline__ V3<float> cross(V3<float> a, V3<float> b) {
+	return mk<float>(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+#endif
+// s*a + b and s*a + t*b with the roundings pinned the same way (fp64: the plain expression)
+template <typename T> __host__ __device__ __forceinline__ V3<T> mad(T s, V3<T> a, V3<T> b) { return s * a + b; }
+template <typename T> __host__ __device__ __forceinline__ V3<T> mad2(T s, V3<T> a, T t, V3<T> b) { return s * a + t * b; }
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ V3<float> mad(float s, V3<float> a, V3<float> b) { return mk<float>(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)); }
+__device__ __forceinline__ V3<float> mad2(float s, V3<float> a, float t, V3<float> b) {
+	return mk<float>(fmaf(s, a.x, t * b.x), fmaf(s, a.y, t * b.y), fmaf(s, a.z, t * b.z));
+}
+#endif
 
 __host__ __device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
 __host__ __device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }

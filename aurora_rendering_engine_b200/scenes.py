@@ -23,7 +23,7 @@ import numpy as np
 
 MAT_DIFFUSE, MAT_REFLECTIVE, MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT = range(6)
 TEX_SOLID, TEX_CHECKER_UV, TEX_CHECKER_3D, TEX_NOISE, TEX_IMAGE = range(5)
-INTEGRATOR_PATH, INTEGRATOR_RT_AO = 0, 1
+INTEGRATOR_PATH, INTEGRATOR_RT_AO, INTEGRATOR_PATH_WAVEFRONT = 0, 1, 2
 
 
 def _p8(*vals):

@@ -69,6 +69,7 @@ def parse():
     ap.add_argument("--kernel", default="auto", choices=["auto", "lean", "generic", "baked-packed"],
                     help="A/B: auto = scene-specialised (baked) kernel where the scene has a lean form; lean = precompiled lean kernel; generic = generic brute-force kernel")
     ap.add_argument("--builder", type=int, default=-1, help="BVH builder: 0 host SAH, 1 device LBVH (default: host; device for the 1 M-primitive scene)")
+    ap.add_argument("--wavefront", action="store_true", help="A/B: the same estimator scheduled as wavefront stages (ARE_INTEGRATOR_PATH_WAVEFRONT)")
     ap.add_argument("--l2-persist", type=int, default=0, help="A/B: BVH renders mark the node array L2-persisting, per cent of the carve-out (ARE_OPT_L2_PERSIST_NODES)")
     ap.add_argument("--job-spp", type=int, default=1024, help="strong-scaling job: total samples per pixel sharded over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -84,7 +85,10 @@ def parse():
 def make_scene(a, name=None, **kw):
     from aurora_rendering_engine_b200 import scenes
     if name is None:
-        return scenes.by_name(a.scene, width=a.width, height=a.height)
+        sc = scenes.by_name(a.scene, width=a.width, height=a.height)
+        if a.wavefront:
+            sc.integrator = scenes.INTEGRATOR_PATH_WAVEFRONT
+        return sc
     return scenes.by_name(name, **kw)
 
 
@@ -288,7 +292,7 @@ def kernel_name(capi, variant):
             capi.KERNEL_BRUTE_LEAN: "k_render_path<brute/smem, lean>",
             capi.KERNEL_BRUTE_BAKED: "k_render_baked (lean kernel, scene compiled in by NVRTC)",
             capi.KERNEL_BVH2: "k_render_path<bvh2>", capi.KERNEL_BVH2_BIG: "k_render_path<bvh2, 12 CTAs/SM>",
-            capi.KERNEL_WIDE: "k_render_path<wide bvh>"}.get(variant, "?")
+            capi.KERNEL_WIDE: "k_render_path<wide bvh>", capi.KERNEL_WAVEFRONT: "k_wf_generate + k_wf_extend<bvh2> + k_wf_shade (wavefront)"}.get(variant, "?")
 
 
 class Bench:

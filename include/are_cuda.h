@@ -65,7 +65,10 @@ typedef enum are_texture_kind {
 
 typedef enum are_integrator {
 	ARE_INTEGRATOR_PATH = 0, /* unbiased path tracer: camera jitter, spp loop, max_depth bounces */
-	ARE_INTEGRATOR_RT_AO = 1 /* the reference's experiments/rt.cpp shading: primary + 32 AO rays + one mirror bounce (+cosine gather) */
+	ARE_INTEGRATOR_RT_AO = 1, /* the reference's experiments/rt.cpp shading: primary + 32 AO rays + one mirror bounce (+cosine gather) */
+	ARE_INTEGRATOR_PATH_WAVEFRONT = 2 /* the PATH estimator (same samples, same image up to summation order) scheduled as wavefront
+	                                    stages over ray queues in HBM — generate / extend (BVH2) / shade + compact — instead of
+	                                    one megakernel; kept for measurement: slower on every BASELINE scene */
 } are_integrator;
 
 typedef enum are_traversal {
@@ -131,6 +134,7 @@ enum {
 	ARE_KERNEL_BVH2_BIG = 4, /* high-occupancy build for hierarchies that live in L2 */
 	ARE_KERNEL_WIDE = 5,
 	ARE_KERNEL_RT_AO = 6,
+	ARE_KERNEL_WAVEFRONT = 8, /* k_wf_generate / k_wf_extend / k_wf_shade */
 	ARE_KERNEL_BRUTE_BAKED = 7 /* the lean kernel with the scene's closest-hit tests compiled in (NVRTC at commit) */
 };
 
