@@ -50,8 +50,10 @@ struct PrimInfo { int user_id, mat, tex, type; };  // per device primitive (devi
 //   r1 = (c.r, c.g, c.b, p0)     albedo (emitted radiance for lights, already scaled); p0 = fuzz | ior
 // SHADE_FAST is set when the effective texture is a solid colour and the material is Diffuse / Lambertian / Metal /
 // Dielectric / DiffuseLight; other primitives take the general path (texture evaluation, Reflective lobe choice).
+// bits: [0..7] material kind, [8] SHADE_FAST, [9..11] kind of the texture that colours the primitive, [12..27] its id
+// (so the render loop knows "this hit needs noise texture 3" without walking info -> material -> texture tables)
 struct ShadeRec { f4 r0, r1; };
-enum { SHADE_FAST = 1 };
+enum { SHADE_FAST = 1, SHADE_TEXKIND_SHIFT = 9, SHADE_TEXID_SHIFT = 12, SHADE_TEXID_MASK = 0xffff };
 
 struct MaterialRec {
 	int kind, pad_;

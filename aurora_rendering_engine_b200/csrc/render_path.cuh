@@ -42,7 +42,7 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 // segment for every lane, classify, then ONE Philox call per lane that feeds either the camera (new path) or the
 // material scatter (continuing path).
 #ifndef RENDER_MIN_BLOCKS
-#define RENDER_MIN_BLOCKS 6
+#define RENDER_MIN_BLOCKS 7  // generic brute-force kernel: 72 registers; measured 6 / 7 / 8 CTAs per SM on the textured scene: 10624 / 10887 / 9973 Msamples/s
 #endif
 #ifndef RENDER_MIN_BLOCKS_BVH2
 #define RENDER_MIN_BLOCKS_BVH2 7  // single-cursor BVH2 traversal, L1-resident hierarchies: 72 registers; measured 6 / 7 / 8 CTAs/SM on RTIOW: 4207 / 4359 / 4211 Msamples/s
@@ -257,7 +257,7 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 				}
 				const int kind = sbits & 255;
 				if (kind == MK_LIGHT) {
-					if (!(sbits >> 8)) {  // textured light: general path
+					if (!((sbits >> 8) & 1)) {  // textured light: general path
 						const Resolved rs = resolve_exact(A.sc, id, sP);
 						const PrimInfo pi = A.sc.info[rs.dev_prim];
 						float u, v;
@@ -269,7 +269,7 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 					done = true;
 				} else {
 					done = bounce >= A.max_depth;  // truncated path contributes nothing (RTIOW depth cut-off)
-					if (sbits >> 8) thr = thr * scol;  // SHADE_FAST: the attenuation is the solid colour, apply it now
+					if ((sbits >> 8) & 1) thr = thr * scol;  // SHADE_FAST: the attenuation is the solid colour, apply it now
 				}
 			}
 			if (done) {
@@ -306,17 +306,12 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 		float turb = 0.0f;
 		bool have_turb = false;
 		if (!LEAN && NOISE && A.sc.has_noise) {
-			const bool general = task >= 0 && !trav && bounce > 0 && !(sbits >> 8);
+			const bool general = task >= 0 && !trav && bounce > 0 && !((sbits >> 8) & 1);
 			if (__any_sync(full, general)) {
-				int noise_tex = -1;
-				if (general) {
-					const PrimInfo pi = A.sc.info[resolve_exact(A.sc, HotIds{ sdev, -1 }, sP).dev_prim];
-					const MaterialRec &m = A.sc.mats[pi.mat];
-					if (m.kind != MK_DIELECTRIC && m.kind != MK_LIGHT) {
-						const int t = mat_texture(m, pi.tex);
-						if (A.sc.texs[t].kind == TK_NOISE) noise_tex = t;
-					}
-				}
+				// the shading record says which texture colours the hit (dev_types.h: ShadeRec bits)
+				const int mk_ = sbits & 255;
+				const int noise_tex = general && ((sbits >> SHADE_TEXKIND_SHIFT) & 7) == TK_NOISE && mk_ != MK_DIELECTRIC && mk_ != MK_LIGHT
+					? ((sbits >> SHADE_TEXID_SHIFT) & SHADE_TEXID_MASK) : -1;
 				if (__any_sync(full, noise_tex >= 0)) {
 					turb = turbulence_coop(A.sc, noise_tex >= 0, noise_tex, sP);
 					have_turb = noise_tex >= 0;
@@ -339,13 +334,13 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 				F3 wo;
 				bool alive;
 				if (LEAN) alive = scatter_dir<float>(sbits & 255, sp0, d, sN, r, wo, sb_frame + 32u * sdev);
-				else if (sbits >> 8) alive = scatter_dir<float>(sbits & 255, sp0, d, sN, r, wo);  // SHADE_FAST: solid colour, simple lobe
+				else if ((sbits >> 8) & 1) alive = scatter_dir<float>(sbits & 255, sp0, d, sN, r, wo);  // SHADE_FAST: solid colour, simple lobe
 				else {  // general path: textures, Reflective's lobe choice
 					const Resolved rs = resolve_exact(A.sc, HotIds{ sdev, -1 }, sP);
 					const PrimInfo pi = A.sc.info[rs.dev_prim];
 					float u, v;
 					F3 att, emit;
-					const int tk = A.sc.texs[mat_texture(A.sc.mats[pi.mat], pi.tex)].kind;
+					const int tk = (sbits >> SHADE_TEXKIND_SHIFT) & 7;
 					surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, u, v, tk == TK_CHECKER_UV || tk == TK_IMAGE);
 					alive = scatter<float>(A.sc, pi.mat, pi.tex, d, sN, sP, u, v, r, wo, att, emit, have_turb ? &turb : nullptr);
 					thr = thr * att;

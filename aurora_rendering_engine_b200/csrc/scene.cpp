@@ -713,11 +713,13 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 			int over = -1;
 			if (m.kind == MK_LAMBERTIAN || m.kind == MK_LIGHT) over = (int)m.p[0];
 			else if (m.kind == MK_METAL) over = (int)m.p[1];
-			const HostTexture &tx = hs.textures[over >= 0 ? over : p.tex];
+			const int te = over >= 0 ? over : p.tex;  // the texture that colours this primitive
+			const HostTexture &tx = hs.textures[te];
 			const bool fast = tx.kind == TK_SOLID && m.kind != MK_REFLECTIVE;
 			const double scale = m.kind == MK_LIGHT ? m.p[1] : 1.0;
 			const double p0 = m.kind == MK_METAL ? m.p[0] : (m.kind == MK_DIELECTRIC ? m.p[0] : 0.0);
-			const unsigned bits = (unsigned)m.kind | (fast ? (unsigned)SHADE_FAST << 8 : 0u);
+			const unsigned bits = (unsigned)m.kind | (fast ? (unsigned)SHADE_FAST << 8 : 0u) | ((unsigned)tx.kind & 7u) << SHADE_TEXKIND_SHIFT |
+				((unsigned)std::min(te, (int)SHADE_TEXID_MASK)) << SHADE_TEXID_SHIFT;
 			float bitsf;
 			std::memcpy(&bitsf, &bits, 4);
 			const HotPrim &pf = out.prim_plane[dp];
@@ -1056,7 +1058,7 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 			const ShadeRec &sr = out.shade[id.a];
 			unsigned bits;
 			std::memcpy(&bits, &sr.r0.w, 4);
-			if (id.b >= 0 || !(bits >> 8)) ok = false;  // halves shade differently, or shading needs textures / a lobe choice
+			if (id.b >= 0 || !((bits >> 8) & 1)) ok = false;  // halves shade differently, or shading needs textures / a lobe choice
 			out.lean_shade.push_back(sr);
 		};
 		out.lean_sbase.assign(out.brute.size(), 0);

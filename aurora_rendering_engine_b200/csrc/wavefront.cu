@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ Render
 			}
 			const int kind = sbits & 255;
 			if (kind == MK_LIGHT) {
-				if (!(sbits >> 8)) {
+				if (!((sbits >> 8) & 1)) {
 					const Resolved rs = resolve_exact(A.sc, id, sP);
 					const PrimInfo pi = A.sc.info[rs.dev_prim];
 					float u, v;
@@ -135,18 +135,18 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ Render
 				done = true;
 			} else {
 				done = bounce >= A.max_depth;
-				if (sbits >> 8) thr = thr * scol;
+				if ((sbits >> 8) & 1) thr = thr * scol;
 			}
 			if (!done) {
 				const Rnd4<float> r = rnd4<float>(A.key, (uint32_t)pixel, (uint32_t)sample, (uint32_t)bounce, 0u);
 				F3 wo;
-				if (sbits >> 8) alive = scatter_dir<float>(kind, s1.w, d, sN, r, wo);
+				if ((sbits >> 8) & 1) alive = scatter_dir<float>(kind, s1.w, d, sN, r, wo);
 				else {
 					const Resolved rs = resolve_exact(A.sc, HotIds{ sdev, -1 }, sP);
 					const PrimInfo pi = A.sc.info[rs.dev_prim];
 					float u, v;
 					F3 att, emit;
-					const int tk = A.sc.texs[mat_texture(A.sc.mats[pi.mat], pi.tex)].kind;
+					const int tk = (sbits >> SHADE_TEXKIND_SHIFT) & 7;
 					surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, u, v, tk == TK_CHECKER_UV || tk == TK_IMAGE);
 					alive = scatter<float>(A.sc, pi.mat, pi.tex, d, sN, sP, u, v, r, wo, att, emit);
 					thr = thr * att;
