@@ -107,18 +107,22 @@ template <int OPEN>
 __device__ __forceinline__ void test_box_se(float s0, float s1, float s2, float e0, float e1, float e2, float h0, float h1, float h2, bool open_flag,
 	float tmin, int idx, Hit &h) {
 	const float i0 = rcp_fast(s0), i1 = rcp_fast(s1), i2 = rcp_fast(s2);
-	const float m0 = e0 * i0, m1 = e1 * i1, m2 = e2 * i2;
 	const float k0 = h0 * fabsf(i0), k1 = h1 * fabsf(i1), k2 = h2 * fabsf(i2);
-	const float n2 = m2 - k2, f2 = m2 + k2;
-	const float t_in = fmaxf(fmaxf(m0 - k0, m1 - k1), n2), t_out = fminf(fminf(m0 + k0, m1 + k1), f2);
-	bool in_ok = t_in > tmin, out_ok = t_out > tmin;
+	// slab interval of axis i: e_i/s_i -/+ h_i/|s_i|, each end ONE fused multiply-add of (e_i, 1/s_i, -/+ k_i)
+	const float n0 = fmaf(e0, i0, -k0), n1 = fmaf(e1, i1, -k1), n2 = fmaf(e2, i2, -k2);
+	const float f0 = fmaf(e0, i0, k0), f1 = fmaf(e1, i1, k1), f2 = fmaf(e2, i2, k2);
+	const float t_in = fmaxf(fmaxf(n0, n1), n2), t_out = fminf(fminf(f0, f1), f2);
 	if (OPEN == 2 || (OPEN == 0 && open_flag)) {  // warp-uniform: all lanes test the same primitive
-		in_ok = in_ok & !((n2 == t_in) & (s2 > 0.0f));
-		out_ok = out_ok & !((f2 == t_out) & (s2 < 0.0f));
+		const bool in_ok = (t_in > tmin) & !((n2 == t_in) & (s2 > 0.0f));
+		const bool out_ok = (t_out > tmin) & !((f2 == t_out) & (s2 < 0.0f));
+		const float t = in_ok ? t_in : t_out;
+		const bool ok = (t_in <= t_out) & (in_ok | out_ok) & (t < h.t);
+		if (ok) { h.t = t; h.idx = idx; }
+	} else {  // closed: the entry if it lies beyond tmin, else the exit; one window test on the chosen distance
+		const float t = t_in > tmin ? t_in : t_out;
+		const bool ok = (t_in <= t_out) & (t > tmin) & (t < h.t);
+		if (ok) { h.t = t; h.idx = idx; }
 	}
-	const float t = in_ok ? t_in : t_out;
-	const bool ok = (t_in <= t_out) & (in_ok | out_ok) & (t < h.t);
-	if (ok) { h.t = t; h.idx = idx; }
 }
 template <int OPEN = 0>
 __device__ __forceinline__ void test_box(float4 r0, float4 r1, float4 r2, float4 r3, V3<float> o, V3<float> d, float tmin, int idx, Hit &h) {
