@@ -168,6 +168,7 @@ bool resolve_traversal(are_cuda_ctx *ctx, int traversal, int &mode) {
 		mode = 0;
 	} else if (traversal == ARE_TRAVERSAL_BVH) mode = 1;
 	else if (traversal == ARE_TRAVERSAL_WIDE) mode = wide_ok ? 2 : 1;  // a single-primitive scene has no wide hierarchy
+	else if (traversal == ARE_TRAVERSAL_BVH4) mode = ctx->dev.nodes4 ? 3 : 1;  // not built (option off, device-built tree, too deep): BVH2
 	else if (traversal == ARE_TRAVERSAL_AUTO) {
 		if (brute_ok && ctx->csp->n_hot <= 32) mode = 0;
 		else mode = (wide_ok && (int)ctx->csp->nodes.size() > ctx->wide_min_nodes) ? 2 : 1;
@@ -372,6 +373,7 @@ int are_cuda_set_option(are_cuda_ctx *ctx, int option, int value) {
 	case ARE_OPT_WIDE_MIN_NODES: ctx->wide_min_nodes = value; return ARE_OK;
 	case ARE_OPT_LBVH_MAX_HEIGHT: ctx->opt_lbvh_max_height = value > 0 ? value : ARE_BVH_STACK; return ARE_OK;
 	case ARE_OPT_L2_PERSIST_NODES: ctx->opt_l2_persist = value; return ARE_OK;
+	case ARE_OPT_BUILD_BVH4: ctx->opt.build_bvh4 = value != 0; return ARE_OK;
 	default: return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown option");
 	}
 }
@@ -566,6 +568,8 @@ static int commit_device(are_cuda_ctx *ctx, const CompiledScene &cs, bool want_d
 #define UP(vec, field)                                                     \
 	if ((st = upload(ctx, cs.vec, &d.field, bytes)) != ARE_OK) return st;
 	UP(brute, brute) UP(brute_ids, brute_ids) UP(bvh_prims, bvh_prims) UP(bvh_ids, bvh_ids) UP(nodes, nodes)
+	if (!device_built) { UP(nodes4, nodes4) }
+	d.n_nodes4 = d.nodes4 ? (int)cs.nodes4.size() : 0;
 	if (cs.wide_depth <= 32) { UP(wnodes, wnodes) UP(wide_prims, wide_prims) UP(wide_ids, wide_ids) UP(wide_kinds, wide_kinds) }  // 32 = ARE_WIDE_STACK
 	UP(info, info) UP(prim_plane, prim_plane) UP(tri_uv, tri_uv) UP(tri64, tri64) UP(quad64, quad64) UP(sph64, sph64)
 	UP(tri_uv64, tri_uv64) UP(mats, mats) UP(texs, texs) UP(tex_data, tex_data) UP(rt_tris, rt_tris) UP(box_faces, box_faces) UP(shade, shade)
@@ -1173,7 +1177,7 @@ static int render_single(are_cuda_ctx *ctx, const are_camera *cam, const are_ren
 			: p->integrator == ARE_INTEGRATOR_RT_AO ? ARE_KERNEL_RT_AO
 			: p->integrator == ARE_INTEGRATOR_PATH_WAVEFRONT ? ARE_KERNEL_WAVEFRONT
 			: mode == 0 ? (baked ? ARE_KERNEL_BRUTE_BAKED : render_path_is_lean(a) ? ARE_KERNEL_BRUTE_LEAN : ARE_KERNEL_BRUTE)
-			: mode == 2 ? ARE_KERNEL_WIDE : (render_path_is_big(a) ? ARE_KERNEL_BVH2_BIG : ARE_KERNEL_BVH2);
+			: mode == 2 ? ARE_KERNEL_WIDE : mode == 3 ? ARE_KERNEL_BVH4 : (render_path_is_big(a) ? ARE_KERNEL_BVH2_BIG : ARE_KERNEL_BVH2);
 	}
 	return ARE_OK;
 }

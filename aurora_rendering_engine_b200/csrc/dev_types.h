@@ -80,6 +80,18 @@ struct BvhNode {
 	int meta[2];
 };
 
+// Uncompressed 4-wide BVH node, 128 B = one cache line, eight 16-byte loads: the boxes of four children as fp32
+// (centre, half-extent) per axis, child k in component k.  Collapsed from the BVH2 (a node absorbs its inner child of
+// largest area until it has four), so one visit replaces up to two dependent BVH2 visits — for hierarchies that live in
+// L2, where the traversal is bound by the latency of its dependent node fetches, not by instruction issue.
+//   child[k] >= 0: inner BVH4 node; < 0: leaf reference as in the BVH2; an empty slot has half-extent -1e30 (never hit)
+struct Bvh4Node {
+	f4 cx, hx, cy, hy, cz, hz;
+	int child[4];
+	int pad_[4];
+};
+#define ARE_BVH4_STACK 96  // entries of the per-thread BVH4 stack: up to three postponed children per level
+
 // Compressed 8-wide BVH node, 80 B = five 16-byte loads (layout after Ylitie, Karras, Laine, "Efficient incoherent
 // ray traversal on GPUs through compressed wide BVHs", HPG 2017): child boxes are 8-bit offsets on a per-node grid
 // origin + 2^e per axis, so 1 M primitives need ~20 MB of nodes instead of 64 MB of BVH2 nodes and a ray makes
@@ -116,6 +128,8 @@ struct DevScene {
 	const BvhNode *nodes;
 	int n_nodes;
 	int root_leaf_meta;        // when the whole scene is one leaf (n_nodes == 0)
+	const Bvh4Node *nodes4;    // 4-wide collapse of `nodes` over the same leaves (nullptr when not built)
+	int n_nodes4;
 	const WideNode *wnodes;    // compressed 8-wide hierarchy over the same hot items (nullptr when n_nodes == 0)
 	const HotPrim *wide_prims; // its leaf-ordered primitives, ids and test kinds (0 box, 1 quad / fused pair, 2 triangle, 3 sphere)
 	const HotIds *wide_ids;

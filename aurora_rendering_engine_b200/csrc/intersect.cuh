@@ -308,6 +308,32 @@ __device__ __forceinline__ void bvh_step(const DevScene &sc, float tmin, const R
 	if (!(hit0 | hit1)) next = stk.pop();
 	cur = next;
 }
+// One BVH4 visit: four slab tests on one 128-byte node.  The nearest hit child becomes the cursor, the other hit
+// children are postponed (slot order).  Nearest = minimum over keys (bits of the entry distance with the slot number
+// in the two low mantissa bits): distances are positive, so their bit patterns order like the floats.
+template <bool COUNT, class STK>
+__device__ __forceinline__ void bvh4_step(const DevScene &sc, float tmin, const RaySlopes &rs, int &cur, STK &stk, const Hit &h, TravCounters *cnt) {
+	const Bvh4Node *n = sc.nodes4 + cur;
+	const float4 cx = ldg4(&n->cx), hx = ldg4(&n->hx), cy = ldg4(&n->cy), hy = ldg4(&n->hy), cz = ldg4(&n->cz), hz = ldg4(&n->hz);
+	const int4 ch = __ldg(reinterpret_cast<const int4 *>(&n->child[0]));
+	if (COUNT) cnt->nodes += 2;  // node_visits counts child-box PAIRS
+#define ARE_SLAB4(k, C)                                                                                                      \
+	const float ax##k = fmaf(cx.C, rs.idx, -rs.oxi), ay##k = fmaf(cy.C, rs.idy, -rs.oyi), az##k = fmaf(cz.C, rs.idz, -rs.ozi); \
+	const float tn##k = fmaxf(fmaxf(fmaf(-hx.C, rs.ax, ax##k), fmaf(-hy.C, rs.ay, ay##k)), fmaxf(fmaf(-hz.C, rs.az, az##k), tmin)); \
+	const float tf##k = fminf(fminf(fmaf(hx.C, rs.ax, ax##k), fmaf(hy.C, rs.ay, ay##k)), fminf(fmaf(hz.C, rs.az, az##k), h.t)); \
+	const bool hit##k = tn##k <= tf##k;                                                                                      \
+	const unsigned key##k = hit##k ? ((__float_as_uint(tn##k) & ~3u) | k##u) : 0xffffffffu;
+	ARE_SLAB4(0, x) ARE_SLAB4(1, y) ARE_SLAB4(2, z) ARE_SLAB4(3, w)
+#undef ARE_SLAB4
+	const unsigned kmin = min(min(key0, key1), min(key2, key3));
+	if (kmin == 0xffffffffu) { cur = stk.pop(); return; }
+	const unsigned nearest = kmin & 3u;
+	if (hit3 & (nearest != 3u)) stk.push(ch.w);
+	if (hit2 & (nearest != 2u)) stk.push(ch.z);
+	if (hit1 & (nearest != 1u)) stk.push(ch.y);
+	if (hit0 & (nearest != 0u)) stk.push(ch.x);
+	cur = nearest == 0u ? ch.x : (nearest == 1u ? ch.y : (nearest == 2u ? ch.z : ch.w));
+}
 // leaf phase of the single-cursor form: test the leaf under the cursor, then pop
 template <bool COUNT, class STK>
 __device__ __forceinline__ void bvh_leaf(const DevScene &sc, V3<float> o, V3<float> d, float tmin, int &cur, STK &stk, Hit &h, TravCounters *cnt) {
@@ -329,6 +355,20 @@ __device__ __forceinline__ void intersect_bvh(const DevScene &sc, V3<float> o, V
 	int cur = 0;
 	while (cur != TRAV_DONE) {
 		if (cur >= 0) bvh_step<COUNT>(sc, tmin, rs, cur, stk, h, cnt);
+		else bvh_leaf<COUNT>(sc, o, d, tmin, cur, stk, h, cnt);
+	}
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void intersect_bvh4(const DevScene &sc, V3<float> o, V3<float> d, float tmin, Hit &h, TravCounters *cnt) {
+	if (sc.n_nodes == 0 || !sc.nodes4) { intersect_bvh<COUNT>(sc, o, d, tmin, h, cnt); return; }
+	const RaySlopes rs = ray_slopes(o, d);
+	int stack[ARE_BVH4_STACK];
+	PtrStack stk;
+	stk.reset(stack);
+	int cur = 0;
+	while (cur != TRAV_DONE) {
+		if (cur >= 0) bvh4_step<COUNT>(sc, tmin, rs, cur, stk, h, cnt);
 		else bvh_leaf<COUNT>(sc, o, d, tmin, cur, stk, h, cnt);
 	}
 }

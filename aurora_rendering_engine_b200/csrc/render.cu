@@ -22,7 +22,7 @@ namespace areb {
 size_t brute_smem_limit_prims() { return BRUTE_MAX_PRIMS; }
 
 template <int MODE, bool COUNT, bool BIG = false, bool LEAN = false, bool NOISE = true>
-__global__ void __launch_bounds__(RENDER_THREADS, BIG ? RENDER_MIN_BLOCKS_BIG : (LEAN ? RENDER_MIN_BLOCKS_LEAN : (MODE == 1 ? RENDER_MIN_BLOCKS_BVH2 : RENDER_MIN_BLOCKS))) k_render_path(const __grid_constant__ RenderArgs A) {
+__global__ void __launch_bounds__(RENDER_THREADS, MODE == 3 ? (BIG ? RENDER_MIN_BLOCKS_BVH4_BIG : RENDER_MIN_BLOCKS_BVH4) : BIG ? RENDER_MIN_BLOCKS_BIG : (LEAN ? RENDER_MIN_BLOCKS_LEAN : (MODE == 1 ? RENDER_MIN_BLOCKS_BVH2 : RENDER_MIN_BLOCKS))) k_render_path(const __grid_constant__ RenderArgs A) {
 	render_path_body<MODE, COUNT, BIG, LEAN, false, NOISE>(A);
 }
 
@@ -50,7 +50,11 @@ int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStre
 	} while (0)
 	if (use_bvh) {
 		const bool big = render_path_is_big(a);
-		if (mode == 2) {
+		if (mode == 3) {
+			if (!a.sc.nodes4) return -1;
+			if (count_tests) { if (big) LAUNCH(3, true, true, 0); else LAUNCH(3, true, false, 0); }
+			else { if (big) LAUNCH(3, false, true, 0); else LAUNCH(3, false, false, 0); }
+		} else if (mode == 2) {
 			if (!a.sc.wnodes) return -1;
 			if (count_tests) { if (big) LAUNCH(2, true, true, 0); else LAUNCH(2, true, false, 0); }
 			else { if (big) LAUNCH(2, false, true, 0); else LAUNCH(2, false, false, 0); }
@@ -79,7 +83,8 @@ __global__ void k_hit32(DevScene sc, int n, const double *__restrict__ Q, const 
 	Hit h;
 	h.t = INFINITY; h.idx = -1; h.orig = -1;
 	TravCounters tc;
-	if (use_bvh == 2) intersect_wide<false>(sc, o, d, tmin, h, &tc);
+	if (use_bvh == 3) intersect_bvh4<false>(sc, o, d, tmin, h, &tc);
+	else if (use_bvh == 2) intersect_wide<false>(sc, o, d, tmin, h, &tc);
 	else if (use_bvh) intersect_bvh<false>(sc, o, d, tmin, h, &tc);
 	else intersect_range<ldg4>(sc.brute, sc.brute_range.first, sc.brute_range.nq, sc.brute_range.nt, sc.brute_range.ns, sc.brute_range.nb, o, d, tmin, h);
 	const float nan = nan_t<float>();

@@ -53,6 +53,12 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #ifndef RENDER_MIN_BLOCKS_BIG
 #define RENDER_MIN_BLOCKS_BIG 12  // hierarchies that live in L2 (not L1) are latency-bound: 48 resident warps/SM at 40 registers (with spills)
 #endif                            // beat 24 at 80 — measured on the 1 M-primitive scene: 467 -> 577 Msamples/s; RTIOW (L1-resident) loses 5 %
+#ifndef RENDER_MIN_BLOCKS_BVH4
+#define RENDER_MIN_BLOCKS_BVH4 6       // 4-wide nodes: 24 box floats + 4 references in flight per step
+#endif
+#ifndef RENDER_MIN_BLOCKS_BVH4_BIG
+#define RENDER_MIN_BLOCKS_BVH4_BIG 8
+#endif
 #ifndef BVH_BIG_NODES
 #define BVH_BIG_NODES 16384       // 1 MiB of 64 B nodes: beyond this the high-occupancy build is launched
 #endif
@@ -64,7 +70,8 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #endif
 // (Postponing leaf tests until several lanes hold one was measured in the first formulation of the traversal: testing a
 // leaf as soon as a lane has it was best on RTIOW and on the 1 M-primitive scene, and needs no votes.)
-// MODE: 0 = brute force from shared memory, 1 = BVH2, 2 = compressed 8-wide BVH
+// MODE: 0 = brute force from shared memory, 1 = BVH2, 2 = compressed 8-wide BVH, 3 = uncompressed 4-wide BVH (the BVH2's
+// traversal loop with bvh4_step as its node phase)
 // LEAN (brute force only): the scene compiler's lean form (scene.h: at most LEAN_MAX boxes / quad tests / triangle
 // tests, no spheres, every surface shaded from its ShadeRec alone).  The tests are a guarded full unroll with
 // compile-time shared-memory offsets instead of four counted loops, and a hit goes straight to its shading record
@@ -76,7 +83,7 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 // the BVH kernels registers: RTIOW lost 4 % with the stage merely present).
 template <int MODE, bool COUNT, bool BIG = false, bool LEAN = false, bool BAKED = false, bool NOISE = true>
 __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
-	constexpr bool BVH = MODE != 0, WIDE = MODE == 2;
+	constexpr bool BVH = MODE != 0, WIDE = MODE == 2, B4 = MODE == 3;
 	static_assert(!LEAN || MODE == 0, "the lean form is a brute-force list");
 	static_assert(!BAKED || LEAN, "a baked kernel is a lean kernel");
 	extern __shared__ float4 s_raw[];
@@ -134,9 +141,9 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 	h.t = INFINITY; h.idx = -1; h.orig = -1;
 	bool trav = false;  // BVH: traversal in progress
 	int node = 0, sp = 0;  // BVH2: `node` is the traversal cursor (intersect.cuh: bvh_step); 8-wide: sp indexes wstack
-	int stack[MODE == 1 ? ARE_BVH_STACK : 1];
+	int stack[MODE == 1 ? ARE_BVH_STACK : (MODE == 3 ? ARE_BVH4_STACK : 1)];
 #ifdef ARE_SHORT_STACK
-	__shared__ int s_short[MODE == 1 ? ARE_SHORT_STACK : 1][RENDER_THREADS];
+	__shared__ int s_short[(MODE == 1 || MODE == 3) ? ARE_SHORT_STACK : 1][RENDER_THREADS];
 	ShortStack<ARE_SHORT_STACK, RENDER_THREADS> stk;
 	stk.sm = &s_short[0][threadIdx.x]; stk.deep = stack; stk.sp = 0;
 #else
@@ -194,7 +201,10 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 				while (true) {
 #pragma unroll 1
 					for (int rep = 0; rep < TRAV_STEPS_PER_VOTE; ++rep) {  // several steps between the warp votes that decide the end of the slice
-						if (node >= 0) bvh_step<COUNT>(A.sc, A.tmin, rs, node, stk, h, &tc);                    // node phase
+						if (node >= 0) {                                                                         // node phase
+							if (B4) bvh4_step<COUNT>(A.sc, A.tmin, rs, node, stk, h, &tc);
+							else bvh_step<COUNT>(A.sc, A.tmin, rs, node, stk, h, &tc);
+						}
 						if (node < 0 && node != TRAV_DONE) bvh_leaf<COUNT>(A.sc, o, d, A.tmin, node, stk, h, &tc);  // leaf phase
 					}
 					const int n_trav = __popc(__ballot_sync(full, node != TRAV_DONE));

@@ -330,6 +330,58 @@ struct Builder {
 	}
 };
 
+// ---- BVH2 -> uncompressed 4-wide collapse (Bvh4Node, dev_types.h) -----------------------------------------
+// A 4-wide node starts from a BVH2 node's two children and absorbs the inner child of largest surface area until it
+// has four (or only leaves are left).  Child boxes are the (centre, half-extent) floats the BVH2 parent already holds,
+// copied bit for bit, so a BVH4 traversal accepts exactly the boxes the BVH2 traversal accepts.
+struct Bvh4Builder {
+	const CompiledScene &src;
+	std::vector<Bvh4Node> &out;
+	int depth = 0;
+	struct Kid {
+		int ref;
+		float c[3], h[3];
+		float area() const { return h[0] * h[1] + h[1] * h[2] + h[2] * h[0]; }
+	};
+	static void kids_of(const BvhNode &n, Kid &a, Kid &b) {
+		a.ref = n.child[0]; b.ref = n.child[1];
+		a.c[0] = n.b0.x; a.h[0] = n.b0.y; a.c[1] = n.b0.z; a.h[1] = n.b0.w; a.c[2] = n.b2.x; a.h[2] = n.b2.y;
+		b.c[0] = n.b1.x; b.h[0] = n.b1.y; b.c[1] = n.b1.z; b.h[1] = n.b1.w; b.c[2] = n.b2.z; b.h[2] = n.b2.w;
+	}
+	int build(int node2, int level) {
+		depth = std::max(depth, level + 1);
+		Kid k[4];
+		int n = 2;
+		kids_of(src.nodes[(size_t)node2], k[0], k[1]);
+		while (n < 4) {
+			int best = -1;
+			for (int i = 0; i < n; ++i)
+				if (k[i].ref >= 0 && (best < 0 || k[i].area() > k[best].area())) best = i;
+			if (best < 0) break;
+			Kid a, b;
+			kids_of(src.nodes[(size_t)k[best].ref], a, b);
+			k[best] = a;
+			k[n++] = b;
+		}
+		const int me = (int)out.size();
+		out.push_back(Bvh4Node());
+		Bvh4Node nd;
+		float *cx = &nd.cx.x, *hx = &nd.hx.x, *cy = &nd.cy.x, *hy = &nd.hy.x, *cz = &nd.cz.x, *hz = &nd.hz.x;
+		for (int i = 0; i < 4; ++i) {
+			if (i < n) {
+				cx[i] = k[i].c[0]; hx[i] = k[i].h[0]; cy[i] = k[i].c[1]; hy[i] = k[i].h[1]; cz[i] = k[i].c[2]; hz[i] = k[i].h[2];
+				nd.child[i] = k[i].ref >= 0 ? build(k[i].ref, level + 1) : k[i].ref;
+			} else {
+				cx[i] = cy[i] = cz[i] = 0.f; hx[i] = hy[i] = hz[i] = -1e30f;  // empty slot: near > far for every ray
+				nd.child[i] = (int)0x80000000;
+			}
+			nd.pad_[i] = 0;
+		}
+		out[(size_t)me] = nd;
+		return me;
+	}
+};
+
 // ---- BVH2 -> compressed 8-wide collapse (WideNode, dev_types.h) -----------------------------------------
 // Greedy: a wide node starts from a BVH2 node's two children and keeps opening the inner child with the largest
 // surface area until it has eight (or only leaves are left).  Children go to the slot whose octant direction
@@ -1122,6 +1174,13 @@ bool compile_scene(const HostScene &hs, const CompileOptions &opt, CompiledScene
 		// The compressed 8-wide hierarchy is an alternative traversal structure (ARE_TRAVERSAL_WIDE), measured slower than
 		// BVH2 on B200 for this kernel: built for small scenes (cheap) and on request for large ones.
 		if (opt.build_wide || out.nodes.size() <= 65536) WideBuilder(out, out).build();
+		if (opt.build_bvh4 && !out.nodes.empty()) {
+			out.nodes4.reserve(out.nodes.size() / 2 + 8);
+			Bvh4Builder b4{ out, out.nodes4 };
+			b4.build(0, 0);
+			out.bvh4_depth = b4.depth;
+			if (3 * b4.depth + 2 > ARE_BVH4_STACK) out.nodes4.clear();  // too deep for the traversal stack: BVH2 serves
+		}
 	}
 	out.host_bvh_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - bvh_t0).count();
 	phase("wide BVH collapse");

@@ -56,6 +56,8 @@ struct CompiledScene {
 	std::vector<HotPrim> bvh_prims;
 	std::vector<HotIds> bvh_ids;
 	std::vector<BvhNode> nodes;
+	std::vector<Bvh4Node> nodes4;  // 4-wide collapse of `nodes` (CompileOptions::build_bvh4; empty otherwise or when too deep for its stack)
+	int bvh4_depth = 0;
 	std::vector<WideNode> wnodes;  // compressed 8-wide collapse of `nodes` (empty when the scene has a single hot item)
 	std::vector<HotPrim> wide_prims;
 	std::vector<HotIds> wide_ids;
@@ -86,7 +88,8 @@ struct CompiledScene {
 	// Empty the scene but keep every array's storage: a re-commit of a large scene then writes into memory that is
 	// already mapped instead of page-faulting ~150 MB per million primitives in again.
 	void reset() {
-		brute.clear(); brute_ids.clear(); box_faces.clear(); bvh_prims.clear(); bvh_ids.clear(); nodes.clear(); wnodes.clear();
+		brute.clear(); brute_ids.clear(); box_faces.clear(); bvh_prims.clear(); bvh_ids.clear(); nodes.clear(); nodes4.clear(); wnodes.clear();
+		bvh4_depth = 0;
 		wide_prims.clear(); wide_ids.clear(); wide_kinds.clear(); mats.clear(); texs.clear(); tex_data.clear();
 		lean_shade.clear(); lean_sbase.clear();
 		// NOT cleared: the per-primitive arrays (info, prim_plane, shade, tri_uv, rt_tris, tri64, quad64, sph64, tri_uv64) and
@@ -104,6 +107,7 @@ struct CompileOptions {
 	bool fuse_boxes = true;
 	int brute_max = 1024;
 	bool build_wide = false;  // also build the compressed 8-wide BVH for scenes beyond 65536 BVH2 nodes
+	bool build_bvh4 = false;  // also collapse the host-built BVH2 into 128-byte 4-wide nodes (ARE_TRAVERSAL_BVH4)
 	bool device_bvh = false;  // leave the hierarchy to the device builder (lbvh.cu): emit its input instead of nodes
 };
 

@@ -292,7 +292,7 @@ def kernel_name(capi, variant):
             capi.KERNEL_BRUTE_LEAN: "k_render_path<brute/smem, lean>",
             capi.KERNEL_BRUTE_BAKED: "k_render_baked (lean kernel, scene compiled in by NVRTC)",
             capi.KERNEL_BVH2: "k_render_path<bvh2>", capi.KERNEL_BVH2_BIG: "k_render_path<bvh2, 12 CTAs/SM>",
-            capi.KERNEL_WIDE: "k_render_path<wide bvh>", capi.KERNEL_WAVEFRONT: "k_wf_generate + k_wf_extend<bvh2> + k_wf_shade (wavefront)"}.get(variant, "?")
+            capi.KERNEL_WIDE: "k_render_path<wide bvh>", capi.KERNEL_BVH4: "k_render_path<bvh4>", capi.KERNEL_WAVEFRONT: "k_wf_generate + k_wf_extend<bvh2> + k_wf_shade (wavefront)"}.get(variant, "?")
 
 
 class Bench:
@@ -526,6 +526,8 @@ def kernel_options(a):
               "baked-packed": {capi.OPT_BAKED_PACKED: 1}}.get(a.kernel, {}))
     if a.l2_persist:
         o[capi.OPT_L2_PERSIST_NODES] = a.l2_persist
+    if a.traversal == 4:  # ARE_TRAVERSAL_BVH4 needs the 4-wide collapse of the host-built tree
+        o[capi.OPT_BUILD_BVH4] = 1
     return o
 
 

@@ -75,7 +75,9 @@ typedef enum are_traversal {
 	ARE_TRAVERSAL_AUTO = 0, /* brute force from shared memory for small scenes, BVH2 for mid-size, compressed wide BVH for large ones */
 	ARE_TRAVERSAL_BRUTE = 1,
 	ARE_TRAVERSAL_BVH = 2, /* binary BVH, 64-byte nodes with both children's boxes */
-	ARE_TRAVERSAL_WIDE = 3 /* compressed 8-wide BVH, 80-byte nodes with 8-bit child boxes (large scenes) */
+	ARE_TRAVERSAL_WIDE = 3, /* compressed 8-wide BVH, 80-byte nodes with 8-bit child boxes (large scenes) */
+	ARE_TRAVERSAL_BVH4 = 4 /* uncompressed 4-wide BVH, 128-byte nodes with four fp32 child boxes (needs ARE_OPT_BUILD_BVH4 and the
+	                          host builder; BVH2 otherwise) */
 } are_traversal;
 
 typedef enum are_encoder {
@@ -134,6 +136,7 @@ enum {
 	ARE_KERNEL_BVH2_BIG = 4, /* high-occupancy build for hierarchies that live in L2 */
 	ARE_KERNEL_WIDE = 5,
 	ARE_KERNEL_RT_AO = 6,
+	ARE_KERNEL_BVH4 = 9, /* k_render_path over the 4-wide hierarchy */
 	ARE_KERNEL_WAVEFRONT = 8, /* k_wf_generate / k_wf_extend / k_wf_shade */
 	ARE_KERNEL_BRUTE_BAKED = 7 /* the lean kernel with the scene's closest-hit tests compiled in (NVRTC at commit) */
 };
@@ -192,8 +195,9 @@ typedef enum are_option {
 	ARE_OPT_BUILD_WIDE = 6, /* 0 (default) / 1: also build the compressed 8-wide BVH for scenes beyond 65536 nodes */
 	ARE_OPT_WIDE_MIN_NODES = 7, /* ARE_TRAVERSAL_AUTO picks the 8-wide BVH above this node count (default: never) */
 	ARE_OPT_LBVH_MAX_HEIGHT = 8, /* test hook: device-built trees taller than this fall back to the host builder */
-	ARE_OPT_L2_PERSIST_NODES = 9 /* 0 (default) / 1..100: BVH renders mark the node array as an L2-persisting access window
+	ARE_OPT_L2_PERSIST_NODES = 9, /* 0 (default) / 1..100: BVH renders mark the node array as an L2-persisting access window
 	                                (cudaAccessPolicyWindow) claiming this per cent of the device's persisting carve-out */
+	ARE_OPT_BUILD_BVH4 = 10 /* 0 (default) / 1: the host builder also collapses its BVH2 into 4-wide nodes (ARE_TRAVERSAL_BVH4) */
 } are_option;
 int are_cuda_set_option(are_cuda_ctx *ctx, int option, int value);
 /* The sm_100a CUBIN of the committed scene's baked kernel (what cuobjdump -sass / nvdisasm -g read next to an ncu capture).

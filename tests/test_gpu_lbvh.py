@@ -212,3 +212,41 @@ def test_refit_refuses_what_it_cannot_do(ctx):
     ctx.update_triangles([0], [Q + 1.0], [u], [v])
     with pytest.raises(capi.AreCudaError, match="commit instead"):
         ctx.refit()
+
+
+def test_bvh4_equals_bvh2(ctx):
+    """The uncompressed 4-wide hierarchy (ARE_OPT_BUILD_BVH4 + ARE_TRAVERSAL_BVH4) is a collapse of the host-built BVH2 whose
+    child boxes are the BVH2's own floats: a ray must meet the same primitive at the same distance, and the images agree up
+    to summation order.  Without the option (or on a device-built tree) the request falls back to the BVH2."""
+    sc = scenes.stress(n_prims=20_000, width=96, height=54)
+    cam = capi.make_camera(**sc.camera_args())
+    rng = np.random.RandomState(7)
+    Q = rng.uniform(-12, 12, (200_000, 3))
+    D = rng.normal(size=(200_000, 3))
+    D[:1000, 0] = 0.0
+    ctx.set_option(capi.OPT_BUILD_BVH4, 1)
+    _commit(ctx, sc, capi.BVH_BUILDER_HOST_SAH)
+    want = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=2)
+    got = ctx.hit_batch(Q, D, t_min=1e-3, precision=32, traversal=4)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b, equal_nan=True)
+    i2, s2 = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=4, traversal=2)))
+    i4, s4 = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=4, traversal=4)))
+    acc = ctx.alloc_accum(sc.width, sc.height)
+    c4 = ctx.render_device(cam, capi.make_params(**sc.params_args(sample_count=4, traversal=4)), acc, want_stats=True, count_tests=True)
+    ctx.free_accum(acc)
+    assert s4.kernel_variant == capi.KERNEL_BVH4 and s2.kernel_variant == capi.KERNEL_BVH2
+    assert s4.rays == s2.rays and np.allclose(i4, i2, rtol=1e-5, atol=1e-5)
+    assert c4.node_visits > 0 and c4.sphere_tests > 0
+    for name, kw in (("rtiow_final", dict(width=96, height=54)), ("cornell_box", dict(width=64, height=64))):
+        s = scenes.by_name(name, **kw)
+        _commit(ctx, s, capi.BVH_BUILDER_HOST_SAH)
+        c = capi.make_camera(**s.camera_args())
+        a2, t2 = ctx.render(c, capi.make_params(**s.params_args(sample_count=4, traversal=2, max_depth=12)))
+        a4, t4 = ctx.render(c, capi.make_params(**s.params_args(sample_count=4, traversal=4, max_depth=12)))
+        assert t4.kernel_variant == capi.KERNEL_BVH4 and t4.rays == t2.rays and np.allclose(a4, a2, rtol=1e-5, atol=1e-5)
+    # not built: the request is served by the BVH2
+    ctx.set_option(capi.OPT_BUILD_BVH4, 0)
+    _commit(ctx, sc, capi.BVH_BUILDER_HOST_SAH)
+    _, sf = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=1, traversal=4)))
+    assert sf.kernel_variant == capi.KERNEL_BVH2
