@@ -9,4 +9,4 @@ mkdir -p variants
 make -C $CS -j4 >/dev/null
 nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -Xcompiler -fPIC -prec-div=false -prec-sqrt=false -ftz=true "$@" -Xptxas -v -c $CS/render.cu -o variants/render_$name.o 2> variants/ptxas_$name.txt
 grep -A2 "k_render_pathILi0ELb0ELb0" variants/ptxas_$name.txt | tail -2 | tr '\n' ' '; echo
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/libare_b200_$name.so variants/render_$name.o $OBJ/harness64.o $OBJ/rtao.o $OBJ/api.o $OBJ/scene.o $OBJ/patch.o $OBJ/lbvh.o $OBJ/bake.o $OBJ/embed.o -lcudart_static -lpthread -ldl -lrt
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/libare_b200_$name.so variants/render_$name.o $OBJ/wavefront.o $OBJ/harness64.o $OBJ/rtao.o $OBJ/api.o $OBJ/scene.o $OBJ/patch.o $OBJ/lbvh.o $OBJ/bake.o $OBJ/embed.o -lcudart_static -lpthread -ldl -lrt

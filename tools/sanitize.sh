@@ -34,6 +34,31 @@ with capi.Context(0) as ctx:
         img, st = ctx.render(capi.make_camera(**sc.camera_args()), capi.make_params(**sc.params_args(sample_count=2, traversal=2, max_depth=8)))
         assert np.isfinite(img).all()
     ctx.set_bvh_builder(capi.BVH_BUILDER_HOST_SAH)
+    # round 2: wavefront schedule, 4-wide BVH, refit, tone-map, L2 probe
+    ctx.set_option(capi.OPT_BUILD_BVH4, 1)
+    sc = scenes.by_name("stress", n_prims=3000, width=48, height=27)
+    ctx.clear(); sc.feed(ctx); ctx.commit()
+    cam = capi.make_camera(**sc.camera_args())
+    for kw in (dict(traversal=4), dict(traversal=2, integrator=scenes.INTEGRATOR_PATH_WAVEFRONT)):
+        img, st = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=2, max_depth=6, **kw)))
+        assert np.isfinite(img).all() and st.rays > 0
+    ctx.set_option(capi.OPT_BUILD_BVH4, 0)
+    ctx.set_bvh_builder(capi.BVH_BUILDER_DEVICE_LBVH)
+    ctx.clear(); sc.feed(ctx); ctx.commit()
+    ctx.update_spheres([0, 5, 9], [[0.1, 0.2, 0.3]] * 3, [0.04, 0.05, 0.03])
+    Q, u, v, *_ = sc.tris[0]
+    ctx.update_triangles([len(sc.spheres)], [Q + 0.5], [u], [v])
+    ctx.refit()
+    img, st = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=2, traversal=2, max_depth=6)))
+    acc = ctx.alloc_accum(48, 27)
+    ctx.render_device(cam, capi.make_params(**sc.params_args(sample_count=2, traversal=2, max_depth=6)), acc)
+    ctx.tonemap(acc, 48, 27, 0.5, 0); ctx.free_accum(acc)
+    ctx.set_bvh_builder(capi.BVH_BUILDER_HOST_SAH)
+    ctx.measure_l2_peak()
+    with capi.Context([0]) as grp:   # a group of one device: the multi-device driver code without a second GPU
+        sc2 = scenes.by_name("cornell_box", width=48, height=48)
+        sc2.feed(grp); grp.commit()
+        grp.render(capi.make_camera(**sc2.camera_args()), capi.make_params(**sc2.params_args(sample_count=3, max_depth=6)))
     ps = scenes.patch_random(1, width=64, height=48, mirror_walls=True)
     ctx.patch_render(ps); ctx.patch_trace_texture(ps, ps.origin, 12, 40, 40)
     dst = np.zeros((40, 50, 3)); src = np.random.RandomState(2).uniform(size=(20, 30, 3))
