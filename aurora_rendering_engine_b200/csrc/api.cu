@@ -60,6 +60,7 @@ struct are_cuda_ctx {
 	bool opt_lean = true;            // lean brute-force kernel for scenes that have a lean form
 	bool opt_bake = true;            // scene-specialised kernel (NVRTC at commit) for the same scenes
 	bool opt_bake_packed = false;    // its slab products as fma.rn.f32x2 pairs
+	int opt_bake_min_blocks = 0;     // its __launch_bounds__ CTAs per SM (0: as the lean kernel)
 	int opt_builder_override = -1;   // -1: are_cuda_set_bvh_builder decides
 	int opt_lbvh_max_height = ARE_BVH_STACK;
 	int opt_l2_persist = 0;          // BVH renders: mark the node array as L2-persisting (cudaAccessPolicyWindow) for the launch
@@ -374,6 +375,7 @@ int are_cuda_set_option(are_cuda_ctx *ctx, int option, int value) {
 	case ARE_OPT_LBVH_MAX_HEIGHT: ctx->opt_lbvh_max_height = value > 0 ? value : ARE_BVH_STACK; return ARE_OK;
 	case ARE_OPT_L2_PERSIST_NODES: ctx->opt_l2_persist = value; return ARE_OK;
 	case ARE_OPT_BUILD_BVH4: ctx->opt.build_bvh4 = value != 0; return ARE_OK;
+	case ARE_OPT_BAKED_MIN_BLOCKS: ctx->opt_bake_min_blocks = value > 0 && value <= 16 ? value : 0; return ARE_OK;
 	default: return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown option");
 	}
 }
@@ -597,7 +599,7 @@ static int commit_device(are_cuda_ctx *ctx, const CompiledScene &cs, bool want_d
 	ctx->bake_note.clear();
 	ctx->opt_lean = lean; ctx->opt_bake = bake; ctx->opt_bake_packed = bake_packed;
 	if (cs.lean_ok && lean && bake) {
-		ctx->baked = bake_get(cs, bake_packed, ctx->device, ctx->bake_note, &info.bake_compile_ms);
+		ctx->baked = bake_get(cs, bake_packed, ctx->parent ? ctx->parent->opt_bake_min_blocks : ctx->opt_bake_min_blocks, ctx->device, ctx->bake_note, &info.bake_compile_ms);
 		info.baked = ctx->baked ? 1 : 0;
 	}
 	info.builder = device_built ? ARE_BVH_BUILDER_DEVICE_LBVH : ARE_BVH_BUILDER_HOST_SAH;

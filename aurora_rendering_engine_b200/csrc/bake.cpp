@@ -99,7 +99,7 @@ uint64_t fnv1a(const std::string &s) {
 
 }  // namespace
 
-std::string bake_source(const CompiledScene &cs, bool packed) {
+std::string bake_source(const CompiledScene &cs, bool packed, int min_blocks) {
 	if (!cs.lean_ok) return std::string();
 	const HotRange &br = cs.brute_range;
 	std::string body;
@@ -123,7 +123,11 @@ std::string bake_source(const CompiledScene &cs, bool packed) {
 	}
 	std::string s;
 	s += "// generated by bake.cpp from the committed scene: the closest-hit tests of its lean form as straight-line code\n";
-	s += "#define ARE_BAKED 1\n#include \"intersect.cuh\"\nnamespace areb {\n";
+	s += "#define ARE_BAKED 1\n";
+	// __launch_bounds__ CTAs per SM.  The kernel needs 55 registers whatever the bound (9 CTAs fit), but ptxas schedules it
+	// differently: measured on the Cornell box 5 / 6 / 7 / 8 / 9 / 10 -> 11 274 / 11 275 / 11 112 / 11 045 / 10 773 / 10 742 Msamples/s
+	s += "#define RENDER_MIN_BLOCKS_LEAN " + std::to_string(min_blocks > 0 ? min_blocks : 6) + "\n";
+	s += "#include \"intersect.cuh\"\nnamespace areb {\n";
 	s += "__device__ __forceinline__ void intersect_baked(V3<float> o, V3<float> d, float tmin, Hit &h) {\n";
 	if (need_pairs) s += "\tconst float2 Dx = make_float2(d.x, -o.x), Dy = make_float2(d.y, -o.y), Dz = make_float2(d.z, -o.z);\n";
 	s += body;
@@ -263,9 +267,9 @@ std::string cu_err(Drv &d, CUresult e) {
 }
 }  // namespace
 
-const BakedKernel *bake_get(const CompiledScene &cs, bool packed, int device, std::string &err, double *compile_ms) {
+const BakedKernel *bake_get(const CompiledScene &cs, bool packed, int min_blocks, int device, std::string &err, double *compile_ms) {
 	if (compile_ms) *compile_ms = 0.0;
-	const std::string src = bake_source(cs, packed);
+	const std::string src = bake_source(cs, packed, min_blocks);
 	if (src.empty()) { err = "scene has no lean form"; return nullptr; }
 	Drv &d = drv();
 	if (!d.ok) { err = "CUDA driver API unavailable: " + d.why; return nullptr; }

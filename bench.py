@@ -69,6 +69,7 @@ def parse():
     ap.add_argument("--kernel", default="auto", choices=["auto", "lean", "generic", "baked-packed"],
                     help="A/B: auto = scene-specialised (baked) kernel where the scene has a lean form; lean = precompiled lean kernel; generic = generic brute-force kernel")
     ap.add_argument("--builder", type=int, default=-1, help="BVH builder: 0 host SAH, 1 device LBVH (default: host; device for the 1 M-primitive scene)")
+    ap.add_argument("--baked-min-blocks", type=int, default=0, help="tuning: CTAs per SM the baked kernel is compiled for")
     ap.add_argument("--wavefront", action="store_true", help="A/B: the same estimator scheduled as wavefront stages (ARE_INTEGRATOR_PATH_WAVEFRONT)")
     ap.add_argument("--l2-persist", type=int, default=0, help="A/B: BVH renders mark the node array L2-persisting, per cent of the carve-out (ARE_OPT_L2_PERSIST_NODES)")
     ap.add_argument("--job-spp", type=int, default=1024, help="strong-scaling job: total samples per pixel sharded over the GPUs")
@@ -526,6 +527,8 @@ def kernel_options(a):
               "baked-packed": {capi.OPT_BAKED_PACKED: 1}}.get(a.kernel, {}))
     if a.l2_persist:
         o[capi.OPT_L2_PERSIST_NODES] = a.l2_persist
+    if a.baked_min_blocks:
+        o[capi.OPT_BAKED_MIN_BLOCKS] = a.baked_min_blocks
     if a.traversal == 4:  # ARE_TRAVERSAL_BVH4 needs the 4-wide collapse of the host-built tree
         o[capi.OPT_BUILD_BVH4] = 1
     return o

@@ -197,7 +197,8 @@ typedef enum are_option {
 	ARE_OPT_LBVH_MAX_HEIGHT = 8, /* test hook: device-built trees taller than this fall back to the host builder */
 	ARE_OPT_L2_PERSIST_NODES = 9, /* 0 (default) / 1..100: BVH renders mark the node array as an L2-persisting access window
 	                                (cudaAccessPolicyWindow) claiming this per cent of the device's persisting carve-out */
-	ARE_OPT_BUILD_BVH4 = 10 /* 0 (default) / 1: the host builder also collapses its BVH2 into 4-wide nodes (ARE_TRAVERSAL_BVH4) */
+	ARE_OPT_BUILD_BVH4 = 10, /* 0 (default) / 1: the host builder also collapses its BVH2 into 4-wide nodes (ARE_TRAVERSAL_BVH4) */
+	ARE_OPT_BAKED_MIN_BLOCKS = 11 /* tuning: CTAs per SM the baked kernel is compiled for (0 = default: 6) */
 } are_option;
 int are_cuda_set_option(are_cuda_ctx *ctx, int option, int value);
 /* The sm_100a CUBIN of the committed scene's baked kernel (what cuobjdump -sass / nvdisasm -g read next to an ncu capture).
