@@ -374,6 +374,8 @@ class Bench:
                 ctx.render(job.cam, job.params(self.sample_base(k), S), out=host)
             api = ("are_cuda_commit + " if recommit else "") + "are_cuda_render (pageable host buffer)"
         else:
+            host_t = self.torch.empty((H, W, 3), dtype=self.torch.float32) if self.rank == 0 else None  # pageable, reused like a host program's frame buffer
+
             def step(k):
                 if recommit:
                     h2d[0] = ctx.commit()
@@ -381,7 +383,7 @@ class Bench:
                 ctx.render_device(job.cam, job.params(self.sample_base(k), S), job.accum.data_ptr())
                 self.engine.reduce_sum_to_root(job.accum, self.world)
                 if self.rank == 0:
-                    job.accum.cpu()  # the summed frame into pageable host memory
+                    host_t.copy_(job.accum)  # the summed frame into pageable host memory (synchronises)
             api = ("are_cuda_commit + " if recommit else "") + "are_cuda_render_device per rank + NCCL sum-reduce + one D2H of the summed frame on rank 0 (pageable)"
         for k in range(warmup):
             step(k)
