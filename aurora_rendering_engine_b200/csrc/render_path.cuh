@@ -59,6 +59,9 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #ifndef RENDER_MIN_BLOCKS_BVH4_BIG
 #define RENDER_MIN_BLOCKS_BVH4_BIG 8
 #endif
+#ifndef TRAV_LEAF_EVERY
+#define TRAV_LEAF_EVERY 1  // node phases per leaf phase inside a slice (must divide TRAV_STEPS_PER_VOTE)
+#endif
 #ifndef BVH_BIG_NODES
 #define BVH_BIG_NODES 16384       // 1 MiB of 64 B nodes: beyond this the high-occupancy build is launched
 #endif
@@ -200,11 +203,16 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 				if (!trav) node = TRAV_DONE;
 				while (true) {
 #pragma unroll 1
-					for (int rep = 0; rep < TRAV_STEPS_PER_VOTE; ++rep) {  // several steps between the warp votes that decide the end of the slice
-						if (node >= 0) {                                                                         // node phase
-							if (B4) bvh4_step<COUNT>(A.sc, A.tmin, rs, node, stk, h, &tc);
-							else bvh_step<COUNT>(A.sc, A.tmin, rs, node, stk, h, &tc);
-						}
+					for (int rep = 0; rep < TRAV_STEPS_PER_VOTE / TRAV_LEAF_EVERY; ++rep) {  // several steps between the warp votes that decide the end of the slice
+						// The warp executes the leaf phase whenever ANY lane holds a leaf — with ~19 lanes traversing that is most
+						// iterations, for one or two lanes each time.  Running it once per TRAV_LEAF_EVERY node phases lets lanes that
+						// reach a leaf wait a step or two and cuts the leaf code's share of the issue slots accordingly.
+#pragma unroll
+						for (int r = 0; r < TRAV_LEAF_EVERY; ++r)
+							if (node >= 0) {                                                                     // node phase
+								if (B4) bvh4_step<COUNT>(A.sc, A.tmin, rs, node, stk, h, &tc);
+								else bvh_step<COUNT>(A.sc, A.tmin, rs, node, stk, h, &tc);
+							}
 						if (node < 0 && node != TRAV_DONE) bvh_leaf<COUNT>(A.sc, o, d, A.tmin, node, stk, h, &tc);  // leaf phase
 					}
 					const int n_trav = __popc(__ballot_sync(full, node != TRAV_DONE));

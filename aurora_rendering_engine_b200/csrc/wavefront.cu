@@ -20,7 +20,7 @@
 #include <algorithm>
 
 #include "kernels.h"
-#include "render_path.cuh"
+#include "path_shade.cuh"
 
 namespace areb {
 
@@ -101,60 +101,12 @@ __global__ void __launch_bounds__(256) k_wf_shade(const __grid_constant__ Render
 		o = mk<float>(a.x, a.y, a.z); d = mk<float>(a.w, b.x, b.y); thr = mk<float>(b.z, b.w, c.x);
 		pixel = __float_as_int(c.y);
 		sample = __float_as_int(c.z) >> 8; bounce = __float_as_int(c.z) & 255;
-		const float t = hr.x;
-		const int idx = __float_as_int(hr.y);
-		F3 contrib = mk<float>(0.f, 0.f, 0.f);
+		PathRay pr;
+		pr.o = o; pr.d = d; pr.thr = thr; pr.bounce = bounce; pr.orig = orig;
+		F3 contrib;
 		bool done;
-		if (idx < 0) {
-			if (!A.bg_black) contrib = thr * background(A, d);
-			done = true;
-		} else {  // the megakernel's classify + scatter stages for one ray (render_path.cuh), BVH2 arrays
-			const F3 sP = o + t * d;
-			orig = idx;
-			const HotIds id = hit_ids<ldg4>(A.sc, A.sc.bvh_prims, A.sc.bvh_ids, idx, sP);
-			const int sdev = id.b >= 0 ? resolve_exact(A.sc, id, sP).dev_prim : id.a;
-			const float4 s0 = __ldg(reinterpret_cast<const float4 *>(&A.sc.shade[sdev].r0));
-			const float4 s1 = __ldg(reinterpret_cast<const float4 *>(&A.sc.shade[sdev].r1));
-			const int sbits = __float_as_int(s0.w);
-			F3 sN = mk<float>(s0.x, s0.y, s0.z), scol = mk<float>(s1.x, s1.y, s1.z);
-			if (sdev >= A.sc.n_tri + A.sc.n_quad) {
-				const float4 cc = __ldg(reinterpret_cast<const float4 *>(&A.sc.prim_plane[sdev].r0));
-				sN = (1.0f / cc.w) * (sP - mk<float>(cc.x, cc.y, cc.z));
-			}
-			const int kind = sbits & 255;
-			if (kind == MK_LIGHT) {
-				if (!((sbits >> 8) & 1)) {
-					const Resolved rs = resolve_exact(A.sc, id, sP);
-					const PrimInfo pi = A.sc.info[rs.dev_prim];
-					float u, v;
-					surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, u, v);
-					const MaterialRec &m = A.sc.mats[pi.mat];
-					scol = m.pf[1] * tex_eval<float>(A.sc, mat_texture(m, pi.tex), u, v, sP);
-				}
-				contrib = thr * scol;
-				done = true;
-			} else {
-				done = bounce >= A.max_depth;
-				if ((sbits >> 8) & 1) thr = thr * scol;
-			}
-			if (!done) {
-				const Rnd4<float> r = rnd4<float>(A.key, (uint32_t)pixel, (uint32_t)sample, (uint32_t)bounce, 0u);
-				F3 wo;
-				if ((sbits >> 8) & 1) alive = scatter_dir<float>(kind, s1.w, d, sN, r, wo);
-				else {
-					const Resolved rs = resolve_exact(A.sc, HotIds{ sdev, -1 }, sP);
-					const PrimInfo pi = A.sc.info[rs.dev_prim];
-					float u, v;
-					F3 att, emit;
-					const int tk = (sbits >> SHADE_TEXKIND_SHIFT) & 7;
-					surface_at(A.sc, rs.dev_prim, sP, rs.a, rs.b, sN, u, v, tk == TK_CHECKER_UV || tk == TK_IMAGE);
-					alive = scatter<float>(A.sc, pi.mat, pi.tex, d, sN, sP, u, v, r, wo, att, emit);
-					thr = thr * att;
-				}
-				o = sP; d = wo;
-				++bounce;
-			}
-		}
+		shade_one(A, pr, hr.x, __float_as_int(hr.y), (uint32_t)pixel, (uint32_t)sample, done, alive, contrib);
+		o = pr.o; d = pr.d; thr = pr.thr; bounce = pr.bounce; orig = pr.orig;
 		if (done) {
 			const float csum = contrib.x + contrib.y + contrib.z;
 			if (csum > 0.0f && csum < INFINITY) {
