@@ -346,5 +346,25 @@ __device__ __forceinline__ void cam_ray(const CamT<T> &c, T inv_w, T inv_h, int 
 		d = nrm(dir);
 	}
 }
+// fp32 (the render kernels, the wavefront's generate stage and the precision=32 camera harness): the same ray with the
+// affine maps folded — fx = (x + sx) kx - c.sx with kx = 2 c.sx / W (warp-uniform, hoisted out of the loop), and the
+// direction as two chained multiply-adds on fwd — 10 instructions fewer per camera ray, which the render loop executes
+// on every trip for the ~5 lanes that start a new path.
+template <>
+__device__ __forceinline__ void cam_ray<float>(const CamT<float> &c, float inv_w, float inv_h, int x, int y, Rnd4<float> r, V3<float> &o, V3<float> &d) {
+	const float kx = 2.0f * inv_w * c.sx, ky = -2.0f * inv_h * c.sy;
+	const float fx = fmaf((float)x + r.x, kx, -c.sx), fy = fmaf((float)y + r.y, ky, c.sy);
+	const V3<float> dir = mad(fx, c.right, mad(fy, c.up, c.fwd));
+	if (c.lens_r > 0.0f) {
+		float rr = c.lens_r * sqrt_t(r.z), sn, cs;
+		sincos2pi_t(r.w, &sn, &cs);
+		const V3<float> off = mad2(rr * cs, c.right, rr * sn, c.up);
+		o = c.pos + off;
+		d = nrm(c.focus * dir - off);
+	} else {
+		o = c.pos;
+		d = nrm(dir);
+	}
+}
 
 }  // namespace areb
