@@ -111,6 +111,20 @@ public:
 	/// Who builds the hierarchy at the next upload(): ARE_BVH_BUILDER_HOST_SAH (default) or ARE_BVH_BUILDER_DEVICE_LBVH
 	/// (milliseconds per million primitives; for scenes that change every frame).
 	void set_bvh_builder(int builder) { check(are_cuda_set_bvh_builder(ctx_, builder)); }
+	/// Context options (are_option in are_cuda.h: kernel choice, scene-compiler switches).
+	void set_option(int option, int value) { check(are_cuda_set_option(ctx_, option, value)); }
+	/// Triangles of the uploaded set moved (same objects, new geometry): hand the ones that changed to move(), then refit().
+	/// refit() returns false when the hierarchy cannot be refitted (host-built tree, fused parallelograms / boxes) — call
+	/// upload() again in that case.  Triangle ids are positions in ObjectSet::triangles as uploaded.
+	void move(int triangle_id, const Triangle &t) {
+		check(are_cuda_update_triangles(ctx_, 1, &triangle_id, t.origin().e(), t.edge_u().e(), t.edge_v().e()));
+	}
+	bool refit(double *device_ms = nullptr) {
+		const int st = are_cuda_refit(ctx_, device_ms);
+		if (st == ARE_ERR_RUNTIME) return false;
+		check(st);
+		return true;
+	}
 	are_commit_info commit_info() {
 		are_commit_info info;
 		check(are_cuda_get_commit_info(ctx_, &info));

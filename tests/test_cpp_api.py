@@ -99,6 +99,15 @@ def test_reference_style_host_program_renders_on_gpu(tmp_path, lib, ctx):
     ctx.commit()
     img, st = ctx.render(capi.make_camera(**sc.camera_args()), capi.make_params(**sc.params_args(sample_count=spp)))
     assert np.array_equal(sums, img), "the C++ host program and the Python driver describe the same scene: images must be identical"
+    # the same program over EVERY visible GPU (are::cuda::Renderer(devices) -> are_cuda_create_multi): same samples, sums equal up
+    # to summation order (identical on a one-GPU box, where the group has one device)
+    raw_all = tmp_path / "sums_all.f32"
+    r = subprocess.run([str(exe), str(tmp_path / "out_all.ppm"), str(W), str(H), str(spp), str(raw_all), "0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    n_gpus = lib.are_cuda_device_count()
+    assert f"on {n_gpus} GPU(s)" in r.stdout, r.stdout
+    sums_all = np.fromfile(raw_all, np.float32).reshape(H, W, 3)
+    assert np.allclose(sums_all, sums, rtol=1e-5, atol=1e-5) and (n_gpus > 1 or np.array_equal(sums_all, sums))
     # the PPM was written by are::Texture::save_texture: linear, truncating (reference src/texture.cpp:384-386)
     data = ppm.read_bytes()
     hdr = f"P6\n{W} {H}\n255\n".encode()
