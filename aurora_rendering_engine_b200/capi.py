@@ -254,14 +254,14 @@ def compile_probe_forms(Q, u, v) -> dict:
     return dict(zip(keys, (int(x) for x in out)))
 
 
-def bake_probe(Q, u, v, packed=False, cubin_path=None) -> str:
+def bake_probe(Q, u, v, packed=False, cubin_path=None, generic=False) -> str:
     """Host-only: the CUDA source generated for the lean form of a triangle scene (are_cuda_bake_probe); with cubin_path
     also the NVRTC-compiled sm_100a CUBIN.  No GPU involved."""
     lib = load_library()
     Q, u, v = (np.ascontiguousarray(x, dtype=np.float64) for x in (Q, u, v))
     n = C.c_uint64(0)
     buf = C.create_string_buffer(1 << 18)
-    st = lib.are_cuda_bake_probe(len(Q), Q.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp), int(bool(packed)), buf, len(buf),
+    st = lib.are_cuda_bake_probe(len(Q), Q.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp), int(bool(packed)) | (2 if generic else 0), buf, len(buf),
                                  C.byref(n), os.fsencode(cubin_path) if cubin_path else None)
     if st != ARE_OK:
         raise AreCudaError(st, (lib.are_cuda_last_error(None) or b"").decode())

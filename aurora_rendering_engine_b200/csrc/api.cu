@@ -66,6 +66,7 @@ struct are_cuda_ctx {
 	int opt_l2_persist = 0;          // BVH renders: mark the node array as L2-persisting (cudaAccessPolicyWindow) for the launch
 	size_t l2_persist_max = 0, l2_window_max = 0;
 	const BakedKernel *baked = nullptr;  // owned by the process-wide cache in bake.cpp
+	bool baked_lean = false;             // it is the lean kernel's baked form (else the generic brute-force kernel's)
 	std::string bake_note;
 	// multi-device context (are_cuda_create_multi): this context drives devices[0]; `peers` are full single-device contexts
 	// on the other devices, owned here.  They share this context's compiled scene (csp) and render sample shards.
@@ -598,9 +599,15 @@ static int commit_device(are_cuda_ctx *ctx, const CompiledScene &cs, bool want_d
 	ctx->baked = nullptr;
 	ctx->bake_note.clear();
 	ctx->opt_lean = lean; ctx->opt_bake = bake; ctx->opt_bake_packed = bake_packed;
-	if (cs.lean_ok && lean && bake) {
-		ctx->baked = bake_get(cs, bake_packed, ctx->parent ? ctx->parent->opt_bake_min_blocks : ctx->opt_bake_min_blocks, ctx->device, ctx->bake_note, &info.bake_compile_ms);
-		info.baked = ctx->baked ? 1 : 0;
+	if (bake && !cs.brute.empty()) {
+		// the lean form where the scene has one (and the lean kernel is allowed), else the whole brute-force list of a scene of
+		// at most BAKE_MAX_SLOTS hot slots around the generic kernel (textures, spheres, any material)
+		ctx->baked_lean = cs.lean_ok && lean;
+		if (ctx->baked_lean || cs.n_hot <= BAKE_MAX_SLOTS) {
+			ctx->baked = bake_get(cs, ctx->baked_lean, bake_packed, ctx->parent ? ctx->parent->opt_bake_min_blocks : ctx->opt_bake_min_blocks, ctx->device,
+				ctx->bake_note, &info.bake_compile_ms);
+			info.baked = ctx->baked ? (ctx->baked_lean ? 1 : 2) : 0;
+		}
 	}
 	info.builder = device_built ? ARE_BVH_BUILDER_DEVICE_LBVH : ARE_BVH_BUILDER_HOST_SAH;
 	info.bvh_nodes = d.n_nodes;
@@ -877,7 +884,7 @@ int are_cuda_bake_probe(int n_tri, const double *Q, const double *u, const doubl
 	CompiledScene cs;
 	std::string err;
 	if (!compile_scene(hs, opt, cs, err)) return ARE_ERR_INVALID_ARGUMENT;
-	const std::string src = bake_source(cs, packed != 0);
+	const std::string src = bake_source(cs, cs.lean_ok && !(packed & 2), (packed & 1) != 0);
 	if (source_len) *source_len = src.size();
 	if (src.empty()) return ARE_ERR_RUNTIME;  // no lean form
 	if (source_out && source_cap) {
@@ -1120,7 +1127,9 @@ static int render_single(are_cuda_ctx *ctx, const are_camera *cam, const are_ren
 		} else {
 			int blocks, threads;
 			size_t smem;
-			baked = mode == 0 && ctx->baked && ctx->opt_bake && render_path_is_lean(a) && render_path_lean_dims(a, blocks, threads, smem);
+			// the baked kernel stands for the brute-force kernel it was generated around: the lean one, or the generic one
+			baked = mode == 0 && ctx->baked && ctx->opt_bake && render_path_is_lean(a) == ctx->baked_lean && render_path_lean_dims(a, blocks, threads, smem);
+			if (baked && !ctx->baked_lean) smem = (size_t)a.sc.n_hot * sizeof(HotPrim);
 			if (baked) {
 				std::string err;
 				launched = bake_launch(ctx->baked, a, blocks, threads, smem, ctx->stream, err);

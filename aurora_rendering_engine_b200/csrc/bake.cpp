@@ -97,43 +97,65 @@ uint64_t fnv1a(const std::string &s) {
 	return h;
 }
 
+void emit_sphere(std::string &s, const HotPrim &r, int idx) {
+	char buf[512];
+	snprintf(buf, sizeof buf, "\ttest_sphere(make_float4(%s, %s, %s, %s), make_float4(%s, 0.0f, 0.0f, 0.0f), o, d, tmin, %d, h);\n", flit(r.r0.x).c_str(),
+		flit(r.r0.y).c_str(), flit(r.r0.z).c_str(), flit(r.r0.w).c_str(), flit(r.r1.x).c_str(), idx);
+	s += buf;
+}
+
 }  // namespace
 
-std::string bake_source(const CompiledScene &cs, bool packed, int min_blocks) {
-	if (!cs.lean_ok) return std::string();
+std::string bake_source(const CompiledScene &cs, bool lean, bool packed, int min_blocks) {
+	if (lean ? !cs.lean_ok : (cs.brute.empty() || cs.n_hot > BAKE_MAX_SLOTS)) return std::string();
 	const HotRange &br = cs.brute_range;
 	std::string body;
 	bool need_pairs = false;
 	char buf[256];
-	int slot = 0;
+	int slot = br.first;
 	for (int i = 0; i < br.nb; ++i, slot += 2) {
-		snprintf(buf, sizeof buf, "\t// box %d (%s), hot slots %d-%d\n", i, i < cs.lean_n_open ? "one face absent" : "closed", slot, slot + 1);
+		// the lean list has its open boxes first; the generic list keeps the record's own flag
+		const bool open = cs.brute[(size_t)slot + 1].r0.w != 0.0f;
+		snprintf(buf, sizeof buf, "\t// box %d (%s), hot slots %d-%d\n", i, open ? "one face absent" : "closed", slot, slot + 1);
 		body += buf;
-		emit_box(body, cs.brute[slot], cs.brute[slot + 1], i < cs.lean_n_open ? 2 : 1, slot, packed, need_pairs);
+		emit_box(body, cs.brute[(size_t)slot], cs.brute[(size_t)slot + 1], open ? 2 : 1, slot, packed, need_pairs);
 	}
 	for (int j = 0; j < br.nq; ++j, ++slot) {
 		snprintf(buf, sizeof buf, "\t// parallelogram, hot slot %d\n", slot);
 		body += buf;
-		emit_plane(body, cs.brute[slot], true, slot);
+		emit_plane(body, cs.brute[(size_t)slot], true, slot);
 	}
 	for (int j = 0; j < br.nt; ++j, ++slot) {
 		snprintf(buf, sizeof buf, "\t// triangle, hot slot %d\n", slot);
 		body += buf;
-		emit_plane(body, cs.brute[slot], false, slot);
+		emit_plane(body, cs.brute[(size_t)slot], false, slot);
 	}
+	for (int j = 0; j < br.ns; ++j, ++slot) {
+		snprintf(buf, sizeof buf, "\t// sphere, hot slot %d\n", slot);
+		body += buf;
+		emit_sphere(body, cs.brute[(size_t)slot], slot);
+	}
+	bool noise = false;
+	for (const TextureRec &t : cs.texs) noise = noise || t.kind == TK_NOISE;
 	std::string s;
-	s += "// generated by bake.cpp from the committed scene: the closest-hit tests of its lean form as straight-line code\n";
+	s += "// generated by bake.cpp from the committed scene: the closest-hit tests of its brute-force list as straight-line code\n";
 	s += "#define ARE_BAKED 1\n";
-	// __launch_bounds__ CTAs per SM.  The kernel needs 55 registers whatever the bound (9 CTAs fit), but ptxas schedules it
+	// __launch_bounds__ CTAs per SM.  The lean kernel needs 55 registers whatever the bound (9 CTAs fit), but ptxas schedules it
 	// differently: measured on the Cornell box 5 / 6 / 7 / 8 / 9 / 10 -> 11 274 / 11 275 / 11 112 / 11 045 / 10 773 / 10 742 Msamples/s
-	s += "#define RENDER_MIN_BLOCKS_LEAN " + std::to_string(min_blocks > 0 ? min_blocks : 6) + "\n";
+	if (lean) s += "#define RENDER_MIN_BLOCKS_LEAN " + std::to_string(min_blocks > 0 ? min_blocks : 6) + "\n";
+	else if (min_blocks > 0) s += "#define RENDER_MIN_BLOCKS " + std::to_string(min_blocks) + "\n";
 	s += "#include \"intersect.cuh\"\nnamespace areb {\n";
 	s += "__device__ __forceinline__ void intersect_baked(V3<float> o, V3<float> d, float tmin, Hit &h) {\n";
 	if (need_pairs) s += "\tconst float2 Dx = make_float2(d.x, -o.x), Dy = make_float2(d.y, -o.y), Dz = make_float2(d.z, -o.z);\n";
 	s += body;
 	s += "}\n}  // namespace areb\n#include \"render_path.cuh\"\n";
-	s += "extern \"C\" __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS_LEAN) k_render_baked(const __grid_constant__ areb::RenderArgs A) {\n";
-	s += "\tareb::render_path_body<0, false, false, true, true>(A);\n}\n";
+	if (lean) {
+		s += "extern \"C\" __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS_LEAN) k_render_baked(const __grid_constant__ areb::RenderArgs A) {\n";
+		s += "\tareb::render_path_body<0, false, false, true, true>(A);\n}\n";
+	} else {
+		s += "extern \"C\" __global__ void __launch_bounds__(RENDER_THREADS, RENDER_MIN_BLOCKS) k_render_baked(const __grid_constant__ areb::RenderArgs A) {\n";
+		s += std::string("\tareb::render_path_body<0, false, false, false, true, ") + (noise ? "true" : "false") + ">(A);\n}\n";
+	}
 	return s;
 }
 
@@ -267,10 +289,10 @@ std::string cu_err(Drv &d, CUresult e) {
 }
 }  // namespace
 
-const BakedKernel *bake_get(const CompiledScene &cs, bool packed, int min_blocks, int device, std::string &err, double *compile_ms) {
+const BakedKernel *bake_get(const CompiledScene &cs, bool lean, bool packed, int min_blocks, int device, std::string &err, double *compile_ms) {
 	if (compile_ms) *compile_ms = 0.0;
-	const std::string src = bake_source(cs, packed, min_blocks);
-	if (src.empty()) { err = "scene has no lean form"; return nullptr; }
+	const std::string src = bake_source(cs, lean, packed, min_blocks);
+	if (src.empty()) { err = lean ? "scene has no lean form" : "scene has no brute-force list of at most 16 slots"; return nullptr; }
 	Drv &d = drv();
 	if (!d.ok) { err = "CUDA driver API unavailable: " + d.why; return nullptr; }
 	const uint64_t key = fnv1a(src);

@@ -23,13 +23,16 @@ namespace areb {
 // The generated translation unit for the lean form of `cs` (empty string when the scene has no lean form).
 // packed: emit the (s, e) slab products as fma.rn.f32x2 pairs (FFMA2) where an axis has two or more non-zero components.
 // min_blocks > 0: CTAs per SM the kernel is compiled for (__launch_bounds__; 0 = the lean kernel's RENDER_MIN_BLOCKS_LEAN).
-std::string bake_source(const CompiledScene &cs, bool packed, int min_blocks = 0);
+// lean: the lean form (cs.lean_ok) around the lean kernel; else the whole brute-force list (boxes, parallelograms, triangles,
+// spheres; at most BAKE_MAX_SLOTS hot slots) around the generic brute-force kernel with its general shading path.
+enum { BAKE_MAX_SLOTS = 16 };
+std::string bake_source(const CompiledScene &cs, bool lean, bool packed, int min_blocks = 0);
 
 struct BakedKernel;  // one loaded module + function (per device), owned by the process-wide cache
 
 // Compile (or fetch from the cache) the baked kernel of `cs` for the CURRENT device.  nullptr + err on failure
 // (no NVRTC, compile error, ...).  compile_ms: time spent in NVRTC + module load, 0 on a cache hit.
-const BakedKernel *bake_get(const CompiledScene &cs, bool packed, int min_blocks, int device, std::string &err, double *compile_ms);
+const BakedKernel *bake_get(const CompiledScene &cs, bool lean, bool packed, int min_blocks, int device, std::string &err, double *compile_ms);
 
 // The CUBIN image a baked kernel was loaded from (for cuobjdump / nvdisasm next to an ncu capture).
 const std::string *bake_cubin(const BakedKernel *k);

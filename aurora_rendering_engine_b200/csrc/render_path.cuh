@@ -79,7 +79,7 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 // tests, no spheres, every surface shaded from its ShadeRec alone).  The tests are a guarded full unroll with
 // compile-time shared-memory offsets instead of four counted loops, and a hit goes straight to its shading record
 // (six per box, one per face) held in shared memory: no id chain, no owner resolution, no general material path.
-// BAKED (LEAN only): the closest-hit tests are not read from shared memory but are straight-line code generated from the
+// BAKED (brute force; lean or generic shading): the closest-hit tests are not read from shared memory but are straight-line code generated from the
 // committed scene and compiled at commit time (bake.cpp): intersect_baked() with every primitive constant an immediate
 // and the zero components of its normals left out.  Everything else is the lean kernel.
 // NOISE = false: the scene has no noise texture, the cooperative turbulence stage is compiled out (its live values cost
@@ -88,7 +88,7 @@ template <int MODE, bool COUNT, bool BIG = false, bool LEAN = false, bool BAKED 
 __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 	constexpr bool BVH = MODE != 0, WIDE = MODE == 2, B4 = MODE == 3;
 	static_assert(!LEAN || MODE == 0, "the lean form is a brute-force list");
-	static_assert(!BAKED || LEAN, "a baked kernel is a lean kernel");
+	static_assert(!BAKED || MODE == 0, "a baked kernel tests a brute-force list");
 	extern __shared__ float4 s_raw[];
 	__shared__ float s_acc[RENDER_THREADS / 32][96];
 	const HotPrim *s_prims = reinterpret_cast<const HotPrim *>(s_raw);

@@ -176,7 +176,8 @@ typedef struct are_commit_info {
 	double host_bvh_ms; /* of which: the host BVH builders (HOST_SAH) / preparing the device builder's input (DEVICE_LBVH) */
 	double device_bvh_ms; /* DEVICE_LBVH: CUDA-event time of the build kernels */
 	uint64_t device_bvh_launches;
-	int32_t baked; /* 1: a scene-specialised render kernel is loaded for this scene (ARE_OPT_BAKED_KERNEL) */
+	int32_t baked; /* a scene-specialised render kernel is loaded for this scene (ARE_OPT_BAKED_KERNEL): 1 = around the lean kernel,
+	                  2 = around the generic brute-force kernel (scenes of at most 16 hot slots: spheres, textures, any material), 0 = none */
 	int32_t pad_;
 	double bake_compile_ms; /* NVRTC + module load time of this commit; 0 when the kernel came from the process-wide cache */
 } are_commit_info;
@@ -186,7 +187,8 @@ int are_cuda_get_commit_info(are_cuda_ctx *ctx, are_commit_info *out);
  * next are_cuda_commit; kernel-choice options (1, 2, 7) at the next render. */
 typedef enum are_option {
 	ARE_OPT_LEAN_KERNEL = 1, /* 1 (default): small flat-shaded scenes use the lean brute-force kernel; 0: the generic one */
-	ARE_OPT_BAKED_KERNEL = 2, /* 1 (default): ... and its scene-specialised form, generated and compiled with NVRTC at commit:
+	ARE_OPT_BAKED_KERNEL = 2, /* 1 (default): ... and the scene-specialised form of either (lean form, or any brute-force list of at most
+	                             16 hot slots), generated and compiled with NVRTC at commit:
 	                             every plane / slab coefficient an immediate, zero components left out, no loads, no guards.
 	                             Bit-identical output; silently absent where NVRTC / the driver API cannot be loaded */
 	ARE_OPT_BAKED_PACKED = 3, /* 0 (default) / 1: baked slab products as fma.rn.f32x2 pairs (FFMA2) */
@@ -251,7 +253,8 @@ int are_cuda_compile_probe_forms(int n_tri, const double *Q, const double *u, co
 
 /* Host-only probe of the scene-specialised ("baked") render kernel (no GPU needed): compiles the n_tri triangles as
  * are_cuda_commit would and writes the CUDA source generated for the lean form of that scene to source_out (at most
- * source_cap bytes, NUL-terminated; *source_len = full length).  packed != 0: slab products as fma.rn.f32x2 pairs.
+ * source_cap bytes, NUL-terminated; *source_len = full length).  packed: bit 0 = slab products as fma.rn.f32x2 pairs, bit 1 =
+ * generate around the GENERIC brute-force kernel even if the scene has a lean form.
  * cubin_path != NULL: additionally compile it with NVRTC for sm_100a and write the CUBIN there (cuobjdump -sass reads
  * it).  ARE_ERR_RUNTIME when the scene has no lean form or NVRTC fails (are_cuda_last_error(NULL) has the log). */
 int are_cuda_bake_probe(int n_tri, const double *Q, const double *u, const double *v, int packed, char *source_out, uint64_t source_cap,

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("kind,traversal,variant", [
-    ("mixed", 1, capi.KERNEL_BRUTE), ("mixed", 2, capi.KERNEL_BVH2), ("mixed", 3, capi.KERNEL_WIDE),
+    ("mixed", 1, capi.KERNEL_BRUTE_BAKED), ("mixed", 1, capi.KERNEL_BRUTE), ("mixed", 2, capi.KERNEL_BVH2), ("mixed", 3, capi.KERNEL_WIDE),
     ("lean", 1, capi.KERNEL_BRUTE_BAKED), ("lean", 1, capi.KERNEL_BRUTE_LEAN), ("lean", 1, capi.KERNEL_BRUTE), ("lean", 2, capi.KERNEL_BVH2),
 ])
 def test_white_furnace(ctx, kind, traversal, variant):
@@ -23,6 +23,8 @@ def test_white_furnace(ctx, kind, traversal, variant):
     if kind == "lean":   # the three brute-force kernels a scene with a lean form can run on
         ctx.set_option(capi.OPT_BAKED_KERNEL, int(variant == capi.KERNEL_BRUTE_BAKED))
         ctx.set_option(capi.OPT_LEAN_KERNEL, int(variant != capi.KERNEL_BRUTE))
+    else:                # spheres, glass, mirrors: the generic brute-force kernel, or its scene-specialised (baked) form
+        ctx.set_option(capi.OPT_BAKED_KERNEL, int(variant != capi.KERNEL_BRUTE))
     img, st = ac.render(ctx, sc, traversal=traversal, sample_count=spp)
     assert st.kernel_variant == variant and st.rays > 2 * st.samples
     lost = int(round(float((1.0 - img).sum() / 3 * spp)))

@@ -492,6 +492,14 @@ def test_lean_kernel_equals_generic_brute_kernel(ctx, oracle, which):
     # the scene-specialised kernel (NVRTC at commit): same tests with the scene's constants as immediates
     assert ctx.commit_info().baked == 1 and st_baked.kernel_variant == capi.KERNEL_BRUTE_BAKED
     assert st_baked.rays == st_lean.rays and np.array_equal(baked, lean), f"max |baked - lean| = {np.abs(baked - lean).max()}"
+    # the generic kernel's own scene-specialised form (what scenes without a lean form get: spheres, textures)
+    ctx.set_option(capi.OPT_LEAN_KERNEL, 0)
+    ctx.commit()
+    gbaked, st_gbaked = ctx.render(cam, par)
+    ctx.set_option(capi.OPT_LEAN_KERNEL, 1)
+    assert ctx.commit_info().baked == 2 and st_gbaked.kernel_variant == capi.KERNEL_BRUTE_BAKED
+    assert st_gbaked.rays == st_gen.rays and np.array_equal(gbaked, gen), f"max |generic baked - generic| = {np.abs(gbaked - gen).max()}"
+    ctx.commit()
     # ... and with its slab products as fma.rn.f32x2 pairs
     ctx.set_option(capi.OPT_BAKED_PACKED, 1)
     ctx.commit()
@@ -502,3 +510,39 @@ def test_lean_kernel_equals_generic_brute_kernel(ctx, oracle, which):
     oimg, ost = osc.render(cam, par)
     p = psnr(np.clip(lean / 8.0, 0, 1), np.clip(oimg / 8.0, 0, 1))
     assert p >= PSNR_MIN and abs(int(st_lean.rays) - int(ost.rays)) < 1e-2 * ost.rays, (p, st_lean.rays, ost.rays)
+
+
+@pytest.mark.parametrize("name,kw,spp", [("textured", dict(width=128, height=72), 8), ("one_sphere", {}, 8), ("spheres_and_tris", {}, 8)])
+def test_generic_baked_kernel_equals_generic_kernel(ctx, name, kw, spp):
+    """Scenes of at most 16 hot slots WITHOUT a lean form (spheres, textures, any material) get the generic brute-force
+    kernel with their closest-hit tests compiled in (are_commit_info.baked == 2): same tests, same order, same arithmetic —
+    the image must be bit-identical to the precompiled generic kernel's."""
+    if name == "textured":
+        sc = scenes.textured(**kw)
+    elif name == "one_sphere":
+        sc = scenes.SceneDesc("one", width=40, height=30)
+        sc.sphere((0, 0, -3), 1.0, sc.mat(scenes.MAT_LAMBERTIAN, -1), sc.solid(0.7, 0.3, 0.2))
+        sc.camera = dict(pos=(0, 0, 0), target=(0, 0, -1), up=(0, 1, 0), vfov_deg=60.0, focus_dist=1.0, jitter=1)
+    else:
+        sc = scenes.SceneDesc("mix", width=96, height=64, max_depth=12)
+        grey, gold = sc.solid(.6, .6, .6), sc.solid(.8, .6, .2)
+        lam, metal, glass = sc.mat(scenes.MAT_LAMBERTIAN, -1), sc.mat(scenes.MAT_METAL, 0.1, -1), sc.mat(scenes.MAT_DIELECTRIC, 1.5)
+        sc.sphere((0, -100.5, -1), 100.0, lam, grey)
+        sc.sphere((0, 0, -1.2), 0.5, glass, grey)
+        sc.sphere((1.1, 0, -1.0), 0.5, metal, gold)
+        sc.tri((-1.5, -0.5, -1.5), (0.9, 0.1, 0.0), (0.2, 0.9, 0.3), lam, gold)
+        sc.tri((-0.6, 0.5, -2.0), (0.5, 0.0, 0.2), (0.1, 0.6, 0.0), metal, grey)
+        sc.quad((-2.0, -0.5, -3.0), (4, 0, 0), (0, 2.0, 0), lam, grey)
+        sc.camera = dict(pos=(0, 0.4, 1.5), target=(0, 0, -1), up=(0, 1, 0), vfov_deg=60.0, focus_dist=2.5, jitter=1)
+    cam = capi.make_camera(**sc.camera_args())
+    par = capi.make_params(**sc.params_args(sample_count=spp, traversal=1, max_depth=12))
+    ctx.clear()
+    sc.feed(ctx)
+    ctx.commit()
+    assert ctx.commit_info().baked == 2
+    baked, sb = ctx.render(cam, par)
+    ctx.set_option(capi.OPT_BAKED_KERNEL, 0)
+    gen, sg = ctx.render(cam, par)
+    ctx.set_option(capi.OPT_BAKED_KERNEL, 1)
+    assert sb.kernel_variant == capi.KERNEL_BRUTE_BAKED and sg.kernel_variant == capi.KERNEL_BRUTE
+    assert sb.rays == sg.rays and np.array_equal(baked, gen), f"max |baked - generic| = {np.abs(baked - gen).max()}"
