@@ -288,7 +288,9 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
-def kernel_name(capi, variant):
+def kernel_name(capi, variant, baked_kind=1):
+    if variant == capi.KERNEL_BRUTE_BAKED and baked_kind == 2:
+        return "k_render_baked (generic brute-force kernel, scene compiled in by NVRTC)"
     return {capi.KERNEL_RT_AO: "k_render_rtao", capi.KERNEL_BRUTE: "k_render_path<brute/smem>",
             capi.KERNEL_BRUTE_LEAN: "k_render_path<brute/smem, lean>",
             capi.KERNEL_BRUTE_BAKED: "k_render_baked (lean kernel, scene compiled in by NVRTC)",
@@ -404,7 +406,7 @@ class Bench:
         achieved = flops / (kernel_ms * 1e-3) / 1e12
         roof = {"bound": "fp32", "achieved": achieved, "peak": peaks["fp32_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["fp32_tflops"] if peaks["fp32_tflops"] else None, "traffic": None,
-                "kernel": kernel_name(self.capi, st.kernel_variant), "kernel_ms": kernel_ms, "flops_per_launch": flops,
+                "kernel": kernel_name(self.capi, st.kernel_variant, self.ctx.commit_info().baked), "kernel_ms": kernel_ms, "flops_per_launch": flops,
                 "counted": {"rays": st.rays, "tri_tests": st.tri_tests, "quad_tests": st.quad_tests, "sphere_tests": st.sphere_tests,
                             "box_tests": st.box_tests, "node_visits": st.node_visits}}
         if st.node_visits > 0 and peaks.get("l2_gbs"):
