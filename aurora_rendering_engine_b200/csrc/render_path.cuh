@@ -91,6 +91,8 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 	static_assert(!BAKED || MODE == 0, "a baked kernel tests a brute-force list");
 	extern __shared__ float4 s_raw[];
 	__shared__ float s_acc[RENDER_THREADS / 32][96];
+	__shared__ float4 s_turb_q[RENDER_THREADS / 32][(!LEAN && NOISE) ? 32 : 1];  // turbulence_coop's queue and sums, per warp
+	__shared__ float s_turb_sum[RENDER_THREADS / 32][(!LEAN && NOISE) ? 32 : 1];
 	const HotPrim *s_prims = reinterpret_cast<const HotPrim *>(s_raw);
 	// LEAN shared-memory layout behind the hot slots: [ShadeRec per record][frame per record: (tangent,0) (bitangent,0)][record base per slot]
 	const uint32_t sb_prims = (uint32_t)__cvta_generic_to_shared(s_raw);
@@ -331,7 +333,7 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 				const int noise_tex = general && ((sbits >> SHADE_TEXKIND_SHIFT) & 7) == TK_NOISE && mk_ != MK_DIELECTRIC && mk_ != MK_LIGHT
 					? ((sbits >> SHADE_TEXID_SHIFT) & SHADE_TEXID_MASK) : -1;
 				if (__any_sync(full, noise_tex >= 0)) {
-					turb = turbulence_coop(A.sc, noise_tex >= 0, noise_tex, sP);
+					turb = turbulence_coop(A.sc, noise_tex >= 0, noise_tex, sP, s_turb_q[warp], s_turb_sum[warp]);
 					have_turb = noise_tex >= 0;
 				}
 			}

@@ -88,41 +88,37 @@ __device__ inline double perlin_noise_tab<double>(const DevScene &sc, const Text
 // A surface hit needs sum_{o<7} 2^-o noise(2^o P) — seven octaves of eight lattice corners, ~770 instructions — and in
 // the render loop only the few lanes whose ray ended on a noise-textured surface need it (5.7 of 32 on BASELINE config
 // 2), so evaluated lane by lane it is the most expensive and the emptiest code of the kernel.  Here the warp shares it:
-// the requesting lanes are counted off four at a time, lane l works on requester l/8 and octave l%8 (the eighth lane of
-// a group idles), i.e. ONE octave per lane with all 32 lanes busy, and three shuffle-adds form each requester's sum.
-// Called by all 32 lanes in converged code.  Returns the sum to the lanes that set `need`; 0 elsewhere.
-__device__ __forceinline__ float turbulence_coop(const DevScene &sc, bool need, int tex_id, V3<float> P) {
+// the requesters queue (P, texture) in the warp's 32 shared-memory slots in ballot order, lane l works on queue entry
+// 4 * round + l/8 and octave l%8 (the eighth lane of a group idles), i.e. ONE octave per lane with all 32 lanes busy,
+// three shuffle-adds form each entry's sum and the group's first lane posts it for the requester to pick up.
+// (First form, round 2: the four requesters of a round were found with find-first-set chains on the ballot and their
+// points fetched by four shuffles — ~45 instructions of bookkeeping per round beside the ~105 of the octave itself;
+// the queue needs ~10.  Same arithmetic, same sums.)
+// Called by all 32 lanes in converged code.  queue / sums: 32 entries each, private to the warp.
+// Returns the sum to the lanes that set `need`; 0 elsewhere.
+__device__ __forceinline__ float turbulence_coop(const DevScene &sc, bool need, int tex_id, V3<float> P, float4 *queue, float *sums) {
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31, slot = lane >> 3, oct = lane & 7;
-	unsigned m = __ballot_sync(full, need);
+	const unsigned m = __ballot_sync(full, need);
+	const int n = __popc(m);
 	const int my_rank = __popc(m & ((1u << lane) - 1u));  // this lane is the my_rank-th requester (if it is one)
-	float result = 0.0f;
-	int round = 0;
-	while (m) {  // warp-uniform
-		// lanes of this round's (up to) four requesters: warp-uniform bit tricks on the ballot (cheaper than four __fns)
-		unsigned mm = m;
-		const int l0 = __ffs(mm) - 1; mm &= mm - 1;
-		const int l1 = __ffs(mm) - 1; mm &= mm - 1;
-		const int l2 = __ffs(mm) - 1; mm &= mm - 1;
-		const int l3 = __ffs(mm) - 1;
-		const int src = slot == 0 ? l0 : (slot == 1 ? l1 : (slot == 2 ? l2 : l3));  // -1 when the round has fewer than slot + 1
-		const int s = src < 0 ? 0 : src;
-		const float px = __shfl_sync(full, P.x, s), py = __shfl_sync(full, P.y, s), pz = __shfl_sync(full, P.z, s);
-		const int tid = __shfl_sync(full, tex_id, s);
+	if (need) queue[my_rank] = make_float4(P.x, P.y, P.z, __int_as_float(tex_id));
+	__syncwarp();
+	for (int base = 0; base < n; base += 4) {  // warp-uniform
+		const int e = base + slot;
 		float v = 0.0f;
-		if (src >= 0 && oct < 7) {
+		if (e < n && oct < 7) {
+			const float4 q = queue[e];
 			const float up = (float)(1 << oct), w = 1.0f / up;  // exact powers of two: the same points and weights as repeated doubling / halving
-			v = w * perlin_noise<float>(sc.tex_data + sc.texs[tid].data_off, mk<float>(px * up, py * up, pz * up));
+			v = w * perlin_noise<float>(sc.tex_data + sc.texs[__float_as_int(q.w)].data_off, mk<float>(q.x * up, q.y * up, q.z * up));
 		}
 		v += __shfl_xor_sync(full, v, 1);
 		v += __shfl_xor_sync(full, v, 2);
 		v += __shfl_xor_sync(full, v, 4);
-		const float got = __shfl_sync(full, v, ((my_rank - 4 * round) & 3) * 8);
-		if (need && my_rank >= 4 * round && my_rank < 4 * round + 4) result = got;
-		m &= m - 1; m &= m - 1; m &= m - 1; m &= m - 1;  // the four lowest requesters are served
-		++round;
+		if (oct == 0 && e < n) sums[e] = v;
 	}
-	return result;
+	__syncwarp();
+	return need ? sums[my_rank] : 0.0f;
 }
 
 // turb: when non-null, the turbulence sum of a TK_NOISE texture at P already formed by turbulence_coop

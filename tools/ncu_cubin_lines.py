@@ -38,7 +38,11 @@ def main():
         print(f"warning: {len(data)} profiled instructions vs {len(seq)} in the cubin — line attribution may be off", file=sys.stderr)
     by_line, by_op, by_file = collections.Counter(), collections.Counter(), collections.Counter()
     thr_line = collections.Counter()
-    tot = tot_thr = 0
+    smp_line, smp_reason = collections.Counter(), collections.Counter()
+    line_reason = collections.defaultdict(collections.Counter)
+    c_smp = hdr.index("# Samples") if "# Samples" in hdr else -1
+    stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+    tot = tot_thr = tot_smp = 0
     for i, r in enumerate(data):
         n, t = int(r[ci]), int(r[ct])
         tot += n
@@ -49,6 +53,15 @@ def main():
         by_line[line] += n
         thr_line[line] += t
         by_file[line[0] if line else None] += n
+        if c_smp >= 0:
+            k = int(r[c_smp] or 0)
+            smp_line[line] += k
+            tot_smp += k
+            for ci_, h in stall_cols:
+                v = int(r[ci_] or 0)
+                if v:
+                    smp_reason[h] += v
+                    line_reason[line][h] += v
     print(f"warp instructions {tot}  avg active threads {tot_thr / max(1, tot):.2f}")
     for f, n in by_file.most_common():
         print(f"  {str(f):34s} {100.0 * n / tot:5.1f}%")
@@ -57,6 +70,14 @@ def main():
     print("-- lines")
     for line, n in by_line.most_common(top):
         print(f"  {str(line):36s} {100.0 * n / tot:5.1f}%  thr/inst {thr_line[line] / max(1, n):5.1f}")
+
+
+    if tot_smp:
+        print(f"-- warp-state samples {tot_smp}: " + "  ".join(f"{k[6:]} {100.0 * v / tot_smp:.1f}%" for k, v in smp_reason.most_common(10)))
+        print("-- lines by samples (where warps wait)")
+        for line, k in smp_line.most_common(top):
+            rs = "  ".join(f"{h[6:]} {100.0 * v / k:.0f}%" for h, v in line_reason[line].most_common(3))
+            print(f"  {str(line):36s} {100.0 * k / tot_smp:5.1f}% of samples  {100.0 * by_line[line] / tot:5.1f}% of instr   {rs}")
 
 
 if __name__ == "__main__":
