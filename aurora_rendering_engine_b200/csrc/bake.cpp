@@ -143,7 +143,7 @@ std::string bake_source(const CompiledScene &cs, bool lean, bool packed, int min
 	// __launch_bounds__ CTAs per SM.  The lean kernel needs 55 registers whatever the bound (9 CTAs fit), but ptxas schedules it
 	// differently: measured on the Cornell box 5 / 6 / 7 / 8 / 9 / 10 -> 11 274 / 11 275 / 11 112 / 11 045 / 10 773 / 10 742 Msamples/s
 	if (lean) s += "#define RENDER_MIN_BLOCKS_LEAN " + std::to_string(min_blocks > 0 ? min_blocks : 6) + "\n";
-	else s += "#define RENDER_MIN_BLOCKS " + std::to_string(min_blocks > 0 ? min_blocks : 6) + "\n";  // textured scene, 5 / 6 / 7 / 8: 13 043 / 12 980 / 12 804 / 12 283
+	else s += "#define RENDER_MIN_BLOCKS " + std::to_string(min_blocks > 0 ? min_blocks : 5) + "\n";  // textured scene, 4 / 5 / 6 / 7: 14 639 / 14 597 / 13 893 / 13 964 Msamples/s
 	s += "#include \"intersect.cuh\"\nnamespace areb {\n";
 	s += "__device__ __forceinline__ void intersect_baked(V3<float> o, V3<float> d, float tmin, Hit &h) {\n";
 	if (need_pairs) s += "\tconst float2 Dx = make_float2(d.x, -o.x), Dy = make_float2(d.y, -o.y), Dz = make_float2(d.z, -o.z);\n";

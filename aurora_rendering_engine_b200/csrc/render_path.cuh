@@ -42,7 +42,7 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 // segment for every lane, classify, then ONE Philox call per lane that feeds either the camera (new path) or the
 // material scatter (continuing path).
 #ifndef RENDER_MIN_BLOCKS
-#define RENDER_MIN_BLOCKS 7  // generic brute-force kernel: 72 registers; measured 6 / 7 / 8 CTAs per SM on the textured scene: 10624 / 10887 / 9973 Msamples/s
+#define RENDER_MIN_BLOCKS 5  // generic brute-force kernel: 96 registers at 4 / 5 CTAs per SM, 72 at 7; textured scene, 4 / 5 / 7: 12 791 / 12 737 / 11 013 Msamples/s
 #endif
 #ifndef RENDER_MIN_BLOCKS_BVH2
 #define RENDER_MIN_BLOCKS_BVH2 7  // single-cursor BVH2 traversal, L1-resident hierarchies: 72 registers; measured 6 / 7 / 8 CTAs/SM on RTIOW: 4207 / 4359 / 4211 Msamples/s
