@@ -54,9 +54,9 @@ class CommitInfo(C.Structure):
 
 
 BVH_BUILDER_HOST_SAH, BVH_BUILDER_DEVICE_LBVH = 0, 1
-KERNEL_NONE, KERNEL_BRUTE, KERNEL_BRUTE_LEAN, KERNEL_BVH2, KERNEL_BVH2_BIG, KERNEL_WIDE, KERNEL_RT_AO, KERNEL_BRUTE_BAKED, KERNEL_WAVEFRONT, KERNEL_BVH4 = range(10)
+KERNEL_NONE, KERNEL_BRUTE, KERNEL_BRUTE_LEAN, KERNEL_BVH2, KERNEL_BVH2_BIG, KERNEL_WIDE, KERNEL_RT_AO, KERNEL_BRUTE_BAKED, KERNEL_WAVEFRONT, KERNEL_BVH4, KERNEL_BVH2_QUANT = range(11)
 (OPT_LEAN_KERNEL, OPT_BAKED_KERNEL, OPT_BAKED_PACKED, OPT_FUSE_PARALLELOGRAMS, OPT_FUSE_BOXES, OPT_BUILD_WIDE, OPT_WIDE_MIN_NODES,
- OPT_LBVH_MAX_HEIGHT, OPT_L2_PERSIST_NODES, OPT_BUILD_BVH4, OPT_BAKED_MIN_BLOCKS) = range(1, 12)
+ OPT_LBVH_MAX_HEIGHT, OPT_L2_PERSIST_NODES, OPT_BUILD_BVH4, OPT_BAKED_MIN_BLOCKS, OPT_QUANTIZED_NODES) = range(1, 13)
 
 
 def make_camera(pos, target, up=(0, 1, 0), vfov_deg=40.0, focus_dist=1.0, defocus_angle_deg=0.0, jitter=1) -> Camera:

@@ -64,6 +64,8 @@ struct are_cuda_ctx {
 	int opt_builder_override = -1;   // -1: are_cuda_set_bvh_builder decides
 	int opt_lbvh_max_height = ARE_BVH_STACK;
 	int opt_l2_persist = 0;          // BVH renders: mark the node array as L2-persisting (cudaAccessPolicyWindow) for the launch
+	bool opt_quant_nodes = true;     // big BVH2 hierarchies get (commit) and use (render) a quantised 32-byte-node copy
+	QGrid qgrid_host = {};           // its grid, for the launch-time guard on the camera's distance
 	size_t l2_persist_max = 0, l2_window_max = 0;
 	const BakedKernel *baked = nullptr;  // owned by the process-wide cache in bake.cpp
 	bool baked_lean = false;             // it is the lean kernel's baked form (else the generic brute-force kernel's)
@@ -377,6 +379,7 @@ int are_cuda_set_option(are_cuda_ctx *ctx, int option, int value) {
 	case ARE_OPT_L2_PERSIST_NODES: ctx->opt_l2_persist = value; return ARE_OK;
 	case ARE_OPT_BUILD_BVH4: ctx->opt.build_bvh4 = value != 0; return ARE_OK;
 	case ARE_OPT_BAKED_MIN_BLOCKS: ctx->opt_bake_min_blocks = value > 0 && value <= 16 ? value : 0; return ARE_OK;
+	case ARE_OPT_QUANTIZED_NODES: ctx->opt_quant_nodes = value != 0; return ARE_OK;  // off: at once; on: from the next commit
 	default: return fail(ctx, ARE_ERR_INVALID_ARGUMENT, "unknown option");
 	}
 }
@@ -500,6 +503,23 @@ int are_cuda_clear(are_cuda_ctx *ctx) {
 
 int are_cuda_num_primitives(are_cuda_ctx *ctx) { return ctx ? (int)ctx->scene.prims.size() : ARE_ERR_INVALID_ARGUMENT; }
 
+// Big BVH2 hierarchies: (re)build the quantised copy of d.nodes (dev_types.h: BvhNodeQ) on ctx's stream.
+static int quantize_nodes(are_cuda_ctx *ctx, DevScene &d, are_commit_info &info) {
+	const are_cuda_ctx *root = ctx->parent ? ctx->parent : ctx;
+	if (!d.nodes_q) {  // commit: allocate
+		if (!root->opt_quant_nodes || !d.nodes || d.n_nodes <= render_path_big_nodes()) return ARE_OK;
+		void *p = nullptr;
+		CK(scene_malloc(ctx, &p, (size_t)d.n_nodes * sizeof(BvhNodeQ))); ctx->scene_allocs.push_back(p); d.nodes_q = static_cast<const BvhNodeQ *>(p);
+		CK(scene_malloc(ctx, &p, sizeof(QGrid))); ctx->scene_allocs.push_back(p); d.qgrid = static_cast<const QGrid *>(p);
+	}
+	const int launched = launch_quantize_nodes(d.nodes, d.n_nodes, const_cast<BvhNodeQ *>(d.nodes_q), const_cast<QGrid *>(d.qgrid), ctx->stream);
+	if (launched < 0) return fail(ctx, ARE_ERR_CUDA, "node quantisation failed");
+	CK(cudaMemcpyAsync(&ctx->qgrid_host, d.qgrid, sizeof(QGrid), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	info.device_bvh_launches += (uint64_t)launched;
+	return ARE_OK;
+}
+
 // Device half of a commit: upload the compiled scene `cs` to ctx's GPU (building the hierarchy there when the device
 // builder was selected).  Returns ARE_OK, a negative status, or 1 when the device-built tree is taller than the traversal
 // stack (the caller recompiles with the host builder).  `cs` may belong to another context (multi-device groups).
@@ -586,6 +606,8 @@ static int commit_device(are_cuda_ctx *ctx, const CompiledScene &cs, bool want_d
 	d.root_leaf_meta = cs.root_leaf_meta;
 	if (device_built) { d.nodes = dev_nodes; d.bvh_prims = dev_bvh_prims; d.bvh_ids = dev_bvh_ids; d.n_nodes = dev_n_nodes; d.root_leaf_meta = dev_root_leaf; }
 	d.n_wnodes = d.wnodes ? (int)cs.wnodes.size() : 0;
+	st = quantize_nodes(ctx, d, info);
+	if (st != ARE_OK) return st;
 	d.n_hot = cs.n_hot;
 	d.n_tri = cs.n_tri; d.n_quad = cs.n_quad; d.n_sph = cs.n_sph;
 	d.n_mat = (int)cs.mats.size(); d.n_tex = (int)cs.texs.size();
@@ -718,6 +740,11 @@ static int refit_device(are_cuda_ctx *ctx, const CompiledScene &cs, const std::v
 	const int launched = lbvh_refit(ctx->lbvh_ws, ctx->lbvh_ws_bytes, ctx->lbvh_items, m, d_item.as<int>(), d_rec.as<HotPrim>(), d_lo.as<f4>(), d_hi.as<f4>(),
 		const_cast<HotPrim *>(ctx->dev.bvh_prims), const_cast<BvhNode *>(ctx->dev.nodes), ctx->stream, err);
 	if (launched < 0) return fail(ctx, ARE_ERR_CUDA, "refit: " + err);
+	if (ctx->dev.nodes_q) {  // the quantised copy follows (new grid: the root box may have grown)
+		are_commit_info dummy = {};
+		const int qs = quantize_nodes(ctx, ctx->dev, dummy);
+		if (qs != ARE_OK) return qs;
+	}
 	CK(cudaEventRecord(ctx->ev1, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -1079,6 +1106,17 @@ static int render_single(are_cuda_ctx *ctx, const are_camera *cam, const are_ren
 	RenderArgs a;
 	std::memset(&a, 0, sizeof a);
 	a.sc = ctx->dev;
+	if (a.sc.nodes_q) {
+		// the quantised nodes' half-step rounding bound holds for ray origins within 64 grid extents of the grid; every
+		// secondary ray starts inside it, the camera is checked here
+		const QGrid &g = ctx->qgrid_host;
+		bool near_enough = (ctx->parent ? ctx->parent : ctx)->opt_quant_nodes;
+		for (int k = 0; k < 3; ++k) {
+			const double ext = (double)g.hi[k] - (double)g.lo[k], dist = std::max((double)g.lo[k] - cam->pos[k], cam->pos[k] - (double)g.hi[k]);
+			near_enough = near_enough && dist <= 64.0 * ext;
+		}
+		if (!near_enough) { a.sc.nodes_q = nullptr; a.sc.qgrid = nullptr; }
+	}
 	make_cam_basis(cam->pos, cam->target, cam->up, cam->vfov_deg, cam->focus_dist, cam->defocus_angle_deg, cam->jitter, p->width, p->height, a.cam);
 	for (int k = 0; k < 3; ++k) {
 		a.camf.pos[k] = (float)a.cam.pos[k]; a.camf.fwd[k] = (float)a.cam.fwd[k];
@@ -1188,7 +1226,7 @@ static int render_single(are_cuda_ctx *ctx, const are_camera *cam, const are_ren
 			: p->integrator == ARE_INTEGRATOR_RT_AO ? ARE_KERNEL_RT_AO
 			: p->integrator == ARE_INTEGRATOR_PATH_WAVEFRONT ? ARE_KERNEL_WAVEFRONT
 			: mode == 0 ? (baked ? ARE_KERNEL_BRUTE_BAKED : render_path_is_lean(a) ? ARE_KERNEL_BRUTE_LEAN : ARE_KERNEL_BRUTE)
-			: mode == 2 ? ARE_KERNEL_WIDE : mode == 3 ? ARE_KERNEL_BVH4 : (render_path_is_big(a) ? ARE_KERNEL_BVH2_BIG : ARE_KERNEL_BVH2);
+			: mode == 2 ? ARE_KERNEL_WIDE : mode == 3 ? ARE_KERNEL_BVH4 : (render_path_is_big(a) ? (a.sc.nodes_q ? ARE_KERNEL_BVH2_QUANT : ARE_KERNEL_BVH2_BIG) : ARE_KERNEL_BVH2);
 	}
 	return ARE_OK;
 }

@@ -80,6 +80,23 @@ struct BvhNode {
 	int meta[2];
 };
 
+// Quantised BVH2 node, 32 B = ONE 256-bit load (sm_100 LDG.E.256): both children's boxes as 16-bit planes on a grid over
+// the root box (QGrid: plane = lo + q * step per axis), padded outwards by one step.  The traversal of a hierarchy that
+// lives in L2 is bound by the L1 data pipe — load requests x distinct lines per request, 91–96 % busy on the
+// 1 M-primitive scene — not by latency and not by issue slots (50 %): halving the requests per node visit is worth the few
+// extra integer instructions of the decode.  Built on the device from the fp32 nodes (lbvh.cu: k_quant_nodes) for
+// hierarchies beyond BVH_BIG_NODES nodes; the fp32 nodes stay (harnesses, refit, the fall-back kernel).
+//   q[3 * c + axis] = lo16 | hi16 << 16 of child c;  child[] as in BvhNode
+struct BvhNodeQ {
+	unsigned q[6];
+	int child[2];
+};
+struct QGrid {
+	float lo[3], step[3];
+	float hi[3];  // lo + 65535 * step: the far corner (the launch-time guard on the camera's distance reads it)
+	float pad_[3];
+};
+
 // Uncompressed 4-wide BVH node, 128 B = one cache line, eight 16-byte loads: the boxes of four children as fp32
 // (centre, half-extent) per axis, child k in component k.  Collapsed from the BVH2 (a node absorbs its inner child of
 // largest area until it has four), so one visit replaces up to two dependent BVH2 visits — for hierarchies that live in
@@ -128,6 +145,8 @@ struct DevScene {
 	const BvhNode *nodes;
 	int n_nodes;
 	int root_leaf_meta;        // when the whole scene is one leaf (n_nodes == 0)
+	const BvhNodeQ *nodes_q;   // quantised copy of `nodes` (nullptr when not built: small hierarchies, option off)
+	const QGrid *qgrid;        // its grid
 	const Bvh4Node *nodes4;    // 4-wide collapse of `nodes` over the same leaves (nullptr when not built)
 	int n_nodes4;
 	const WideNode *wnodes;    // compressed 8-wide hierarchy over the same hot items (nullptr when n_nodes == 0)

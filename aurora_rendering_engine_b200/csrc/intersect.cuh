@@ -22,6 +22,23 @@ struct Hit {
 };
 
 __device__ __forceinline__ float4 ldg4(const f4 *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+// 32 bytes in one request (sm_100: LDG.E.256): p is 32-byte aligned.  A hierarchy node is then two (BVH2) or four (BVH4)
+// requests instead of four / seven — what the divergent node fetches of a traversing warp load the L1 data pipe with is
+// requests x distinct lines, not bytes.
+#ifndef ARE_LDG256
+#define ARE_LDG256 1
+#endif
+#ifndef ARE_STACK_CACHE
+#define ARE_STACK_CACHE 0  // top entries of the traversal stack held in registers (CachedStack below): 0, 1 or 2
+#endif
+__device__ __forceinline__ void ldg8(const f4 *p, float4 &a, float4 &b) {
+#if ARE_LDG256
+	asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+		: "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#else
+	a = ldg4(p); b = ldg4(p + 1);
+#endif
+}
 __device__ __forceinline__ float4 lds4(const f4 *p) { return *reinterpret_cast<const float4 *>(p); }
 
 // single MUFU.RCP; rcp(0) = inf, so a ray parallel to the plane gives t = +-inf / NaN and fails the window test
@@ -271,6 +288,49 @@ struct PtrStack {
 	__device__ __forceinline__ void push(int v) { *top++ = v; }
 	__device__ __forceinline__ int pop() { return *--top; }
 };
+// PtrStack with its top entry (ARE_STACK_CACHE == 1) or top two entries (== 2) held in registers.  The local-memory
+// stack of a traversing warp is addressed lane by lane at different depths, so every push / pop request costs the L1 data
+// pipe one wavefront per distinct depth — and that pipe, not latency, is what bounds the 1 M-primitive scene (91–96 %
+// busy, profiles/r02_l1_pipe.md).  A push directly followed by a pop (both children hit, the nearer subtree then missed)
+// never reaches memory.
+#define TRAV_EMPTY ((int)0x80000001)  // = ~(slot 2^29 - 2 | kind 3 << 29): cannot occur as a reference
+struct CachedStack {
+	int *top;
+	int c0;
+#if ARE_STACK_CACHE >= 2
+	int c1;
+#endif
+	__device__ __forceinline__ void reset(int *base) {
+		base[0] = TRAV_DONE_V; top = base + 1; c0 = TRAV_EMPTY;
+#if ARE_STACK_CACHE >= 2
+		c1 = TRAV_EMPTY;
+#endif
+	}
+#if ARE_STACK_CACHE >= 2
+	// c0 = top of stack, c1 = the entry under it; memory holds the rest
+	__device__ __forceinline__ void push(int v) {
+		if (c1 != TRAV_EMPTY) *top++ = c1;
+		c1 = c0; c0 = v;
+	}
+	__device__ __forceinline__ int pop() {
+		int r = c0;
+		c0 = c1; c1 = TRAV_EMPTY;
+		if (r == TRAV_EMPTY) r = *--top;
+		return r;
+	}
+#else
+	__device__ __forceinline__ void push(int v) {
+		if (c0 != TRAV_EMPTY) *top++ = c0;
+		c0 = v;
+	}
+	__device__ __forceinline__ int pop() {
+		int r = c0;
+		c0 = TRAV_EMPTY;
+		if (r == TRAV_EMPTY) r = *--top;
+		return r;
+	}
+#endif
+};
 template <int N, int THREADS>
 struct ShortStack {
 	int *deep;      // local-memory overflow, entries N, N + 1, ...
@@ -290,8 +350,10 @@ struct ShortStack {
 template <bool COUNT, class STK>
 __device__ __forceinline__ void bvh_step(const DevScene &sc, float tmin, const RaySlopes &rs, int &cur, STK &stk, const Hit &h, TravCounters *cnt) {
 	const BvhNode *n = sc.nodes + cur;
-	const float4 b0 = ldg4(&n->b0), b1 = ldg4(&n->b1), b2 = ldg4(&n->b2);
-	const int2 ch = __ldg(reinterpret_cast<const int2 *>(&n->child[0]));
+	float4 b0, b1, b2, cm;  // cm = (child[0], child[1], meta[0], meta[1]) as bits
+	ldg8(&n->b0, b0, b1);
+	ldg8(&n->b2, b2, cm);
+	const int2 ch = make_int2(__float_as_int(cm.x), __float_as_int(cm.y));
 	if (COUNT) cnt->nodes++;
 	const float c0x = fmaf(b0.x, rs.idx, -rs.oxi), c0y = fmaf(b0.z, rs.idy, -rs.oyi), c0z = fmaf(b2.x, rs.idz, -rs.ozi);
 	const float c1x = fmaf(b1.x, rs.idx, -rs.oxi), c1y = fmaf(b1.z, rs.idy, -rs.oyi), c1z = fmaf(b2.z, rs.idz, -rs.ozi);
@@ -308,13 +370,84 @@ __device__ __forceinline__ void bvh_step(const DevScene &sc, float tmin, const R
 	if (!(hit0 | hit1)) next = stk.pop();
 	cur = next;
 }
+// ---- quantised nodes (dev_types.h: BvhNodeQ) ----------------------------------------------------------------
+// A 16-bit plane index q becomes the float 2^23 + q by ONE byte permute (0x4b000000 | q), and the slab distance
+//   t = (lo + q step - o) / d = (2^23 + q) * A + B',   A = step / d,  B' = (lo - o) / d - 2^23 A
+// by ONE multiply-add — the de-quantisation costs nothing beyond the permute.  Which 16 bits of a (lo, hi) word are the
+// near plane is a per-ray permute selector (the sign of d), so there are no per-axis min / max either.
+// Rounding: B' is rounded at the magnitude of 2^23 A, i.e. to half a grid step; the builder pads every box by a whole
+// step.  (Ray origins farther than 64 grid extents from the grid would need more: such a launch uses the fp32 nodes.)
+struct RaySlopesQ {
+	float ax, ay, az, bx, by, bz;
+	unsigned sx, sy, sz;  // permute selector of the near plane: 0x7610 (low half) when d >= 0, 0x7632 (high half) otherwise
+};
+__device__ __forceinline__ RaySlopesQ ray_slopes_q(const QGrid *g, V3<float> o, V3<float> d) {
+	const float big = 1e18f;
+	const float4 g0 = __ldg(reinterpret_cast<const float4 *>(g)), g1 = __ldg(reinterpret_cast<const float4 *>(g) + 1);  // lo.xyz step.x | step.yz
+	const float ix = fabsf(d.x) > 1e-18f ? 1.0f / d.x : (d.x < 0 ? -big : big);
+	const float iy = fabsf(d.y) > 1e-18f ? 1.0f / d.y : (d.y < 0 ? -big : big);
+	const float iz = fabsf(d.z) > 1e-18f ? 1.0f / d.z : (d.z < 0 ? -big : big);
+	RaySlopesQ r;
+	r.ax = g0.w * ix; r.ay = g1.x * iy; r.az = g1.y * iz;
+	r.bx = fmaf(-8388608.0f, r.ax, (g0.x - o.x) * ix);
+	r.by = fmaf(-8388608.0f, r.ay, (g0.y - o.y) * iy);
+	r.bz = fmaf(-8388608.0f, r.az, (g0.z - o.z) * iz);
+	r.sx = ix >= 0.0f ? 0x7610u : 0x7632u;
+	r.sy = iy >= 0.0f ? 0x7610u : 0x7632u;
+	r.sz = iz >= 0.0f ? 0x7610u : 0x7632u;
+	return r;
+}
+#define ARE_QPLANE(w, sel) __uint_as_float(__byte_perm((w), 0x4b000000u, (sel)))
+template <bool COUNT, class STK>
+__device__ __forceinline__ void bvhq_step(const DevScene &sc, float tmin, const RaySlopesQ &rs, int &cur, STK &stk, const Hit &h, TravCounters *cnt) {
+	float4 w0, w1;  // bits: (c0.x, c0.y, c0.z, c1.x) (c1.y, c1.z, child[0], child[1])
+	ldg8(reinterpret_cast<const f4 *>(sc.nodes_q + cur), w0, w1);
+	const unsigned q0x = __float_as_uint(w0.x), q0y = __float_as_uint(w0.y), q0z = __float_as_uint(w0.z);
+	const unsigned q1x = __float_as_uint(w0.w), q1y = __float_as_uint(w1.x), q1z = __float_as_uint(w1.y);
+	const int2 ch = make_int2(__float_as_int(w1.z), __float_as_int(w1.w));
+	if (COUNT) cnt->nodes++;
+	const unsigned fx = rs.sx ^ 0x22u, fy = rs.sy ^ 0x22u, fz = rs.sz ^ 0x22u;
+	const float t0n = fmaxf(fmaxf(fmaf(ARE_QPLANE(q0x, rs.sx), rs.ax, rs.bx), fmaf(ARE_QPLANE(q0y, rs.sy), rs.ay, rs.by)), fmaxf(fmaf(ARE_QPLANE(q0z, rs.sz), rs.az, rs.bz), tmin));
+	const float t0f = fminf(fminf(fmaf(ARE_QPLANE(q0x, fx), rs.ax, rs.bx), fmaf(ARE_QPLANE(q0y, fy), rs.ay, rs.by)), fminf(fmaf(ARE_QPLANE(q0z, fz), rs.az, rs.bz), h.t));
+	const float t1n = fmaxf(fmaxf(fmaf(ARE_QPLANE(q1x, rs.sx), rs.ax, rs.bx), fmaf(ARE_QPLANE(q1y, rs.sy), rs.ay, rs.by)), fmaxf(fmaf(ARE_QPLANE(q1z, rs.sz), rs.az, rs.bz), tmin));
+	const float t1f = fminf(fminf(fmaf(ARE_QPLANE(q1x, fx), rs.ax, rs.bx), fmaf(ARE_QPLANE(q1y, fy), rs.ay, rs.by)), fminf(fmaf(ARE_QPLANE(q1z, fz), rs.az, rs.bz), h.t));
+	const bool hit0 = t0n <= t0f, hit1 = t1n <= t1f;
+	const float d0 = hit0 ? t0n : INFINITY, d1 = hit1 ? t1n : INFINITY;
+	const bool near0 = d0 <= d1;
+	int next = near0 ? ch.x : ch.y;
+	const int farc = near0 ? ch.y : ch.x;
+	if (hit0 & hit1) stk.push(farc);
+	if (!(hit0 | hit1)) next = stk.pop();
+	cur = next;
+}
+// The node phase of a traversal MODE (render_path.cuh): 1 = BVH2 (fp32 nodes), 3 = BVH4, 4 = BVH2 over quantised nodes.
+template <int MODE> struct Trav {
+	typedef RaySlopes Slopes;
+	static __device__ __forceinline__ Slopes slopes(const DevScene &, V3<float> o, V3<float> d) { return ray_slopes(o, d); }
+	template <bool COUNT, class STK>
+	static __device__ __forceinline__ void step(const DevScene &sc, float tmin, const Slopes &rs, int &cur, STK &stk, const Hit &h, TravCounters *cnt) {
+		bvh_step<COUNT>(sc, tmin, rs, cur, stk, h, cnt);
+	}
+};
+template <> struct Trav<4> {
+	typedef RaySlopesQ Slopes;
+	static __device__ __forceinline__ Slopes slopes(const DevScene &sc, V3<float> o, V3<float> d) { return ray_slopes_q(sc.qgrid, o, d); }
+	template <bool COUNT, class STK>
+	static __device__ __forceinline__ void step(const DevScene &sc, float tmin, const Slopes &rs, int &cur, STK &stk, const Hit &h, TravCounters *cnt) {
+		bvhq_step<COUNT>(sc, tmin, rs, cur, stk, h, cnt);
+	}
+};
+
 // One BVH4 visit: four slab tests on one 128-byte node.  The nearest hit child becomes the cursor, the other hit
 // children are postponed (slot order).  Nearest = minimum over keys (bits of the entry distance with the slot number
 // in the two low mantissa bits): distances are positive, so their bit patterns order like the floats.
 template <bool COUNT, class STK>
 __device__ __forceinline__ void bvh4_step(const DevScene &sc, float tmin, const RaySlopes &rs, int &cur, STK &stk, const Hit &h, TravCounters *cnt) {
 	const Bvh4Node *n = sc.nodes4 + cur;
-	const float4 cx = ldg4(&n->cx), hx = ldg4(&n->hx), cy = ldg4(&n->cy), hy = ldg4(&n->hy), cz = ldg4(&n->cz), hz = ldg4(&n->hz);
+	float4 cx, hx, cy, hy, cz, hz;
+	ldg8(&n->cx, cx, hx);
+	ldg8(&n->cy, cy, hy);
+	ldg8(&n->cz, cz, hz);
 	const int4 ch = __ldg(reinterpret_cast<const int4 *>(&n->child[0]));
 	if (COUNT) cnt->nodes += 2;  // node_visits counts child-box PAIRS
 #define ARE_SLAB4(k, C)                                                                                                      \
@@ -334,6 +467,14 @@ __device__ __forceinline__ void bvh4_step(const DevScene &sc, float tmin, const 
 	if (hit0 & (nearest != 0u)) stk.push(ch.x);
 	cur = nearest == 0u ? ch.x : (nearest == 1u ? ch.y : (nearest == 2u ? ch.z : ch.w));
 }
+template <> struct Trav<3> {
+	typedef RaySlopes Slopes;
+	static __device__ __forceinline__ Slopes slopes(const DevScene &, V3<float> o, V3<float> d) { return ray_slopes(o, d); }
+	template <bool COUNT, class STK>
+	static __device__ __forceinline__ void step(const DevScene &sc, float tmin, const Slopes &rs, int &cur, STK &stk, const Hit &h, TravCounters *cnt) {
+		bvh4_step<COUNT>(sc, tmin, rs, cur, stk, h, cnt);
+	}
+};
 // leaf phase of the single-cursor form: test the leaf under the cursor, then pop
 template <bool COUNT, class STK>
 __device__ __forceinline__ void bvh_leaf(const DevScene &sc, V3<float> o, V3<float> d, float tmin, int &cur, STK &stk, Hit &h, TravCounters *cnt) {

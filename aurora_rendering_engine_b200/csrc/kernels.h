@@ -48,6 +48,7 @@ void launch_camera32(const CamBasis &cb, int W, int H, int n, const int *px, con
 int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStream_t s);
 bool render_path_is_lean(const RenderArgs &a);  // brute force: the lean kernel is the one launched
 bool render_path_lean_dims(const RenderArgs &a, int &blocks, int &threads, size_t &smem);  // launch shape of the lean (and baked) kernel
+int render_path_big_nodes();                    // BVH_BIG_NODES
 bool render_path_is_big(const RenderArgs &a);   // BVH: the high-occupancy build is the one launched
 int launch_render_rtao(const RenderArgs &a, cudaStream_t s);
 // wavefront schedule of the same path integrator (wavefront.cu): generate / extend / shade + compact over ray queues in HBM
@@ -112,6 +113,8 @@ struct PrimScatterArgs {
 	int n_tri, n_quad;
 };
 void launch_prim_scatter(const PrimScatterArgs &a, cudaStream_t s);
+// quantised copy of a BVH2 (dev_types.h: BvhNodeQ): grid from the root box, then every node; returns kernels launched (< 0: error)
+int launch_quantize_nodes(const BvhNode *nodes, int n, BvhNodeQ *out, QGrid *grid, cudaStream_t s);
 int lbvh_refit(void *workspace, size_t workspace_bytes, int n_items, int m, const int *item, const HotPrim *rec, const f4 *lo, const f4 *hi,
 	HotPrim *prims, BvhNode *nodes, cudaStream_t s, std::string &err);
 

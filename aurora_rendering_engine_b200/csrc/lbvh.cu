@@ -322,4 +322,50 @@ int lbvh_build(const LbvhInput &in, LbvhOutput &out, void *workspace, size_t wor
 	return 5 + 2;  // kernels launched: five of ours + cub's sort and scan passes (counted as two)
 }
 
+// ---- quantised copy of the hierarchy (dev_types.h: BvhNodeQ) --------------------------------------------------
+// Grid: the root box (union of node 0's child boxes) widened by four steps on every side, 65535 steps per axis.
+// Planes: lo -> floor - 1, hi -> ceil + 1 (in double: the (centre, half-extent) pair of an fp32 node denotes c -+ h
+// exactly), clamped to the grid — the widening makes the clamp unreachable for boxes inside the root box.
+__global__ void k_quant_grid(const BvhNode *__restrict__ nodes, QGrid *grid) {
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	const BvhNode n = nodes[0];
+	const double c[2][3] = { { n.b0.x, n.b0.z, n.b2.x }, { n.b1.x, n.b1.z, n.b2.z } }, h[2][3] = { { n.b0.y, n.b0.w, n.b2.y }, { n.b1.y, n.b1.w, n.b2.w } };
+	for (int k = 0; k < 3; ++k) {
+		const double lo = fmin(c[0][k] - h[0][k], c[1][k] - h[1][k]), hi = fmax(c[0][k] + h[0][k], c[1][k] + h[1][k]);
+		double ext = hi - lo;
+		const double mag = fmax(fabs(lo), fabs(hi));
+		ext = fmax(ext, fmax(mag * 1e-4, 1e-30));  // a flat scene still gets a grid its fp32 coordinates resolve
+		const float step = (float)(ext / 65520.0);   // 65520 + 2 * 4 widening steps < 65535
+		grid->step[k] = step;
+		grid->lo[k] = (float)(lo - 4.0 * (double)step);
+		grid->hi[k] = (float)((double)grid->lo[k] + 65535.0 * (double)step);
+	}
+	grid->pad_[0] = grid->pad_[1] = grid->pad_[2] = 0.f;
+}
+__device__ __forceinline__ unsigned quant_pair(double c, double h, double glo, double inv_step) {
+	double a = floor((c - h - glo) * inv_step) - 1.0, b = ceil((c + h - glo) * inv_step) + 1.0;
+	a = fmin(fmax(a, 0.0), 65535.0);
+	b = fmin(fmax(b, 0.0), 65535.0);
+	return (unsigned)a | ((unsigned)b << 16);
+}
+__global__ void k_quant_nodes(int n, const BvhNode *__restrict__ nodes, const QGrid *__restrict__ grid, BvhNodeQ *__restrict__ out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const BvhNode nd = nodes[i];
+	const double gx = grid->lo[0], gy = grid->lo[1], gz = grid->lo[2];
+	const double ix = 1.0 / (double)grid->step[0], iy = 1.0 / (double)grid->step[1], iz = 1.0 / (double)grid->step[2];
+	BvhNodeQ q;
+	q.q[0] = quant_pair(nd.b0.x, nd.b0.y, gx, ix); q.q[1] = quant_pair(nd.b0.z, nd.b0.w, gy, iy); q.q[2] = quant_pair(nd.b2.x, nd.b2.y, gz, iz);
+	q.q[3] = quant_pair(nd.b1.x, nd.b1.y, gx, ix); q.q[4] = quant_pair(nd.b1.z, nd.b1.w, gy, iy); q.q[5] = quant_pair(nd.b2.z, nd.b2.w, gz, iz);
+	q.child[0] = nd.child[0]; q.child[1] = nd.child[1];
+	out[i] = q;
+}
+// nodes -> (grid, out); two kernels on s
+int launch_quantize_nodes(const BvhNode *nodes, int n, BvhNodeQ *out, QGrid *grid, cudaStream_t s) {
+	if (n <= 0) return 0;
+	k_quant_grid<<<1, 32, 0, s>>>(nodes, grid);
+	k_quant_nodes<<<(n + 255) / 256, 256, 0, s>>>(n, nodes, grid, out);
+	return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+
 }  // namespace areb

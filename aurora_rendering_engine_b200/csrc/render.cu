@@ -22,7 +22,7 @@ namespace areb {
 size_t brute_smem_limit_prims() { return BRUTE_MAX_PRIMS; }
 
 template <int MODE, bool COUNT, bool BIG = false, bool LEAN = false, bool NOISE = true>
-__global__ void __launch_bounds__(RENDER_THREADS, MODE == 3 ? (BIG ? RENDER_MIN_BLOCKS_BVH4_BIG : RENDER_MIN_BLOCKS_BVH4) : BIG ? RENDER_MIN_BLOCKS_BIG : (LEAN ? RENDER_MIN_BLOCKS_LEAN : (MODE == 1 ? RENDER_MIN_BLOCKS_BVH2 : RENDER_MIN_BLOCKS))) k_render_path(const __grid_constant__ RenderArgs A) {
+__global__ void __launch_bounds__(RENDER_THREADS, MODE == 3 ? (BIG ? RENDER_MIN_BLOCKS_BVH4_BIG : RENDER_MIN_BLOCKS_BVH4) : MODE == 4 ? RENDER_MIN_BLOCKS_Q : BIG ? RENDER_MIN_BLOCKS_BIG : (LEAN ? RENDER_MIN_BLOCKS_LEAN : (MODE == 1 ? RENDER_MIN_BLOCKS_BVH2 : RENDER_MIN_BLOCKS))) k_render_path(const __grid_constant__ RenderArgs A) {
 	render_path_body<MODE, COUNT, BIG, LEAN, false, NOISE>(A);
 }
 
@@ -35,6 +35,7 @@ bool render_path_lean_dims(const RenderArgs &a, int &blocks, int &threads, size_
 	smem = (size_t)a.sc.n_hot * sizeof(HotPrim) + (size_t)a.sc.n_lean_shade * (sizeof(ShadeRec) + 2 * sizeof(float4)) + (size_t)a.sc.n_hot * sizeof(int);
 	return blocks > 0 && a.sc.brute && a.sc.n_hot <= BRUTE_MAX_PRIMS;
 }
+int render_path_big_nodes() { return BVH_BIG_NODES; }
 bool render_path_is_big(const RenderArgs &a) { return a.sc.n_nodes > BVH_BIG_NODES; }
 
 int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStream_t s) {
@@ -58,6 +59,8 @@ int launch_render_path(const RenderArgs &a, int mode, bool count_tests, cudaStre
 			if (!a.sc.wnodes) return -1;
 			if (count_tests) { if (big) LAUNCH(2, true, true, 0); else LAUNCH(2, true, false, 0); }
 			else { if (big) LAUNCH(2, false, true, 0); else LAUNCH(2, false, false, 0); }
+		} else if (big && a.sc.nodes_q) {  // big hierarchy with a quantised copy: one 256-bit load per node visit
+			if (count_tests) LAUNCH(4, true, true, 0); else LAUNCH(4, false, true, 0);
 		} else if (count_tests) { if (big) LAUNCH(1, true, true, 0); else LAUNCH(1, true, false, 0); }
 		else { if (big) LAUNCH(1, false, true, 0); else LAUNCH(1, false, false, 0); }
 	} else {

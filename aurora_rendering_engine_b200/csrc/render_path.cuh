@@ -53,6 +53,9 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #ifndef RENDER_MIN_BLOCKS_BIG
 #define RENDER_MIN_BLOCKS_BIG 12  // hierarchies that live in L2 (not L1) are latency-bound: 48 resident warps/SM at 40 registers (with spills)
 #endif                            // beat 24 at 80 — measured on the 1 M-primitive scene: 467 -> 577 Msamples/s; RTIOW (L1-resident) loses 5 %
+#ifndef RENDER_MIN_BLOCKS_Q
+#define RENDER_MIN_BLOCKS_Q 12    // big hierarchies over quantised nodes
+#endif
 #ifndef RENDER_MIN_BLOCKS_BVH4
 #define RENDER_MIN_BLOCKS_BVH4 6       // 4-wide nodes: 24 box floats + 4 references in flight per step
 #endif
@@ -74,7 +77,7 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 // (Postponing leaf tests until several lanes hold one was measured in the first formulation of the traversal: testing a
 // leaf as soon as a lane has it was best on RTIOW and on the 1 M-primitive scene, and needs no votes.)
 // MODE: 0 = brute force from shared memory, 1 = BVH2, 2 = compressed 8-wide BVH, 3 = uncompressed 4-wide BVH (the BVH2's
-// traversal loop with bvh4_step as its node phase)
+// traversal loop with bvh4_step as its node phase), 4 = BVH2 over the quantised 32-byte nodes (bvhq_step; big hierarchies)
 // LEAN (brute force only): the scene compiler's lean form (scene.h: at most LEAN_MAX boxes / quad tests / triangle
 // tests, no spheres, every surface shaded from its ShadeRec alone).  The tests are a guarded full unroll with
 // compile-time shared-memory offsets instead of four counted loops, and a hit goes straight to its shading record
@@ -86,7 +89,7 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 // the BVH kernels registers: RTIOW lost 4 % with the stage merely present).
 template <int MODE, bool COUNT, bool BIG = false, bool LEAN = false, bool BAKED = false, bool NOISE = true>
 __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
-	constexpr bool BVH = MODE != 0, WIDE = MODE == 2, B4 = MODE == 3;
+	constexpr bool BVH = MODE != 0, WIDE = MODE == 2;
 	static_assert(!LEAN || MODE == 0, "the lean form is a brute-force list");
 	static_assert(!BAKED || MODE == 0, "a baked kernel tests a brute-force list");
 	extern __shared__ float4 s_raw[];
@@ -146,14 +149,19 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 	h.t = INFINITY; h.idx = -1; h.orig = -1;
 	bool trav = false;  // BVH: traversal in progress
 	int node = 0, sp = 0;  // BVH2: `node` is the traversal cursor (intersect.cuh: bvh_step); 8-wide: sp indexes wstack
-	int stack[MODE == 1 ? ARE_BVH_STACK : (MODE == 3 ? ARE_BVH4_STACK : 1)];
+	int stack[(MODE == 1 || MODE == 4) ? ARE_BVH_STACK : (MODE == 3 ? ARE_BVH4_STACK : 1)];
 #ifdef ARE_SHORT_STACK
 	__shared__ int s_short[(MODE == 1 || MODE == 3) ? ARE_SHORT_STACK : 1][RENDER_THREADS];
 	ShortStack<ARE_SHORT_STACK, RENDER_THREADS> stk;
 	stk.sm = &s_short[0][threadIdx.x]; stk.deep = stack; stk.sp = 0;
 #else
+#if ARE_STACK_CACHE
+	CachedStack stk;
+	stk.reset(stack);
+#else
 	PtrStack stk;  // BVH2 stack pointer
 	stk.top = stack;
+#endif
 #endif
 	uint2 ng = make_uint2(0u, 0u), tg = ng;  // wide-BVH cursor
 	uint2 wstack[WIDE ? ARE_WIDE_STACK : 1];
@@ -201,7 +209,7 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 			}
 			const int n_rays = __popc(__ballot_sync(full, ray_ok));
 			if (__any_sync(full, trav)) {
-				const RaySlopes rs = ray_slopes(o, d);
+				const typename Trav<MODE>::Slopes rs = Trav<MODE>::slopes(A.sc, o, d);
 				if (!trav) node = TRAV_DONE;
 				while (true) {
 #pragma unroll 1
@@ -211,10 +219,7 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 						// reach a leaf wait a step or two and cuts the leaf code's share of the issue slots accordingly.
 #pragma unroll
 						for (int r = 0; r < TRAV_LEAF_EVERY; ++r)
-							if (node >= 0) {                                                                     // node phase
-								if (B4) bvh4_step<COUNT>(A.sc, A.tmin, rs, node, stk, h, &tc);
-								else bvh_step<COUNT>(A.sc, A.tmin, rs, node, stk, h, &tc);
-							}
+							if (node >= 0) Trav<MODE>::template step<COUNT>(A.sc, A.tmin, rs, node, stk, h, &tc);  // node phase
 						if (node < 0 && node != TRAV_DONE) bvh_leaf<COUNT>(A.sc, o, d, A.tmin, node, stk, h, &tc);  // leaf phase
 					}
 					const int n_trav = __popc(__ballot_sync(full, node != TRAV_DONE));

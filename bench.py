@@ -294,7 +294,7 @@ def kernel_name(capi, variant, baked_kind=1):
     return {capi.KERNEL_RT_AO: "k_render_rtao", capi.KERNEL_BRUTE: "k_render_path<brute/smem>",
             capi.KERNEL_BRUTE_LEAN: "k_render_path<brute/smem, lean>",
             capi.KERNEL_BRUTE_BAKED: "k_render_baked (lean kernel, scene compiled in by NVRTC)",
-            capi.KERNEL_BVH2: "k_render_path<bvh2>", capi.KERNEL_BVH2_BIG: "k_render_path<bvh2, 12 CTAs/SM>",
+            capi.KERNEL_BVH2: "k_render_path<bvh2>", capi.KERNEL_BVH2_BIG: "k_render_path<bvh2, 12 CTAs/SM>", capi.KERNEL_BVH2_QUANT: "k_render_path<bvh2, quantised 32-byte nodes, 12 CTAs/SM>",
             capi.KERNEL_WIDE: "k_render_path<wide bvh>", capi.KERNEL_BVH4: "k_render_path<bvh4>", capi.KERNEL_WAVEFRONT: "k_wf_generate + k_wf_extend<bvh2> + k_wf_shade (wavefront)"}.get(variant, "?")
 
 

@@ -138,6 +138,7 @@ enum {
 	ARE_KERNEL_RT_AO = 6,
 	ARE_KERNEL_BVH4 = 9, /* k_render_path over the 4-wide hierarchy */
 	ARE_KERNEL_WAVEFRONT = 8, /* k_wf_generate / k_wf_extend / k_wf_shade */
+	ARE_KERNEL_BVH2_QUANT = 10, /* big hierarchy through its quantised 32-byte nodes: one 256-bit load per node visit */
 	ARE_KERNEL_BRUTE_BAKED = 7 /* the lean kernel with the scene's closest-hit tests compiled in (NVRTC at commit) */
 };
 
@@ -200,7 +201,11 @@ typedef enum are_option {
 	ARE_OPT_L2_PERSIST_NODES = 9, /* 0 (default) / 1..100: BVH renders mark the node array as an L2-persisting access window
 	                                (cudaAccessPolicyWindow) claiming this per cent of the device's persisting carve-out */
 	ARE_OPT_BUILD_BVH4 = 10, /* 0 (default) / 1: the host builder also collapses its BVH2 into 4-wide nodes (ARE_TRAVERSAL_BVH4) */
-	ARE_OPT_BAKED_MIN_BLOCKS = 11 /* tuning: CTAs per SM the baked kernel is compiled for (0 = default: 6) */
+	ARE_OPT_BAKED_MIN_BLOCKS = 11, /* tuning: CTAs per SM the baked kernel is compiled for (0 = default: 6 lean, 5 generic) */
+	ARE_OPT_QUANTIZED_NODES = 12 /* 1 (default): BVH2 hierarchies of more than 16384 nodes are also stored as 32-byte nodes — child boxes as
+	                                16-bit planes on a grid over the root box, padded outwards, so every hit the fp32 nodes report is still
+	                                found — and ARE_TRAVERSAL_BVH2 renders through them (ARE_KERNEL_BVH2_QUANT); 0: fp32 nodes only
+	                                (renders: at once; the copy itself: from the next commit) */
 } are_option;
 int are_cuda_set_option(are_cuda_ctx *ctx, int option, int value);
 /* The sm_100a CUBIN of the committed scene's baked kernel (what cuobjdump -sass / nvdisasm -g read next to an ncu capture).

@@ -153,7 +153,7 @@ def test_config4_stress_1M_matches_cpu_twin(ctx, oracle):
         sc.feed(ctx)
         ctx.commit()
         img, st = ctx.render(cam, par)
-        assert st.kernel_variant == capi.KERNEL_BVH2_BIG
+        assert st.kernel_variant == capi.KERNEL_BVH2_QUANT   # 1 M nodes: the quantised 32-byte nodes
         for (x0, y0, x1, y1), (oimg, ost) in zip(windows, want):
             a = np.clip(img[y0:y1, x0:x1].astype(np.float64) / spp, 0, 1)
             b = np.clip(oimg[y0:y1, x0:x1] / spp, 0, 1)

@@ -235,7 +235,7 @@ def test_bvh4_equals_bvh2(ctx):
     acc = ctx.alloc_accum(sc.width, sc.height)
     c4 = ctx.render_device(cam, capi.make_params(**sc.params_args(sample_count=4, traversal=4)), acc, want_stats=True, count_tests=True)
     ctx.free_accum(acc)
-    assert s4.kernel_variant == capi.KERNEL_BVH4 and s2.kernel_variant in (capi.KERNEL_BVH2, capi.KERNEL_BVH2_BIG)
+    assert s4.kernel_variant == capi.KERNEL_BVH4 and s2.kernel_variant in (capi.KERNEL_BVH2, capi.KERNEL_BVH2_BIG, capi.KERNEL_BVH2_QUANT)
     assert s4.rays == s2.rays and np.allclose(i4, i2, rtol=1e-5, atol=1e-5)
     assert c4.node_visits > 0 and c4.sphere_tests > 0
     for name, kw in (("rtiow_final", dict(width=96, height=54)), ("cornell_box", dict(width=64, height=64))):
@@ -249,4 +249,48 @@ def test_bvh4_equals_bvh2(ctx):
     ctx.set_option(capi.OPT_BUILD_BVH4, 0)
     _commit(ctx, sc, capi.BVH_BUILDER_HOST_SAH)
     _, sf = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=1, traversal=4)))
-    assert sf.kernel_variant in (capi.KERNEL_BVH2, capi.KERNEL_BVH2_BIG)
+    assert sf.kernel_variant in (capi.KERNEL_BVH2, capi.KERNEL_BVH2_BIG, capi.KERNEL_BVH2_QUANT)
+
+
+def test_quantised_nodes_equal_fp32_nodes(ctx):
+    """Hierarchies beyond 16384 nodes are traversed through 32-byte nodes whose child boxes are 16-bit planes on a grid
+    over the root box, padded outwards (ARE_OPT_QUANTIZED_NODES, dev_types.h: BvhNodeQ): a superset of every fp32 box, so
+    each ray must end on the same primitive — identical ray counts, images equal up to summation order — at the price of
+    a few more node visits.  Both builders; switching the option off renders through the fp32 nodes at once; a camera too
+    far from the scene for the decode's rounding bound falls back to them by itself."""
+    sc = scenes.stress(n_prims=40_000, width=192, height=108)
+    cam = capi.make_camera(**sc.camera_args())
+    par = capi.make_params(**sc.params_args(sample_count=8, traversal=2))
+    for builder in (capi.BVH_BUILDER_HOST_SAH, capi.BVH_BUILDER_DEVICE_LBVH):
+        info = _commit(ctx, sc, builder)
+        assert info.bvh_nodes > 16384
+        out = {}
+        for q in (1, 0):
+            ctx.set_option(capi.OPT_QUANTIZED_NODES, q)
+            img, st = ctx.render(cam, par)
+            acc = ctx.alloc_accum(sc.width, sc.height)
+            cnt = ctx.render_device(cam, par, acc, want_stats=True, count_tests=True)
+            ctx.free_accum(acc)
+            out[q] = (img, st, cnt)
+        ctx.set_option(capi.OPT_QUANTIZED_NODES, 1)
+        (iq, sq, cq), (i32, s32, c32) = out[1], out[0]
+        assert sq.kernel_variant == capi.KERNEL_BVH2_QUANT and s32.kernel_variant == capi.KERNEL_BVH2_BIG
+        assert sq.rays == s32.rays == cq.rays == c32.rays
+        assert np.allclose(iq, i32, rtol=1e-5, atol=1e-5)
+        more = cq.node_visits / c32.node_visits
+        print(f"[quantised nodes, builder {builder}] node visits x{more:.4f}, primitive tests x"
+              f"{(cq.sphere_tests + cq.tri_tests) / (c32.sphere_tests + c32.tri_tests):.4f}")
+        assert 0.999 <= more < 1.10
+        assert cq.sphere_tests + cq.tri_tests >= 0.999 * (c32.sphere_tests + c32.tri_tests)
+    # a ragged frame, a camera inside the cloud looking along an axis (zero direction components on the centre column)
+    inside = capi.make_camera(pos=(0.25, 0.5, 0.125), target=(0.25, 0.5, -30.0), up=(0, 1, 0), vfov_deg=60.0, jitter=0)
+    par2 = capi.make_params(**sc.params_args(width=61, height=35, sample_count=3, traversal=2))
+    a, sa = ctx.render(inside, par2)
+    ctx.set_option(capi.OPT_QUANTIZED_NODES, 0)
+    b, sb = ctx.render(inside, par2)
+    ctx.set_option(capi.OPT_QUANTIZED_NODES, 1)
+    assert sa.kernel_variant == capi.KERNEL_BVH2_QUANT and sa.rays == sb.rays and np.allclose(a, b, rtol=1e-5, atol=1e-5)
+    # far away: |camera - grid| > 64 grid extents -> the fp32 nodes render
+    far = capi.make_camera(pos=(0, 0, 5000.0), target=(0, 0, 0), up=(0, 1, 0), vfov_deg=0.5)
+    _, sf = ctx.render(far, par)
+    assert sf.kernel_variant == capi.KERNEL_BVH2_BIG
