@@ -46,7 +46,7 @@ class RenderStats(C.Structure):
 class CommitInfo(C.Structure):
     """are_commit_info"""
     _fields_ = [("builder", C.c_int), ("bvh_nodes", C.c_int), ("bvh_height", C.c_int), ("hot_slots", C.c_int), ("host_compile_ms", C.c_double),
-                ("host_bvh_ms", C.c_double), ("device_bvh_ms", C.c_double), ("device_bvh_launches", C.c_uint64), ("baked", C.c_int32), ("pad_", C.c_int32),
+                ("host_bvh_ms", C.c_double), ("device_bvh_ms", C.c_double), ("device_bvh_launches", C.c_uint64), ("baked", C.c_int32), ("quant_area_permille", C.c_int32),
                 ("bake_compile_ms", C.c_double)]
 
     def as_dict(self):

@@ -517,6 +517,10 @@ static int quantize_nodes(are_cuda_ctx *ctx, DevScene &d, are_commit_info &info)
 	CK(cudaMemcpyAsync(&ctx->qgrid_host, d.qgrid, sizeof(QGrid), cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	info.device_bvh_launches += (uint64_t)launched;
+	// A scene whose extent dwarfs its primitives (one huge sphere under thousands of small ones) has a grid too coarse for
+	// its small boxes; the padding then costs more visits than the smaller nodes save.  Measured by surface area.
+	info.quant_area_permille = ctx->qgrid_host.area32 > 0.f ? (int32_t)std::min(1e6, 1000.0 * (double)ctx->qgrid_host.area_q / (double)ctx->qgrid_host.area32) : 1000;
+	if (info.quant_area_permille > 1250) { d.nodes_q = nullptr; d.qgrid = nullptr; }
 	return ARE_OK;
 }
 

@@ -94,7 +94,8 @@ struct BvhNodeQ {
 struct QGrid {
 	float lo[3], step[3];
 	float hi[3];  // lo + 65535 * step: the far corner (the launch-time guard on the camera's distance reads it)
-	float pad_[3];
+	float area32, area_q;  // k_quant_nodes: child boxes counted / sum of (surface area as quantised : surface area of the fp32 box)
+	float pad_;
 };
 
 // Uncompressed 4-wide BVH node, 128 B = one cache line, eight 16-byte loads: the boxes of four children as fp32

@@ -340,7 +340,7 @@ __global__ void k_quant_grid(const BvhNode *__restrict__ nodes, QGrid *grid) {
 		grid->lo[k] = (float)(lo - 4.0 * (double)step);
 		grid->hi[k] = (float)((double)grid->lo[k] + 65535.0 * (double)step);
 	}
-	grid->pad_[0] = grid->pad_[1] = grid->pad_[2] = 0.f;
+	grid->area32 = grid->area_q = grid->pad_ = 0.f;
 }
 __device__ __forceinline__ unsigned quant_pair(double c, double h, double glo, double inv_step) {
 	double a = floor((c - h - glo) * inv_step) - 1.0, b = ceil((c + h - glo) * inv_step) + 1.0;
@@ -348,9 +348,10 @@ __device__ __forceinline__ unsigned quant_pair(double c, double h, double glo, d
 	b = fmin(fmax(b, 0.0), 65535.0);
 	return (unsigned)a | ((unsigned)b << 16);
 }
-__global__ void k_quant_nodes(int n, const BvhNode *__restrict__ nodes, const QGrid *__restrict__ grid, BvhNodeQ *__restrict__ out) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+__global__ void k_quant_nodes(int n, const BvhNode *__restrict__ nodes, QGrid *__restrict__ grid, BvhNodeQ *__restrict__ out) {
+	const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = i0 < n;
+	const int i = live ? i0 : n - 1;  // idle threads of the last warp redo the last node (same values, and they add no area)
 	const BvhNode nd = nodes[i];
 	const double gx = grid->lo[0], gy = grid->lo[1], gz = grid->lo[2];
 	const double ix = 1.0 / (double)grid->step[0], iy = 1.0 / (double)grid->step[1], iz = 1.0 / (double)grid->step[2];
@@ -359,6 +360,20 @@ __global__ void k_quant_nodes(int n, const BvhNode *__restrict__ nodes, const QG
 	q.q[3] = quant_pair(nd.b1.x, nd.b1.y, gx, ix); q.q[4] = quant_pair(nd.b1.z, nd.b1.w, gy, iy); q.q[5] = quant_pair(nd.b2.z, nd.b2.w, gz, iz);
 	q.child[0] = nd.child[0]; q.child[1] = nd.child[1];
 	out[i] = q;
+	// what the padding costs: per child box, surface area as stored here over that of the fp32 box (a ray that reaches the
+	// parent visits the child in proportion to it); the commit reads the mean over all child boxes
+	const float sx = grid->step[0], sy = grid->step[1], sz = grid->step[2];
+	float a32 = 0.f, aq = 0.f;  // number of boxes counted, sum of their ratios
+#pragma unroll
+	for (int c = 0; c < 2; ++c) {
+		const float wx = 2.f * (c ? nd.b1.y : nd.b0.y), wy = 2.f * (c ? nd.b1.w : nd.b0.w), wz = 2.f * (c ? nd.b2.w : nd.b2.y);
+		const float qx = sx * (float)((q.q[3 * c] >> 16) - (q.q[3 * c] & 0xffffu)), qy = sy * (float)((q.q[3 * c + 1] >> 16) - (q.q[3 * c + 1] & 0xffffu)),
+			qz = sz * (float)((q.q[3 * c + 2] >> 16) - (q.q[3 * c + 2] & 0xffffu));
+		const float s32 = wx * wy + wy * wz + wz * wx, sq = qx * qy + qy * qz + qz * qx;
+		if (live && s32 > 0.f) { a32 += 1.f; aq += fminf(sq / s32, 1e6f); }
+	}
+	for (int off = 16; off > 0; off >>= 1) { a32 += __shfl_down_sync(0xffffffffu, a32, off); aq += __shfl_down_sync(0xffffffffu, aq, off); }
+	if ((threadIdx.x & 31) == 0) { atomicAdd(&grid->area32, a32); atomicAdd(&grid->area_q, aq); }
 }
 // nodes -> (grid, out); two kernels on s
 int launch_quantize_nodes(const BvhNode *nodes, int n, BvhNodeQ *out, QGrid *grid, cudaStream_t s) {

@@ -96,7 +96,7 @@ def make_scene(a, name=None, **kw):
 BASELINE_CONFIG = {"rt_cornell": "0; reference program: 1 primary + 32 AO rays per pixel", "rtiow_final": "1; full job = 500 spp",
                    "textured": "2; full job = 1024 spp", "cornell_box": "3; full job = 16384 spp", "stress": "4; full job = 256 spp"}
 # (scene, spp per step) of the short runs in `configs`
-OTHER_CONFIGS = (("rt_cornell", 1), ("rtiow_final", 100), ("textured", 128), ("stress", 4))
+OTHER_CONFIGS = (("rt_cornell", 1), ("rtiow_final", 100), ("textured", 256), ("stress", 16))
 
 
 def workload_name(sc, S):
@@ -410,10 +410,12 @@ class Bench:
                 "counted": {"rays": st.rays, "tri_tests": st.tri_tests, "quad_tests": st.quad_tests, "sphere_tests": st.sphere_tests,
                             "box_tests": st.box_tests, "node_visits": st.node_visits}}
         if st.node_visits > 0 and peaks.get("l2_gbs"):
-            byt = B_NODE * st.node_visits + B_PLANE * (st.tri_tests + st.quad_tests) + B_SPHERE * st.sphere_tests + B_BOXREC * st.box_tests
+            b_node = 32 if st.kernel_variant == self.capi.KERNEL_BVH2_QUANT else B_NODE  # quantised nodes: one 32-byte record per visit
+            byt = b_node * st.node_visits + B_PLANE * (st.tri_tests + st.quad_tests) + B_SPHERE * st.sphere_tests + B_BOXREC * st.box_tests
             gbs = byt / (kernel_ms * 1e-3) / 1e9
             roof["l2"] = {"bound": "l2", "achieved": gbs, "peak": peaks["l2_gbs"], "unit": "GB/s", "frac": gbs / peaks["l2_gbs"],
-                          "bytes_per_launch": byt, "note": "algorithmic node + primitive record bytes (SURVEY §8d) against the L2 read bandwidth measured by are_cuda_measure_l2_peak"}
+                          "bytes_per_launch": byt, "node_bytes": b_node,
+                          "note": "algorithmic node + primitive record bytes (SURVEY §8d; 32 B per visit through quantised nodes) against the L2 read bandwidth measured by are_cuda_measure_l2_peak"}
         return roof
 
     def close(self):

@@ -179,7 +179,9 @@ typedef struct are_commit_info {
 	uint64_t device_bvh_launches;
 	int32_t baked; /* a scene-specialised render kernel is loaded for this scene (ARE_OPT_BAKED_KERNEL): 1 = around the lean kernel,
 	                  2 = around the generic brute-force kernel (scenes of at most 16 hot slots: spheres, textures, any material), 0 = none */
-	int32_t pad_;
+	int32_t quant_area_permille; /* quantised 32-byte nodes (ARE_OPT_QUANTIZED_NODES): 0 = not built; else 1000 x the mean over all child
+	                                boxes of (surface area as quantised : surface area of the fp32 box) (1 M-primitive test scene: ~1040).  Above 1250 the grid
+	                                is too coarse for the scene's small boxes and renders use the fp32 nodes */
 	double bake_compile_ms; /* NVRTC + module load time of this commit; 0 when the kernel came from the process-wide cache */
 } are_commit_info;
 int are_cuda_get_commit_info(are_cuda_ctx *ctx, are_commit_info *out);

@@ -263,7 +263,7 @@ def test_quantised_nodes_equal_fp32_nodes(ctx):
     par = capi.make_params(**sc.params_args(sample_count=8, traversal=2))
     for builder in (capi.BVH_BUILDER_HOST_SAH, capi.BVH_BUILDER_DEVICE_LBVH):
         info = _commit(ctx, sc, builder)
-        assert info.bvh_nodes > 16384
+        assert info.bvh_nodes > 16384 and 1000 <= info.quant_area_permille < 1100
         out = {}
         for q in (1, 0):
             ctx.set_option(capi.OPT_QUANTIZED_NODES, q)
@@ -294,3 +294,11 @@ def test_quantised_nodes_equal_fp32_nodes(ctx):
     far = capi.make_camera(pos=(0, 0, 5000.0), target=(0, 0, 0), up=(0, 1, 0), vfov_deg=0.5)
     _, sf = ctx.render(far, par)
     assert sf.kernel_variant == capi.KERNEL_BVH2_BIG
+    # a scene whose extent dwarfs its primitives: the grid is too coarse, the commit says so and the fp32 nodes render
+    lam, grey = sc.spheres[0][2], sc.spheres[0][3]
+    sc.spheres.append((np.array([0.0, -1e5 - 20.0, 0.0]), 1e5, lam, grey))
+    sc.order.append(("s", len(sc.spheres) - 1))
+    info = _commit(ctx, sc, capi.BVH_BUILDER_HOST_SAH)
+    assert info.quant_area_permille > 1250
+    _, sg = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=1, traversal=2)))
+    assert sg.kernel_variant == capi.KERNEL_BVH2_BIG
