@@ -71,6 +71,15 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #ifndef TRAV_MIN_LANES
 #define TRAV_MIN_LANES 6   // BVH slices end when fewer lanes than this are still traversing and others are waiting
 #endif
+// ... of the traversal over quantised nodes (MODE 4: big hierarchies, long rays).  1 M primitives at 16 / 4 spp per launch,
+// (steps per vote, min lanes): (4, 6) 1 110 / 988, (8, 6) 1 153 / 1 016, (16, 6) 1 173 / 1 031, (8, 20) 1 166 / 1 050,
+// (16, 16) 1 175 / 1 047, (16, 20) 1 187 / 1 068, (16, 24) 1 175 / 1 071, (24, 20) 1 202 / 1 074, (32, 20) 1 200 / 1 073
+#ifndef TRAV_MIN_LANES_Q
+#define TRAV_MIN_LANES_Q 20
+#endif
+#ifndef TRAV_STEPS_PER_VOTE_Q
+#define TRAV_STEPS_PER_VOTE_Q 16
+#endif
 #ifndef TRAV_STEPS_PER_VOTE
 #define TRAV_STEPS_PER_VOTE 4  // measured 1 / 2 / 4 / 8: RTIOW 3498 / 3582 / 3596 / 3417, 1 M primitives 584 / 591 / 602 / 607 Msamples/s
 #endif
@@ -213,7 +222,7 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 				if (!trav) node = TRAV_DONE;
 				while (true) {
 #pragma unroll 1
-					for (int rep = 0; rep < TRAV_STEPS_PER_VOTE / TRAV_LEAF_EVERY; ++rep) {  // several steps between the warp votes that decide the end of the slice
+					for (int rep = 0; rep < (MODE == 4 ? TRAV_STEPS_PER_VOTE_Q : TRAV_STEPS_PER_VOTE) / TRAV_LEAF_EVERY; ++rep) {  // several steps between the warp votes that decide the end of the slice
 						// The warp executes the leaf phase whenever ANY lane holds a leaf — with ~19 lanes traversing that is most
 						// iterations, for one or two lanes each time.  Running it once per TRAV_LEAF_EVERY node phases lets lanes that
 						// reach a leaf wait a step or two and cuts the leaf code's share of the issue slots accordingly.
@@ -223,7 +232,7 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 						if (node < 0 && node != TRAV_DONE) bvh_leaf<COUNT>(A.sc, o, d, A.tmin, node, stk, h, &tc);  // leaf phase
 					}
 					const int n_trav = __popc(__ballot_sync(full, node != TRAV_DONE));
-					if (n_trav == 0 || (n_trav < TRAV_MIN_LANES && n_trav < n_rays)) break;
+					if (n_trav == 0 || (n_trav < (MODE == 4 ? TRAV_MIN_LANES_Q : TRAV_MIN_LANES) && n_trav < n_rays)) break;
 				}
 				trav = node != TRAV_DONE;
 			}

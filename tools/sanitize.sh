@@ -33,6 +33,12 @@ with capi.Context(0) as ctx:
         assert ctx.commit_info().builder == capi.BVH_BUILDER_DEVICE_LBVH
         img, st = ctx.render(capi.make_camera(**sc.camera_args()), capi.make_params(**sc.params_args(sample_count=2, traversal=2, max_depth=8)))
         assert np.isfinite(img).all()
+        if name == "stress":  # 30 000 nodes: the quantised 32-byte nodes (k_quant_grid, k_quant_nodes, bvhq_step), then the fp32 nodes (256-bit loads)
+            assert st.kernel_variant == capi.KERNEL_BVH2_QUANT, st.kernel_variant
+            ctx.set_option(capi.OPT_QUANTIZED_NODES, 0)
+            img, st = ctx.render(capi.make_camera(**sc.camera_args()), capi.make_params(**sc.params_args(sample_count=2, traversal=2, max_depth=8)))
+            assert st.kernel_variant == capi.KERNEL_BVH2_BIG and np.isfinite(img).all()
+            ctx.set_option(capi.OPT_QUANTIZED_NODES, 1)
     ctx.set_bvh_builder(capi.BVH_BUILDER_HOST_SAH)
     # round 2: wavefront schedule, 4-wide BVH, refit, tone-map, L2 probe
     ctx.set_option(capi.OPT_BUILD_BVH4, 1)
