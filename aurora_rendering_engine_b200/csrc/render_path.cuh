@@ -66,7 +66,9 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #define TRAV_LEAF_EVERY 1  // node phases per leaf phase inside a slice (must divide TRAV_STEPS_PER_VOTE)
 #endif
 #ifndef BVH_BIG_NODES
-#define BVH_BIG_NODES 16384       // 1 MiB of 64 B nodes: beyond this the high-occupancy build is launched
+#define BVH_BIG_NODES 8192        // beyond this: the high-occupancy build over quantised nodes.  Crossover measured on the random-cloud scene at
+                                  // 3 k / 6 k / 12 k / 16 k / 24 k / 50 k / 200 k / 1 M primitives, quantised against the L1-resident fp32 kernel:
+                                  // -8 % / -2 % / +7 % / +10 % / (against the big fp32 kernel:) +18 % / +30 % / +53 % / +66 %
 #endif
 #ifndef TRAV_MIN_LANES
 #define TRAV_MIN_LANES 6   // BVH slices end when fewer lanes than this are still traversing and others are waiting

@@ -72,6 +72,8 @@ def parse():
     ap.add_argument("--baked-min-blocks", type=int, default=0, help="tuning: CTAs per SM the baked kernel is compiled for")
     ap.add_argument("--wavefront", action="store_true", help="A/B: the same estimator scheduled as wavefront stages (ARE_INTEGRATOR_PATH_WAVEFRONT)")
     ap.add_argument("--l2-persist", type=int, default=0, help="A/B: BVH renders mark the node array L2-persisting, per cent of the carve-out (ARE_OPT_L2_PERSIST_NODES)")
+    ap.add_argument("--n-prims", type=int, default=0, help="A/B: primitive count of the `stress` scene (default: its 1 000 000)")
+    ap.add_argument("--no-quant", action="store_true", help="A/B: big hierarchies through their fp32 nodes (ARE_OPT_QUANTIZED_NODES = 0)")
     ap.add_argument("--job-spp", type=int, default=1024, help="strong-scaling job: total samples per pixel sharded over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -86,7 +88,8 @@ def parse():
 def make_scene(a, name=None, **kw):
     from aurora_rendering_engine_b200 import scenes
     if name is None:
-        sc = scenes.by_name(a.scene, width=a.width, height=a.height)
+        kw = {"n_prims": a.n_prims} if a.scene == "stress" and a.n_prims > 0 else {}
+        sc = scenes.by_name(a.scene, width=a.width, height=a.height, **kw)
         if a.wavefront:
             sc.integrator = scenes.INTEGRATOR_PATH_WAVEFRONT
         return sc
@@ -533,6 +536,8 @@ def kernel_options(a):
               "baked-packed": {capi.OPT_BAKED_PACKED: 1}}.get(a.kernel, {}))
     if a.l2_persist:
         o[capi.OPT_L2_PERSIST_NODES] = a.l2_persist
+    if a.no_quant:
+        o[capi.OPT_QUANTIZED_NODES] = 0
     if a.baked_min_blocks:
         o[capi.OPT_BAKED_MIN_BLOCKS] = a.baked_min_blocks
     if a.traversal == 4:  # ARE_TRAVERSAL_BVH4 needs the 4-wide collapse of the host-built tree

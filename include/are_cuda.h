@@ -204,7 +204,7 @@ typedef enum are_option {
 	                                (cudaAccessPolicyWindow) claiming this per cent of the device's persisting carve-out */
 	ARE_OPT_BUILD_BVH4 = 10, /* 0 (default) / 1: the host builder also collapses its BVH2 into 4-wide nodes (ARE_TRAVERSAL_BVH4) */
 	ARE_OPT_BAKED_MIN_BLOCKS = 11, /* tuning: CTAs per SM the baked kernel is compiled for (0 = default: 6 lean, 5 generic) */
-	ARE_OPT_QUANTIZED_NODES = 12 /* 1 (default): BVH2 hierarchies of more than 16384 nodes are also stored as 32-byte nodes — child boxes as
+	ARE_OPT_QUANTIZED_NODES = 12 /* 1 (default): BVH2 hierarchies of more than 8192 nodes are also stored as 32-byte nodes — child boxes as
 	                                16-bit planes on a grid over the root box, padded outwards, so every hit the fp32 nodes report is still
 	                                found — and ARE_TRAVERSAL_BVH2 renders through them (ARE_KERNEL_BVH2_QUANT); 0: fp32 nodes only
 	                                (renders: at once; the copy itself: from the next commit) */

@@ -253,7 +253,7 @@ def test_bvh4_equals_bvh2(ctx):
 
 
 def test_quantised_nodes_equal_fp32_nodes(ctx):
-    """Hierarchies beyond 16384 nodes are traversed through 32-byte nodes whose child boxes are 16-bit planes on a grid
+    """Hierarchies beyond 8192 nodes are traversed through 32-byte nodes whose child boxes are 16-bit planes on a grid
     over the root box, padded outwards (ARE_OPT_QUANTIZED_NODES, dev_types.h: BvhNodeQ): a superset of every fp32 box, so
     each ray must end on the same primitive — identical ray counts, images equal up to summation order — at the price of
     a few more node visits.  Both builders; switching the option off renders through the fp32 nodes at once; a camera too
