@@ -351,7 +351,7 @@ __device__ __forceinline__ unsigned quant_pair(double c, double h, double glo, d
 __global__ void k_quant_nodes(int n, const BvhNode *__restrict__ nodes, QGrid *__restrict__ grid, BvhNodeQ *__restrict__ out) {
 	const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool live = i0 < n;
-	const int i = live ? i0 : n - 1;  // idle threads of the last warp redo the last node (same values, and they add no area)
+	const int i = live ? i0 : n - 1;  // idle threads of the last warp stay for the warp sums below (they store nothing and add no area)
 	const BvhNode nd = nodes[i];
 	const double gx = grid->lo[0], gy = grid->lo[1], gz = grid->lo[2];
 	const double ix = 1.0 / (double)grid->step[0], iy = 1.0 / (double)grid->step[1], iz = 1.0 / (double)grid->step[2];
@@ -359,7 +359,7 @@ __global__ void k_quant_nodes(int n, const BvhNode *__restrict__ nodes, QGrid *_
 	q.q[0] = quant_pair(nd.b0.x, nd.b0.y, gx, ix); q.q[1] = quant_pair(nd.b0.z, nd.b0.w, gy, iy); q.q[2] = quant_pair(nd.b2.x, nd.b2.y, gz, iz);
 	q.q[3] = quant_pair(nd.b1.x, nd.b1.y, gx, ix); q.q[4] = quant_pair(nd.b1.z, nd.b1.w, gy, iy); q.q[5] = quant_pair(nd.b2.z, nd.b2.w, gz, iz);
 	q.child[0] = nd.child[0]; q.child[1] = nd.child[1];
-	out[i] = q;
+	if (live) out[i] = q;
 	// what the padding costs: per child box, surface area as stored here over that of the fp32 box (a ray that reaches the
 	// parent visits the child in proportion to it); the commit reads the mean over all child boxes
 	const float sx = grid->step[0], sy = grid->step[1], sz = grid->step[2];
