@@ -82,6 +82,10 @@ __device__ __forceinline__ void warp_tile_origin(int W, int &x0, int &y0) {
 #ifndef TRAV_STEPS_PER_VOTE_Q
 #define TRAV_STEPS_PER_VOTE_Q 16
 #endif
+#ifndef TRAV_LEAF_EVERY_Q
+#define TRAV_LEAF_EVERY_Q 2   // node phases per leaf phase (must divide TRAV_STEPS_PER_VOTE_Q); 1 / 2 / 4 / 8 on the random cloud at 1 M primitives:
+                              // 1 190 / 1 235 / 1 214 / 1 230, at 50 k: 3 657 / 3 777 / 3 771 / 3 828, at 12 k: 6 187 / 6 397 / 6 258 / 6 437
+#endif
 #ifndef TRAV_STEPS_PER_VOTE
 #define TRAV_STEPS_PER_VOTE 4  // measured 1 / 2 / 4 / 8: RTIOW 3498 / 3582 / 3596 / 3417, 1 M primitives 584 / 591 / 602 / 607 Msamples/s
 #endif
@@ -224,12 +228,12 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 				if (!trav) node = TRAV_DONE;
 				while (true) {
 #pragma unroll 1
-					for (int rep = 0; rep < (MODE == 4 ? TRAV_STEPS_PER_VOTE_Q : TRAV_STEPS_PER_VOTE) / TRAV_LEAF_EVERY; ++rep) {  // several steps between the warp votes that decide the end of the slice
+					for (int rep = 0; rep < (MODE == 4 ? TRAV_STEPS_PER_VOTE_Q / TRAV_LEAF_EVERY_Q : TRAV_STEPS_PER_VOTE / TRAV_LEAF_EVERY); ++rep) {  // several steps between the warp votes that decide the end of the slice
 						// The warp executes the leaf phase whenever ANY lane holds a leaf — with ~19 lanes traversing that is most
 						// iterations, for one or two lanes each time.  Running it once per TRAV_LEAF_EVERY node phases lets lanes that
 						// reach a leaf wait a step or two and cuts the leaf code's share of the issue slots accordingly.
 #pragma unroll
-						for (int r = 0; r < TRAV_LEAF_EVERY; ++r)
+						for (int r = 0; r < (MODE == 4 ? TRAV_LEAF_EVERY_Q : TRAV_LEAF_EVERY); ++r)
 							if (node >= 0) Trav<MODE>::template step<COUNT>(A.sc, A.tmin, rs, node, stk, h, &tc);  // node phase
 						if (node < 0 && node != TRAV_DONE) bvh_leaf<COUNT>(A.sc, o, d, A.tmin, node, stk, h, &tc);  // leaf phase
 					}
