@@ -174,7 +174,10 @@ bool resolve_traversal(are_cuda_ctx *ctx, int traversal, int &mode) {
 	else if (traversal == ARE_TRAVERSAL_WIDE) mode = wide_ok ? 2 : 1;  // a single-primitive scene has no wide hierarchy
 	else if (traversal == ARE_TRAVERSAL_BVH4) mode = ctx->dev.nodes4 ? 3 : 1;  // not built (option off, device-built tree, too deep): BVH2
 	else if (traversal == ARE_TRAVERSAL_AUTO) {
-		if (brute_ok && ctx->csp->n_hot <= 32) mode = 0;
+		// Brute force (baked, from shared memory) against the BVH2, measured: a room where every ray hits something — textured
+		// scene, 6 slots: 14.5 against 8.9 Gsamples/s; Cornell, 4 fused items: 11.1 against 4.9 — and a sparse cloud where most rays
+		// miss everything, 4 / 8 / 16 / 32 slots: 85 / 65 / 41 / 24 against 71 / 66 / 54 / 50.  16 = BAKE_MAX_SLOTS.
+		if (brute_ok && ctx->csp->n_hot <= 16) mode = 0;
 		else mode = (wide_ok && (int)ctx->csp->nodes.size() > ctx->wide_min_nodes) ? 2 : 1;
 	} else return false;
 	return true;

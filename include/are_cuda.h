@@ -72,7 +72,8 @@ typedef enum are_integrator {
 } are_integrator;
 
 typedef enum are_traversal {
-	ARE_TRAVERSAL_AUTO = 0, /* brute force from shared memory for small scenes, BVH2 for mid-size, compressed wide BVH for large ones */
+	ARE_TRAVERSAL_AUTO = 0, /* brute force (scene-specialised kernel) up to 16 hot slots, else the BVH2 — through quantised 32-byte nodes beyond
+	                           8192 nodes (ARE_OPT_QUANTIZED_NODES); the compressed wide BVH only above ARE_OPT_WIDE_MIN_NODES (default: never) */
 	ARE_TRAVERSAL_BRUTE = 1,
 	ARE_TRAVERSAL_BVH = 2, /* binary BVH, 64-byte nodes with both children's boxes */
 	ARE_TRAVERSAL_WIDE = 3, /* compressed 8-wide BVH, 80-byte nodes with 8-bit child boxes (large scenes) */
