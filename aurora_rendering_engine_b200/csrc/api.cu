@@ -1113,17 +1113,7 @@ static int render_single(are_cuda_ctx *ctx, const are_camera *cam, const are_ren
 	RenderArgs a;
 	std::memset(&a, 0, sizeof a);
 	a.sc = ctx->dev;
-	if (a.sc.nodes_q) {
-		// the quantised nodes' half-step rounding bound holds for ray origins within 64 grid extents of the grid; every
-		// secondary ray starts inside it, the camera is checked here
-		const QGrid &g = ctx->qgrid_host;
-		bool near_enough = (ctx->parent ? ctx->parent : ctx)->opt_quant_nodes;
-		for (int k = 0; k < 3; ++k) {
-			const double ext = (double)g.hi[k] - (double)g.lo[k], dist = std::max((double)g.lo[k] - cam->pos[k], cam->pos[k] - (double)g.hi[k]);
-			near_enough = near_enough && dist <= 64.0 * ext;
-		}
-		if (!near_enough) { a.sc.nodes_q = nullptr; a.sc.qgrid = nullptr; }
-	}
+	if (a.sc.nodes_q && !(ctx->parent ? ctx->parent : ctx)->opt_quant_nodes) { a.sc.nodes_q = nullptr; a.sc.qgrid = nullptr; }
 	make_cam_basis(cam->pos, cam->target, cam->up, cam->vfov_deg, cam->focus_dist, cam->defocus_angle_deg, cam->jitter, p->width, p->height, a.cam);
 	for (int k = 0; k < 3; ++k) {
 		a.camf.pos[k] = (float)a.cam.pos[k]; a.camf.fwd[k] = (float)a.cam.fwd[k];

@@ -375,8 +375,9 @@ __device__ __forceinline__ void bvh_step(const DevScene &sc, float tmin, const R
 //   t = (lo + q step - o) / d = (2^23 + q) * A + B',   A = step / d,  B' = (lo - o) / d - 2^23 A
 // by ONE multiply-add — the de-quantisation costs nothing beyond the permute.  Which 16 bits of a (lo, hi) word are the
 // near plane is a per-ray permute selector (the sign of d), so there are no per-axis min / max either.
-// Rounding: B' is rounded at the magnitude of 2^23 A, i.e. to half a grid step; the builder pads every box by a whole
-// step.  (Ray origins farther than 64 grid extents from the grid would need more: such a launch uses the fp32 nodes.)
+// Rounding: B' is rounded at the magnitude of max(2^23 A, |lo - o| / d), i.e. to half a grid step for ray origins within
+// 128 grid extents of the grid — the builder pads every box by a whole step — and beyond that to the same ulp of the
+// distance that the fp32 step's c / d - o / d carries: never worse than the fp32 nodes by more than the padding covers.
 struct RaySlopesQ {
 	float ax, ay, az, bx, by, bz;
 	unsigned sx, sy, sz;  // permute selector of the near plane: 0x7610 (low half) when d >= 0, 0x7632 (high half) otherwise

@@ -330,14 +330,20 @@ __global__ void k_quant_grid(const BvhNode *__restrict__ nodes, QGrid *grid) {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
 	const BvhNode n = nodes[0];
 	const double c[2][3] = { { n.b0.x, n.b0.z, n.b2.x }, { n.b1.x, n.b1.z, n.b2.z } }, h[2][3] = { { n.b0.y, n.b0.w, n.b2.y }, { n.b1.y, n.b1.w, n.b2.w } };
+	double lo[3], hi[3], widest = 0.0;
 	for (int k = 0; k < 3; ++k) {
-		const double lo = fmin(c[0][k] - h[0][k], c[1][k] - h[1][k]), hi = fmax(c[0][k] + h[0][k], c[1][k] + h[1][k]);
-		double ext = hi - lo;
-		const double mag = fmax(fabs(lo), fabs(hi));
-		ext = fmax(ext, fmax(mag * 1e-4, 1e-30));  // a flat scene still gets a grid its fp32 coordinates resolve
+		lo[k] = fmin(c[0][k] - h[0][k], c[1][k] - h[1][k]);
+		hi[k] = fmax(c[0][k] + h[0][k], c[1][k] + h[1][k]);
+		widest = fmax(widest, hi[k] - lo[k]);
+	}
+	for (int k = 0; k < 3; ++k) {
+		// a scene with no extent along an axis (coplanar primitives) still gets a grid: at least 1e-4 of its widest axis, and
+		// never finer than the fp32 coordinates themselves resolve
+		const double mag = fmax(fabs(lo[k]), fabs(hi[k]));
+		const double ext = fmax(fmax(hi[k] - lo[k], 1e-4 * widest), fmax(mag * 1e-4, 1e-20));
 		const float step = (float)(ext / 65520.0);   // 65520 + 2 * 4 widening steps < 65535
 		grid->step[k] = step;
-		grid->lo[k] = (float)(lo - 4.0 * (double)step);
+		grid->lo[k] = (float)(lo[k] - 4.0 * (double)step);
 		grid->hi[k] = (float)((double)grid->lo[k] + 65535.0 * (double)step);
 	}
 	grid->area32 = grid->area_q = grid->pad_ = 0.f;

@@ -256,8 +256,8 @@ def test_quantised_nodes_equal_fp32_nodes(ctx):
     """Hierarchies beyond 8192 nodes are traversed through 32-byte nodes whose child boxes are 16-bit planes on a grid
     over the root box, padded outwards (ARE_OPT_QUANTIZED_NODES, dev_types.h: BvhNodeQ): a superset of every fp32 box, so
     each ray must end on the same primitive — identical ray counts, images equal up to summation order — at the price of
-    a few more node visits.  Both builders; switching the option off renders through the fp32 nodes at once; a camera too
-    far from the scene for the decode's rounding bound falls back to them by itself."""
+    a few more node visits.  Both builders; switching the option off renders through the fp32 nodes at once; a camera 150
+    scene extents away sees the same picture through either."""
     sc = scenes.stress(n_prims=40_000, width=192, height=108)
     cam = capi.make_camera(**sc.camera_args())
     par = capi.make_params(**sc.params_args(sample_count=8, traversal=2))
@@ -290,10 +290,15 @@ def test_quantised_nodes_equal_fp32_nodes(ctx):
     b, sb = ctx.render(inside, par2)
     ctx.set_option(capi.OPT_QUANTIZED_NODES, 1)
     assert sa.kernel_variant == capi.KERNEL_BVH2_QUANT and sa.rays == sb.rays and np.allclose(a, b, rtol=1e-5, atol=1e-5)
-    # far away: |camera - grid| > 64 grid extents -> the fp32 nodes render
+    # far away (150 scene extents): the decode's B' is then rounded at the ulp of the distance, as the fp32 step's o / d is
     far = capi.make_camera(pos=(0, 0, 5000.0), target=(0, 0, 0), up=(0, 1, 0), vfov_deg=0.5)
-    _, sf = ctx.render(far, par)
-    assert sf.kernel_variant == capi.KERNEL_BVH2_BIG
+    a, sa = ctx.render(far, par)
+    ctx.set_option(capi.OPT_QUANTIZED_NODES, 0)
+    b, sb = ctx.render(far, par)
+    ctx.set_option(capi.OPT_QUANTIZED_NODES, 1)
+    assert sa.kernel_variant == capi.KERNEL_BVH2_QUANT and sb.kernel_variant == capi.KERNEL_BVH2_BIG
+    # at this distance fp32 places a hit to ~5e-4, the size of the smallest primitives' features: grazing decisions may differ
+    assert abs(sa.rays - sb.rays) <= 2e-3 * sb.rays and psnr(np.clip(a / 8, 0, 1), np.clip(b / 8, 0, 1)) > 35.0
     # a scene whose extent dwarfs its primitives: the grid is too coarse, the commit says so and the fp32 nodes render
     lam, grey = sc.spheres[0][2], sc.spheres[0][3]
     sc.spheres.append((np.array([0.0, -1e5 - 20.0, 0.0]), 1e5, lam, grey))
@@ -302,3 +307,45 @@ def test_quantised_nodes_equal_fp32_nodes(ctx):
     assert info.quant_area_permille > 1250
     _, sg = ctx.render(cam, capi.make_params(**sc.params_args(sample_count=1, traversal=2)))
     assert sg.kernel_variant == capi.KERNEL_BVH2_BIG
+
+
+@pytest.mark.parametrize("case", ["flat", "far_from_origin", "one_huge_axis"])
+def test_quantised_nodes_on_awkward_extents(ctx, case):
+    """The quantisation grid is derived from the root box: a scene with NO extent along an axis (coplanar triangles), a scene
+    10^4 units from the origin (coordinates that fp32 resolves to 1e-3 only), and a scene 1000 times longer along one axis
+    than along the others must all render what their fp32 nodes render."""
+    rng = np.random.RandomState(5)
+    n = 12_000
+    s = scenes.SceneDesc(case, width=160, height=90, spp=4, max_depth=6, t_min=1e-3)
+    lam = s.mat(scenes.MAT_LAMBERTIAN, -1)
+    grey = s.solid(0.6, 0.5, 0.4)
+    if case == "flat":  # small triangles in the plane z = 0 (disjoint cells of a grid, so no two are coplanar AND overlapping)
+        k = int(np.ceil(np.sqrt(n)))
+        for i in range(n):
+            x, y = (i % k) * 0.1 - 0.05 * k, (i // k) * 0.1 - 0.05 * k
+            s.tri((x, y, 0.0), (0.08, 0.0, 0.0), (0.0, 0.08, 0.0), lam, grey)
+        cam = dict(pos=(0.3, -0.2, 9.0), target=(0, 0, 0), up=(0, 1, 0), vfov_deg=50.0)
+    else:
+        off = np.array([1e4, -2e4, 1.5e4]) if case == "far_from_origin" else np.zeros(3)
+        scale = np.array([1.0, 1.0, 1.0]) if case == "far_from_origin" else np.array([1000.0, 1.0, 1.0])
+        c = rng.uniform(-5, 5, (n, 3)) * scale + off
+        r = rng.uniform(0.03, 0.08, n)
+        for i in range(n):
+            s.sphere(c[i], float(r[i]), lam, grey)
+        cam = dict(pos=tuple(off + np.array([0.0, 0.0, 16.0])), target=tuple(off), up=(0, 1, 0), vfov_deg=45.0)
+    s.camera = dict(cam, focus_dist=10.0, jitter=1)
+    camera = capi.make_camera(**s.camera_args())
+    par = capi.make_params(**s.params_args(sample_count=4, traversal=2))
+    for builder in (capi.BVH_BUILDER_HOST_SAH, capi.BVH_BUILDER_DEVICE_LBVH):
+        info = _commit(ctx, s, builder)
+        assert info.bvh_nodes > 8192 and info.quant_area_permille >= 1000, info.as_dict()
+        # 1000 : 1 extents put 0.06-wide spheres on a 0.15-wide grid along x: the commit measures that and keeps the fp32 nodes
+        used = info.quant_area_permille <= 1250
+        assert used == (case != "one_huge_axis"), info.as_dict()
+        iq, sq = ctx.render(camera, par)
+        ctx.set_option(capi.OPT_QUANTIZED_NODES, 0)
+        i32, s32 = ctx.render(camera, par)
+        ctx.set_option(capi.OPT_QUANTIZED_NODES, 1)
+        assert sq.kernel_variant == (capi.KERNEL_BVH2_QUANT if used else capi.KERNEL_BVH2_BIG) and s32.kernel_variant == capi.KERNEL_BVH2_BIG
+        assert sq.rays == s32.rays and sq.rays > s.width * s.height * 4
+        assert np.allclose(iq, i32, rtol=1e-5, atol=1e-5)
