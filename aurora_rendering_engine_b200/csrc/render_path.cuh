@@ -117,6 +117,11 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 	const uint32_t sb_shade = sb_prims + 48u * A.sc.n_hot, sb_frame = sb_shade + 32u * A.sc.n_lean_shade, sb_sbase = sb_frame + 32u * A.sc.n_lean_shade;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	for (int i = lane; i < 96; i += 32) s_acc[warp][i] = 0.0f;
+	// The warp's shared-memory areas as 32-bit shared addresses held in registers (the empty asm makes them opaque: left as
+	// expressions of threadIdx.x they are re-derived inside the loop, see shade.cuh: turbulence_coop)
+	uint32_t acc_sb = (uint32_t)__cvta_generic_to_shared(&s_acc[warp][0]);
+	uint32_t turb_q_sb = (uint32_t)__cvta_generic_to_shared(&s_turb_q[warp][0]), turb_sum_sb = (uint32_t)__cvta_generic_to_shared(&s_turb_sum[warp][0]);
+	if (!LEAN) asm volatile("" : "+r"(acc_sb), "+r"(turb_q_sb), "+r"(turb_sum_sb));  // (the lean / baked kernel never re-derived them, and loses 1.6 % with the register pinned)
 	if (!BVH) {
 		const float4 *src = reinterpret_cast<const float4 *>(A.sc.brute);
 		const int n4 = A.sc.n_hot * 3;
@@ -317,8 +322,15 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 				// (measured: dropping the finiteness half of this test in the lean kernel — its contributions are finite by
 				// construction — removes six instructions and LOSES 1.8 %: the compiler schedules the loop differently)
 				if (csum > 0.0f && csum < INFINITY) {
-					float *acc = &s_acc[warp][(task & 31) * 3];
-					atomicAdd(acc, contrib.x); atomicAdd(acc + 1, contrib.y); atomicAdd(acc + 2, contrib.z);
+					if (LEAN) {
+						float *acc = &s_acc[warp][(task & 31) * 3];
+						atomicAdd(acc, contrib.x); atomicAdd(acc + 1, contrib.y); atomicAdd(acc + 2, contrib.z);
+					} else {
+						const uint32_t acc = acc_sb + 12u * (uint32_t)(task & 31);
+						asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(acc), "f"(contrib.x) : "memory");
+						asm volatile("red.shared.add.f32 [%0 + 4], %1;" ::"r"(acc), "f"(contrib.y) : "memory");
+						asm volatile("red.shared.add.f32 [%0 + 8], %1;" ::"r"(acc), "f"(contrib.z) : "memory");
+					}
 				}
 				task = -1;
 			}
@@ -353,7 +365,7 @@ __device__ __forceinline__ void render_path_body(const RenderArgs &A) {
 				const int noise_tex = general && ((sbits >> SHADE_TEXKIND_SHIFT) & 7) == TK_NOISE && mk_ != MK_DIELECTRIC && mk_ != MK_LIGHT
 					? ((sbits >> SHADE_TEXID_SHIFT) & SHADE_TEXID_MASK) : -1;
 				if (__any_sync(full, noise_tex >= 0)) {
-					turb = turbulence_coop(A.sc, noise_tex >= 0, noise_tex, sP, s_turb_q[warp], s_turb_sum[warp]);
+					turb = turbulence_coop(A.sc, noise_tex >= 0, noise_tex, sP, turb_q_sb, turb_sum_sb);
 					have_turb = noise_tex >= 0;
 				}
 			}

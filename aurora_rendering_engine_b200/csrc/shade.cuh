@@ -94,31 +94,38 @@ __device__ inline double perlin_noise_tab<double>(const DevScene &sc, const Text
 // (First form, round 2: the four requesters of a round were found with find-first-set chains on the ballot and their
 // points fetched by four shuffles — ~45 instructions of bookkeeping per round beside the ~105 of the octave itself;
 // the queue needs ~10.  Same arithmetic, same sums.)
-// Called by all 32 lanes in converged code.  queue / sums: 32 entries each, private to the warp.
+// Called by all 32 lanes in converged code.  queue_sb / sums_sb: 32-bit shared-memory addresses of the warp's 32 queue
+// entries (float4) and 32 sums (float) — explicit ld / st.shared on a base that lives in one register: through generic
+// pointers the compiler re-derives the shared window and the warp index inside the loop (S2R SR_TID.X, S2R SR_CgaCtaId,
+// LEA: 29 S2R in the textured kernel, 2 % of its warp-state samples).
 // Returns the sum to the lanes that set `need`; 0 elsewhere.
-__device__ __forceinline__ float turbulence_coop(const DevScene &sc, bool need, int tex_id, V3<float> P, float4 *queue, float *sums) {
+__device__ __forceinline__ float turbulence_coop(const DevScene &sc, bool need, int tex_id, V3<float> P, uint32_t queue_sb, uint32_t sums_sb) {
 	const unsigned full = 0xffffffffu;
 	const int lane = threadIdx.x & 31, slot = lane >> 3, oct = lane & 7;
 	const unsigned m = __ballot_sync(full, need);
 	const int n = __popc(m);
 	const int my_rank = __popc(m & ((1u << lane) - 1u));  // this lane is the my_rank-th requester (if it is one)
-	if (need) queue[my_rank] = make_float4(P.x, P.y, P.z, __int_as_float(tex_id));
+	if (need)
+		asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(queue_sb + 16u * my_rank), "f"(P.x), "f"(P.y), "f"(P.z), "f"(__int_as_float(tex_id)) : "memory");
 	__syncwarp();
 	for (int base = 0; base < n; base += 4) {  // warp-uniform
 		const int e = base + slot;
 		float v = 0.0f;
 		if (e < n && oct < 7) {
-			const float4 q = queue[e];
+			float4 q;
+			asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(queue_sb + 16u * e) : "memory");
 			const float up = (float)(1 << oct), w = 1.0f / up;  // exact powers of two: the same points and weights as repeated doubling / halving
 			v = w * perlin_noise<float>(sc.tex_data + sc.texs[__float_as_int(q.w)].data_off, mk<float>(q.x * up, q.y * up, q.z * up));
 		}
 		v += __shfl_xor_sync(full, v, 1);
 		v += __shfl_xor_sync(full, v, 2);
 		v += __shfl_xor_sync(full, v, 4);
-		if (oct == 0 && e < n) sums[e] = v;
+		if (oct == 0 && e < n) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sums_sb + 4u * e), "f"(v) : "memory");
 	}
 	__syncwarp();
-	return need ? sums[my_rank] : 0.0f;
+	float result = 0.0f;
+	if (need) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(result) : "r"(sums_sb + 4u * my_rank) : "memory");
+	return result;
 }
 
 // turb: when non-null, the turbulence sum of a TK_NOISE texture at P already formed by turbulence_coop
