@@ -49,6 +49,26 @@ def test_struct_layouts_match_header(tmp_path):
     assert got == exp
 
 
+def test_enums_and_commit_info_match_header(tmp_path):
+    """Every ARE_OPT_* / ARE_KERNEL_* / ARE_TRAVERSAL_* value and the are_commit_info layout, as the C compiler sees the header,
+    equal the constants and the ctypes mirror the Python plumbing uses."""
+    names = {"OPT": ["LEAN_KERNEL", "BAKED_KERNEL", "BAKED_PACKED", "FUSE_PARALLELOGRAMS", "FUSE_BOXES", "BUILD_WIDE", "WIDE_MIN_NODES", "LBVH_MAX_HEIGHT",
+                     "L2_PERSIST_NODES", "BUILD_BVH4", "BAKED_MIN_BLOCKS", "QUANTIZED_NODES"],
+             "KERNEL": ["NONE", "BRUTE", "BRUTE_LEAN", "BVH2", "BVH2_BIG", "WIDE", "RT_AO", "BRUTE_BAKED", "WAVEFRONT", "BVH4", "BVH2_QUANT"]}
+    lines = [f'printf("%d ", (int)ARE_{g}_{n});' for g, ns in names.items() for n in ns]
+    lines += ['printf("%zu %zu %zu %zu ", sizeof(are_commit_info), offsetof(are_commit_info, baked), offsetof(are_commit_info, quant_area_permille), '
+              'offsetof(are_commit_info, bake_compile_ms));']
+    f = tmp_path / "e.c"
+    f.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "are_cuda.h"\nint main(void){' + "".join(lines) + "return 0;}\n")
+    exe = tmp_path / "e"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(f), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    got = [int(x) for x in out]
+    exp = [getattr(capi, f"{g}_{n}") for g, ns in names.items() for n in ns]
+    exp += [C.sizeof(capi.CommitInfo), capi.CommitInfo.baked.offset, capi.CommitInfo.quant_area_permille.offset, capi.CommitInfo.bake_compile_ms.offset]
+    assert got == exp
+
+
 def test_no_cpu_fallback(lib):
     if lib.are_cuda_device_count() > 0:
         pytest.skip("a CUDA device is present")
